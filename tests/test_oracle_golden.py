@@ -1,0 +1,70 @@
+"""The CPU restatement (oracle/policy_oracle.py) against fixtures produced by the REAL reference
+(oracle/make_golden.py).  CPU only; this is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import policy_oracle as po
+from oracle.make_golden import CASES, PROBE
+from oracle.synth import make_sample, make_state_dict, trainable_keys
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _probe(t, full):
+    a = t.detach().cpu().numpy()
+    return a if full else a.reshape(-1)[::PROBE][:4096]
+
+
+def _check_case(name):
+    spec, batch, full = CASES[name]
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    sd = make_state_dict(spec, seed=3407)
+    sample = make_sample(spec, batch, seed=0)
+    keys = trainable_keys(spec, sd)
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in keys}
+    work = dict(sd)
+    work.update(leaves)
+    logits = po.policy_logits(work, sample, spec, training=True)
+    out = {f"{h}_heatmap": z.sigmoid() for h, z in logits.items()}
+    loss, inter = po.bce_gaussmap(out, sample, spec)
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=2e-5)
+    for h in spec.heads_out:
+        np.testing.assert_allclose(inter[h].item(), g[f"loss/{h}"], rtol=2e-5)
+        scale = float(g[f"logits_absmax/{h}"])
+        np.testing.assert_allclose(_probe(logits[h], full), g[f"logits/{h}"], atol=2e-5 * scale, rtol=0)
+        np.testing.assert_allclose(_probe(out[f"{h}_heatmap"], full), g[f"heatmap/{h}"], atol=1e-5, rtol=0)
+    grads = dict(zip(keys, torch.autograd.grad(loss, [leaves[k] for k in keys])))
+    for k in keys:
+        gn = float(g[f"gradnorm/{k}"])
+        np.testing.assert_allclose(grads[k].double().norm().item(), gn, rtol=1e-3, atol=1e-9, err_msg=k)
+        np.testing.assert_allclose(_probe(grads[k], full), g[f"grad/{k}"], atol=2e-4 * gn / max(1.0, np.sqrt(grads[k].numel() / 64)) + 1e-9, rtol=1e-3, err_msg=k)
+    # one Adam step, lr 1e-3 as in make_golden.py
+    with torch.no_grad():
+        params = {k: sd[k] for k in keys}
+        po.adam_step(params, grads, {}, lr=1e-3)
+    for k in keys:
+        np.testing.assert_allclose(_probe(sd[k], full), g[f"param1/{k}"], atol=2e-5, rtol=1e-5, err_msg=k)
+    with torch.no_grad():
+        out2 = po.policy_forward(sd, sample, spec)
+        loss2, _ = po.bce_gaussmap(out2, sample, spec)
+        loss2m, _ = po.bce_gaussmap(out2, sample, spec, mask_pick_heatmap=True)
+    np.testing.assert_allclose(loss2.item(), g["loss_after_step"], rtol=1e-3)
+    np.testing.assert_allclose(loss2m.item(), g["loss_after_step_masked"], rtol=1e-3)
+    action = po.get_action(out2, sample, spec)
+    for k, v in action.items():
+        np.testing.assert_array_equal(np.asarray(v).astype(np.int64), g[f"action/{k}"], err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["tiny_uni", "tiny_bi_lora", "tiny_bi_seq_lora"])
+def test_oracle_matches_reference_tiny(name):
+    _check_case(name)
+
+
+@pytest.mark.parametrize("name", ["base224_bi_lora"])
+def test_oracle_matches_reference_base(name):
+    if not os.path.exists(os.path.join(GOLDEN, f"{name}.npz")):
+        pytest.skip("fixture not generated")
+    _check_case(name)
