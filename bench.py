@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — BiFold policy hot path on B200 (driver contract: see the task statement).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # our arm, 1 GPU
+    torchrun ... bench.py --gpus N --steps K --warmup W       # our arm, N GPUs (batch-sharded DDP, weak scaling)
+    python bench.py --impl reference --steps 2 --warmup 1     # CPU arm: the oracle restatement of the reference
+
+Workload (BASELINE.json configs[1]): BiFold bimanual single-frame TRAINING step, per-GPU batch 64,
+224x224 RGB + 1 instruction, SigLIP-base towers with LoRA (r=8) on q/v, 8-layer fusion transformer,
+4 ConvDecoder heads, BCE loss, Adam.  bf16 operands on tcgen05, fp32 accumulate / residual / loss.
+One step = forward + loss + backward + optimizer step over one synthetic batch.
+Metric: train samples/s (whole job).  `--mode infer` reports inference actions/s instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
+    ap.add_argument("--context", type=int, default=0, help="context frames T (0 = single-frame, config 2; 3 = config 3)")
+    ap.add_argument("--image-size", type=int, default=224)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=8, help="bounded sample for the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+def model_cfg(args, device):
+    from bifold_b200.config import Cfg
+    cfg = Cfg(name="siglip_sequential" if args.context else "siglip", image_size=args.image_size, is_bimanual=True,
+              requires_graph=False, patch_size=16, automodel_name=f"google/siglip-base-patch16-{args.image_size}", dim=768,
+              emb_dropout=0.0, lora=True, r=8, lora_alpha=32, lora_dropout=0.01, target_modules=["q_proj", "v_proj"],
+              threshold=0.5, text_encoder=None, pick_place_model="pick_place_convdecoder", fusion_model="concat_transformer",
+              depth=8, heads=16, mlp_ratio=4, dropout=0.0, precision=args.precision)
+    if args.context:
+        cfg["context_length"] = args.context
+    return cfg
+
+
+def synth_batch(args, batch, seed, pinned=True):
+    """Synthetic sample dict on the HOST (SURVEY.md §8d shapes; values do not need to match the oracle's)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    H = args.image_size
+    s = {"rgb": torch.randn(batch, 3, H, H, generator=g),
+         "instruction": torch.randint(0, 32000, (batch, 64), generator=g)}
+    if args.context:
+        s["rgb_context"] = torch.randn(batch, args.context, 3, H, H, generator=g)
+        s["context_attention_mask"] = (torch.arange(args.context)[None] < (torch.arange(batch) % (args.context + 1))[:, None]).long()
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(H, dtype=torch.float32), indexing="ij")
+    for h in ("left_pick", "left_place", "right_pick", "right_place"):
+        c = torch.randint(0, H, (batch, 2), generator=g).float()
+        s[f"{h}_heatmap"] = torch.exp(-((xs[None] - c[:, 0, None, None]) ** 2 + (ys[None] - c[:, 1, None, None]) ** 2) / 50.0)
+    s["mask"] = (((xs - H / 2) / (0.35 * H)) ** 2 + ((ys - H / 2) / (0.3 * H)) ** 2 <= 1).float()[None, None].repeat(batch, 1, 1, 1)
+    if pinned:
+        s = {k: v.contiguous().pin_memory() for k, v in s.items()}
+    return s
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def train_flops_per_sample(args):
+    """Algorithmic GEMM+attention FLOPs of one training step per sample (SURVEY.md §8d formulas):
+    forward x (2 for LoRA towers: fwd + dgrad; 3 for the fully trainable fusion)."""
+    D, M, Np, L = 768, 3072, (args.image_size // 16) ** 2, 64
+    layer = lambda N: 8 * N * D * D + 4 * N * D * M + 4 * N * N * D
+    T = args.context
+    vision = (12 * layer(Np) + 2 * Np * D * 768) * (T + 1)
+    text = 12 * layer(L)
+    Nf = 65 + (T + 1) * (Np + 1)
+    fusion = 8 * layer(Nf)
+    return 2 * (vision + text) + 3 * fusion, vision + text + fusion
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """CPU arm: the oracle restatement of the reference (oracle/policy_oracle.py), all host threads."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import policy_oracle as po
+    from oracle.synth import PolicySpec, make_sample, make_state_dict, trainable_keys
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = PolicySpec(name="siglip_sequential" if args.context else "siglip", image_size=args.image_size, is_bimanual=True,
+                      lora=True, lora_dropout=0.0, context_length=args.context)
+    sd = make_state_dict(spec)
+    keys = trainable_keys(spec, sd)
+    B = args.cpu_batch
+    sample = make_sample(spec, B, seed=0)
+    state = {}
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        if args.mode == "train":
+            po.train_step(sd, sample, spec, keys, state, lr=1e-4)
+        else:
+            with torch.no_grad():
+                out = po.policy_forward(sd, sample, spec)
+                po.get_action(out, sample, spec)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = B / (ms / 1e3)
+    metric = "train_samples_per_s" if args.mode == "train" else "infer_actions_per_s"
+    unit = "samples/s" if args.mode == "train" else "actions/s"
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, B, 1),
+            "cpu_baseline": {"value": value, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{args.steps} steps of batch {B} (same model/shapes as the GPU workload; CPU oracle port of the reference, fp32)"},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_gpu_batch, world):
+    return {"workload": f"BiFold bimanual {'context T=%d ' % args.context if args.context else 'single-frame '}"
+                        f"{'training step (fwd+BCE+bwd+Adam)' if args.mode == 'train' else 'inference (heatmaps + per-arm argmax action)'}, "
+                        f"SigLIP-base-patch16-{args.image_size} towers + LoRA r=8, 8-layer fusion, 4 ConvDecoder heads",
+            "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * world, "image": args.image_size,
+            "context_frames": args.context, "parallelism": f"dp{world}",
+            "l2_policy": "working set per step (activations + weights, several GB) is far larger than the 126 MB L2; no explicit flush"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from bifold_b200.build import build
+    if local_rank == 0:
+        build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from bifold_b200.losses import Losses
+    from bifold_b200.models import Models
+    from bifold_b200.optim import Optimizers
+    from bifold_b200.config import Cfg
+
+    torch.manual_seed(3407)
+    model = Models.get_by_name(model_cfg(args, dev), device=dev).to(dev)
+    # LoRA B is zero at init (peft); give it values so the LoRA path carries signal in the timed step
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if ".lora_B." in n:
+                p.normal_(0, 0.02)
+    loss_fn = Losses.get_by_name(cfg=Cfg(name="bce_gaussmap", is_bimanual=True, mask_pick_heatmap=False))
+    optim = Optimizers.get_by_name(cfg=Cfg(name="adam", lr=1e-4, betas=[0.9, 0.999], eps=1e-8, weight_decay=0),
+                                   params=filter(lambda p: p.requires_grad, model.parameters()))
+    if world > 1:
+        from bifold_b200.ddp import BatchShardedDDP
+        BatchShardedDDP(model, optim)
+    B = args.batch
+    host = synth_batch(args, B, seed=1000 + rank)
+    dev_sample = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    eng = model._ensure_engine()
+    train = args.mode == "train"
+    model.train(train)
+
+    def step(sample, read_back):
+        if train:
+            eng.step_seed += 1
+            out = model(sample)
+            loss, _ = loss_fn(out, sample)
+            optim.zero_grad()
+            loss.backward()
+            optim.step()
+            return loss.item() if read_back else loss
+        action = model.get_action(sample)      # D2H of the (heads,B,2) pixel table happens inside
+        return action
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step(dev_sample, False)
+    # ---- device-resident inputs: `value` ----
+    l0, o0 = eng.k.launches, optim.launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev = timed(lambda: step(dev_sample, False), args.steps)
+    clocks = sampler.stop()
+    launches = (eng.k.launches - l0) + (optim.launches - o0)
+    # ---- end-to-end through the public API with HOST (pinned) buffers: `e2e` ----
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def e2e_step():
+        s = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        step(s, True)
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    d2h = 4 if train else 4 * B * 2 * 4
+    per_step = ms_dev / args.steps
+    value = B * world / (per_step / 1e3)
+    e2e_value = B * world / (ms_e2e / args.steps / 1e3)
+    metric = "train_samples_per_s" if train else "infer_actions_per_s"
+    unit = "samples/s" if train else "actions/s"
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM), one extra instrumented step ----
+    roofline = None
+    if rank == 0 and not args.no_roofline:
+        roofline = gemm_roofline(eng, lambda: step(dev_sample, False))
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_leg(args)
+    if rank == 0:
+        tr_flops, fw_flops = train_flops_per_sample(args)
+        peaks = load_peaks()
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic", "config": workload_config(args, B, world),
+                "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks,
+                "model_flops_per_sample": tr_flops if train else fw_flops,
+                "model_tflops_per_gpu": (tr_flops if train else fw_flops) * B / (per_step / 1e3) / 1e12,
+                "model_frac_of_bf16_peak": (tr_flops if train else fw_flops) * B / (per_step / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
+                "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        p["source"] = "measured (MEASURED_PEAKS.json)"
+        return p
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def gemm_roofline(eng, step_fn):
+    """CUDA-event timing of every tcgen05 GEMM launch of one extra (untimed-for-the-headline) step, on the
+    launching stream: achieved = sum(2*M*N*K) / sum(duration)."""
+    import torch
+    k = eng.k
+    recs = []
+    orig = k.gemm
+
+    def timed_gemm(A, B, D, M, N, Kd, *a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(A, B, D, M, N, Kd, *a, **kw)
+        e1.record()
+        recs.append((2.0 * M * N * Kd, e0, e1, A.dtype == torch.bfloat16))
+
+    k.gemm = timed_gemm
+    try:
+        step_fn()
+        torch.cuda.synchronize()
+    finally:
+        k.gemm = orig
+    fl = sum(r[0] for r in recs if r[3])
+    ms = sum(r[1].elapsed_time(r[2]) for r in recs if r[3])
+    peaks = load_peaks()
+    if not recs or ms <= 0:
+        return None
+    ach = fl / (ms / 1e3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::f16, TMA-fed, TMEM accumulators)", "achieved": ach,
+            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "launches": len(recs),
+            "gemm_ms_per_step": ms, "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"}
+
+
+def cpu_baseline_leg(args):
+    """The oracle port of the reference timed on this box's host cores (bounded sample)."""
+    import torch
+    from oracle import policy_oracle as po
+    from oracle.synth import PolicySpec, make_sample, make_state_dict, trainable_keys
+    nthr = os.cpu_count() or 1
+    torch.set_num_threads(nthr)
+    spec = PolicySpec(name="siglip_sequential" if args.context else "siglip", image_size=args.image_size, is_bimanual=True,
+                      lora=True, lora_dropout=0.0, context_length=args.context)
+    sd = make_state_dict(spec)
+    keys = trainable_keys(spec, sd)
+    B = args.cpu_batch
+    sample = make_sample(spec, B, seed=0)
+    state, times = {}, []
+    for it in range(3):
+        t0 = time.perf_counter()
+        if args.mode == "train":
+            po.train_step(sd, sample, spec, keys, state, lr=1e-4)
+        else:
+            with torch.no_grad():
+                po.get_action(po.policy_forward(sd, sample, spec), sample, spec)
+        if it >= 1:
+            times.append(time.perf_counter() - t0)
+    v = B / (sum(times) / len(times))
+    return {"value": v, "unit": "samples/s" if args.mode == "train" else "actions/s", "cores": nthr, "kind": "port",
+            "sample": f"2 timed steps (1 warm-up) of batch {B}, same model and shapes, fp32 torch CPU oracle of the reference"}
+
+
+if __name__ == "__main__":
+    main()

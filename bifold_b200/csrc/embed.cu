@@ -1,0 +1,362 @@
+// Bandwidth-bound glue kernels around the towers: im2col for the patch-embedding GEMM, text
+// embedding gather, LoRA rank-r side path, fusion-token assembly and its backward.
+#include "common.cuh"
+
+namespace bfk {
+
+// ---- im2col (HF:178-179) -------------------------------------------------------------------------
+// One thread per 4 consecutive pixels of a patch row (p % 4 == 0).
+template <typename T>
+__global__ void im2col_kernel(const float* __restrict__ rgb, int B, int C, int H, int W, int p, T* __restrict__ out,
+                              long long ld) {
+  const int g = W / p, gh = H / p;
+  const long long total = (long long)B * C * H * (W / 4);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    int x4 = (int)(t % (W / 4));
+    long long r = t / (W / 4);
+    int y = (int)(r % H); r /= H;
+    int c = (int)(r % C);
+    int b = (int)(r / C);
+    float4 v = reinterpret_cast<const float4*>(rgb)[t];
+    int x = x4 * 4, py = y / p, i = y % p, px = x / p, j = x % p;
+    long long row = ((long long)b * gh + py) * g + px;
+    T* o = out + row * ld + ((long long)c * p + i) * p + j;
+    o[0] = from_f32<T>(v.x); o[1] = from_f32<T>(v.y); o[2] = from_f32<T>(v.z); o[3] = from_f32<T>(v.w);
+  }
+}
+
+// ---- text embedding (HF:217-224) -------------------------------------------------------------------
+__global__ void text_embed_kernel(const long long* __restrict__ ids, int L, int D, int vocab,
+                                  const float* __restrict__ tok, const float* __restrict__ pos, float* __restrict__ out) {
+  const int row = blockIdx.x;  // b*L + t
+  long long id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const float4* tr = reinterpret_cast<const float4*>(tok + id * D);
+  const float4* pr = reinterpret_cast<const float4*>(pos + (long long)(row % L) * D);
+  float4* o = reinterpret_cast<float4*>(out + (long long)row * D);
+  for (int c = threadIdx.x; c < D / 4; c += blockDim.x) {
+    float4 a = __ldg(tr + c), b = __ldg(pr + c);
+    o[c] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+// ---- LoRA down projection: h[m, D+j] = sum_k drop(h[m,k]) Acat[j,k], j < 16 ------------------------
+// One warp per row; Acat (16 x D) staged in shared memory as fp32.
+template <typename T>
+__global__ void __launch_bounds__(256) lora_down_kernel(T* __restrict__ h, long long ldh, int M, int D,
+                                                        const T* __restrict__ Acat, float p_drop, uint64_t seed) {
+  extern __shared__ float A_s[];  // [16][D]
+  for (int i = threadIdx.x; i < 16 * D; i += blockDim.x) A_s[i] = to_f32<T>(Acat[i]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+    float acc[16] = {};
+    T* hr = h + (long long)row * ldh;
+    for (int k = lane; k < D; k += 32) {
+      float x = to_f32<T>(hr[k]);
+      if (p_drop > 0.f) x = hash_uniform(seed, row, k) < p_drop ? 0.f : x * keep_scale;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = fmaf(x, A_s[j * D + k], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane < 16) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (lane == j) v = acc[j];
+      hr[D + lane] = from_f32<T>(v);
+    }
+  }
+}
+
+// dh[m,k] += mask(m,k) * sum_j dh[m,D+j] Acat[j,k]
+template <typename T>
+__global__ void __launch_bounds__(256) lora_down_bwd_kernel(T* __restrict__ dh, long long ldh, int M, int D,
+                                                            const T* __restrict__ Acat, float p_drop, uint64_t seed) {
+  extern __shared__ float A_s[];
+  for (int i = threadIdx.x; i < 16 * D; i += blockDim.x) A_s[i] = to_f32<T>(Acat[i]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+    T* hr = dh + (long long)row * ldh;
+    float du[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) du[j] = to_f32<T>(hr[D + j]);
+    for (int k = lane; k < D; k += 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s = fmaf(du[j], A_s[j * D + k], s);
+      if (p_drop > 0.f) s = hash_uniform(seed, row, k) < p_drop ? 0.f : s * keep_scale;
+      hr[k] = from_f32<T>(to_f32<T>(hr[k]) + s);
+    }
+  }
+}
+
+// ---- tall-skinny Gram: out[i,j] = alpha * sum_m P[m,i] * drop(Q[m,j]) -------------------------------
+constexpr int SG_ROWS = 512;  // rows per first-stage block
+template <typename T>
+__global__ void __launch_bounds__(128) skinny_gram_stage1(const T* __restrict__ P, long long ldp, int ni,
+                                                          const T* __restrict__ Q, long long ldq, int nj, int M,
+                                                          float p_drop, uint64_t seed, float* __restrict__ partials) {
+  // block: 128 threads = 128 columns j; loops over SG_ROWS rows; P rows staged in smem 32 at a time
+  __shared__ float P_s[32][16];
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int r0 = blockIdx.y * SG_ROWS, r1 = min(M, r0 + SG_ROWS);
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  float acc[16] = {};
+  for (int rb = r0; rb < r1; rb += 32) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 32 * 16; t += 128) {
+      int rr = t / 16, i = t % 16;
+      P_s[rr][i] = (rb + rr < r1 && i < ni) ? to_f32<T>(P[(long long)(rb + rr) * ldp + i]) : 0.f;
+    }
+    __syncthreads();
+    if (j < nj) {
+      const int re = min(32, r1 - rb);
+      for (int rr = 0; rr < re; ++rr) {
+        float q = to_f32<T>(Q[(long long)(rb + rr) * ldq + j]);
+        if (p_drop > 0.f) q = hash_uniform(seed, rb + rr, j) < p_drop ? 0.f : q * keep_scale;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fmaf(P_s[rr][i], q, acc[i]);
+      }
+    }
+  }
+  if (j < nj) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) partials[((long long)blockIdx.y * 16 + i) * nj + j] = acc[i];
+  }
+}
+__global__ void skinny_gram_stage2(const float* __restrict__ partials, int nb, int ni, int nj, float alpha,
+                                   float* __restrict__ out, long long ldo, int transpose_out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ni * nj) return;
+  int i = t / nj, j = t % nj;
+  float s = 0.f;
+  for (int b = 0; b < nb; ++b) s += partials[((long long)b * 16 + i) * nj + j];
+  s *= alpha;
+  if (transpose_out) out[(long long)j * ldo + i] = s; else out[(long long)i * ldo + j] = s;
+}
+
+// ---- fusion-token assembly (bifold/models/siglip.py:62-68,91-130; fusion.py:46-56) ---------------------
+// grid: (Nf, B); block: D/4 threads (capped at 256, loops)
+__global__ void assemble_fwd_kernel(bfk_assemble_args a) {
+  const int r = blockIdx.x, b = blockIdx.y;
+  const int L1 = a.L + 1, P1 = a.Np + 1;
+  const int Nf = L1 + (a.T + 1) * P1;
+  const float* src = nullptr;   // tower feature row (or token)
+  const float* pos = nullptr;   // context positional embedding row
+  int type;
+  float mask = 1.f;
+  if (r < L1) {
+    type = 0;
+    src = r == 0 ? a.text_token : a.txt + ((long long)b * a.L + (r - 1)) * a.D;
+  } else {
+    type = 1;
+    int q = r - L1, blk = q / P1, w = q % P1;
+    if (blk < a.T) {
+      src = w == 0 ? a.image_token : a.ctx + (((long long)b * a.T + blk) * a.Np + (w - 1)) * a.D;
+      pos = a.ctx_pos + (long long)q * a.D;
+      mask = (float)a.ctx_mask[(long long)b * a.T + blk];
+    } else {
+      src = w == 0 ? a.image_token : a.img + ((long long)b * a.Np + (w - 1)) * a.D;
+    }
+  }
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  const float4* p4 = reinterpret_cast<const float4*>(pos);
+  const float4* e4 = reinterpret_cast<const float4*>(a.type_emb + (long long)type * a.D);
+  float4* o4 = reinterpret_cast<float4*>(a.X + ((long long)b * Nf + r) * a.D);
+  for (int c = threadIdx.x; c < a.D / 4; c += blockDim.x) {
+    float4 v = s4[c], e = __ldg(e4 + c);
+    v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+    if (pos) { float4 q = __ldg(p4 + c); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+    o4[c] = v;
+  }
+  if (a.mask_out && threadIdx.x == 0) a.mask_out[(long long)b * Nf + r] = mask;
+}
+
+// feature gradients: pure row gather.  grid: (Nf, B)
+__global__ void assemble_bwd_gather_kernel(bfk_assemble_bwd_args a) {
+  const int r = blockIdx.x, b = blockIdx.y;
+  const int L1 = a.L + 1, P1 = a.Np + 1;
+  const int Nf = L1 + (a.T + 1) * P1;
+  float* dst = nullptr;
+  if (r < L1) {
+    if (r > 0 && a.dtxt) dst = a.dtxt + ((long long)b * a.L + (r - 1)) * a.D;
+  } else {
+    int q = r - L1, blk = q / P1, w = q % P1;
+    if (w > 0) {
+      if (blk < a.T) { if (a.dctx) dst = a.dctx + (((long long)b * a.T + blk) * a.Np + (w - 1)) * a.D; }
+      else if (a.dimg) dst = a.dimg + ((long long)b * a.Np + (w - 1)) * a.D;
+    }
+  }
+  if (!dst) return;
+  const float4* s4 = reinterpret_cast<const float4*>(a.dX + ((long long)b * Nf + r) * a.D);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int c = threadIdx.x; c < a.D / 4; c += blockDim.x) d4[c] = s4[c];
+}
+
+// parameter gradients: column-parallel, deterministic sums over (b, r).
+// small jobs: grid (ceil(D/128), n_jobs) with jobs 0 text_token, 1 image_token, 2.. ctx_pos rows
+__global__ void assemble_bwd_param_kernel(bfk_assemble_bwd_args a) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= a.D) return;
+  const int L1 = a.L + 1, P1 = a.Np + 1;
+  const int Nf = L1 + (a.T + 1) * P1;
+  const int job = blockIdx.y;
+  float s = 0.f;
+  auto at = [&](int b, int r) { return a.dX[((long long)b * Nf + r) * a.D + d]; };
+  if (job == 0) {
+    for (int b = 0; b < a.B; ++b) s += at(b, 0);
+    a.d_text_token[d] = s;
+  } else if (job == 1) {
+    for (int b = 0; b < a.B; ++b)
+      for (int blk = 0; blk <= a.T; ++blk) s += at(b, L1 + blk * P1);
+    a.d_image_token[d] = s;
+  } else {
+    const int q = job - 2;  // context position row
+    for (int b = 0; b < a.B; ++b) s += at(b, L1 + q);
+    a.d_ctx_pos[(long long)q * a.D + d] = s;
+  }
+}
+
+// type-embedding gradient: sum over all rows of a type, split AS_SPLIT ways, then reduced.
+constexpr int AS_SPLIT = 64;
+// grid (ceil(D/128), 2, AS_SPLIT)
+__global__ void assemble_bwd_type_stage1(bfk_assemble_bwd_args a, float* __restrict__ partials) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= a.D) return;
+  const int L1 = a.L + 1, P1 = a.Np + 1;
+  const int Nf = L1 + (a.T + 1) * P1;
+  const int type = blockIdx.y;
+  const int rlo = type == 0 ? 0 : L1, rn = type == 0 ? L1 : Nf - L1;
+  const long long total = (long long)a.B * rn;
+  const long long per = (total + AS_SPLIT - 1) / AS_SPLIT;
+  const long long t0 = per * blockIdx.z, t1 = min(total, t0 + per);
+  float s = 0.f;
+  for (long long t = t0; t < t1; ++t) {
+    int b = (int)(t / rn), r = rlo + (int)(t % rn);
+    s += a.dX[((long long)b * Nf + r) * a.D + d];
+  }
+  partials[((long long)type * AS_SPLIT + blockIdx.z) * a.D + d] = s;
+}
+__global__ void assemble_bwd_type_stage2(const float* __restrict__ partials, int D, float* __restrict__ d_type_emb) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * D) return;
+  const int type = t / D, d = t % D;
+  float s = 0.f;
+  for (int k = 0; k < AS_SPLIT; ++k) s += partials[((long long)type * AS_SPLIT + k) * D + d];
+  d_type_emb[t] = s;
+}
+
+}  // namespace bfk
+
+using namespace bfk;
+
+extern "C" int32_t bfk_im2col(const float* rgb, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p, void* out,
+                              int64_t ld_out, int32_t out_dtype, bfk_stream_t s_) {
+  BFK_CHECK_ARG(rgb && out && B > 0 && p > 0 && p % 4 == 0 && H % p == 0 && W % p == 0, "bfk_im2col: bad shape");
+  long long total = (long long)B * C * H * (W / 4);
+  int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  if (out_dtype == BFK_BF16) im2col_kernel<__nv_bfloat16><<<grid, 256, 0, to_stream(s_)>>>(rgb, B, C, H, W, p, (__nv_bfloat16*)out, ld_out);
+  else im2col_kernel<float><<<grid, 256, 0, to_stream(s_)>>>(rgb, B, C, H, W, p, (float*)out, ld_out);
+  BFK_CHECK_LAUNCH("bfk_im2col");
+  return BFK_OK;
+}
+
+extern "C" int32_t bfk_text_embed(const int64_t* ids, int32_t B, int32_t L, int32_t D, int32_t vocab,
+                                  const float* tok_emb, const float* pos_emb, float* out, bfk_stream_t s_) {
+  BFK_CHECK_ARG(ids && tok_emb && pos_emb && out && B > 0 && L > 0 && D % 4 == 0, "bfk_text_embed: bad arguments");
+  text_embed_kernel<<<B * L, std::min(256, std::max(32, D / 4)), 0, to_stream(s_)>>>((const long long*)ids, L, D, vocab, tok_emb, pos_emb, out);
+  BFK_CHECK_LAUNCH("bfk_text_embed");
+  return BFK_OK;
+}
+
+template <typename K>
+static int lora_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { set_error("lora: smem %zu: %s", bytes, cudaGetErrorString(e)); return BFK_E_CUDA; }
+  }
+  return BFK_OK;
+}
+
+extern "C" int32_t bfk_lora_down(void* h, int64_t ldh, int32_t dtype, int32_t M, int32_t D, const void* Acat,
+                                 float dropout_p, uint64_t seed, bfk_stream_t s_) {
+  BFK_CHECK_ARG(h && Acat && M > 0 && D > 0 && ldh >= D + 16, "bfk_lora_down: bad arguments");
+  size_t smem = (size_t)16 * D * sizeof(float);
+  int grid = std::min((M + 7) / 8, sm_count() * 4);
+  if (dtype == BFK_BF16) {
+    if (int rc = lora_smem(lora_down_kernel<__nv_bfloat16>, smem)) return rc;
+    lora_down_kernel<__nv_bfloat16><<<grid, 256, smem, to_stream(s_)>>>((__nv_bfloat16*)h, ldh, M, D, (const __nv_bfloat16*)Acat, dropout_p, seed);
+  } else {
+    if (int rc = lora_smem(lora_down_kernel<float>, smem)) return rc;
+    lora_down_kernel<float><<<grid, 256, smem, to_stream(s_)>>>((float*)h, ldh, M, D, (const float*)Acat, dropout_p, seed);
+  }
+  BFK_CHECK_LAUNCH("bfk_lora_down");
+  return BFK_OK;
+}
+
+extern "C" int32_t bfk_lora_down_bwd(void* dh, int64_t ldh, int32_t dtype, int32_t M, int32_t D, const void* Acat,
+                                     float dropout_p, uint64_t seed, bfk_stream_t s_) {
+  BFK_CHECK_ARG(dh && Acat && M > 0 && D > 0 && ldh >= D + 16, "bfk_lora_down_bwd: bad arguments");
+  size_t smem = (size_t)16 * D * sizeof(float);
+  int grid = std::min((M + 7) / 8, sm_count() * 4);
+  if (dtype == BFK_BF16) {
+    if (int rc = lora_smem(lora_down_bwd_kernel<__nv_bfloat16>, smem)) return rc;
+    lora_down_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, to_stream(s_)>>>((__nv_bfloat16*)dh, ldh, M, D, (const __nv_bfloat16*)Acat, dropout_p, seed);
+  } else {
+    if (int rc = lora_smem(lora_down_bwd_kernel<float>, smem)) return rc;
+    lora_down_bwd_kernel<float><<<grid, 256, smem, to_stream(s_)>>>((float*)dh, ldh, M, D, (const float*)Acat, dropout_p, seed);
+  }
+  BFK_CHECK_LAUNCH("bfk_lora_down_bwd");
+  return BFK_OK;
+}
+
+extern "C" size_t bfk_skinny_gram_workspace_floats(int32_t M, int32_t ni, int32_t nj) {
+  (void)ni;
+  return (size_t)((M + SG_ROWS - 1) / SG_ROWS) * 16 * (size_t)nj;
+}
+
+extern "C" int32_t bfk_skinny_gram(const void* P, int64_t ldp, int32_t ni, const void* Q, int64_t ldq, int32_t nj,
+                                   int32_t dtype, int32_t M, float alpha, float* out, int64_t ldo,
+                                   int32_t transpose_out, float dropout_p, uint64_t seed, float* partials,
+                                   bfk_stream_t s_) {
+  BFK_CHECK_ARG(P && Q && out && partials && ni > 0 && ni <= 16 && nj > 0 && M > 0, "bfk_skinny_gram: bad arguments");
+  int nb = (M + SG_ROWS - 1) / SG_ROWS;
+  dim3 grid((nj + 127) / 128, nb);
+  cudaStream_t s = to_stream(s_);
+  if (dtype == BFK_BF16)
+    skinny_gram_stage1<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16*)P, ldp, ni, (const __nv_bfloat16*)Q, ldq, nj, M, dropout_p, seed, partials);
+  else
+    skinny_gram_stage1<float><<<grid, 128, 0, s>>>((const float*)P, ldp, ni, (const float*)Q, ldq, nj, M, dropout_p, seed, partials);
+  skinny_gram_stage2<<<(ni * nj + 127) / 128, 128, 0, s>>>(partials, nb, ni, nj, alpha, out, ldo, transpose_out);
+  BFK_CHECK_LAUNCH("bfk_skinny_gram");
+  return BFK_OK;
+}
+
+extern "C" int32_t bfk_assemble_fwd(const bfk_assemble_args* a, bfk_stream_t s_) {
+  BFK_CHECK_ARG(a && a->txt && a->img && a->text_token && a->image_token && a->type_emb && a->X, "bfk_assemble_fwd: null pointer");
+  BFK_CHECK_ARG(a->D % 4 == 0 && a->B > 0 && (a->T == 0 || (a->ctx && a->ctx_pos && a->ctx_mask)), "bfk_assemble_fwd: bad arguments");
+  int Nf = (a->L + 1) + (a->T + 1) * (a->Np + 1);
+  assemble_fwd_kernel<<<dim3(Nf, a->B), std::min(256, std::max(32, a->D / 4)), 0, to_stream(s_)>>>(*a);
+  BFK_CHECK_LAUNCH("bfk_assemble_fwd");
+  return BFK_OK;
+}
+
+extern "C" int32_t bfk_assemble_bwd(const bfk_assemble_bwd_args* a, bfk_stream_t s_) {
+  BFK_CHECK_ARG(a && a->dX && a->d_text_token && a->d_image_token && a->d_type_emb, "bfk_assemble_bwd: null pointer");
+  BFK_CHECK_ARG(a->D % 4 == 0 && a->B > 0 && (a->T == 0 || a->d_ctx_pos), "bfk_assemble_bwd: bad arguments");
+  int Nf = (a->L + 1) + (a->T + 1) * (a->Np + 1);
+  cudaStream_t s = to_stream(s_);
+  if (a->dtxt || a->dimg || a->dctx)
+    assemble_bwd_gather_kernel<<<dim3(Nf, a->B), std::min(256, std::max(32, a->D / 4)), 0, s>>>(*a);
+  BFK_CHECK_ARG(a->partials, "bfk_assemble_bwd: partials workspace (2*64*D floats) required");
+  int jobs = 2 + a->T * (a->Np + 1);
+  assemble_bwd_param_kernel<<<dim3((a->D + 127) / 128, jobs), 128, 0, s>>>(*a);
+  assemble_bwd_type_stage1<<<dim3((a->D + 127) / 128, 2, AS_SPLIT), 128, 0, s>>>(*a, a->partials);
+  assemble_bwd_type_stage2<<<(2 * a->D + 127) / 128, 128, 0, s>>>(a->partials, a->D, a->d_type_emb);
+  BFK_CHECK_LAUNCH("bfk_assemble_bwd");
+  return BFK_OK;
+}

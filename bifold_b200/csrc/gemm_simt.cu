@@ -1,0 +1,117 @@
+// SIMT GEMM with the fused epilogue: the fp32 "parity mode" GEMM (and the checker of the tcgen05 path).
+// D[M,N] = epi(A[M,K] * B[N,K]^T), any combination of operand transposes, fp32 accumulate.
+#include "epilogue.cuh"
+
+namespace bfk {
+
+constexpr int SB_M = 64, SB_N = 64, SB_K = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, long long lda, int ta,
+                                                        const T* __restrict__ B, long long ldb, int tb, int K,
+                                                        EpiParams p) {
+  __shared__ float As[SB_K][SB_M + 4];
+  __shared__ float Bs[SB_K][SB_N + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * SB_M, n0 = blockIdx.x * SB_N;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += SB_K) {
+#pragma unroll
+    for (int i = tid; i < SB_M * SB_K; i += 256) {
+      int mm, kk;
+      if (ta) { kk = i / SB_M; mm = i % SB_M; } else { mm = i / SB_K; kk = i % SB_K; }
+      int m = m0 + mm, k = k0 + kk;
+      float v = 0.f;
+      if (m < p.M && k < K) v = to_f32<T>(ta ? A[(long long)k * lda + m] : A[(long long)m * lda + k]);
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int i = tid; i < SB_N * SB_K; i += 256) {
+      int nn, kk;
+      if (tb) { kk = i / SB_N; nn = i % SB_N; } else { nn = i / SB_K; kk = i % SB_K; }
+      int n = n0 + nn, k = k0 + kk;
+      float v = 0.f;
+      if (n < p.N && k < K) v = to_f32<T>(tb ? B[(long long)k * ldb + n] : B[(long long)n * ldb + k]);
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SB_K; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n < p.N) epi_store(p, m, n, acc[i][j]);
+    }
+  }
+}
+
+int gemm_simt(const bfk_gemm_args* a, cudaStream_t s) {
+  EpiParams p;
+  epi_from_args(a, p);
+  dim3 grid((a->N + SB_N - 1) / SB_N, (a->M + SB_M - 1) / SB_M);
+  if (a->in_dtype == BFK_BF16)
+    gemm_simt_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)a->A, a->lda, a->trans_a,
+                                                         (const __nv_bfloat16*)a->B, a->ldb, a->trans_b, a->K, p);
+  else
+    gemm_simt_kernel<float><<<grid, 256, 0, s>>>((const float*)a->A, a->lda, a->trans_a, (const float*)a->B, a->ldb,
+                                                 a->trans_b, a->K, p);
+  BFK_CHECK_LAUNCH("gemm_simt");
+  return BFK_OK;
+}
+
+// ---- column sums (bias gradients) --------------------------------------------------------------
+constexpr int CS_ROWS = 256;  // rows per first-stage block
+
+template <typename T>
+__global__ void colsum_stage1(const T* __restrict__ X, int M, int N, long long ld, float* __restrict__ partials) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int r0 = blockIdx.y * CS_ROWS, r1 = min(M, r0 + CS_ROWS);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += to_f32<T>(X[(long long)r * ld + n]);
+  partials[(long long)blockIdx.y * N + n] = s;
+}
+__global__ void colsum_stage2(const float* __restrict__ partials, int nb, int N, float* __restrict__ out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int b = 0; b < nb; ++b) s += partials[(long long)b * N + n];
+  out[n] = s;
+}
+
+}  // namespace bfk
+
+extern "C" size_t bfk_colsum_workspace_floats(int32_t M, int32_t N) {
+  return (size_t)((M + bfk::CS_ROWS - 1) / bfk::CS_ROWS) * (size_t)N;
+}
+
+extern "C" int32_t bfk_colsum(const void* X, int32_t dtype, int32_t M, int32_t N, int64_t ld, float* out,
+                              float* partials, bfk_stream_t s_) {
+  using namespace bfk;
+  BFK_CHECK_ARG(X && out && partials && M > 0 && N > 0, "bfk_colsum: bad arguments");
+  cudaStream_t s = to_stream(s_);
+  int nb = (M + CS_ROWS - 1) / CS_ROWS;
+  dim3 grid((N + 127) / 128, nb);
+  if (dtype == BFK_BF16) colsum_stage1<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16*)X, M, N, ld, partials);
+  else colsum_stage1<float><<<grid, 128, 0, s>>>((const float*)X, M, N, ld, partials);
+  colsum_stage2<<<(N + 127) / 128, 128, 0, s>>>(partials, nb, N, out);
+  BFK_CHECK_LAUNCH("bfk_colsum");
+  return BFK_OK;
+}

@@ -1,0 +1,361 @@
+// tcgen05 GEMM for sm_100a: D = epi(A * B^T), bf16 operands, fp32 accumulation in TMEM.
+//
+//   * persistent: one CTA per SM loops over 128 x BN output tiles (BN = 256 or 128)
+//   * warp 0      : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 64-wide K blocks, mbarrier ring)
+//   * warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16)
+//   * warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused bias/GELU/residual -> global)
+//   * two TMEM accumulator buffers so the epilogue of tile i overlaps the main loop of tile i+1
+//   * operands may be K-major (row-major [rows,K]) or MN-major (row-major [K,rows]); the latter serves
+//     dgrad (B = W as stored) and wgrad (A = dY, B = X as stored) without any transposed copies.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "epilogue.cuh"
+
+namespace bfk {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, 128-byte swizzle (layout type 2), descriptor version 1.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// descriptor of the k-th UMMA_K(=16) slice of an operand tile
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint64_t operand_desc(uint32_t tile_base, int k) {
+  if constexpr (!MN_MAJOR) {
+    // K-major: rows of 128 B (64 bf16 of K), 8-row swizzle atoms 1024 B apart; K advances 32 B per slice
+    return make_sdesc(tile_base + k * 32, 16, 1024);
+  } else {
+    // MN-major: TMA boxes of [64 k-rows][64 mn] = 8192 B; k-rows of 128 B; 8-row groups 1024 B apart
+    return make_sdesc(tile_base + k * 2048, 8192, 1024);
+  }
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, majorness, N>>3, M>>4
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN> struct TcCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool AMN, bool BMN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
+               EpiParams ep) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (M + TC_BM - 1) / TC_BM, num_n = (N + BN - 1) / BN;
+  const int tiles = num_m * num_n;
+  const int num_kb = (K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * TC_BM, n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+          const int k0 = kb * TC_BK;
+          if constexpr (!AMN) {
+            tma_load_2d(sa, &tma_a, full_bar(stage), k0, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < TC_BM / 64; ++i) tma_load_2d(sa + i * 8192, &tma_a, full_bar(stage), m0 + 64 * i, k0);
+          }
+          if constexpr (!BMN) {
+            tma_load_2d(sb, &tma_b, full_bar(stage), k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &tma_b, full_bar(stage), n0 + 64 * i, k0);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(TC_BM, BN, AMN, BMN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            tc_mma_bf16(tmem_d, operand_desc<AMN>(sa, k), operand_desc<BMN>(sb, k), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(empty_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===== epilogue warps (2..5): TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * TC_BM, n0 = (tile % num_n) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n0 + c * 32 >= N) break;  // warp-uniform
+        uint32_t r[32];
+        tc_ld32(taddr + (uint32_t)(c * 32), r);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[j * 8 + t]);
+          epi_store8(ep, m, n0 + c * 32 + j * 8, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side: tensor maps --------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+    else
+      (void)cudaGetLastError();
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; long long inner, outer, ld; int box_inner, box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix((size_t)k.inner); mix((size_t)k.outer); mix((size_t)k.ld); mix((size_t)k.box_inner); mix((size_t)k.box_outer);
+    return h;
+  }
+};
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch ld elements; 128B swizzle.
+static bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return true; }
+  }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return false; }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld", (int)r, inner, outer, ld); return false; }
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return true;
+}
+
+bool gemm_tc_supported(const bfk_gemm_args* a, const char** why) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  if (a->in_dtype != BFK_BF16) { *why = "operands must be bf16"; return false; }
+  if (!al16(a->A) || !al16(a->B)) { *why = "operand pointers must be 16-byte aligned"; return false; }
+  if ((a->lda * 2) % 16 != 0 || (a->ldb * 2) % 16 != 0) { *why = "leading dimensions must be multiples of 8 elements"; return false; }
+  if (!get_encode()) { *why = "driver entry point cuTensorMapEncodeTiled missing"; return false; }
+  return true;
+}
+
+template <int BN, bool AMN, bool BMN>
+static int launch_tc(const bfk_gemm_args* a, cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  CUtensorMap ma, mb;
+  bool ok;
+  if (!AMN) ok = make_map(&ma, a->A, a->K, a->M, a->lda, TC_BK, TC_BM);
+  else      ok = make_map(&ma, a->A, a->M, a->K, a->lda, 64, TC_BK);
+  if (!ok) return BFK_E_CUDA;
+  if (!BMN) ok = make_map(&mb, a->B, a->K, a->N, a->ldb, TC_BK, BN);
+  else      ok = make_map(&mb, a->B, a->N, a->K, a->ldb, 64, TC_BK);
+  if (!ok) return BFK_E_CUDA;
+  EpiParams ep;
+  epi_from_args(a, ep);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("gemm_tc: cannot set smem %d: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return BFK_E_CUDA; }
+    attr_set = true;
+  }
+  const int tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + BN - 1) / BN);
+  const int grid = std::min(tiles, sm_count());
+  gemm_tc_kernel<BN, AMN, BMN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, a->M, a->N, a->K, ep);
+  BFK_CHECK_LAUNCH("gemm_tc");
+  return BFK_OK;
+}
+
+int gemm_tc(const bfk_gemm_args* a, cudaStream_t s) {
+  const int w256 = ((a->N + 255) / 256) * 256 - a->N, w128 = ((a->N + 127) / 128) * 128 - a->N;
+  const bool bn256 = w256 <= w128;
+  const bool ta = a->trans_a != 0, tb = a->trans_b != 0;
+#define DISPATCH(BN)                                                  \
+  do {                                                                \
+    if (!ta && !tb) return launch_tc<BN, false, false>(a, s);         \
+    if (!ta && tb) return launch_tc<BN, false, true>(a, s);           \
+    if (ta && tb) return launch_tc<BN, true, true>(a, s);             \
+    return launch_tc<BN, true, false>(a, s);                          \
+  } while (0)
+  if (bn256) DISPATCH(256);
+  DISPATCH(128);
+#undef DISPATCH
+}
+
+}  // namespace bfk

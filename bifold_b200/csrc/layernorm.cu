@@ -1,0 +1,228 @@
+// LayerNorm forward / backward: one warp per row, fp32 statistics, float4 accesses.
+// HBM-bound: forward reads 4D bytes and writes 2D (bf16) or 4D per row; backward reads dy, x (+dres)
+// and writes dx (+ a bf16 copy).
+#include "common.cuh"
+
+namespace bfk {
+
+constexpr int LN_WARPS = 8;
+constexpr int LN_MAXC = 12;  // float4 chunks per lane: D <= 1536
+
+template <typename TY>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(bfk_layernorm_fwd_args a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * LN_WARPS + warp;
+  if (row >= a.M) return;
+  const int nc = a.D >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(a.x + (long long)row * a.ldx);
+  float4 xv[LN_MAXC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXC; ++i) {
+    int c = lane + 32 * i;
+    if (c < nc) {
+      xv[i] = x4[c];
+      s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)a.D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXC; ++i) {
+    int c = lane + 32 * i;
+    if (c < nc) {
+      float d0 = xv[i].x - mean, d1 = xv[i].y - mean, d2 = xv[i].z - mean, d3 = xv[i].w - mean;
+      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)a.D + a.eps);
+  if (lane == 0) {
+    if (a.mean) a.mean[row] = mean;
+    if (a.rstd) a.rstd[row] = rstd;
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(a.beta);
+  TY* y = reinterpret_cast<TY*>(a.y) + (long long)row * a.ldy;
+#pragma unroll
+  for (int i = 0; i < LN_MAXC; ++i) {
+    int c = lane + 32 * i;
+    if (c < nc) {
+      float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+      float o0 = (xv[i].x - mean) * rstd * g.x + b.x, o1 = (xv[i].y - mean) * rstd * g.y + b.y;
+      float o2 = (xv[i].z - mean) * rstd * g.z + b.z, o3 = (xv[i].w - mean) * rstd * g.w + b.w;
+      if constexpr (sizeof(TY) == 4) {
+        reinterpret_cast<float4*>(y)[c] = make_float4(o0, o1, o2, o3);
+      } else {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&p0);
+        u.y = *reinterpret_cast<uint32_t*>(&p1);
+        reinterpret_cast<uint2*>(y)[c] = u;
+      }
+    }
+  }
+}
+
+template <typename T> __device__ __forceinline__ float4 load4(const T* p, int c);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p, int c) {
+  return reinterpret_cast<const float4*>(p)[c];
+}
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p, int c) {
+  uint2 u = reinterpret_cast<const uint2*>(p)[c];
+  float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x));
+  float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, int c, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, int c, float4 v) {
+  reinterpret_cast<float4*>(p)[c] = v;
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, int c, float4 v) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&p0);
+  u.y = *reinterpret_cast<uint32_t*>(&p1);
+  reinterpret_cast<uint2*>(p)[c] = u;
+}
+
+template <typename TDY, typename TDX2, bool PARAM_GRADS>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(bfk_layernorm_bwd_args a, int rows_per_block) {
+  __shared__ float red[PARAM_GRADS ? LN_WARPS : 1][PARAM_GRADS ? 132 : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nc = a.D >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+  float4 dg[LN_MAXC], db[LN_MAXC];
+  if constexpr (PARAM_GRADS) {
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int r_begin = blockIdx.x * rows_per_block;
+  const int r_end = min(a.M, r_begin + rows_per_block);
+  for (int row = r_begin + warp; row < r_end; row += LN_WARPS) {
+    const float mean = a.mean[row], rstd = a.rstd[row];
+    const float* x = a.x + (long long)row * a.ldx;
+    const TDY* dy = reinterpret_cast<const TDY*>(a.dy) + (long long)row * a.ld_dy;
+    float4 gv[LN_MAXC], xh[LN_MAXC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+      int c = lane + 32 * i;
+      if (c < nc) {
+        float4 xv = load4<float>(x, c), d = load4<TDY>(dy, c), g = __ldg(g4 + c);
+        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        if constexpr (PARAM_GRADS) {
+          dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+          db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+        }
+        gv[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+        s1 += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+        s2 += (gv[i].x * xh[i].x + gv[i].y * xh[i].y) + (gv[i].z * xh[i].z + gv[i].w * xh[i].w);
+      }
+    }
+    const float c1 = warp_sum(s1) / (float)a.D, c2 = warp_sum(s2) / (float)a.D;
+    float* dx = a.dx + (long long)row * a.ld_dx;
+    const float* dres = a.dres ? a.dres + (long long)row * a.ld_dres : nullptr;
+    TDX2* dx2 = a.dx2 ? reinterpret_cast<TDX2*>(a.dx2) + (long long)row * a.ld_dx2 : nullptr;
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+      int c = lane + 32 * i;
+      if (c < nc) {
+        float4 o = make_float4(rstd * (gv[i].x - c1 - xh[i].x * c2), rstd * (gv[i].y - c1 - xh[i].y * c2),
+                               rstd * (gv[i].z - c1 - xh[i].z * c2), rstd * (gv[i].w - c1 - xh[i].w * c2));
+        if (dres) {
+          float4 r = load4<float>(dres, c);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        store4<float>(dx, c, o);
+        if (dx2) store4<TDX2>(dx2, c, o);
+      }
+    }
+  }
+  if constexpr (PARAM_GRADS) {
+    // block reduce of per-warp column sums, 128 columns (one float4 chunk per lane) at a time
+    float* pg = a.partials + (long long)blockIdx.x * 2 * a.D;
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+      int c = lane + 32 * i;
+      if (32 * i >= nc) break;
+      for (int pass = 0; pass < 2; ++pass) {
+        float4 v = pass == 0 ? dg[i] : db[i];
+        red[warp][lane * 4 + 0] = v.x; red[warp][lane * 4 + 1] = v.y;
+        red[warp][lane * 4 + 2] = v.z; red[warp][lane * 4 + 3] = v.w;
+        __syncthreads();
+        if (warp == 0 && c < nc) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int w = 0; w < LN_WARPS; ++w) {
+            t.x += red[w][lane * 4 + 0]; t.y += red[w][lane * 4 + 1];
+            t.z += red[w][lane * 4 + 2]; t.w += red[w][lane * 4 + 3];
+          }
+          reinterpret_cast<float4*>(pg + pass * a.D)[c] = t;
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+__global__ void ln_bwd_reduce(const float* __restrict__ partials, int nb, int D, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= 2 * D) return;
+  float s = 0.f;
+  for (int b = 0; b < nb; ++b) s += partials[(long long)b * 2 * D + n];
+  if (n < D) dgamma[n] = s; else dbeta[n - D] = s;
+}
+
+static int ln_bwd_blocks(int M, int& rows_per_block) {
+  int target = sm_count() * 4;
+  rows_per_block = (M + target - 1) / target;
+  rows_per_block = ((rows_per_block + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
+  return (M + rows_per_block - 1) / rows_per_block;
+}
+
+}  // namespace bfk
+
+extern "C" int32_t bfk_layernorm_fwd(const bfk_layernorm_fwd_args* a, bfk_stream_t s_) {
+  using namespace bfk;
+  BFK_CHECK_ARG(a && a->x && a->y && a->gamma && a->beta, "bfk_layernorm_fwd: null pointer");
+  BFK_CHECK_ARG(a->M > 0 && a->D > 0 && a->D % 4 == 0 && a->D <= 128 * LN_MAXC && a->ldx % 4 == 0 && a->ldy % 4 == 0,
+                "bfk_layernorm_fwd: need D%%4==0, D<=%d, ld%%4==0 (D=%d)", 128 * LN_MAXC, a->D);
+  cudaStream_t s = to_stream(s_);
+  int grid = (a->M + LN_WARPS - 1) / LN_WARPS;
+  if (a->y_dtype == BFK_BF16) ln_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, s>>>(*a);
+  else ln_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, s>>>(*a);
+  BFK_CHECK_LAUNCH("bfk_layernorm_fwd");
+  return BFK_OK;
+}
+
+extern "C" size_t bfk_layernorm_bwd_workspace_floats(int32_t M, int32_t D) {
+  int rpb;
+  return (size_t)bfk::ln_bwd_blocks(M, rpb) * 2 * (size_t)D;
+}
+
+extern "C" int32_t bfk_layernorm_bwd(const bfk_layernorm_bwd_args* a, bfk_stream_t s_) {
+  using namespace bfk;
+  BFK_CHECK_ARG(a && a->dy && a->x && a->mean && a->rstd && a->gamma && a->dx, "bfk_layernorm_bwd: null pointer");
+  BFK_CHECK_ARG(a->M > 0 && a->D % 4 == 0 && a->D <= 128 * LN_MAXC && a->ldx % 4 == 0 && a->ld_dy % 4 == 0 &&
+                    a->ld_dx % 4 == 0 && (!a->dres || a->ld_dres % 4 == 0) && (!a->dx2 || a->ld_dx2 % 4 == 0),
+                "bfk_layernorm_bwd: need D%%4==0, D<=%d, ld%%4==0", 128 * LN_MAXC);
+  const bool pg = a->dgamma != nullptr;
+  BFK_CHECK_ARG(!pg || (a->dbeta && a->partials), "bfk_layernorm_bwd: dgamma needs dbeta and partials");
+  cudaStream_t s = to_stream(s_);
+  int rpb;
+  int grid = ln_bwd_blocks(a->M, rpb);
+  const bool dyb = a->dy_dtype == BFK_BF16, d2b = a->dx2 && a->dx2_dtype == BFK_BF16;
+#define LAUNCH(TDY, TDX2, PG) ln_bwd_kernel<TDY, TDX2, PG><<<grid, LN_WARPS * 32, 0, s>>>(*a, rpb)
+  if (dyb) {
+    if (d2b) { if (pg) LAUNCH(__nv_bfloat16, __nv_bfloat16, true); else LAUNCH(__nv_bfloat16, __nv_bfloat16, false); }
+    else     { if (pg) LAUNCH(__nv_bfloat16, float, true); else LAUNCH(__nv_bfloat16, float, false); }
+  } else {
+    if (d2b) { if (pg) LAUNCH(float, __nv_bfloat16, true); else LAUNCH(float, __nv_bfloat16, false); }
+    else     { if (pg) LAUNCH(float, float, true); else LAUNCH(float, float, false); }
+  }
+#undef LAUNCH
+  if (pg) ln_bwd_reduce<<<(2 * a->D + 127) / 128, 128, 0, s>>>(a->partials, grid, a->D, a->dgamma, a->dbeta);
+  BFK_CHECK_LAUNCH("bfk_layernorm_bwd");
+  return BFK_OK;
+}

@@ -1,0 +1,118 @@
+"""Batch-sharded data parallelism for the policy (one process per GPU, torch.distributed / NCCL).
+
+The reference is single-process; this is the one parallel strategy the hot path
+admits: samples are independent in the forward, the loss is a mean over B*H*W, so with
+equal per-rank batches the mean of the rank gradients is the global-batch gradient.
+
+The engine hands out all parameter gradients as views of ONE flat fp32 arena and announces, during
+its explicit backward, when a group of them is final ("decoders", "fusion.7" ... "fusion.0", "tokens",
+"text", "vision").  Each announcement all-reduces that group's arena ranges on a side stream while
+the backward keeps computing; the optimizer waits for the outstanding work and folds 1/world_size
+into its fused Adam kernel (``grad_scale``), so there is no separate averaging pass.
+Inference is batch-sharded with no collective.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def plan_groups(names: List[str], sizes: List[int]) -> Dict[str, List[Tuple[int, int]]]:
+    """Arena ranges (offset, length in floats; parameters padded to 4 floats) of every gradient group."""
+    groups: Dict[str, List[Tuple[int, int]]] = {}
+    off = 0
+    for n, s in zip(names, sizes):
+        padded = (s + 3) // 4 * 4
+        if "_decoder." in n:
+            g = "decoders"
+        elif ".transformer_encoder.layers." in n:
+            g = "fusion." + n.split(".transformer_encoder.layers.")[1].split(".")[0]
+        elif ".text_model." in n:
+            g = "text"
+        elif ".vision_model." in n:
+            g = "vision"
+        else:
+            g = "tokens"
+        r = groups.setdefault(g, [])
+        if r and r[-1][0] + r[-1][1] == off:
+            r[-1] = (r[-1][0], r[-1][1] + padded)
+        else:
+            r.append((off, padded))
+        off += padded
+    return groups
+
+
+class GradReducer:
+    """All-reduce (sum) of arena ranges as soon as the engine reports them final."""
+
+    def __init__(self, names: List[str], sizes: List[int], process_group=None, comm_stream=None):
+        self.groups = plan_groups(names, sizes)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.comm_stream = comm_stream
+        self.pending = []
+        self.arena = None
+        self.bytes_reduced = 0
+
+    def bind(self, arena: torch.Tensor):
+        self.arena = arena
+
+    def on_ready(self, group: str):
+        if self.world == 1 or self.arena is None:
+            return
+        for off, n in self.groups.get(group, []):
+            view = self.arena[off:off + n]
+            if view.is_cuda:
+                ev = torch.cuda.Event()
+                ev.record()
+                self.comm_stream.wait_event(ev)
+                with torch.cuda.stream(self.comm_stream):
+                    w = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            else:
+                w = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            self.pending.append(w)
+            self.bytes_reduced += 4 * n
+
+    def wait(self):
+        for w in self.pending:
+            w.wait()
+        if self.pending and self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.pending = []
+
+
+class BatchShardedDDP:
+    """Wires a model (bifold_b200.models.SigLip*) and its FusedAdam for data-parallel training."""
+
+    def __init__(self, model, optimizer, process_group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.model, self.optimizer = model, optimizer
+        eng = model._ensure_engine()
+        names = eng.trainable_names()
+        sizes = [eng.params[n].numel() for n in names]
+        self.reducer = GradReducer(names, sizes, process_group, torch.cuda.Stream())
+        self.world = self.reducer.world
+        # identical weights on every rank
+        for p in model.parameters():
+            dist.broadcast(p.data, src=0, group=process_group)
+        orig_backward = eng.backward
+
+        def backward(ctx, dheat, dloss):
+            # the arena is allocated at the start of Engine.backward; bind lazily through the hook
+            return orig_backward(ctx, dheat, dloss)
+
+        def hook(group):
+            self.reducer.bind(eng.last_arena)
+            self.reducer.on_ready(group)
+
+        eng.grad_ready_hook = hook
+        optimizer.grad_scale = 1.0 / self.world
+        optimizer.pre_step_hook = self.reducer.wait
+
+    def shard(self, global_batch: int, rank: int = None):
+        rank = dist.get_rank() if rank is None else rank
+        per = global_batch // self.world
+        return rank * per, per

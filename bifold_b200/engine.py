@@ -1,0 +1,630 @@
+"""Policy executor: chains the C-ABI kernels of libbifold_b200.so into the BiFold forward and an
+explicit backward.  PyTorch is used for device memory and streams only — every arithmetic step is
+one of our CUDA kernels (no eager/CPU fallback).
+
+Reference call stack being replaced: SigLip/SiglipSequential.forward
+(bifold/models/siglip.py:56-137) -> HF SiglipModel towers -> PickPlaceConvDecoder.forward
+(bifold/models/pickplace.py:59-124) -> ConcatTransformer/Transformer (fusion.py:35-64,
+transformer.py:26-64) -> ConvDecoder x heads (modules.py:33-74) -> sigmoid.
+
+Data layout in HBM
+  * residual streams x: fp32 [rows, D] (rows = samples*tokens, token-major within a sample)
+  * GEMM operands / activations: T = bf16 ("bf16" precision, tcgen05 GEMMs) or fp32 ("fp32" parity mode)
+  * packed QKV: T [rows, 3D] = [q(h,d) | k(h,d) | v(h,d)];  LoRA rides as 16 extra K columns of the
+    LayerNorm output / QKV weight ([W | (alpha/r) B]) so q,v get their rank-r update inside the QKV GEMM
+  * heatmaps: fp32 [heads, B, H, W]
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _cabi as K
+from .config import PolicyConfig
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return K.F32
+    if t.dtype == torch.bfloat16:
+        return K.BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Kernels:
+    """Typed wrappers over the C ABI working on torch CUDA tensors, launched on the current stream."""
+
+    def __init__(self):
+        self.lib = K.load()
+        self.launches = 0          # C-ABI calls issued (each is >= 1 kernel launch); bench.py reports it
+        self.backend = K.BACKEND_AUTO
+
+    # -- GEMM ------------------------------------------------------------------------------------
+    def gemm(self, A, B, D, M, N, Kd, lda, ldb, ldd, trans_a=False, trans_b=False, bias=None, act=K.ACT_NONE,
+             aux=None, ld_aux=0, residual=None, ldr=0, res_row_mod=0, alpha=1.0, accumulate=False, backend=None):
+        a = K.GemmArgs(M, N, Kd, A.data_ptr(), lda, int(trans_a), B.data_ptr(), ldb, int(trans_b), _dt(A),
+                       D.data_ptr(), ldd, _dt(D), K.ptr(bias), act, K.ptr(aux), ld_aux, K.ptr(residual), ldr,
+                       res_row_mod, alpha, int(accumulate), self.backend if backend is None else backend)
+        assert _dt(A) == _dt(B)
+        K.check(self.lib.bfk_gemm(C.byref(a), _stream()), "bfk_gemm")
+        self.launches += 1
+
+    def colsum(self, X, M, N, ld, out):
+        ws = torch.empty(self.lib.bfk_colsum_workspace_floats(M, N), device=X.device, dtype=torch.float32)
+        K.check(self.lib.bfk_colsum(X.data_ptr(), _dt(X), M, N, ld, out.data_ptr(), ws.data_ptr(), _stream()), "bfk_colsum")
+        self.launches += 2
+
+    # -- LayerNorm ---------------------------------------------------------------------------------
+    def layernorm_fwd(self, x, M, D, gamma, beta, eps, y, ldy, mean=None, rstd=None):
+        a = K.LayerNormFwdArgs(M, D, x.data_ptr(), D, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(), ldy, _dt(y),
+                               K.ptr(mean), K.ptr(rstd))
+        K.check(self.lib.bfk_layernorm_fwd(C.byref(a), _stream()), "bfk_layernorm_fwd")
+        self.launches += 1
+
+    def layernorm_bwd(self, dy, ld_dy, x, M, D, mean, rstd, gamma, dres, dx, dx2=None, dgamma=None, dbeta=None):
+        ws = None
+        if dgamma is not None:
+            ws = torch.empty(self.lib.bfk_layernorm_bwd_workspace_floats(M, D), device=x.device, dtype=torch.float32)
+        a = K.LayerNormBwdArgs(M, D, dy.data_ptr(), ld_dy, _dt(dy), x.data_ptr(), D, mean.data_ptr(), rstd.data_ptr(),
+                               gamma.data_ptr(), K.ptr(dres), D, dx.data_ptr(), D, K.ptr(dx2), D,
+                               _dt(dx2) if dx2 is not None else 0, K.ptr(dgamma), K.ptr(dbeta), K.ptr(ws))
+        K.check(self.lib.bfk_layernorm_bwd(C.byref(a), _stream()), "bfk_layernorm_bwd")
+        self.launches += 2 if dgamma is not None else 1
+
+    # -- attention -----------------------------------------------------------------------------------
+    def attention_fwd(self, qkv, out, lse, B, N, H, hd, scale, row_mask=None, mask_fill=-100000.0):
+        a = K.AttentionArgs(B, N, H, hd, qkv.data_ptr(), 3 * H * hd, out.data_ptr(), H * hd, K.ptr(lse), K.ptr(row_mask),
+                            scale, mask_fill, _dt(qkv), self.backend, None, 0, None, 0, None)
+        K.check(self.lib.bfk_attention_fwd(C.byref(a), _stream()), "bfk_attention_fwd")
+        self.launches += 1
+
+    def attention_bwd(self, qkv, out, lse, dout, dqkv, B, N, H, hd, scale, row_mask=None, mask_fill=-100000.0):
+        delta = torch.empty(B * H * N, device=qkv.device, dtype=torch.float32)
+        a = K.AttentionArgs(B, N, H, hd, qkv.data_ptr(), 3 * H * hd, out.data_ptr(), H * hd, lse.data_ptr(), K.ptr(row_mask),
+                            scale, mask_fill, _dt(qkv), self.backend, dout.data_ptr(), H * hd, dqkv.data_ptr(), 3 * H * hd,
+                            delta.data_ptr())
+        K.check(self.lib.bfk_attention_bwd(C.byref(a), _stream()), "bfk_attention_bwd")
+        self.launches += 3
+
+    # -- misc ------------------------------------------------------------------------------------------
+    def cast(self, src, dst, rows, cols, ld_src, ld_dst):
+        K.check(self.lib.bfk_cast_f32_to(src.data_ptr(), dst.data_ptr(), _dt(dst), rows, cols, ld_src, ld_dst, _stream()),
+                "bfk_cast_f32_to")
+        self.launches += 1
+
+
+class LayerWeights:
+    """Operand-dtype copies ("shadows") of one pre-LN transformer layer's weights."""
+    __slots__ = ("ln1_w", "ln1_b", "Wqkv", "bqkv", "Acat", "Wo", "bo", "ln2_w", "ln2_b", "W1", "b1", "W2", "b2",
+                 "Dk", "names")
+
+
+class Engine:
+    def __init__(self, cfg: PolicyConfig, params: Dict[str, torch.nn.Parameter], precision: str = "bf16"):
+        assert precision in ("bf16", "fp32")
+        if cfg.lora and cfg.r > 8:
+            raise K.BfkError("LoRA rank > 8 is not supported by the packed QKV layout")
+        self.cfg = cfg
+        self.params = params
+        self.precision = precision
+        self.T = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.k = Kernels()
+        self.device = None
+        self._frozen_ready = False
+        self._train_version = None
+        self._taps = {}
+        self._ptr_tables = {}
+        self._frozen_version = None
+        self.step_seed = 0
+        self.tw_prefix = "siglip_model.model." if cfg.lora else "siglip_model."
+        self.grad_ready_hook = None   # DDP: called as hook(name_list) when a group of grads is final
+
+    # ------------------------------------------------------------------------------------------------
+    # weight preparation
+    # ------------------------------------------------------------------------------------------------
+    def _p(self, name) -> torch.Tensor:
+        return self.params[name].data
+
+    def _shadow(self, w: torch.Tensor, cols_pad: int = 0) -> torch.Tensor:
+        """[rows, cols] fp32 -> T [rows, cols + cols_pad] (pad columns zero)."""
+        rows, cols = w.shape[0], w[0].numel()
+        if self.T == torch.float32 and cols_pad == 0:
+            return w.reshape(rows, cols)
+        out = torch.zeros(rows, cols + cols_pad, device=w.device, dtype=self.T) if cols_pad else \
+            torch.empty(rows, cols, device=w.device, dtype=self.T)
+        self.k.cast(w, out, rows, cols, cols, cols + cols_pad)
+        return out
+
+    def _tower_layer_weights(self, prefix: str) -> LayerWeights:
+        cfg, D = self.cfg, self.cfg.dim
+        lw = LayerWeights()
+        a = prefix + ".self_attn."
+        lw.names = {}
+        lw.ln1_w, lw.ln1_b = self._p(prefix + ".layer_norm1.weight"), self._p(prefix + ".layer_norm1.bias")
+        lw.ln2_w, lw.ln2_b = self._p(prefix + ".layer_norm2.weight"), self._p(prefix + ".layer_norm2.bias")
+        base = ".base_layer" if cfg.lora else ""
+        lw.Dk = D + 16 if cfg.lora else D
+        Wqkv = torch.zeros(3 * D, lw.Dk, device=self.device, dtype=self.T)
+        bqkv = torch.empty(3 * D, device=self.device, dtype=torch.float32)
+        for i, proj in enumerate(("q_proj", "k_proj", "v_proj")):
+            b = base if proj != "k_proj" else ""
+            self.k.cast(self._p(f"{a}{proj}{b}.weight"), Wqkv[i * D:], D, D, D, lw.Dk)
+            bqkv[i * D:(i + 1) * D].copy_(self._p(f"{a}{proj}{b}.bias"))
+        lw.Wqkv, lw.bqkv = Wqkv, bqkv
+        lw.Acat = torch.zeros(16, D, device=self.device, dtype=self.T) if cfg.lora else None
+        if cfg.lora:
+            lw.names = {k: f"{a}{p}.lora_{m}.siglip_adapter.weight" for k, p, m in
+                        (("Aq", "q_proj", "A"), ("Bq", "q_proj", "B"), ("Av", "v_proj", "A"), ("Bv", "v_proj", "B"))}
+        lw.Wo, lw.bo = self._shadow(self._p(a + "out_proj.weight")), self._p(a + "out_proj.bias")
+        lw.W1, lw.b1 = self._shadow(self._p(prefix + ".mlp.fc1.weight")), self._p(prefix + ".mlp.fc1.bias")
+        lw.W2, lw.b2 = self._shadow(self._p(prefix + ".mlp.fc2.weight")), self._p(prefix + ".mlp.fc2.bias")
+        return lw
+
+    def _refresh_lora(self, lw: LayerWeights):
+        """Re-pack the trainable LoRA factors into the extended QKV weight and the down-projection."""
+        cfg, D, r = self.cfg, self.cfg.dim, self.cfg.r
+        s = cfg.lora_alpha / cfg.r
+        Bq, Bv = self._p(lw.names["Bq"]), self._p(lw.names["Bv"])
+        # Wqkv[0:D, D:D+r] = s*Bq ; Wqkv[2D:3D, D+8:D+8+r] = s*Bv   (tiny: torch copy, not on the activation path)
+        lw.Wqkv[0:D, D:D + r].copy_(Bq * s)
+        lw.Wqkv[2 * D:3 * D, D + 8:D + 8 + r].copy_(Bv * s)
+        lw.Acat[0:r].copy_(self._p(lw.names["Aq"]))
+        lw.Acat[8:8 + r].copy_(self._p(lw.names["Av"]))
+
+    def _fusion_layer_weights(self, l: int) -> LayerWeights:
+        D = self.cfg.dim
+        p = f"pick_place.fusion.transformer_encoder.layers.{l}"
+        lw = LayerWeights()
+        lw.Dk = D
+        lw.names = {"ln1_w": p + ".0.norm.weight", "ln1_b": p + ".0.norm.bias", "Wqkv": p + ".0.fn.to_qkv.weight",
+                    "Wo": p + ".0.fn.to_out.0.weight", "bo": p + ".0.fn.to_out.0.bias",
+                    "ln2_w": p + ".1.norm.weight", "ln2_b": p + ".1.norm.bias",
+                    "W1": p + ".1.fn.net.0.weight", "b1": p + ".1.fn.net.0.bias",
+                    "W2": p + ".1.fn.net.3.weight", "b2": p + ".1.fn.net.3.bias"}
+        lw.bqkv, lw.Acat = None, None
+        return lw
+
+    def _refresh_fusion(self, lw: LayerWeights):
+        n = lw.names
+        lw.ln1_w, lw.ln1_b, lw.ln2_w, lw.ln2_b = (self._p(n[k]) for k in ("ln1_w", "ln1_b", "ln2_w", "ln2_b"))
+        lw.bo, lw.b1, lw.b2 = self._p(n["bo"]), self._p(n["b1"]), self._p(n["b2"])
+        for k in ("Wqkv", "Wo", "W1", "W2"):
+            w = self._p(n[k])
+            if self.T == torch.float32:
+                setattr(lw, k, w)
+            else:
+                cur = getattr(lw, k, None) if hasattr(lw, k) else None
+                if cur is None or cur.shape != w.shape:
+                    cur = torch.empty_like(w, dtype=self.T)
+                    setattr(lw, k, cur)
+                self.k.cast(w, cur, w.shape[0], w.shape[1], w.shape[1], w.shape[1])
+
+    def prepare(self, device):
+        """(Re)build operand-dtype shadows.  Frozen tower weights once; trainable ones when changed."""
+        cfg = self.cfg
+        if self.device != device:
+            self.device, self._frozen_ready, self._train_version = device, False, None
+            self._taps, self._ptr_tables = {}, {}
+        fver = sum(p._version + (p.data_ptr() % 1000003) for p in self.params.values() if not p.requires_grad)
+        if fver != self._frozen_version:   # e.g. load_state_dict after a forward
+            self._frozen_ready, self._frozen_version, self._train_version = False, fver, None
+        if not self._frozen_ready:
+            tp, vp = self.tw_prefix + "text_model", self.tw_prefix + "vision_model"
+            self.text_layers = [self._tower_layer_weights(f"{tp}.encoder.layers.{i}") for i in range(cfg.tower_layers)]
+            self.vis_layers = [self._tower_layer_weights(f"{vp}.encoder.layers.{i}") for i in range(cfg.tower_layers)]
+            kpe = 3 * cfg.patch_size * cfg.patch_size
+            self.kpe_ld = (kpe + 7) // 8 * 8
+            self.W_pe = self._shadow(self._p(vp + ".embeddings.patch_embedding.weight"), self.kpe_ld - kpe)
+            self.fusion_layers = [self._fusion_layer_weights(l) for l in range(cfg.depth)]
+            for lw in self.fusion_layers:
+                for k in ("Wqkv", "Wo", "W1", "W2"):
+                    setattr(lw, k, None)
+            self._frozen_ready = True
+        version = sum(p._version for p in self.params.values() if p.requires_grad) + \
+            sum(p.data_ptr() % 1000003 for p in self.params.values() if p.requires_grad)
+        if version != self._train_version:
+            if cfg.lora:
+                for lw in self.text_layers + self.vis_layers:
+                    self._refresh_lora(lw)
+            for lw in self.fusion_layers:
+                self._refresh_fusion(lw)
+            self._train_version = version
+
+    def taps(self, g: int):
+        if g not in self._taps:
+            H = 16 * g
+            ts = torch.empty(H, dtype=torch.int32)
+            tw = torch.empty(H, 3, dtype=torch.float32)
+            K.check(self.k.lib.bfk_upsample16_taps(g, ts.data_ptr(), tw.data_ptr()), "bfk_upsample16_taps")
+            self._taps[g] = (ts.to(self.device), tw.to(self.device))
+        return self._taps[g]
+
+    # ------------------------------------------------------------------------------------------------
+    # one pre-LN transformer layer
+    # ------------------------------------------------------------------------------------------------
+    def _layer_fwd(self, x, nseq, N, lw: LayerWeights, heads, eps, act, row_mask, save, lora_seed=0):
+        """x: fp32 [nseq*N, D] residual stream.  Returns the new stream; appends saved tensors to `save`."""
+        k, D, T, dev = self.k, self.cfg.dim, self.T, x.device
+        M, Dk, hd = nseq * N, lw.Dk, D // heads
+        Mlp = lw.W1.shape[0]
+        h1 = torch.empty(M, Dk, device=dev, dtype=T)
+        mean1 = torch.empty(M, device=dev, dtype=torch.float32); rstd1 = torch.empty_like(mean1)
+        k.layernorm_fwd(x, M, D, lw.ln1_w, lw.ln1_b, eps, h1, Dk, mean1, rstd1)
+        p_drop = self.cfg.lora_dropout if (lw.Acat is not None and self.training) else 0.0
+        if lw.Acat is not None:
+            K.check(k.lib.bfk_lora_down(h1.data_ptr(), Dk, _dt(h1), M, D, lw.Acat.data_ptr(), p_drop, lora_seed, _stream()),
+                    "bfk_lora_down")
+            k.launches += 1
+        qkv = torch.empty(M, 3 * D, device=dev, dtype=T)
+        k.gemm(h1, lw.Wqkv, qkv, M, 3 * D, Dk, Dk, Dk, 3 * D, bias=lw.bqkv)
+        ctx = torch.empty(M, D, device=dev, dtype=T)
+        lse = torch.empty(nseq * heads * N, device=dev, dtype=torch.float32)
+        k.attention_fwd(qkv, ctx, lse, nseq, N, heads, hd, hd ** -0.5, row_mask)
+        x1 = torch.empty(M, D, device=dev, dtype=torch.float32)
+        k.gemm(ctx, lw.Wo, x1, M, D, D, D, D, D, bias=lw.bo, residual=x, ldr=D)
+        h2 = torch.empty(M, D, device=dev, dtype=T)
+        mean2 = torch.empty(M, device=dev, dtype=torch.float32); rstd2 = torch.empty_like(mean2)
+        k.layernorm_fwd(x1, M, D, lw.ln2_w, lw.ln2_b, eps, h2, D, mean2, rstd2)
+        pa = torch.empty(M, Mlp, device=dev, dtype=T) if save is not None else None
+        a = torch.empty(M, Mlp, device=dev, dtype=T)
+        k.gemm(h2, lw.W1, a, M, Mlp, D, D, D, Mlp, bias=lw.b1, act=act, aux=pa, ld_aux=Mlp)
+        x2 = torch.empty(M, D, device=dev, dtype=torch.float32)
+        k.gemm(a, lw.W2, x2, M, D, Mlp, Mlp, Mlp, D, bias=lw.b2, residual=x1, ldr=D)
+        if save is not None:
+            save.append(dict(x=x, h1=h1, mean1=mean1, rstd1=rstd1, qkv=qkv, ctx=ctx, lse=lse, x1=x1, h2=h2, mean2=mean2,
+                             rstd2=rstd2, pa=pa, a=a, p_drop=p_drop, seed=lora_seed))
+        return x2
+
+    def _layer_bwd(self, dx2, dx2_T, sv, nseq, N, lw: LayerWeights, heads, eps, act, row_mask, grads, trainable):
+        """dx2 (fp32) / dx2_T (operand dtype): gradient w.r.t. the layer output.  Returns (dx, dx_T)."""
+        k, D, T, dev = self.k, self.cfg.dim, self.T, dx2.device
+        M, Dk, hd = nseq * N, lw.Dk, D // heads
+        Mlp = lw.W1.shape[0]
+        dact = K.ACT_DGELU_TANH if act == K.ACT_GELU_TANH else K.ACT_DGELU_ERF
+        n = lw.names
+        # fc2: x2 = a W2^T + b2 + x1
+        dpa = torch.empty(M, Mlp, device=dev, dtype=T)
+        k.gemm(dx2_T, lw.W2, dpa, M, Mlp, D, D, Mlp, Mlp, trans_b=True, act=dact, aux=sv["pa"], ld_aux=Mlp)
+        if trainable:
+            k.gemm(dx2_T, sv["a"], grads[n["W2"]], D, Mlp, M, D, Mlp, Mlp, trans_a=True, trans_b=True)
+            k.colsum(dx2, M, D, D, grads[n["b2"]])
+        # fc1: pa = h2 W1^T + b1
+        dh2 = torch.empty(M, D, device=dev, dtype=T)
+        k.gemm(dpa, lw.W1, dh2, M, D, Mlp, Mlp, D, D, trans_b=True)
+        if trainable:
+            k.gemm(dpa, sv["h2"], grads[n["W1"]], Mlp, D, M, Mlp, D, D, trans_a=True, trans_b=True)
+            k.colsum(dpa, M, Mlp, Mlp, grads[n["b1"]])
+        del dpa
+        # LN2 + residual
+        dx1 = torch.empty(M, D, device=dev, dtype=torch.float32)
+        dx1_T = torch.empty(M, D, device=dev, dtype=T) if T != torch.float32 else None
+        k.layernorm_bwd(dh2, D, sv["x1"], M, D, sv["mean2"], sv["rstd2"], lw.ln2_w, dx2, dx1, dx1_T,
+                        grads[n["ln2_w"]] if trainable else None, grads[n["ln2_b"]] if trainable else None)
+        if dx1_T is None:
+            dx1_T = dx1
+        # out-proj: x1 = ctx Wo^T + bo + x
+        dctx = dh2  # reuse buffer [M, D]
+        k.gemm(dx1_T, lw.Wo, dctx, M, D, D, D, D, D, trans_b=True)
+        if trainable:
+            k.gemm(dx1_T, sv["ctx"], grads[n["Wo"]], D, D, M, D, D, D, trans_a=True, trans_b=True)
+            k.colsum(dx1, M, D, D, grads[n["bo"]])
+        # attention
+        dqkv = torch.empty(M, 3 * D, device=dev, dtype=T)
+        k.attention_bwd(sv["qkv"], sv["ctx"], sv["lse"], dctx, dqkv, nseq, N, heads, hd, hd ** -0.5, row_mask)
+        # QKV: qkv = h1 Wqkv^T (+ bqkv); dh1 carries the 16 LoRA columns when present
+        dh1 = torch.empty(M, Dk, device=dev, dtype=T)
+        k.gemm(dqkv, lw.Wqkv, dh1, M, Dk, 3 * D, 3 * D, Dk, Dk, trans_b=True)
+        if trainable:
+            k.gemm(dqkv, sv["h1"], grads[n["Wqkv"]], 3 * D, D, M, 3 * D, Dk, D, trans_a=True, trans_b=True)
+        if lw.Acat is not None:
+            self._lora_bwd(sv, dqkv, dh1, M, lw, grads)
+        # LN1 + residual
+        dx = torch.empty(M, D, device=dev, dtype=torch.float32)
+        dx_T = torch.empty(M, D, device=dev, dtype=T) if T != torch.float32 else None
+        k.layernorm_bwd(dh1, Dk, sv["x"], M, D, sv["mean1"], sv["rstd1"], lw.ln1_w, dx1, dx, dx_T,
+                        grads[n["ln1_w"]] if trainable else None, grads[n["ln1_b"]] if trainable else None)
+        return dx, (dx_T if dx_T is not None else dx)
+
+    def _lora_bwd(self, sv, dqkv, dh1, M, lw, grads):
+        """LoRA factor gradients and the rank-r contribution to dh1 (peft LoRA backward)."""
+        k, cfg, D, r = self.k, self.cfg, self.cfg.dim, self.cfg.r
+        s = cfg.lora_alpha / cfg.r
+        lib, st = k.lib, _stream()
+        es = dqkv.element_size()
+        h1, Dk = sv["h1"], lw.Dk
+        ws = torch.empty(max(lib.bfk_skinny_gram_workspace_floats(M, 16, D), 1), device=dqkv.device, dtype=torch.float32)
+        n = lw.names
+        # dB_q[d, i] = s * sum_m u_q[m,i] dq[m,d]   (u = h1[:, D:D+16]);  out stored transposed: [D, r]
+        for (Bn, ucol, qoff) in ((n["Bq"], 0, 0), (n["Bv"], 8, 2 * D)):
+            K.check(lib.bfk_skinny_gram(h1.data_ptr() + (D + ucol) * es, Dk, r, dqkv.data_ptr() + qoff * es, 3 * D, D,
+                                        _dt(dqkv), M, s, grads[Bn].data_ptr(), r, 1, 0.0, 0, ws.data_ptr(), st), "bfk_skinny_gram")
+        # dA[i, k] = sum_m du[m,i] * drop(h1)[m,k]   (du = dh1[:, D:D+16])
+        for (An, ucol) in ((n["Aq"], 0), (n["Av"], 8)):
+            K.check(lib.bfk_skinny_gram(dh1.data_ptr() + (D + ucol) * es, Dk, r, h1.data_ptr(), Dk, D, _dt(dqkv), M, 1.0,
+                                        grads[An].data_ptr(), D, 0, sv["p_drop"], sv["seed"], ws.data_ptr(), st), "bfk_skinny_gram")
+        K.check(lib.bfk_lora_down_bwd(dh1.data_ptr(), Dk, _dt(dh1), M, D, lw.Acat.data_ptr(), sv["p_drop"], sv["seed"], st),
+                "bfk_lora_down_bwd")
+        k.launches += 9
+
+    # ------------------------------------------------------------------------------------------------
+    # towers
+    # ------------------------------------------------------------------------------------------------
+    def _final_ln_fwd(self, x, M, wname, bname, save):
+        D = self.cfg.dim
+        y = torch.empty(M, D, device=x.device, dtype=torch.float32)
+        mean = torch.empty(M, device=x.device, dtype=torch.float32); rstd = torch.empty_like(mean)
+        self.k.layernorm_fwd(x, M, D, self._p(wname), self._p(bname), self.cfg.tower_ln_eps, y, D, mean, rstd)
+        if save is not None:
+            save.append(dict(x=x, mean=mean, rstd=rstd))
+        return y
+
+    def _vision_fwd(self, images, save):
+        cfg, k, D = self.cfg, self.k, self.cfg.dim
+        Bv, Np, p = images.shape[0], cfg.num_patches, cfg.patch_size
+        vp = self.tw_prefix + "vision_model"
+        kpe = 3 * p * p
+        cols = torch.empty(Bv * Np, self.kpe_ld, device=images.device, dtype=self.T)
+        if self.kpe_ld != kpe:
+            cols.zero_()
+        K.check(k.lib.bfk_im2col(images.data_ptr(), Bv, 3, cfg.image_size, cfg.image_size, p, cols.data_ptr(), self.kpe_ld,
+                                 _dt(cols), _stream()), "bfk_im2col")
+        k.launches += 1
+        x = torch.empty(Bv * Np, D, device=images.device, dtype=torch.float32)
+        k.gemm(cols, self.W_pe, x, Bv * Np, D, self.kpe_ld, self.kpe_ld, self.kpe_ld, D,
+               bias=self._p(vp + ".embeddings.patch_embedding.bias"),
+               residual=self._p(vp + ".embeddings.position_embedding.weight"), ldr=D, res_row_mod=Np)
+        del cols
+        for i, lw in enumerate(self.vis_layers):
+            x = self._layer_fwd(x, Bv, Np, lw, cfg.tower_heads, cfg.tower_ln_eps, K.ACT_GELU_TANH, None, save,
+                                lora_seed=self.step_seed * 4096 + 1000 + i)
+        return self._final_ln_fwd(x, Bv * Np, vp + ".post_layernorm.weight", vp + ".post_layernorm.bias", save)
+
+    def _text_fwd(self, ids, save):
+        cfg, k, D = self.cfg, self.k, self.cfg.dim
+        B, L = ids.shape
+        tp = self.tw_prefix + "text_model"
+        x = torch.empty(B * L, D, device=ids.device, dtype=torch.float32)
+        K.check(k.lib.bfk_text_embed(ids.data_ptr(), B, L, D, cfg.vocab_size,
+                                     self._p(tp + ".embeddings.token_embedding.weight").data_ptr(),
+                                     self._p(tp + ".embeddings.position_embedding.weight").data_ptr(), x.data_ptr(), _stream()),
+                "bfk_text_embed")
+        k.launches += 1
+        for i, lw in enumerate(self.text_layers):
+            x = self._layer_fwd(x, B, L, lw, cfg.tower_heads, cfg.tower_ln_eps, K.ACT_GELU_TANH, None, save,
+                                lora_seed=self.step_seed * 4096 + 2000 + i)
+        return self._final_ln_fwd(x, B * L, tp + ".final_layer_norm.weight", tp + ".final_layer_norm.bias", save)
+
+    def _tower_bwd(self, dy, saves, layers, nseq, N, final_w, grads):
+        """dy fp32 [nseq*N, D] gradient w.r.t. the tower's last_hidden_state; LoRA grads into `grads`."""
+        cfg, k, D, T = self.cfg, self.k, self.cfg.dim, self.T
+        M = nseq * N
+        fin = saves[-1]
+        dx = torch.empty(M, D, device=dy.device, dtype=torch.float32)
+        dx_T = torch.empty(M, D, device=dy.device, dtype=T) if T != torch.float32 else None
+        k.layernorm_bwd(dy, D, fin["x"], M, D, fin["mean"], fin["rstd"], self._p(final_w), None, dx, dx_T)
+        dx_T = dx if dx_T is None else dx_T
+        for i in range(len(layers) - 1, -1, -1):
+            dx, dx_T = self._layer_bwd(dx, dx_T, saves[i], nseq, N, layers[i], cfg.tower_heads, cfg.tower_ln_eps,
+                                       K.ACT_GELU_TANH, None, grads, trainable=False)
+            saves[i] = None
+        # patch/text embeddings are frozen and the inputs need no gradient: stop here.
+
+    # ------------------------------------------------------------------------------------------------
+    # full forward
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, sample, need_grad: bool, training: bool, targets=None, want_argmax=False):
+        """Returns (heat [heads,B,H,W] fp32, losses [heads] or None, argmax keys or None, ctx or None)."""
+        cfg, k, D = self.cfg, self.k, self.cfg.dim
+        rgb = sample["rgb"]
+        dev = rgb.device
+        self.training = training
+        self.prepare(dev)
+        B, Np, L = rgb.shape[0], cfg.num_patches, cfg.text_len
+        T_ctx = sample["rgb_context"].shape[1] if cfg.sequential else 0
+        tower_grad = need_grad and cfg.lora
+        ctx = dict(B=B, T=T_ctx) if need_grad else None
+        vsave = [] if tower_grad else None
+        tsave = [] if tower_grad else None
+        fsave = [] if need_grad else None
+
+        if T_ctx:
+            images = torch.cat((rgb, sample["rgb_context"].reshape(B * T_ctx, *rgb.shape[1:])), dim=0).contiguous()
+        else:
+            images = rgb.contiguous()
+        vis = self._vision_fwd(images.float(), vsave)            # [(B + B*T)*Np, D]
+        txt = self._text_fwd(sample["instruction"].contiguous(), tsave)   # [B*L, D]
+
+        Nf = cfg.fusion_len(T_ctx)
+        X = torch.empty(B * Nf, D, device=dev, dtype=torch.float32)
+        mask = torch.empty(B * Nf, device=dev, dtype=torch.float32) if cfg.sequential else None
+        cmask = sample["context_attention_mask"].to(torch.int64).contiguous() if T_ctx else None
+        a = K.AssembleArgs(B, L, Np, T_ctx, D, txt.data_ptr(), vis.data_ptr(),
+                           vis.data_ptr() + B * Np * D * 4 if T_ctx else None,
+                           self._p("text_token").data_ptr(), self._p("image_token").data_ptr(),
+                           self._p("pick_place.fusion.token_type_embeddings.weight").data_ptr(),
+                           self._p("context_pos_embedding").data_ptr() if T_ctx else None,
+                           K.ptr(cmask), X.data_ptr(), K.ptr(mask))
+        K.check(k.lib.bfk_assemble_fwd(C.byref(a), _stream()), "bfk_assemble_fwd")
+        k.launches += 1
+        del vis, txt
+
+        x = X
+        for lw in self.fusion_layers:
+            x = self._layer_fwd(x, B, Nf, lw, cfg.heads, 1e-5, K.ACT_GELU_ERF, mask, fsave)
+
+        # ---- heatmap tail ----
+        heads = len(cfg.heads_out)
+        tail = self._tail_fwd(x, B, Nf, targets, want_argmax, need_grad)
+        if need_grad:
+            ctx.update(vsave=vsave, tsave=tsave, fsave=fsave, mask=mask, xf=x, Nf=Nf, tail=tail, targets=targets,
+                       heads=heads)
+        return tail["heat"], tail.get("loss"), tail.get("key"), ctx
+
+    def _decoder_ptr_tables(self, grads=None):
+        cfg = self.cfg
+        ws, bs, dws, dbs = [], [], [], []
+        for h in cfg.heads_out:
+            for j in range(5):
+                wn, bn = f"pick_place.{h}_decoder.decoder_net.{2 * j}.weight", f"pick_place.{h}_decoder.decoder_net.{2 * j}.bias"
+                ws.append(self._p(wn).data_ptr()); bs.append(self._p(bn).data_ptr())
+                if grads is not None:
+                    dws.append(grads[wn].data_ptr()); dbs.append(grads[bn].data_ptr())
+        mk = self._ptr_table
+        return (mk(ws), mk(bs)) if grads is None else (mk(ws), mk(bs), mk(dws), mk(dbs))
+
+    def _ptr_table(self, ptrs) -> torch.Tensor:
+        """Device array of pointers, cached by value (pointer tables are stable in steady state, so no
+        per-step H2D copy and CUDA-graph capture stays legal)."""
+        key = tuple(ptrs)
+        t = self._ptr_tables.get(key)
+        if t is None:
+            if len(self._ptr_tables) > 256:
+                self._ptr_tables.clear()
+            t = torch.tensor(list(key), dtype=torch.int64).to(self.device)
+            self._ptr_tables[key] = t
+        return t
+
+    def _tail_fwd(self, x, B, Nf, targets, want_argmax, need_grad):
+        cfg, k, D, dev = self.cfg, self.k, self.cfg.dim, x.device
+        heads, Np, g = len(cfg.heads_out), cfg.num_patches, cfg.grid
+        H = 16 * g
+        lib, st = k.lib, _stream()
+        Wt, bt = self._decoder_ptr_tables()
+        w_eff = torch.empty(heads, D, device=dev, dtype=torch.float32)
+        b_eff = torch.empty(heads, device=dev, dtype=torch.float32)
+        chain = torch.empty(heads, 4, D, device=dev, dtype=torch.float32)
+        ca = K.DecoderCollapseArgs(heads, D, Wt.data_ptr(), bt.data_ptr(), w_eff.data_ptr(), b_eff.data_ptr(), chain.data_ptr(),
+                                   None, None, None, None)
+        K.check(lib.bfk_decoder_collapse_fwd(C.byref(ca), st), "bfk_decoder_collapse_fwd")
+        grid = torch.empty(B, heads, Np, device=dev, dtype=torch.float32)
+        row0 = Nf - Np
+        pa = K.HeadProjectArgs(B, heads, Np, D, x.data_ptr(), Nf * D, row0, w_eff.data_ptr(), b_eff.data_ptr(), grid.data_ptr(),
+                               None, Nf, None, None, 0, None, None, None)
+        K.check(lib.bfk_head_project_fwd(C.byref(pa), st), "bfk_head_project_fwd")
+        ts, tw = self.taps(g)
+        heat = torch.empty(heads, B, H, H, device=dev, dtype=torch.float32)
+        out = dict(heat=heat, w_eff=w_eff, b_eff=b_eff, chain=chain, grid=grid, tables=(Wt, bt))
+        tptr = loss = part = key = None
+        if targets is not None:
+            tptr = self._ptr_table([t.data_ptr() for t in targets])
+            loss = torch.empty(heads + 1, device=dev, dtype=torch.float32)
+            part = torch.empty(heads * B * lib.bfk_heatmap_bands(g), device=dev, dtype=torch.float32)
+            out.update(loss=loss, tptr=tptr)
+        if want_argmax:
+            key = torch.empty(heads * B, device=dev, dtype=torch.int64)
+            out["key"] = key
+        ha = K.HeatmapFwdArgs(B, heads, g, grid.data_ptr(), ts.data_ptr(), tw.data_ptr(), heat.data_ptr(), K.ptr(tptr), None, 0,
+                              K.ptr(loss), K.ptr(key), K.ptr(part))
+        K.check(lib.bfk_heatmap_fwd(C.byref(ha), st), "bfk_heatmap_fwd")
+        k.launches += 3 + (1 if targets is not None else 0)
+        return out
+
+    # ------------------------------------------------------------------------------------------------
+    # full backward
+    # ------------------------------------------------------------------------------------------------
+    def trainable_names(self) -> List[str]:
+        return [n for n, p in self.params.items() if p.requires_grad]
+
+    def backward(self, ctx, dheat: Optional[torch.Tensor], dloss: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """dheat: [heads,B,H,W] gradient w.r.t. the heatmaps (or None); dloss: [heads] gradient w.r.t. the fused
+        per-head BCE losses (or None).  Returns {param name: fp32 grad}, views of one flat arena."""
+        cfg, k, D, T = self.cfg, self.k, self.cfg.dim, self.T
+        lib, st = k.lib, _stream()
+        B, T_ctx, Nf, heads = ctx["B"], ctx["T"], ctx["Nf"], ctx["heads"]
+        Np, L, g = cfg.num_patches, cfg.text_len, cfg.grid
+        H = 16 * g
+        dev = ctx["xf"].device
+        names = self.trainable_names()
+        sizes = [self.params[n].numel() for n in names]
+        offs, tot = [], 0
+        for s in sizes:
+            offs.append(tot); tot += (s + 3) // 4 * 4
+        arena = torch.empty(tot, device=dev, dtype=torch.float32)
+        grads = {n: arena[o:o + s].view(self.params[n].shape) for n, o, s in zip(names, offs, sizes)}
+        self.last_arena = arena
+        tail = ctx["tail"]
+        ts, tw = self.taps(g)
+
+        # ---- tail backward: dlogit -> dgrid -> (dX, d w_eff) -> decoder weights ----
+        dgrid = torch.empty(B, heads, Np, device=dev, dtype=torch.float32)
+        first = True
+        if dloss is not None:
+            gscale = dloss.contiguous()     # [heads + 1]: per-head grads then the grad of their sum
+            ba = K.HeatmapBwdArgs(B, heads, g, 0, tail["heat"].data_ptr(), tail["tptr"].data_ptr(), None, 0, gscale.data_ptr(),
+                                  1.0 / float(B * H * H), 1, None, ts.data_ptr(), tw.data_ptr(), dgrid.data_ptr())
+            K.check(lib.bfk_heatmap_bwd(C.byref(ba), st), "bfk_heatmap_bwd")
+            first = False
+        if dheat is not None:
+            dheat = dheat.contiguous()
+            dptr = self._ptr_table([dheat[h].data_ptr() for h in range(heads)])
+            tgt = dgrid if first else torch.empty_like(dgrid)
+            ba = K.HeatmapBwdArgs(B, heads, g, 1, tail["heat"].data_ptr(), None, None, 0, None, 1.0, 0, dptr.data_ptr(),
+                                  ts.data_ptr(), tw.data_ptr(), tgt.data_ptr())
+            K.check(lib.bfk_heatmap_bwd(C.byref(ba), st), "bfk_heatmap_bwd")
+            if not first:
+                dgrid.add_(tgt)   # both a fused-loss and a heatmap gradient (rare): tiny [B,heads,Np] add
+            first = False
+        if first:
+            dgrid.zero_()
+        dX = torch.empty(B * Nf, D, device=dev, dtype=torch.float32)
+        dX_T = torch.empty(B * Nf, D, device=dev, dtype=T) if T != torch.float32 else None
+        d_w_eff = torch.empty(heads, D, device=dev, dtype=torch.float32)
+        d_b_eff = torch.empty(heads, device=dev, dtype=torch.float32)
+        ws = torch.empty(lib.bfk_head_project_bwd_workspace_floats(B, heads, Np, D), device=dev, dtype=torch.float32)
+        pa = K.HeadProjectArgs(B, heads, Np, D, ctx["xf"].data_ptr(), Nf * D, Nf - Np, tail["w_eff"].data_ptr(),
+                               tail["b_eff"].data_ptr(), None, dgrid.data_ptr(), Nf, dX.data_ptr(), K.ptr(dX_T),
+                               _dt(dX_T) if dX_T is not None else 0, d_w_eff.data_ptr(), d_b_eff.data_ptr(), ws.data_ptr())
+        K.check(lib.bfk_head_project_bwd(C.byref(pa), st), "bfk_head_project_bwd")
+        Wt, bt, dWt, dbt = self._decoder_ptr_tables(grads)
+        ca = K.DecoderCollapseArgs(heads, D, Wt.data_ptr(), bt.data_ptr(), None, None, tail["chain"].data_ptr(),
+                                   d_w_eff.data_ptr(), d_b_eff.data_ptr(), dWt.data_ptr(), dbt.data_ptr())
+        K.check(lib.bfk_decoder_collapse_bwd(C.byref(ca), st), "bfk_decoder_collapse_bwd")
+        k.launches += 7
+        if self.grad_ready_hook:
+            self.grad_ready_hook("decoders")
+
+        # ---- fusion transformer ----
+        dx, dx_T = dX, (dX_T if dX_T is not None else dX)
+        fsave = ctx["fsave"]
+        for l in range(cfg.depth - 1, -1, -1):
+            dx, dx_T = self._layer_bwd(dx, dx_T, fsave[l], B, Nf, self.fusion_layers[l], cfg.heads, 1e-5, K.ACT_GELU_ERF,
+                                       ctx["mask"], grads, trainable=True)
+            fsave[l] = None
+            if self.grad_ready_hook:
+                self.grad_ready_hook(f"fusion.{l}")
+
+        # ---- assembly ----
+        need_tower = cfg.lora
+        dtxt = torch.empty(B * L, D, device=dev, dtype=torch.float32) if need_tower else None
+        dvis = torch.empty((B + B * T_ctx) * Np, D, device=dev, dtype=torch.float32) if need_tower else None
+        wsp = torch.empty(2 * 64 * D, device=dev, dtype=torch.float32)
+        aa = K.AssembleBwdArgs(B, L, Np, T_ctx, D, dx.data_ptr(), K.ptr(dtxt), K.ptr(dvis),
+                               (dvis.data_ptr() + B * Np * D * 4) if (need_tower and T_ctx) else None,
+                               grads["text_token"].data_ptr(), grads["image_token"].data_ptr(),
+                               grads["pick_place.fusion.token_type_embeddings.weight"].data_ptr(),
+                               grads["context_pos_embedding"].data_ptr() if T_ctx else None, wsp.data_ptr())
+        K.check(lib.bfk_assemble_bwd(C.byref(aa), st), "bfk_assemble_bwd")
+        k.launches += 4
+        if cfg.sequential and not T_ctx:
+            grads["context_pos_embedding"].zero_()
+        if self.grad_ready_hook:
+            self.grad_ready_hook("tokens")
+        del dx, dx_T
+
+        # ---- towers (only LoRA factors are trainable; gradients flow through the frozen base) ----
+        if need_tower:
+            tp, vp = self.tw_prefix + "text_model", self.tw_prefix + "vision_model"
+            self._tower_bwd(dtxt, ctx["tsave"], self.text_layers, B, L, tp + ".final_layer_norm.weight", grads)
+            if self.grad_ready_hook:
+                self.grad_ready_hook("text")
+            self._tower_bwd(dvis, ctx["vsave"], self.vis_layers, B + B * T_ctx, Np, vp + ".post_layernorm.weight", grads)
+            if self.grad_ready_hook:
+                self.grad_ready_hook("vision")
+        return grads

@@ -1,0 +1,113 @@
+"""Host-side mirror of ``bifold.losses`` for the hot path (bifold/losses/__init__.py:5-109).
+
+``BCEGaussMap`` computes nn.BCELoss per head (mean over B*H*W, log clamped at -100) summed over
+heads, on our CUDA kernels:
+
+* fused path  – when the model already computed the per-head BCE inside its heatmap kernel against
+  the very same target tensors (``PolicyOutput.fused_loss``), the loss is just read back and the
+  gradient goes into the tail backward kernel as (p - t)/(B*H*W);
+* general path – ``bfk_bce_prob`` / ``bfk_bce_prob_bwd`` on the probabilities (any caller-supplied
+  heatmaps, or ``mask_pick_heatmap=True``).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi as K
+
+
+class Losses:
+    @staticmethod
+    def get_by_name(cfg=None, name=None, *args, **kwargs):
+        if cfg is not None:
+            name = cfg.name
+        if name == "bce_gaussmap":
+            Loss = BCEGaussMap
+        elif name == "composed":
+            Loss = ComposedLoss
+        elif name in ("bce_mask", "dice", "focal"):
+            raise ValueError(f"Loss {name} needs mask_heatmap (compute_mask=True), which is outside the accelerated hot path")
+        else:
+            raise ValueError(f"Loss {name} not recognized")
+        if cfg is not None:
+            del cfg.name
+            return Loss(*args, **cfg, **kwargs)
+        return Loss(*args, **kwargs)
+
+
+class ComposedLoss:   # bifold/losses/__init__.py:30-51
+    def __init__(self, loss_names, weights, **kwargs):
+        assert len(loss_names) == len(weights)
+        self.loss_dict = {n: Losses.get_by_name(name=n, **kwargs) for n in loss_names}
+        self.weights = dict(zip(loss_names, weights))
+
+    def __call__(self, output, sample):
+        loss, inter = None, {}
+        for n, fn in self.loss_dict.items():
+            cur, cur_inter = fn(output, sample)
+            loss = cur * self.weights[n] if loss is None else loss + cur * self.weights[n]
+            inter[n] = cur
+            for k, v in cur_inter.items():
+                inter[n + " " + k] = v
+        return loss, inter
+
+
+class _BCEProbFn(torch.autograd.Function):
+    """nn.BCELoss()(p, t [* mask]) on device via the C ABI."""
+
+    @staticmethod
+    def forward(ctx, p, t, t_mask):
+        lib = K.load()
+        p = p.contiguous()
+        t = t.to(torch.float32).contiguous()
+        tm = t_mask.to(torch.float32).contiguous() if t_mask is not None else None
+        loss = torch.empty(1, device=p.device, dtype=torch.float32)
+        part = torch.empty(1024, device=p.device, dtype=torch.float32)
+        st = torch.cuda.current_stream().cuda_stream
+        K.check(lib.bfk_bce_prob(p.data_ptr(), t.data_ptr(), K.ptr(tm), p.numel(), loss.data_ptr(), part.data_ptr(), st),
+                "bfk_bce_prob")
+        ctx.save_for_backward(p, t, tm if tm is not None else p.new_zeros(0))
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        p, t, tm = ctx.saved_tensors
+        tm = tm if tm.numel() else None
+        lib = K.load()
+        gs = (g.reshape(1).float() / p.numel()).contiguous()
+        dp = torch.empty_like(p)
+        st = torch.cuda.current_stream().cuda_stream
+        K.check(lib.bfk_bce_prob_bwd(p.data_ptr(), t.data_ptr(), K.ptr(tm), p.numel(), gs.data_ptr(), dp.data_ptr(), st),
+                "bfk_bce_prob_bwd")
+        return dp, None, None
+
+
+class BCEGaussMap:    # bifold/losses/__init__.py:54-109
+    def __init__(self, is_bimanual, mask_pick_heatmap, **kwargs):
+        self.is_bimanual = is_bimanual
+        self.mask_pick_heatmap = mask_pick_heatmap
+
+    def _heads(self):
+        if self.is_bimanual:
+            return [f"{arm}_{action}" for arm in ("left", "right") for action in ("pick", "place")]
+        return ["pick", "place"]
+
+    def __call__(self, output, sample):
+        heads = self._heads()
+        fused = getattr(output, "fused_loss", None)
+        if fused is not None and not self.mask_pick_heatmap and len(heads) + 1 == fused.numel():
+            ptrs = tuple(sample[f"{h}_heatmap"].data_ptr() for h in heads)
+            if ptrs == output.fused_targets:
+                # fused[:heads] = per-head BCE, fused[heads] = their sum (computed in the finalize kernel)
+                return fused[len(heads)], {h: fused[i] for i, h in enumerate(heads)}
+        inter, loss = {}, None
+        for h in heads:
+            p = output[f"{h}_heatmap"]
+            if not p.is_cuda:
+                raise K.BfkError("bifold_b200 losses run on CUDA only (no CPU fallback)")
+            t = sample[f"{h}_heatmap"].to(p.device)
+            tm = sample["mask"].squeeze(1).to(p.device) if (self.mask_pick_heatmap and h.endswith("pick")) else None
+            cur = _BCEProbFn.apply(p, t, tm)
+            inter[h] = cur
+            loss = cur if loss is None else loss + cur
+        return loss, inter

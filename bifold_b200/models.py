@@ -1,0 +1,412 @@
+"""Host-side mirror of ``bifold.models`` for the policy hot path (drop-in interface).
+
+Same factories, constructor kwargs (= keys of bifold/conf/model/siglip*.yaml), ``forward`` /
+``get_action`` signatures, attributes and ``state_dict`` key names as the reference:
+
+* ``Models.get_by_name`` / ``Components.get_by_name``  <- bifold/models/__init__.py:12-43
+* ``BaseModel``                                         <- bifold/models/__init__.py:46-173
+* ``SigLip`` / ``SiglipSequential``                     <- bifold/models/siglip.py:10-137
+
+The nn.Modules below only *hold* parameters (with the reference's names, shapes and default
+initialisation).  All arithmetic of ``forward`` runs in ``bifold_b200.engine.Engine`` on our CUDA
+kernels; there is no eager fallback, so ``forward`` raises on a non-CUDA device.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _cabi as K
+from .config import PolicyConfig, tower_shape_from_name
+from .engine import Engine
+
+DUMMY_PICK = -np.ones(2)
+
+
+class Action:
+    """Same container as bifold/env/__init__.py:1-22 (2 or 4 keyword arrays)."""
+
+    def __init__(self, **kwargs):
+        if len(kwargs) not in (2, 4):
+            raise ValueError(f"Cannot instantiate action with {kwargs}")
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+
+class PolicyOutput(dict):
+    """The reference's output dict plus (non-key) handles used by the fused loss / action paths."""
+    fused_loss = None      # tensor [heads] with autograd, or None
+    fused_targets = None   # tuple of target data_ptrs the fused loss was computed against
+    heat_all = None        # [heads, B, H, W] tensor the per-head views come from
+
+
+# ----------------------------------------------------------------------------------------------------
+# parameter containers with the reference's module tree (names == reference state_dict keys)
+# ----------------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError("parameter container only; the computation runs in bifold_b200.engine")
+
+
+class _LoraLinear(_Holder):
+    """peft ``lora.Linear`` key layout: base_layer + lora_A/lora_B ModuleDicts keyed by adapter name."""
+
+    def __init__(self, in_f, out_f, r, adapter):
+        super().__init__()
+        self.base_layer = nn.Linear(in_f, out_f)
+        self.lora_A = nn.ModuleDict({adapter: nn.Linear(in_f, r, bias=False)})
+        self.lora_B = nn.ModuleDict({adapter: nn.Linear(r, out_f, bias=False)})
+        nn.init.kaiming_uniform_(self.lora_A[adapter].weight, a=math.sqrt(5))
+        nn.init.zeros_(self.lora_B[adapter].weight)
+
+
+def _tower_layer(D, mlp, lora, r, adapter):
+    layer = _Holder()
+    layer.layer_norm1 = nn.LayerNorm(D)
+    attn = _Holder()
+    for proj in ("k_proj", "v_proj", "q_proj", "out_proj"):
+        if lora and proj in ("q_proj", "v_proj"):
+            setattr(attn, proj, _LoraLinear(D, D, r, adapter))
+        else:
+            setattr(attn, proj, nn.Linear(D, D))
+    layer.self_attn = attn
+    layer.layer_norm2 = nn.LayerNorm(D)
+    mlp_m = _Holder()
+    mlp_m.fc1, mlp_m.fc2 = nn.Linear(D, mlp), nn.Linear(mlp, D)
+    layer.mlp = mlp_m
+    return layer
+
+
+def _encoder(cfg: PolicyConfig, lora, adapter):
+    enc = _Holder()
+    enc.layers = nn.ModuleList([_tower_layer(cfg.dim, cfg.tower_mlp, lora, cfg.r, adapter) for _ in range(cfg.tower_layers)])
+    return enc
+
+
+class _SiglipShell(_Holder):
+    """HF SiglipModel parameter tree (HF modeling_siglip.py: text_model / vision_model / logit_*)."""
+
+    def __init__(self, cfg: PolicyConfig, lora: bool, adapter: str):
+        super().__init__()
+        D = cfg.dim
+        text = _Holder()
+        emb = _Holder()
+        emb.token_embedding = nn.Embedding(cfg.vocab_size, D)
+        emb.position_embedding = nn.Embedding(cfg.text_len, D)
+        text.embeddings = emb
+        text.encoder = _encoder(cfg, lora, adapter)
+        text.final_layer_norm = nn.LayerNorm(D)
+        text.head = nn.Linear(D, D)                    # unused by BiFold (HF:521-522)
+        self.text_model = text
+        vis = _Holder()
+        vemb = _Holder()
+        vemb.patch_embedding = nn.Conv2d(3, D, cfg.patch_size, cfg.patch_size)
+        vemb.position_embedding = nn.Embedding(cfg.num_patches, D)
+        vis.embeddings = vemb
+        vis.encoder = _encoder(cfg, lora, adapter)
+        vis.post_layernorm = nn.LayerNorm(D)
+        head = _Holder()                               # pooling head, unused by BiFold (HF:620)
+        head.probe = nn.Parameter(torch.randn(1, 1, D))
+        head.attention = nn.MultiheadAttention(D, cfg.tower_heads, batch_first=True)
+        head.layernorm = nn.LayerNorm(D)
+        hm = _Holder()
+        hm.fc1, hm.fc2 = nn.Linear(D, cfg.tower_mlp), nn.Linear(cfg.tower_mlp, D)
+        head.mlp = hm
+        vis.head = head
+        self.vision_model = vis
+        self.logit_scale = nn.Parameter(torch.randn(1))
+        self.logit_bias = nn.Parameter(torch.randn(1))
+
+
+class _LoraModelShell(_Holder):
+    """peft ``LoraModel`` wrapper: wrapped model under ``.model`` and everything but LoRA frozen."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+        for n, p in model.named_parameters():
+            p.requires_grad = ".lora_A." in n or ".lora_B." in n
+
+
+class _PreNorm(_Holder):       # bifold/models/modules.py:8-15
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+
+class _Attention(_Holder):     # bifold/models/transformer.py:8-24
+    def __init__(self, dim, heads, dim_head):
+        super().__init__()
+        inner = dim_head * heads
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(0.0))
+
+
+class _FeedForward(_Holder):   # bifold/models/modules.py:18-30
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Dropout(0.0), nn.Linear(hidden, dim), nn.Dropout(0.0))
+
+
+class _Transformer(_Holder):   # bifold/models/transformer.py:45-58
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim):
+        super().__init__()
+        self.layers = nn.ModuleList([
+            nn.ModuleList([_PreNorm(dim, _Attention(dim, heads, dim_head)), _PreNorm(dim, _FeedForward(dim, mlp_dim))])
+            for _ in range(depth)])
+
+
+class ConcatTransformer(_Holder):   # bifold/models/fusion.py:8-34
+    def __init__(self, dim, heads, depth, dropout=0.0, mlp_ratio=4, num_modalities=2, num_registers=0, **kwargs):
+        super().__init__()
+        if dropout != 0.0 or num_registers != 0:
+            raise K.BfkError("concat_transformer: dropout and registers are not on the accelerated path")
+        self.num_modalities = num_modalities
+        self.token_type_embeddings = nn.Embedding(num_modalities, dim)
+        self.token_type_embeddings.weight.data.normal_(mean=0.0, std=0.02)   # bifold/models/utils.py:86-89
+        self.dim_head = int(dim / heads)
+        self.mlp_dim = dim * mlp_ratio
+        self.transformer_encoder = _Transformer(dim, depth, heads, self.dim_head, self.mlp_dim)
+        self.registers = None
+
+
+class ConvDecoder(_Holder):         # bifold/models/modules.py:33-74
+    def __init__(self, input_dim, output_dim=1):
+        super().__init__()
+        c1, c2 = int(input_dim / 2), int(input_dim / 4)
+        chans = [(input_dim, c1), (c1, c1), (c1, c2), (c2, c2), (c2, output_dim)]
+        mods = []
+        for i, (ci, co) in enumerate(chans):
+            mods.append(nn.Conv2d(ci, co, kernel_size=1))
+            if i != 4:
+                mods.append(nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False))
+        self.decoder_net = nn.Sequential(*mods)
+
+
+class PickPlaceConvDecoder(_Holder):   # bifold/models/pickplace.py:10-47
+    def __init__(self, dim, is_bimanual, fusion_model, num_patches, patch_size, compute_mask=False, detach_mask=False,
+                 **kwargs):
+        super().__init__()
+        if compute_mask:
+            raise K.BfkError("pick_place_convdecoder: compute_mask=True is not on the accelerated path (no shipped config sets it)")
+        self.is_bimanual = is_bimanual
+        self.fusion = Components.get_by_name(fusion_model, dim=dim, **kwargs)
+        self.num_patches_sqrt = int(math.sqrt(num_patches))
+        self.mask_head = None
+        if is_bimanual:
+            self.left_pick_decoder, self.right_pick_decoder = ConvDecoder(dim), ConvDecoder(dim)
+            self.left_place_decoder, self.right_place_decoder = ConvDecoder(dim), ConvDecoder(dim)
+        else:
+            self.pick_decoder, self.place_decoder = ConvDecoder(dim), ConvDecoder(dim)
+
+
+class Models:
+    @staticmethod
+    def get_by_name(cfg, *args, **kwargs):
+        if cfg.name == "siglip":
+            Model = SigLip
+        elif cfg.name == "siglip_sequential":
+            Model = SiglipSequential
+        elif cfg.name in ("rgb_clip", "text_unet"):
+            raise ValueError(f"Model {cfg.name} is an ablation baseline outside the accelerated hot path")
+        else:
+            raise ValueError(f"Model {cfg.name} not recognized")
+        del cfg.name
+        return Model(*args, **cfg, **kwargs)
+
+
+class Components:
+    @staticmethod
+    def get_by_name(name, *args, **kwargs):
+        if name == "pick_place_convdecoder":
+            return PickPlaceConvDecoder(*args, **kwargs)
+        if name == "concat_transformer":
+            return ConcatTransformer(*args, **kwargs)
+        if name in ("pick_place_transdecoder", "crossattention"):
+            raise ValueError(f"Model {name} is not on the accelerated hot path (no shipped config selects it)")
+        raise ValueError(f"Model {name} not recognized")
+
+
+# ----------------------------------------------------------------------------------------------------
+class _PolicyFn(torch.autograd.Function):
+    """Whole-policy autograd node: forward = Engine.forward, backward = Engine.backward."""
+
+    @staticmethod
+    def forward(ctx, model, sample, targets, want_argmax, *params):
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        heat, loss, key, ectx = model.engine.forward(sample, need_grad, model.training, targets, want_argmax)
+        ctx.model, ctx.ectx = model, ectx
+        ctx.set_materialize_grads(False)
+        ctx.n_params = len(params)
+        model._last_key = key
+        if loss is None:
+            loss = heat.new_zeros(0)
+        ctx.mark_non_differentiable(*([] if targets is not None else [loss]))
+        return heat, loss
+
+    @staticmethod
+    def backward(ctx, dheat, dloss):
+        model = ctx.model
+        if ctx.ectx is None:
+            raise RuntimeError("backward through a forward that ran without grad")
+        grads = model.engine.backward(ctx.ectx, dheat, dloss if (dloss is not None and dloss.numel()) else None)
+        ctx.ectx = None
+        out = [grads.get(n) if p.requires_grad else None for n, p in zip(model._param_names, model._param_list)]
+        return (None, None, None, None, *out)
+
+
+class BaseModel(nn.Module):
+    def __init__(self, image_size, is_bimanual, device, threshold=0.01, requires_graph=False, constrain_pick_mask=True,
+                 **kwargs):
+        super().__init__()
+        self.image_size = image_size
+        self.is_bimanual = is_bimanual
+        self.device = device
+        self.threshold = 0.01          # the reference ignores its argument (bifold/models/__init__.py:61)
+        self.requires_graph = requires_graph
+        self.constrain_pick_mask = constrain_pick_mask
+        if requires_graph:
+            raise K.BfkError("requires_graph=True (point-cloud picks) is not on the accelerated path")
+        if not self.constrain_pick_mask:
+            print("This run will not constrain the pick to the mask")
+
+    def frozen_submodule(self, submodule_name):
+        for n, p in self.named_parameters():
+            if submodule_name in n:
+                p.requires_grad = False
+
+    def frozen_all(self):
+        for p in self.parameters():
+            p.requires_grad = False
+
+    # -- get_action: bifold/models/__init__.py:79-173 with argmax / mask snap / gate on device -------------
+    def get_action(self, sample, return_raw_output=False):
+        with torch.no_grad():
+            output = self.forward(sample, _want_argmax=True)
+        cfg = self.cfg
+        heat = output.heat_all
+        heads, B, H, W = heat.shape
+        names = cfg.heads_out
+        if self.is_bimanual:
+            pick = [names.index("left_pick"), names.index("right_pick")]
+            place = [names.index("left_place"), names.index("right_place")]
+            n_arms, mask = 2, sample["mask"]
+        else:
+            pick, place = [names.index("pick"), 0], [names.index("place"), 0]
+            n_arms = 1
+            mask = sample.get("mask") if self.constrain_pick_mask else None
+        if mask is not None:
+            mask = mask.to(device=heat.device, dtype=torch.float32).reshape(B, H, W).contiguous()
+        xy = torch.empty(heads, B, 2, device=heat.device, dtype=torch.int32)
+        conf = torch.empty(heads, B, device=heat.device, dtype=torch.float32)
+        import ctypes as C
+        a = K.ActionArgs(B, heads, H, W, n_arms, heat.data_ptr(), self._last_key.data_ptr(), K.ptr(mask),
+                         (C.c_int32 * 2)(*pick), (C.c_int32 * 2)(*place), float(self.threshold), xy.data_ptr(), conf.data_ptr())
+        K.check(self.engine.k.lib.bfk_action(C.byref(a), torch.cuda.current_stream().cuda_stream), "bfk_action")
+        self.engine.k.launches += 1
+        xy = xy.cpu().numpy().astype(np.int64)
+        action = Action(**{n: xy[i] for i, n in enumerate(names)})
+        if return_raw_output:
+            return action, output
+        return action
+
+
+class SigLip(BaseModel):
+    def __init__(self, patch_size, dim, lora, r, lora_alpha, lora_dropout, automodel_name, target_modules,
+                 pick_place_model, precision="bf16", tower_config=None, **kwargs):
+        super().__init__(**kwargs)
+        self.patch_size = patch_size
+        self.hidden_size = dim
+        self.num_patches = (self.image_size // self.patch_size) ** 2
+        if lora and sorted(target_modules) != ["q_proj", "v_proj"]:
+            raise K.BfkError("LoRA target_modules other than [q_proj, v_proj] are not on the accelerated path")
+        tower = dict(tower_shape_from_name(automodel_name, dim))
+        tower.update(tower_config or {})
+        tower.pop("dim", None)
+        fusion_kw = {k: kwargs[k] for k in ("depth", "heads", "mlp_ratio") if k in kwargs}
+        self.cfg = PolicyConfig(name="siglip", image_size=self.image_size, patch_size=patch_size, dim=dim,
+                                is_bimanual=self.is_bimanual, lora=bool(lora), r=r, lora_alpha=lora_alpha,
+                                lora_dropout=lora_dropout, **fusion_kw, **tower)
+        siglip = _SiglipShell(self.cfg, bool(lora), "siglip_adapter")
+        self._maybe_load_pretrained(siglip, automodel_name)
+        if lora:
+            self.siglip_model = _LoraModelShell(siglip)
+        else:
+            self.siglip_model = siglip
+            self.frozen_submodule("siglip_model")
+        self.text_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.image_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.pick_place = Components.get_by_name(pick_place_model, dim=dim, patch_size=patch_size,
+                                                 num_patches=self.num_patches, **kwargs)
+        self.precision = precision
+        self.engine = None
+        self._last_key = None
+
+    @staticmethod
+    def _maybe_load_pretrained(shell, automodel_name):
+        """Load a locally cached HF checkpoint when one exists (offline); otherwise keep the random init."""
+        try:
+            import os
+            if not automodel_name or not os.path.isdir(str(automodel_name)):
+                return
+            from transformers import AutoModel
+            hf = AutoModel.from_pretrained(automodel_name, local_files_only=True)
+            shell.load_state_dict(hf.state_dict(), strict=False)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------
+    def _ensure_engine(self):
+        if self.engine is None:
+            self._param_names = [n for n, _ in self.named_parameters()]
+            self._param_list = [p for _, p in self.named_parameters()]
+            self.engine = Engine(self.cfg, dict(zip(self._param_names, self._param_list)), self.precision)
+        return self.engine
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self.engine = None       # parameters may have been replaced (.to(device))
+        return r
+
+    def forward(self, x, _want_argmax=False):
+        rgb = x["rgb"]
+        if not rgb.is_cuda:
+            raise K.BfkError("bifold_b200 runs on CUDA only (no CPU fallback): move the sample to the GPU")
+        self._ensure_engine()
+        cfg = self.cfg
+        # fused BCE when the targets travel with the sample (training loop: bifold/__main__.py:135-137)
+        targets = None
+        if self.training and torch.is_grad_enabled():
+            ts = [x.get(f"{h}_heatmap") for h in cfg.heads_out]
+            if all(t is not None and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                   and tuple(t.shape) == (rgb.shape[0], cfg.image_size, cfg.image_size) for t in ts):
+                targets = ts
+        heat, loss = _PolicyFn.apply(self, x, targets, _want_argmax, *self._param_list)
+        out = PolicyOutput(attn_weights=None)
+        for i, h in enumerate(cfg.heads_out):
+            out[f"{h}_heatmap"] = heat[i]
+        out.heat_all = heat
+        if targets is not None:
+            out.fused_loss = loss
+            out.fused_targets = tuple(t.data_ptr() for t in targets)
+        return out
+
+
+class SiglipSequential(SigLip):
+    def __init__(self, context_length, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.cfg.name = "siglip_sequential"
+        self.cfg.context_length = context_length
+        self.context_pos_embedding = nn.Parameter(torch.randn(1, context_length * (self.num_patches + 1), self.hidden_size))
+
+    def forward(self, x, _want_argmax=False):
+        t = x["rgb_context"].shape[1]
+        if t != self.cfg.context_length:
+            # the reference adds context_pos_embedding of fixed length (bifold/models/siglip.py:117)
+            raise ValueError(f"rgb_context has {t} frames, context_length is {self.cfg.context_length}")
+        return super().forward(x, _want_argmax)

@@ -1,0 +1,157 @@
+"""Host-side mirror of ``bifold.optim`` (bifold/optim/__init__.py:4-92): Adam / AdamW with torch
+semantics executed by one fused CUDA kernel over flat buffers (bfk_adamw), plus the LinearWarmup
+scheduler (host Python, unchanged semantics)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi as K
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam (L2 weight decay) / AdamW (decoupled) on the bfk_adamw kernel.
+
+    Parameters are re-homed into one flat fp32 buffer per param group (the nn.Parameter objects keep
+    their identity; ``p.data`` becomes a view), so a step is ONE launch when the gradients are views of
+    one flat arena laid out the same way (that is how bifold_b200.engine hands them out) and one launch
+    per tensor otherwise.  ``self.state`` is torch-compatible (per-parameter ``step``, ``exp_avg``,
+    ``exp_avg_sq``), so ``state_dict()`` / ``load_state_dict()`` interoperate with torch.optim.Adam.
+    """
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, **unused):
+        defaults = dict(lr=float(lr), betas=tuple(float(b) for b in betas), eps=float(eps), weight_decay=float(weight_decay),
+                        decoupled=bool(decoupled))
+        super().__init__(params, defaults)
+        self.grad_scale = 1.0          # DDP folds 1/world_size in here
+        self.pre_step_hook = None      # DDP: wait for the gradient all-reduce
+        self._flat = {}
+        self.launches = 0
+
+    def _flatten(self, gi, group):
+        ps = [p for p in group["params"] if p.requires_grad]
+        if not ps:
+            return None
+        dev = ps[0].device
+        if dev.type != "cuda":
+            raise K.BfkError("bifold_b200 optimizers run on CUDA only (no CPU fallback)")
+        offs, tot = [], 0
+        for p in ps:
+            offs.append(tot)
+            tot += (p.numel() + 3) // 4 * 4
+        flat = torch.zeros(tot, device=dev, dtype=torch.float32)
+        m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+        step = 0
+        for p, o in zip(ps, offs):
+            flat[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = flat[o:o + p.numel()].view(p.shape)
+            s = self.state[p]
+            if "exp_avg" in s:      # state loaded from a checkpoint: keep it
+                m[o:o + p.numel()].copy_(s["exp_avg"].reshape(-1))
+                v[o:o + p.numel()].copy_(s["exp_avg_sq"].reshape(-1))
+                step = max(step, int(s["step"]))
+            s["step"] = torch.tensor(float(step))
+            s["exp_avg"] = m[o:o + p.numel()].view(p.shape)
+            s["exp_avg_sq"] = v[o:o + p.numel()].view(p.shape)
+        st = dict(ps=ps, offs=offs, tot=tot, p=flat, m=m, v=v, step=step)
+        self._flat[gi] = st
+        return st
+
+    def _launch(self, n, p, g, m, v, group, step):
+        b1, b2 = group["betas"]
+        a = K.AdamWArgs(n, p, g, m, v, None, group["lr"], b1, b2, group["eps"], group["weight_decay"],
+                        int(group["decoupled"]), step, float(self.grad_scale))
+        K.check(K.load().bfk_adamw(C.byref(a), torch.cuda.current_stream().cuda_stream), "bfk_adamw")
+        self.launches += 1
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        if self.pre_step_hook is not None:
+            self.pre_step_hook()
+        for gi, group in enumerate(self.param_groups):
+            st = self._flat.get(gi)
+            if st is None or any(p.data_ptr() != st["p"].data_ptr() + 4 * o for p, o in zip(st["ps"], st["offs"])) or \
+                    any(self.state[p].get("exp_avg") is None or
+                        self.state[p]["exp_avg"].data_ptr() != st["m"].data_ptr() + 4 * o for p, o in zip(st["ps"], st["offs"])):
+                st = self._flatten(gi, group)
+            if st is None:
+                continue
+            st["step"] += 1
+            for p in st["ps"]:
+                self.state[p]["step"] += 1
+            ps, offs = st["ps"], st["offs"]
+            g0 = ps[0].grad
+            flat_ok = g0 is not None and g0.dtype == torch.float32 and all(
+                p.grad is not None and p.grad.is_contiguous() and p.grad.data_ptr() == g0.data_ptr() + 4 * o
+                for p, o in zip(ps, offs))
+            if flat_ok:
+                self._launch(st["tot"], st["p"].data_ptr(), g0.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(), group, st["step"])
+            else:
+                for p, o in zip(ps, offs):
+                    if p.grad is None:
+                        continue
+                    g = p.grad.contiguous().float()
+                    if g.data_ptr() % 16:
+                        g = g.clone()
+                    self._launch(p.numel(), st["p"].data_ptr() + 4 * o, g.data_ptr(), st["m"].data_ptr() + 4 * o,
+                                 st["v"].data_ptr() + 4 * o, group, st["step"])
+        return loss
+
+
+class Optimizers:
+    @staticmethod
+    def get_by_name(cfg, params):
+        if cfg.name == "adam":
+            del cfg.name
+            return FusedAdam(params, decoupled=False, **cfg)
+        if cfg.name == "adamw":
+            del cfg.name
+            return FusedAdam(params, decoupled=True, **cfg)
+        raise ValueError(f"Optimizer {cfg.name} not recognized")
+
+
+class Schedulers:
+    @staticmethod
+    def get_by_name(cfg, *args, **kwargs):
+        if cfg.name is None:
+            return None
+        if cfg.name == "linear_warmup":
+            return LinearWarmup(cfg, *args, **kwargs)
+        raise ValueError(f"Scheduler {cfg.name} not recognized")
+
+
+class LinearWarmup:   # bifold/optim/__init__.py:28-92 (host-side; mutates param_groups[i]["lr"])
+    def __init__(self, cfg, optimizer, max_iters):
+        self.warmup_steps = int(cfg.warmup_portion * max_iters)
+        self.optimizer = optimizer
+        self.base_lrs = [g["lr"] for g in optimizer.param_groups]
+        self.last_step = -1
+        if isinstance(cfg.warmup_start_lr, (list, tuple)):
+            assert len(cfg.warmup_start_lr) == len(self.base_lrs)
+            self.warmup_start_lrs = cfg.warmup_start_lr
+        else:
+            self.warmup_start_lrs = [cfg.warmup_start_lr] * len(self.base_lrs)
+        self.lr_scheduler = (torch.optim.lr_scheduler.CosineAnnealingLR(optimizer=optimizer, T_max=max_iters - self.warmup_steps)
+                             if cfg.use_cosine_decay else None)
+        self.step()
+
+    def get_last_lr(self):
+        return self._last_lr
+
+    def state_dict(self):
+        return {k: v for k, v in self.__dict__.items() if k not in ("optimizer", "lr_scheduler")}
+
+    def load_state_dict(self, state_dict):
+        self.__dict__.update(state_dict)
+
+    def step(self, epoch=None):
+        if self.last_step <= self.warmup_steps:
+            values = [w + (b - w) * (self.last_step / self.warmup_steps) for w, b in zip(self.warmup_start_lrs, self.base_lrs)]
+            for g, lr in zip(self.optimizer.param_groups, values):
+                g["lr"] = lr
+            self.last_step += 1
+        elif self.lr_scheduler is not None:
+            self.lr_scheduler.step()
+        self._last_lr = [g["lr"] for g in self.optimizer.param_groups]

@@ -1,0 +1,310 @@
+/*
+ * bifold_b200 — C ABI of the B200-native BiFold policy hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes and a CUDA stream, never
+ * allocates, never synchronises, never throws.  Return value: 0 on success, a negative BFK_E_* code
+ * otherwise (text via bfk_last_error()).  All pointers are DEVICE pointers unless stated.  The caller
+ * owns every buffer.
+ *
+ * The reference (Barbany/bifold) has no native code and no FFI on this path: it is eager PyTorch.
+ * Each entry point therefore cites the reference *Python* call it replaces (path:line relative to the
+ * reference root; `HF:` = transformers/models/siglip/modeling_siglip.py 5.5.0, which the reference
+ * calls at bifold/models/siglip.py:26,57,102).  INTEGRATION.md shows the ctypes binding a maintainer
+ * adds on the reference side.
+ */
+#ifndef BIFOLD_B200_H_
+#define BIFOLD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* bfk_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define BFK_API __attribute__((visibility("default")))
+#else
+#define BFK_API
+#endif
+
+enum { BFK_F32 = 0, BFK_BF16 = 1 };
+enum { BFK_OK = 0, BFK_E_INVALID = -1, BFK_E_UNSUPPORTED = -2, BFK_E_CUDA = -3 };
+enum { BFK_BACKEND_AUTO = 0, BFK_BACKEND_SIMT = 1, BFK_BACKEND_TCGEN05 = 2 };
+enum {
+  BFK_ACT_NONE = 0,
+  BFK_ACT_GELU_TANH = 1,   /* HF:323-327 (gelu_pytorch_tanh)            */
+  BFK_ACT_GELU_ERF = 2,    /* bifold/models/modules.py:23 (nn.GELU())   */
+  BFK_ACT_DGELU_TANH = 3,  /* out = acc * gelu_tanh'(aux)  (backward)   */
+  BFK_ACT_DGELU_ERF = 4    /* out = acc * gelu_erf'(aux)   (backward)   */
+};
+
+BFK_API int32_t bfk_version(void);
+BFK_API const char* bfk_last_error(void);        /* thread-local, host string */
+BFK_API int32_t bfk_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM with fused epilogue:  D = act(alpha * A·Bᵀ + bias) + residual      (fp32 accumulate)
+ *   A element (m,k): trans_a ? A[k*lda + m] : A[m*lda + k]
+ *   B element (n,k): trans_b ? B[k*ldb + n] : B[n*ldb + k]    (trans_b = 0 is the nn.Linear layout)
+ * Replaces: nn.Linear / F.linear in HF:285-287,309,324-326; bifold/models/transformer.py:28,42;
+ * bifold/models/modules.py:22-25; nn.Conv2d patch embedding HF:124-130,178 (after bfk_im2col) and
+ * their autograd backward (dgrad: trans_b = 1; wgrad: trans_a = trans_b = 1).
+ * in_dtype BF16 + backend AUTO/TCGEN05 runs on tcgen05 tensor cores (TMA-fed, TMEM accumulators);
+ * in_dtype F32 runs the SIMT fp32 kernel ("fp32 parity mode").
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t M, N, K;
+  const void* A; int64_t lda; int32_t trans_a;
+  const void* B; int64_t ldb; int32_t trans_b;
+  int32_t in_dtype;
+  void* D; int64_t ldd; int32_t out_dtype;
+  const float* bias;                 /* [N] fp32 or NULL */
+  int32_t act;                       /* BFK_ACT_*  */
+  void* aux; int64_t ld_aux;         /* GELU_*: optional store of the pre-activation (out_dtype);
+                                        DGELU_*: pre-activation to read (in_dtype) */
+  const float* residual; int64_t ldr; int32_t res_row_mod; /* fp32; row = res_row_mod ? m % res_row_mod : m */
+  float alpha;
+  int32_t accumulate;                /* D += ... (fp32 output only) */
+  int32_t backend;
+} bfk_gemm_args;
+BFK_API int32_t bfk_gemm(const bfk_gemm_args* a, bfk_stream_t s);
+
+/* Column sums of a row-major matrix: out[n] = sum_m X[m*ld + n]  (bias gradients).  Deterministic
+ * two-stage reduction; `partials` must hold bfk_colsum_workspace_floats(M,N) floats. */
+BFK_API size_t bfk_colsum_workspace_floats(int32_t M, int32_t N);
+BFK_API int32_t bfk_colsum(const void* X, int32_t dtype, int32_t M, int32_t N, int64_t ld, float* out,
+                   float* partials, bfk_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (biased variance, eps inside sqrt), fp32 statistics.
+ * Replaces nn.LayerNorm at HF:334-336,348,357,518,618 (eps 1e-6) and bifold/models/modules.py:11
+ * (eps 1e-5).  Backward fuses the residual-gradient add and can emit a second copy in `dx2_dtype`.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t M, D;
+  const float* x; int64_t ldx;
+  const float* gamma; const float* beta; float eps;
+  void* y; int64_t ldy; int32_t y_dtype;
+  float* mean; float* rstd;          /* [M] saved for backward (may be NULL) */
+} bfk_layernorm_fwd_args;
+BFK_API int32_t bfk_layernorm_fwd(const bfk_layernorm_fwd_args* a, bfk_stream_t s);
+
+typedef struct {
+  int32_t M, D;
+  const void* dy; int64_t ld_dy; int32_t dy_dtype;
+  const float* x; int64_t ldx;
+  const float* mean; const float* rstd; const float* gamma;
+  const float* dres; int64_t ld_dres;        /* residual-branch gradient added to dx, or NULL */
+  float* dx; int64_t ld_dx;
+  void* dx2; int64_t ld_dx2; int32_t dx2_dtype; /* optional second copy of dx, or NULL */
+  float* dgamma; float* dbeta;               /* [D] overwritten, or NULL (frozen LN) */
+  float* partials;                           /* bfk_layernorm_bwd_workspace_floats(M,D) floats if dgamma */
+} bfk_layernorm_bwd_args;
+BFK_API size_t bfk_layernorm_bwd_workspace_floats(int32_t M, int32_t D);
+BFK_API int32_t bfk_layernorm_bwd(const bfk_layernorm_bwd_args* a, bfk_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-head attention on a packed QKV matrix.
+ *   qkv row (b*N+n): [ q(h,d) | k(h,d) | v(h,d) ],  out row: [ (h,d) ].
+ *   row_mask (B,N) fp32 or NULL: rows with mask == 0 get EVERY score set to mask_fill before the
+ *   softmax (the reference's query-row mask, bifold/models/transformer.py:33-35) => uniform
+ *   attention over all keys, and no gradient to q/k from that row.
+ * Replaces HF:275-311 (SDPA, no mask) and bifold/models/transformer.py:26-41.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, N, H, hd;
+  const void* qkv; int64_t ld_qkv;
+  void* out; int64_t ld_out;
+  float* lse;                        /* [B,H,N] log-sum-exp of the scaled scores (for backward) */
+  const float* row_mask;
+  float scale; float mask_fill;
+  int32_t dtype;                     /* BFK_F32 | BFK_BF16 */
+  int32_t backend;
+  /* backward only */
+  const void* dout; int64_t ld_dout;
+  void* dqkv; int64_t ld_dqkv;
+  float* delta;                      /* [B,H,N] workspace: rowsum(dout*out) */
+} bfk_attention_args;
+BFK_API int32_t bfk_attention_fwd(const bfk_attention_args* a, bfk_stream_t s);
+BFK_API int32_t bfk_attention_bwd(const bfk_attention_args* a, bfk_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Embeddings and token assembly.
+ * ---------------------------------------------------------------------------------------------- */
+/* im2col of non-overlapping p x p patches: out[(b*g*g + py*g + px), c*p*p + i*p + j] =
+ * rgb[b,c,py*p+i,px*p+j]  (matches conv weight (D,3,p,p).flatten(1)); HF:178-179. */
+BFK_API int32_t bfk_im2col(const float* rgb, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p,
+                   void* out, int64_t ld_out, int32_t out_dtype, bfk_stream_t s);
+/* out[b*L + t, :] = tok_emb[ids[b,t], :] + pos_emb[t, :]   (HF:217-224); ids int64. */
+BFK_API int32_t bfk_text_embed(const int64_t* ids, int32_t B, int32_t L, int32_t D, int32_t vocab,
+                       const float* tok_emb, const float* pos_emb, float* out, bfk_stream_t s);
+
+/* LoRA down-projection on the LayerNorm output (peft LoRA; bifold/models/siglip.py:33-40):
+ *   h[m, D + j] = sum_k drop(h[m,k]) * Acat[j,k],  j < 16  (rows of Acat beyond 2r are zero).
+ * The 16 extra columns ride along the K dimension of the QKV GEMM whose weight is [W | scale*B].
+ * dropout_p > 0 applies an inverted-dropout mask from a counter-based hash of (seed, m, k). */
+BFK_API int32_t bfk_lora_down(void* h, int64_t ldh, int32_t dtype, int32_t M, int32_t D, const void* Acat,
+                      float dropout_p, uint64_t seed, bfk_stream_t s);
+/* backward of the above w.r.t. h:  dh[m,k] += mask(m,k) * sum_j dh[m, D+j] * Acat[j,k] */
+BFK_API int32_t bfk_lora_down_bwd(void* dh, int64_t ldh, int32_t dtype, int32_t M, int32_t D, const void* Acat,
+                          float dropout_p, uint64_t seed, bfk_stream_t s);
+/* Tall-skinny Gram product used for the LoRA weight gradients (deterministic split over rows):
+ *   out[i, j] = alpha * sum_m P[m*ldp + i] * mask?(Q[m*ldq + j]),  i < ni (<=16), j < nj.
+ * `partials`: bfk_skinny_gram_workspace_floats(M, ni, nj). */
+BFK_API size_t bfk_skinny_gram_workspace_floats(int32_t M, int32_t ni, int32_t nj);
+BFK_API int32_t bfk_skinny_gram(const void* P, int64_t ldp, int32_t ni, const void* Q, int64_t ldq, int32_t nj,
+                        int32_t dtype, int32_t M, float alpha, float* out, int64_t ldo, int32_t transpose_out,
+                        float dropout_p, uint64_t seed, float* partials, bfk_stream_t s);
+
+/* Fusion input assembly (bifold/models/siglip.py:62-68,91-130 + type embedding add
+ * bifold/models/fusion.py:46-56):  X[b, r, :] for r in [0, Nf),
+ *   Nf = (L+1) + (T+1)*(Np+1);  text rows get type 0, context and image rows type 1;
+ *   context rows also get ctx_pos.  mask_out (B,Nf) fp32 is the attention-mask vector (or NULL). */
+typedef struct {
+  int32_t B, L, Np, T, D;
+  const float* txt;        /* [B, L, D]   text tower output                     */
+  const float* img;        /* [B, Np, D]  vision tower output of the frame      */
+  const float* ctx;        /* [B*T, Np, D] vision tower output of context (T>0) */
+  const float* text_token; const float* image_token;   /* [D] */
+  const float* type_emb;   /* [2, D] */
+  const float* ctx_pos;    /* [T*(Np+1), D] (T>0) */
+  const int64_t* ctx_mask; /* [B, T] int64 (T>0) */
+  float* X;                /* [B, Nf, D] */
+  float* mask_out;         /* [B, Nf] or NULL */
+} bfk_assemble_args;
+BFK_API int32_t bfk_assemble_fwd(const bfk_assemble_args* a, bfk_stream_t s);
+/* backward: dX [B,Nf,D] -> dtxt/dimg/dctx (any may be NULL) and parameter grads (fp32, overwritten). */
+typedef struct {
+  int32_t B, L, Np, T, D;
+  const float* dX;
+  float* dtxt; float* dimg; float* dctx;
+  float* d_text_token; float* d_image_token; float* d_type_emb; float* d_ctx_pos;
+  float* partials;         /* workspace: 2*64*D floats */
+} bfk_assemble_bwd_args;
+BFK_API int32_t bfk_assemble_bwd(const bfk_assemble_bwd_args* a, bfk_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Heatmap tail.  The reference ConvDecoder (bifold/models/modules.py:33-74) is five 1x1 convs with
+ * x2 bilinear upsamples between them and NO non-linearity, so each head is exactly
+ *   logit = Up16( w_eff . token + b_eff ),  w_eff = W5 W4 W3 W2 W1,  Up16 = four x2 bilinear stages.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t heads, D;                   /* channels: D -> D/2 -> D/2 -> D/4 -> D/4 -> 1 (int division) */
+  const float* const* W;              /* DEVICE array [heads*5] of weight pointers (cout,cin) row-major */
+  const float* const* b;              /* DEVICE array [heads*5] of bias pointers */
+  float* w_eff; float* b_eff;         /* [heads, D], [heads] */
+  float* chain;                       /* [heads, 4, D] saved row vectors v2..v5 (for backward) */
+  /* backward */
+  const float* d_w_eff; const float* d_b_eff;
+  float* const* dW; float* const* db; /* DEVICE arrays [heads*5] of gradient pointers (overwritten) */
+} bfk_decoder_collapse_args;
+BFK_API int32_t bfk_decoder_collapse_fwd(const bfk_decoder_collapse_args* a, bfk_stream_t s);
+BFK_API int32_t bfk_decoder_collapse_bwd(const bfk_decoder_collapse_args* a, bfk_stream_t s);
+
+/* grid[b, h, n] = w_eff[h] . X[b*x_batch_stride + (row0 + n)*D ...] + b_eff[h]
+ * (bifold/models/pickplace.py:49-57,71 token -> grid map + collapsed decoder). */
+typedef struct {
+  int32_t B, heads, Np, D;
+  const float* X; int64_t x_batch_stride; int32_t row0;   /* fp32 fused tokens */
+  const float* w_eff; const float* b_eff;
+  float* grid;                       /* [B, heads, Np] */
+  /* backward */
+  const float* dgrid;                /* [B, heads, Np] */
+  int32_t Nf;                        /* rows per sample of dX */
+  float* dX;                         /* [B, Nf, D] fully written (zeros outside the Np token rows) */
+  void* dX2; int32_t dX2_dtype;      /* optional copy */
+  float* d_w_eff; float* d_b_eff;    /* [heads, D], [heads] overwritten */
+  float* partials;                   /* bfk_head_project_bwd_workspace_floats(B, heads, Np, D) */
+} bfk_head_project_args;
+BFK_API int32_t bfk_head_project_fwd(const bfk_head_project_args* a, bfk_stream_t s);
+BFK_API size_t bfk_head_project_bwd_workspace_floats(int32_t B, int32_t heads, int32_t Np, int32_t D);
+BFK_API int32_t bfk_head_project_bwd(const bfk_head_project_args* a, bfk_stream_t s);
+
+/* Fills the 1-D taps of the composite x16 upsample (four x2 bilinear stages, align_corners=False;
+ * bifold/models/modules.py:68-69): for output index y in [0, 16g): first input index and 3 weights.
+ * HOST pointers.  Returns BFK_E_UNSUPPORTED if some output needs more than 3 taps. */
+BFK_API int32_t bfk_upsample16_taps(int32_t g, int32_t* tap_start, float* tap_w /* [16g,3] */);
+
+/* heat[h][b,y,x] = sigmoid(Up16(grid[b,h])) ; optional fused BCE (nn.BCELoss semantics,
+ * bifold/losses/__init__.py:61,80-83) and first-max argmax (bifold/models/utils.py:66).
+ * Replaces bifold/models/pickplace.py:75-106 + modules.py:57-74. */
+typedef struct {
+  int32_t B, heads, g;               /* H = W = 16 g */
+  const float* grid;                 /* [B, heads, g*g] */
+  const int32_t* tap_start; const float* tap_w;  /* DEVICE copies of bfk_upsample16_taps */
+  float* heat;                       /* [heads, B, H, W] */
+  const float* const* target;        /* DEVICE array [heads] of (B,H,W) fp32 target pointers, or NULL */
+  const float* target_mask;          /* (B,H,W) fp32 multiplied into targets of heads flagged below, or NULL */
+  uint32_t mask_heads;               /* bit h set: target_h *= target_mask */
+  float* loss;                       /* [heads+1]: mean BCE per head, then their sum (if target) */
+  unsigned long long* argmax_key;    /* [heads, B] workspace+result: (float bits << 32) | ~index, or NULL */
+  float* partials;                   /* [heads*B*bfk_heatmap_bands(g)] workspace (if target) */
+} bfk_heatmap_fwd_args;
+BFK_API int32_t bfk_heatmap_bands(int32_t g);
+BFK_API int32_t bfk_heatmap_fwd(const bfk_heatmap_fwd_args* a, bfk_stream_t s);
+
+/* dgrid from either the fused BCE gradient  dlogit = g_h*(p - t)         (mode 0)
+ * or a generic upstream gradient             dlogit = dheat * p*(1-p)     (mode 1). */
+typedef struct {
+  int32_t B, heads, g, mode;
+  const float* heat;                 /* [heads, B, H, W] */
+  const float* const* target; const float* target_mask; uint32_t mask_heads;   /* mode 0 */
+  const float* gscale;               /* DEVICE [heads (+1)]: dLoss/dloss_h (+ dLoss/dtotal)  (mode 0) */
+  float gscale_mul; int32_t gscale_has_total; /* dlogit = gscale_mul*(gscale[h] (+ gscale[heads]))*(p - t) */
+  const float* const* dheat;         /* DEVICE array [heads] of (B,H,W) pointers (mode 1); NULL entry = zero */
+  const int32_t* tap_start; const float* tap_w;
+  float* dgrid;                      /* [B, heads, g*g] */
+} bfk_heatmap_bwd_args;
+BFK_API int32_t bfk_heatmap_bwd(const bfk_heatmap_bwd_args* a, bfk_stream_t s);
+
+/* Standalone nn.BCELoss on probabilities (used when the caller only has heatmaps):
+ * loss[0] = mean( -[t*max(log p,-100) + (1-t)*max(log1p(-p),-100)] ). partials: >= 1024 floats. */
+BFK_API int32_t bfk_bce_prob(const float* p, const float* t, const float* t_mask, int64_t n, float* loss,
+                     float* partials, bfk_stream_t s);
+/* dp = gscale[0] * (p - t) / max(p*(1-p), 1e-12)   (torch binary_cross_entropy_backward) */
+BFK_API int32_t bfk_bce_prob_bwd(const float* p, const float* t, const float* t_mask, int64_t n,
+                         const float* gscale, float* dp, bfk_stream_t s);
+
+/* First-max argmax per map: maps [n_maps, hw] fp32 -> key[n_maps] as in bfk_heatmap_fwd.
+ * Replaces the D2H + numpy loop of bifold/models/utils.py:60-77. */
+BFK_API int32_t bfk_argmax2d(const float* maps, int32_t n_maps, int32_t hw, unsigned long long* key, bfk_stream_t s);
+/* get_action tail on device (bifold/models/utils.py:80-83, bifold/models/__init__.py:108-141):
+ * decode keys, snap pick heads to the nearest mask pixel (first in row-major order among ties),
+ * confidence gate.  heat [heads,B,H,W]; mask (B,H,W) fp32 or NULL; pick_heads/place_heads: indices
+ * of the (left,right) pick / place heads (n_arms = 1 or 2).  out_xy int32 [heads,B,2] ([x,y], -1 for
+ * a dropped arm), out_conf fp32 [heads,B]. */
+typedef struct {
+  int32_t B, heads, H, W, n_arms;
+  const float* heat; const unsigned long long* key; const float* mask;
+  int32_t pick_heads[2]; int32_t place_heads[2];
+  float threshold;
+  int32_t* out_xy; float* out_conf;
+} bfk_action_args;
+BFK_API int32_t bfk_action(const bfk_action_args* a, bfk_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused Adam / AdamW over a flat fp32 buffer (torch.optim.Adam/AdamW semantics,
+ * bifold/optim/__init__.py:9,12): g' = grad_scale*g (+ wd*p if !decoupled); p *= 1-lr*wd if
+ * decoupled; m,v update; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).  Optionally writes a bf16
+ * shadow of the updated parameters.  `step` is the 1-based step count AFTER increment.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t n;
+  float* p; const float* g; float* m; float* v;
+  void* shadow_bf16;                 /* or NULL */
+  float lr, beta1, beta2, eps, weight_decay; int32_t decoupled;
+  int32_t step; float grad_scale;
+} bfk_adamw_args;
+BFK_API int32_t bfk_adamw(const bfk_adamw_args* a, bfk_stream_t s);
+/* fp32 -> bf16 cast (shadow weights), optional transpose of a [rows, cols] matrix. */
+BFK_API int32_t bfk_cast_bf16(const float* src, void* dst, int64_t n, bfk_stream_t s);
+BFK_API int32_t bfk_cast_f32_to(const float* src, void* dst, int32_t dst_dtype, int64_t rows, int64_t cols,
+                        int64_t ld_src, int64_t ld_dst, bfk_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIFOLD_B200_H_ */

@@ -1,0 +1,270 @@
+"""GPU: each C-ABI kernel against a plain torch fp32 reference of the same op (through the C ABI)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kern():
+    from bifold_b200.engine import Kernels
+    return Kernels()
+
+
+def _gemm_ref(A, B, ta, tb, bias, act, aux_in, residual, res_mod, alpha):
+    a = A.float().t() if ta else A.float()
+    b = B.float() if tb else B.float().t()
+    out = alpha * (a @ b)
+    if bias is not None:
+        out = out + bias
+    pre = out.clone()
+    if act == 1:
+        out = F.gelu(out, approximate="tanh")
+    elif act == 2:
+        out = F.gelu(out)
+    elif act in (3, 4):
+        h = aux_in.float().requires_grad_(True)
+        y = F.gelu(h, approximate="tanh") if act == 3 else F.gelu(h)
+        (dg,) = torch.autograd.grad(y.sum(), h)
+        out = out * dg
+    if residual is not None:
+        r = residual
+        if res_mod:
+            r = residual[torch.arange(out.shape[0], device=out.device) % res_mod]
+        out = out + r
+    return out, pre
+
+
+GEMM_CASES = [
+    # M, N, K, ta, tb, bias, act, residual, res_mod, out_bf16
+    (200, 136, 72, 0, 0, True, 0, False, 0, False),
+    (200, 136, 72, 0, 0, True, 1, False, 0, False),
+    (129, 256, 64, 0, 0, True, 2, True, 0, False),
+    (300, 784, 784, 0, 1, False, 0, False, 0, False),
+    (256, 128, 520, 1, 1, False, 0, False, 0, False),
+    (130, 264, 200, 0, 1, False, 3, False, 0, False),
+    (130, 264, 200, 0, 1, False, 4, False, 0, False),
+    (392, 768, 768, 0, 0, True, 0, True, 196, False),
+    (1000, 2304, 784, 0, 0, True, 0, False, 0, True),
+    (2304, 768, 1048, 1, 1, False, 0, False, 0, False),
+    (64, 16, 4304, 0, 0, False, 0, False, 0, False),
+]
+
+
+@pytest.mark.parametrize("dtype,backend", [("f32", 1), ("bf16", 1), ("bf16", 2)])
+@pytest.mark.parametrize("case", GEMM_CASES)
+def test_gemm(kern, case, dtype, backend):
+    M, N, Kd, ta, tb, use_bias, act, use_res, res_mod, out_bf16 = case
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(hash(case) % 2**31)
+    T = torch.float32 if dtype == "f32" else torch.bfloat16
+    A = (torch.randn((Kd, M) if ta else (M, Kd), generator=g) * 0.5).to(dev).to(T)
+    B = (torch.randn((Kd, N) if tb else (N, Kd), generator=g) * 0.5).to(dev).to(T)
+    bias = torch.randn(N, generator=g).to(dev) if use_bias else None
+    res = torch.randn(res_mod or M, N, generator=g).to(dev) if use_res else None
+    aux_in = (torch.randn(M, N, generator=g)).to(dev).to(T) if act in (3, 4) else None
+    out_T = torch.bfloat16 if (out_bf16 and dtype == "bf16") else torch.float32
+    D = torch.full((M, N), float("nan"), device=dev, dtype=out_T)
+    aux = aux_in if act in (3, 4) else (torch.full((M, N), float("nan"), device=dev, dtype=out_T) if act in (1, 2) else None)
+    kern.gemm(A, B, D, M, N, Kd, A.shape[1], B.shape[1], N, trans_a=bool(ta), trans_b=bool(tb), bias=bias, act=act,
+              aux=aux, ld_aux=N, residual=res, ldr=N, res_row_mod=res_mod, alpha=0.75, backend=backend)
+    torch.cuda.synchronize()
+    ref, pre = _gemm_ref(A, B, ta, tb, bias, act, aux_in, res, res_mod, 0.75)
+    tol = 2e-4 if dtype == "f32" else (2e-2 if out_T == torch.bfloat16 else 2e-3)
+    scale = ref.abs().max().item()
+    err = (D.float() - ref).abs().max().item()
+    assert math.isfinite(err) and err <= tol * scale, f"gemm {case} {dtype} backend={backend}: err {err:.3e} scale {scale:.3e}"
+    if act in (1, 2):
+        err2 = (aux.float() - pre).abs().max().item()
+        assert err2 <= tol * pre.abs().max().item(), f"pre-activation store: {err2:.3e}"
+
+
+def test_gemm_accumulate(kern):
+    M, N, Kd = 130, 72, 40
+    A = torch.randn(M, Kd, device="cuda"); B = torch.randn(N, Kd, device="cuda")
+    D = torch.randn(M, N, device="cuda"); D0 = D.clone()
+    kern.gemm(A, B, D, M, N, Kd, Kd, Kd, N, accumulate=True)
+    assert torch.allclose(D, D0 + A @ B.t(), atol=1e-4, rtol=1e-4)
+
+
+def test_colsum(kern):
+    for T in (torch.float32, torch.bfloat16):
+        X = torch.randn(1000, 300, device="cuda").to(T)
+        out = torch.empty(300, device="cuda")
+        kern.colsum(X, 1000, 300, 300, out)
+        assert torch.allclose(out, X.float().sum(0), atol=2e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize("D,ydt", [(64, torch.float32), (768, torch.bfloat16), (1152, torch.float32), (768, torch.float32)])
+def test_layernorm_fwd_bwd(kern, D, ydt):
+    M = 777
+    x = (torch.randn(M, D, device="cuda") * 2 + 0.3).requires_grad_(True)
+    gam = (1 + 0.1 * torch.randn(D, device="cuda")).requires_grad_(True)
+    bet = (0.1 * torch.randn(D, device="cuda")).requires_grad_(True)
+    ld = D + 16
+    y = torch.zeros(M, ld, device="cuda", dtype=ydt)
+    mean = torch.empty(M, device="cuda"); rstd = torch.empty(M, device="cuda")
+    kern.layernorm_fwd(x.detach(), M, D, gam.detach(), bet.detach(), 1e-6, y, ld, mean, rstd)
+    ref = F.layer_norm(x, (D,), gam, bet, 1e-6)
+    tol = 1e-5 if ydt == torch.float32 else 1e-2
+    assert (y[:, :D].float() - ref).abs().max().item() <= tol * ref.abs().max().item()
+    dy = torch.randn(M, D, device="cuda")
+    dres = torch.randn(M, D, device="cuda")
+    gx, gg, gb = torch.autograd.grad(ref, (x, gam, bet), dy)
+    dy_in = torch.zeros(M, ld, device="cuda", dtype=ydt); dy_in[:, :D] = dy.to(ydt)
+    dx = torch.empty(M, D, device="cuda"); dx2 = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    dgam = torch.empty(D, device="cuda"); dbet = torch.empty(D, device="cuda")
+    kern.layernorm_bwd(dy_in, ld, x.detach(), M, D, mean, rstd, gam.detach(), dres, dx, dx2, dgam, dbet)
+    tol = 2e-4 if ydt == torch.float32 else 2e-2
+    assert (dx - (gx + dres)).abs().max().item() <= tol * (gx + dres).abs().max().item()
+    assert (dx2.float() - dx).abs().max().item() <= 1e-2 * dx.abs().max().item()
+    assert (dgam - gg).abs().max().item() <= tol * gg.abs().max().item()
+    assert (dbet - gb).abs().max().item() <= tol * gb.abs().max().item()
+    dx_b = torch.empty(M, D, device="cuda")
+    kern.layernorm_bwd(dy_in, ld, x.detach(), M, D, mean, rstd, gam.detach(), None, dx_b)
+    assert (dx_b - gx).abs().max().item() <= tol * gx.abs().max().item()
+
+
+def _attn_ref(qkv, B, N, H, hd, mask, scale):
+    q, k, v = qkv.float().view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    dots = q @ k.transpose(-1, -2) * scale
+    if mask is not None:
+        dots = dots.masked_fill(mask[:, None, :, None] == 0, -100000)
+    return (torch.softmax(dots, -1) @ v).transpose(1, 2).reshape(B * N, H * hd)
+
+
+@pytest.mark.parametrize("T,backend", [(torch.float32, 1), (torch.bfloat16, 1), (torch.bfloat16, 0)])
+@pytest.mark.parametrize("B,N,H,hd,masked", [(2, 70, 3, 16, True), (3, 197, 2, 64, False), (2, 262, 4, 48, True),
+                                              (1, 300, 2, 72, True), (2, 64, 12, 64, False), (1, 853, 2, 48, True)])
+def test_attention_fwd_bwd(kern, T, backend, B, N, H, hd, masked):
+    kern.backend = backend
+    try:
+        g = torch.Generator().manual_seed(B * 1000 + N)
+        qkv = (torch.randn(B * N, 3 * H * hd, generator=g)).cuda().to(T)
+        mask = None
+        if masked:
+            mask = torch.ones(B, N)
+            mask[0, 5:5 + N // 3] = 0
+            mask = mask.cuda()
+        out = torch.empty(B * N, H * hd, device="cuda", dtype=T)
+        lse = torch.empty(B * H * N, device="cuda")
+        scale = hd ** -0.5
+        kern.attention_fwd(qkv, out, lse, B, N, H, hd, scale, mask)
+        q32 = qkv.float().requires_grad_(True)
+        ref = _attn_ref(q32, B, N, H, hd, mask, scale)
+        tol = 2e-4 if T == torch.float32 else 2e-2
+        err = (out.float() - ref).abs().max().item()
+        assert math.isfinite(err) and err <= tol * ref.abs().max().item(), f"attention fwd err {err:.3e}"
+        dout = torch.randn(B * N, H * hd, generator=g).cuda().to(T)
+        (gref,) = torch.autograd.grad(ref, q32, dout.float())
+        dqkv = torch.full_like(qkv, float("nan"))
+        kern.attention_bwd(qkv, out, lse, dout, dqkv, B, N, H, hd, scale, mask)
+        err = (dqkv.float() - gref).abs().max().item()
+        tol = 5e-4 if T == torch.float32 else 4e-2
+        assert math.isfinite(err) and err <= tol * gref.abs().max().item(), f"attention bwd err {err:.3e} vs {gref.abs().max().item():.3e}"
+    finally:
+        kern.backend = 0
+
+
+def test_adamw_matches_torch(kern):
+    from bifold_b200 import _cabi as K
+    n = 100003
+    for decoupled, wd in ((0, 0.0), (0, 0.1), (1, 0.01)):
+        p = torch.randn(n, device="cuda"); g = torch.randn(n, device="cuda")
+        ref = p.clone().requires_grad_(True)
+        opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)([ref], lr=1e-3, weight_decay=wd, foreach=False)
+        m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+        sh = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+        for step in range(1, 4):
+            ref.grad = g.clone() * step
+            opt.step()
+            a = K.AdamWArgs(n, p.data_ptr(), (g * step).data_ptr(), m.data_ptr(), v.data_ptr(), sh.data_ptr(), 1e-3, 0.9, 0.999,
+                            1e-8, wd, decoupled, step, 1.0)
+            gg = g * step
+            a.g = gg.data_ptr()
+            K.check(kern.lib.bfk_adamw(C.byref(a), torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+        assert torch.allclose(p, ref.detach(), atol=1e-6, rtol=1e-5), (decoupled, wd)
+        assert torch.allclose(sh.float(), p, atol=1e-2, rtol=1e-2)
+
+
+def test_heatmap_fwd_matches_literal_decoder(kern):
+    """Collapsed decoder + composite upsample + sigmoid + BCE + argmax against the literal
+    ConvDecoder pyramid of the oracle (bifold/models/modules.py:33-74)."""
+    from oracle import policy_oracle as po
+    from oracle.synth import make_sample, make_state_dict, tiny_spec
+    from tests.util import build_model, to_device
+    spec = tiny_spec(name="siglip", is_bimanual=True, lora=False)
+    model, sd = build_model(spec, "fp32")
+    sample = make_sample(spec, 3)
+    eng = model._ensure_engine()
+    eng.prepare(torch.device("cuda"))
+    eng.training = False
+    D, Np, B = spec.dim, spec.num_patches, 3
+    Nf = spec.fusion_len()
+    xf = torch.randn(B * Nf, D, device="cuda")
+    targets = [to_device(sample)[f"{h}_heatmap"].contiguous() for h in spec.heads_out]
+    tail = eng._tail_fwd(xf, B, Nf, targets, True, False)
+    fused = xf.view(B, Nf, D)[:, Nf - Np - 1:, :].cpu()
+    logits = po.pick_place_logits(sd, fused, spec)
+    for i, h in enumerate(spec.heads_out):
+        ref = logits[h].sigmoid()
+        got = tail["heat"][i].cpu()
+        assert (got - ref).abs().max().item() < 2e-6, h
+        loss_ref = F.binary_cross_entropy(ref, sample[f"{h}_heatmap"])
+        assert abs(tail["loss"][i].item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item()) + 1e-7
+        key = tail["key"].view(len(spec.heads_out), B).cpu().numpy().astype(np.uint64)
+        for b in range(B):
+            idx = 0xFFFFFFFF - int(key[i, b] & np.uint64(0xFFFFFFFF))
+            assert idx == int(got[b].numpy().argmax()), (h, b)
+    total = sum(tail["loss"][i].item() for i in range(len(spec.heads_out)))
+    assert abs(tail["loss"][len(spec.heads_out)].item() - total) < 1e-5
+
+
+def test_argmax2d_first_max_and_action_gate(kern):
+    from bifold_b200 import _cabi as K
+    B, H, W, heads = 5, 64, 64, 4
+    g = torch.Generator().manual_seed(5)
+    heat = torch.rand(heads, B, H, W, generator=g) * 0.5
+    heat[0, 0, 10, 20] = 0.9; heat[0, 0, 30, 5] = 0.9        # tie -> first (row-major)
+    heat[2, 1] *= 0.01                                      # right arm low confidence on sample 1
+    heat[0, 2] *= 0.001; heat[2, 2] *= 0.0001               # both below threshold on sample 2
+    heat = heat.cuda().contiguous()
+    key = torch.empty(heads * B, device="cuda", dtype=torch.int64)
+    K.check(kern.lib.bfk_argmax2d(heat.data_ptr(), heads * B, H * W, key.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    idx = 0xFFFFFFFF - (key.cpu().numpy().astype(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    ref_idx = heat.view(heads * B, -1).cpu().numpy().argmax(1)
+    np.testing.assert_array_equal(idx, ref_idx)
+    mask = torch.zeros(B, 1, H, W); mask[:, :, 20:40, 25:50] = 1
+    from oracle import policy_oracle as po
+    from oracle.synth import PolicySpec
+    spec = PolicySpec(is_bimanual=True)
+    out = {f"{h}_heatmap": heat[i].cpu() for i, h in enumerate(spec.heads_out)}
+    ref = po.get_action(out, {"mask": mask}, spec, threshold=0.01)
+    xy = torch.empty(heads, B, 2, device="cuda", dtype=torch.int32); conf = torch.empty(heads, B, device="cuda")
+    mk = mask.reshape(B, H, W).cuda().contiguous()
+    a = K.ActionArgs(B, heads, H, W, 2, heat.data_ptr(), key.data_ptr(), mk.data_ptr(), (C.c_int32 * 2)(0, 2), (C.c_int32 * 2)(1, 3),
+                     0.01, xy.data_ptr(), conf.data_ptr())
+    K.check(kern.lib.bfk_action(C.byref(a), torch.cuda.current_stream().cuda_stream))
+    xy = xy.cpu().numpy()
+    for i, h in enumerate(spec.heads_out):
+        np.testing.assert_array_equal(xy[i], ref[h].astype(np.int64), err_msg=h)
+    assert (xy[2, 1] == -1).all() and (xy[3, 1] == -1).all()      # gated arm
+    assert (xy[0, 2] != -1).all() and (xy[2, 2] == -1).all()      # more confident arm kept
+
+
+def test_bce_prob_clamp_matches_torch(kern):
+    from bifold_b200.losses import _BCEProbFn
+    p = torch.tensor([0.0, 1.0, 0.5, 1e-30, 1 - 1e-7, 0.3], device="cuda").repeat(100).requires_grad_(True)
+    t = torch.tensor([1.0, 0.0, 0.5, 1.0, 0.2, 0.0], device="cuda").repeat(100)
+    loss = _BCEProbFn.apply(p, t, None)
+    ref_p = p.detach().clone().requires_grad_(True)
+    ref = F.binary_cross_entropy(ref_p, t)
+    assert abs(loss.item() - ref.item()) <= 1e-5 * ref.item()
+    loss.backward(); ref.backward()
+    assert torch.allclose(p.grad, ref_p.grad, rtol=1e-4, atol=1e-6)
