@@ -237,8 +237,8 @@ class _PolicyFn(torch.autograd.Function):
     """Whole-policy autograd node: forward = Engine.forward, backward = Engine.backward."""
 
     @staticmethod
-    def forward(ctx, model, sample, targets, want_argmax, *params):
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    def forward(ctx, model, sample, targets, want_argmax, need_grad, *params):
+        # (grad mode is always off inside Function.forward, so the caller decides `need_grad`)
         heat, loss, key, ectx = model.engine.forward(sample, need_grad, model.training, targets, want_argmax)
         ctx.model, ctx.ectx = model, ectx
         ctx.set_materialize_grads(False)
@@ -257,7 +257,7 @@ class _PolicyFn(torch.autograd.Function):
         grads = model.engine.backward(ctx.ectx, dheat, dloss if (dloss is not None and dloss.numel()) else None)
         ctx.ectx = None
         out = [grads.get(n) if p.requires_grad else None for n, p in zip(model._param_names, model._param_list)]
-        return (None, None, None, None, *out)
+        return (None, None, None, None, None, *out)
 
 
 class BaseModel(nn.Module):
@@ -386,7 +386,8 @@ class SigLip(BaseModel):
             if all(t is not None and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
                    and tuple(t.shape) == (rgb.shape[0], cfg.image_size, cfg.image_size) for t in ts):
                 targets = ts
-        heat, loss = _PolicyFn.apply(self, x, targets, _want_argmax, *self._param_list)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list)
+        heat, loss = _PolicyFn.apply(self, x, targets, _want_argmax, need_grad, *self._param_list)
         out = PolicyOutput(attn_weights=None)
         for i, h in enumerate(cfg.heads_out):
             out[f"{h}_heatmap"] = heat[i]
