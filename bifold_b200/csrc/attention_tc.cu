@@ -1,8 +1,612 @@
-// Tensor-core attention (placeholder until the tcgen05 kernels land): reports "unsupported" so the
-// dispatcher uses the SIMT kernels.
-#include "common.cuh"
+// tcgen05 flash attention for sm_100a on the packed QKV matrix (bf16 operands, fp32 softmax statistics).
+//
+// Three kernels, all with the same skeleton (one control warp issuing TMA + tcgen05.mma from a single
+// thread, four "row" warps that own one TMEM lane = one matrix row each, mbarrier hand-offs):
+//   attn_fwd_tc   : CTA = (128 query rows, head, sample).  Loop over 128-key blocks:
+//                   S = Q K^T (TMEM) -> online softmax in registers -> P (bf16, swizzled smem) ->
+//                   O += P V (TMEM), O rescaled in TMEM when the running max moves.
+//   attn_bwd_dq_tc: same ownership; S and dP = dO V^T recomputed per key block, dS -> smem,
+//                   dQ += dS K (K tile re-read MN-major).
+//   attn_bwd_dkv_tc: CTA = (128 key rows, head, sample).  Loop over 128-query blocks with the
+//                   transposed products S^T = K Q^T, dP^T = V dO^T, then dV += P^T dO, dK += dS^T Q.
+// Q/K/V/dO tiles are fetched by 4-D TMA maps {head_dim, slot, token, sample} straight from the packed
+// [rows, 3*H*hd] layout; the 64-wide (128-byte swizzle) box zero-fills beyond head_dim and beyond
+// the sample's last token, so head dims 48 / 72 and ragged sequence lengths need no padding copies.
+// Query-row mask (bifold/models/transformer.py:33-35): a masked row has p == 1/N for every key and dS == 0.
+#include <mutex>
+#include <unordered_map>
+
+#include "tc_common.cuh"
+
 namespace bfk {
-bool attention_tc_supported(const bfk_attention_args*, bool, const char** why) { *why = "not built"; return false; }
-int attention_fwd_tc(const bfk_attention_args*, cudaStream_t) { set_error("attention_tc: not built"); return BFK_E_UNSUPPORTED; }
-int attention_bwd_tc(const bfk_attention_args*, cudaStream_t) { set_error("attention_tc: not built"); return BFK_E_UNSUPPORTED; }
+
+constexpr uint32_t AT_ATOM = 128 * 128;  // one 128-row x 128-byte swizzle atom column
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+
+struct AttnTcParams {
+  int B, N, H, hd;
+  int ksteps;  // ceil(hd/16): UMMA_K steps over the head dim
+  int n_o;     // ksteps*16: MMA N of the head-dim-wide products
+  float scale;
+  const float* row_mask;
+  float* lse;
+  const float* delta;
+  __nv_bfloat16* out; long long ld_out;
+  __nv_bfloat16* dqkv; long long ld_dqkv;
+};
+
+// K-major operand (rows x head_dim or rows x 128 keys), atoms stacked every AT_ATOM bytes; k-th UMMA_K slice
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t tile, int k) {
+  return make_sdesc(tile + (uint32_t)(k >> 2) * AT_ATOM + (uint32_t)(k & 3) * 32u, 16, 1024);
+}
+// MN-major view of a [128 rows][NA*64 cols] tile: reduction over rows (slice k = rows 16k..16k+15), MN = columns
+__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t tile, int k) {
+  return make_sdesc(tile + (uint32_t)k * 2048u, AT_ATOM, 1024);
+}
+template <int NA>
+__device__ __forceinline__ void load_tile(uint32_t dst, const CUtensorMap* map, uint32_t bar, int slot, int row0, int b) {
+#pragma unroll
+  for (int a = 0; a < NA; ++a) tma_load_4d(dst + a * AT_ATOM, map, bar, 64 * a, slot, row0, b);
+}
+// write 8 bf16 (one 16-byte chunk `c16` of 16 per 128-key row) of row r into a K-major swizzled [128 x 128] tile
+__device__ __forceinline__ void store_p_chunk(uint32_t tile, int r, int c16, const float (&v)[8]) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint32_t addr = tile + (uint32_t)(c16 >> 3) * AT_ATOM + (uint32_t)r * 128u + (uint32_t)(((c16 & 7) ^ (r & 7)) << 4);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+               "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
+               "r"(*reinterpret_cast<uint32_t*>(&h3))
+               : "memory");
+}
+// store 16 consecutive head-dim columns [d0, d0+16) of one row as bf16 (16-byte pieces, clipped at hd)
+__device__ __forceinline__ void store_row16(__nv_bfloat16* dst, int d0, int hd, const uint32_t (&r)[16], float mul) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    if (d0 + half * 8 + 8 <= hd) {
+      __nv_bfloat162 h[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        h[t] = __floats2bfloat162_rn(__uint_as_float(r[half * 8 + 2 * t]) * mul, __uint_as_float(r[half * 8 + 2 * t + 1]) * mul);
+      *reinterpret_cast<uint4*>(dst + d0 + half * 8) = *reinterpret_cast<uint4*>(h);
+    }
+  }
+}
+
+struct AttnSmem {
+  uint32_t bar_q, bar_kv[2], bar_s, bar_p, bar_o, tmem_slot;
+};
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+template <int NA>
+__global__ void __launch_bounds__(160, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t TILE = NA * AT_ATOM;
+  const uint32_t base = smem_u32(smem_raw);
+  const uint32_t sQ = base, sK = sQ + TILE, sV = sK + 2 * TILE, sP = sV + 2 * TILE, bars = sP + 2 * AT_ATOM;
+  const uint32_t bar_q = bars, bar_kv0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40, tmem_slot = bars + 48;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (p.N + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    if (base & 1023u) __trap();
+    mbar_init(bar_q, 1); mbar_init(bar_kv0, 1); mbar_init(bar_kv0 + 8, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
+  const uint32_t tS = tmem, tO = tmem + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(128, 128, false, false);
+      const uint32_t idesc_o = make_idesc(128, p.n_o, false, true);
+      mbar_expect_tx(bar_q, TILE);
+      load_tile<NA>(sQ, &map_qkv, bar_q, h, q0, b);
+      mbar_expect_tx(bar_kv0, 2 * TILE);
+      load_tile<NA>(sK, &map_qkv, bar_kv0, p.H + h, 0, b);
+      load_tile<NA>(sV, &map_qkv, bar_kv0, 2 * p.H + h, 0, b);
+      for (int j = 0; j < nblk; ++j) {
+        if (j > 0) mbar_wait(bar_o, (j - 1) & 1);
+        if (j + 1 < nblk) {
+          const int nb = (j + 1) & 1;
+          mbar_expect_tx(bar_kv0 + 8 * nb, 2 * TILE);
+          load_tile<NA>(sK + nb * TILE, &map_qkv, bar_kv0 + 8 * nb, p.H + h, (j + 1) * 128, b);
+          load_tile<NA>(sV + nb * TILE, &map_qkv, bar_kv0 + 8 * nb, 2 * p.H + h, (j + 1) * 128, b);
+        }
+        if (j == 0) mbar_wait(bar_q, 0);
+        mbar_wait(bar_kv0 + 8 * (j & 1), (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t k_t = sK + (j & 1) * TILE, v_t = sV + (j & 1) * TILE;
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tS, kmajor_desc(sQ, k), kmajor_desc(k_t, k), idesc_s, k > 0);
+        tc_commit(bar_s);
+        mbar_wait(bar_p, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tc_mma_bf16(tO, kmajor_desc(sP, k), mnmajor_desc(v_t, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        tc_commit(bar_o);
+      }
+    }
+  } else {
+    // ---- row threads: thread r owns query row q0 + r (TMEM lane r) ----
+    const int r = threadIdx.x, q = q0 + r;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const bool masked = p.row_mask && q < p.N && p.row_mask[(long long)b * p.N + q] == 0.f;
+    const float sl2 = p.scale * LOG2E;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tc_ld32(tS + lane_off + c * 32, s);
+        tc_wait_ld();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int col = j * 128 + c * 32 + t;
+          const float x = masked ? 0.f : __uint_as_float(s[t]) * sl2;
+          if (col < p.N) mx = fmaxf(mx, x);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = exp2f(m_run - m_new);
+      if (j > 0) { mbar_wait(bar_o, (j - 1) & 1); tc_fence_after(); }
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tc_ld32(tS + lane_off + c * 32, s);
+        tc_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int col = j * 128 + c * 32 + g * 8 + t;
+            const float x = masked ? 0.f : __uint_as_float(s[g * 8 + t]) * sl2;
+            v[t] = col < p.N ? exp2f(x - m_new) : 0.f;
+            rowsum += v[t];
+          }
+          store_p_chunk(sP, r, c * 4 + g, v);
+        }
+      }
+      l_run = l_run * alpha + rowsum;
+      m_run = m_new;
+      if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {
+        for (int c = 0; c < p.n_o / 16; ++c) {
+          uint32_t o[16];
+          tc_ld16(tO + lane_off + c * 16, o);
+          tc_wait_ld();
+#pragma unroll
+          for (int t = 0; t < 16; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
+          tc_st16(tO + lane_off + c * 16, o);
+        }
+        tc_wait_st();
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    mbar_wait(bar_o, (nblk - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    __nv_bfloat16* orow = p.out + ((long long)b * p.N + q) * p.ld_out + h * p.hd;
+    for (int c = 0; c < p.n_o / 16; ++c) {
+      uint32_t o[16];
+      tc_ld16(tO + lane_off + c * 16, o);
+      tc_wait_ld();
+      if (q < p.N) store_row16(orow, c * 16, p.hd, o, inv);
+    }
+    if (q < p.N && p.lse) p.lse[((long long)b * p.H + h) * p.N + q] = m_run * LN2 + logf(l_run);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+  }
+}
+
+// =====================================================================================================
+// backward: dQ
+// =====================================================================================================
+template <int NA, int NBUF>
+__global__ void __launch_bounds__(160, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t TILE = NA * AT_ATOM;
+  const uint32_t base = smem_u32(smem_raw);
+  const uint32_t sQ = base, sdO = sQ + TILE, sK = sdO + TILE, sV = sK + NBUF * TILE, sdS = sV + NBUF * TILE, bars = sdS + 2 * AT_ATOM;
+  const uint32_t bar_q = bars, bar_kv0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40, tmem_slot = bars + 48;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (p.N + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    if (base & 1023u) __trap();
+    mbar_init(bar_q, 1); mbar_init(bar_kv0, 1); mbar_init(bar_kv0 + 8, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
+  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(128, 128, false, false);
+      const uint32_t idesc_q = make_idesc(128, p.n_o, false, true);
+      auto issue_kv = [&](int j) {
+        const int nb = j % NBUF;
+        mbar_expect_tx(bar_kv0 + 8 * nb, 2 * TILE);
+        load_tile<NA>(sK + nb * TILE, &map_qkv, bar_kv0 + 8 * nb, p.H + h, j * 128, b);
+        load_tile<NA>(sV + nb * TILE, &map_qkv, bar_kv0 + 8 * nb, 2 * p.H + h, j * 128, b);
+      };
+      mbar_expect_tx(bar_q, 2 * TILE);
+      load_tile<NA>(sQ, &map_qkv, bar_q, h, q0, b);
+      load_tile<NA>(sdO, &map_do, bar_q, h, q0, b);
+      issue_kv(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j > 0) mbar_wait(bar_o, (j - 1) & 1);
+        if (NBUF == 2) { if (j + 1 < nblk) issue_kv(j + 1); } else { if (j > 0) issue_kv(j); }
+        if (j == 0) mbar_wait(bar_q, 0);
+        mbar_wait(bar_kv0 + 8 * (j % NBUF), (j / NBUF) & 1);
+        tc_fence_after();
+        const uint32_t k_t = sK + (j % NBUF) * TILE, v_t = sV + (j % NBUF) * TILE;
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tS, kmajor_desc(sQ, k), kmajor_desc(k_t, k), idesc_s, k > 0);
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tdP, kmajor_desc(sdO, k), kmajor_desc(v_t, k), idesc_s, k > 0);
+        tc_commit(bar_s);
+        mbar_wait(bar_p, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tc_mma_bf16(tdQ, kmajor_desc(sdS, k), mnmajor_desc(k_t, k), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+        tc_commit(bar_o);
+      }
+    }
+  } else {
+    const int r = threadIdx.x, q = q0 + r;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const bool live = q < p.N && !(p.row_mask && p.row_mask[(long long)b * p.N + q] == 0.f);
+    const float sl2 = p.scale * LOG2E;
+    const long long si = ((long long)b * p.H + h) * p.N + q;
+    const float lse2 = q < p.N ? p.lse[si] * LOG2E : 0.f, delta = q < p.N ? p.delta[si] : 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+      if (j > 0) { mbar_wait(bar_o, (j - 1) & 1); tc_fence_after(); }
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32], d[32];
+        tc_ld32(tS + lane_off + c * 32, s);
+        tc_ld32(tdP + lane_off + c * 32, d);
+        tc_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int col = j * 128 + c * 32 + g * 8 + t;
+            const float pr = exp2f(__uint_as_float(s[g * 8 + t]) * sl2 - lse2);
+            v[t] = (live && col < p.N) ? pr * (__uint_as_float(d[g * 8 + t]) - delta) : 0.f;
+          }
+          store_p_chunk(sdS, r, c * 4 + g, v);
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    mbar_wait(bar_o, (nblk - 1) & 1);
+    tc_fence_after();
+    __nv_bfloat16* drow = p.dqkv + ((long long)b * p.N + q) * p.ld_dqkv + h * p.hd;
+    for (int c = 0; c < p.n_o / 16; ++c) {
+      uint32_t o[16];
+      tc_ld16(tdQ + lane_off + c * 16, o);
+      tc_wait_ld();
+      if (q < p.N) store_row16(drow, c * 16, p.hd, o, p.scale);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// =====================================================================================================
+// backward: dK, dV
+// =====================================================================================================
+template <int NA, int NBUF>
+__global__ void __launch_bounds__(160, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t TILE = NA * AT_ATOM;
+  const uint32_t base = smem_u32(smem_raw);
+  const uint32_t sK = base, sV = sK + TILE, sQ = sV + TILE, sdO = sQ + NBUF * TILE, sPt = sdO + NBUF * TILE, sdSt = sPt + 2 * AT_ATOM,
+                 bars = sdSt + 2 * AT_ATOM;
+  float* s_lse2 = reinterpret_cast<float*>(smem_raw + (bars - base) + 64);   // per-query-column statistics
+  float* s_delta = s_lse2 + 128;
+  float* s_live = s_delta + 128;
+  const uint32_t bar_kv = bars, bar_q0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40, tmem_slot = bars + 48;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int nq = (p.N + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    if (base & 1023u) __trap();
+    mbar_init(bar_kv, 1); mbar_init(bar_q0, 1); mbar_init(bar_q0 + 8, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
+  const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(128, 128, false, false);
+      const uint32_t idesc_g = make_idesc(128, p.n_o, false, true);
+      auto issue_q = [&](int i) {
+        const int nb = i % NBUF;
+        mbar_expect_tx(bar_q0 + 8 * nb, 2 * TILE);
+        load_tile<NA>(sQ + nb * TILE, &map_qkv, bar_q0 + 8 * nb, h, i * 128, b);
+        load_tile<NA>(sdO + nb * TILE, &map_do, bar_q0 + 8 * nb, h, i * 128, b);
+      };
+      mbar_expect_tx(bar_kv, 2 * TILE);
+      load_tile<NA>(sK, &map_qkv, bar_kv, p.H + h, j0, b);
+      load_tile<NA>(sV, &map_qkv, bar_kv, 2 * p.H + h, j0, b);
+      issue_q(0);
+      for (int i = 0; i < nq; ++i) {
+        if (i > 0) mbar_wait(bar_o, (i - 1) & 1);
+        if (NBUF == 2) { if (i + 1 < nq) issue_q(i + 1); } else { if (i > 0) issue_q(i); }
+        if (i == 0) mbar_wait(bar_kv, 0);
+        mbar_wait(bar_q0 + 8 * (i % NBUF), (i / NBUF) & 1);
+        tc_fence_after();
+        const uint32_t q_t = sQ + (i % NBUF) * TILE, do_t = sdO + (i % NBUF) * TILE;
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tSt, kmajor_desc(sK, k), kmajor_desc(q_t, k), idesc_s, k > 0);
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tdPt, kmajor_desc(sV, k), kmajor_desc(do_t, k), idesc_s, k > 0);
+        tc_commit(bar_s);
+        mbar_wait(bar_p, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tc_mma_bf16(tdV, kmajor_desc(sPt, k), mnmajor_desc(do_t, k), idesc_g, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tc_mma_bf16(tdK, kmajor_desc(sdSt, k), mnmajor_desc(q_t, k), idesc_g, (i > 0 || k > 0) ? 1u : 0u);
+        tc_commit(bar_o);
+      }
+    }
+  } else {
+    const int r = threadIdx.x, kv = j0 + r;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float sl2 = p.scale * LOG2E;
+    const float inv_n = 1.f / (float)p.N;
+    const bool kv_ok = kv < p.N;
+    for (int i = 0; i < nq; ++i) {
+      // per-query-column statistics of this block (thread t loads column t)
+      named_bar_sync(1, 128);
+      {
+        const int q = i * 128 + r;
+        const long long si = ((long long)b * p.H + h) * p.N + q;
+        const bool ok = q < p.N;
+        s_lse2[r] = ok ? p.lse[si] * LOG2E : INFINITY;   // +inf => p == 0 for out-of-range queries
+        s_delta[r] = ok ? p.delta[si] : 0.f;
+        s_live[r] = (ok && p.row_mask && p.row_mask[(long long)b * p.N + q] == 0.f) ? 0.f : 1.f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(bar_s, i & 1);
+      tc_fence_after();
+      if (i > 0) { mbar_wait(bar_o, (i - 1) & 1); tc_fence_after(); }
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32], d[32];
+        tc_ld32(tSt + lane_off + c * 32, s);
+        tc_ld32(tdPt + lane_off + c * 32, d);
+        tc_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8], dv[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int qc = c * 32 + g * 8 + t;
+            const bool qlive = s_live[qc] != 0.f;
+            float pr = qlive ? exp2f(__uint_as_float(s[g * 8 + t]) * sl2 - s_lse2[qc]) : (s_lse2[qc] == INFINITY ? 0.f : inv_n);
+            if (!kv_ok) pr = 0.f;
+            pv[t] = pr;
+            dv[t] = qlive ? pr * (__uint_as_float(d[g * 8 + t]) - s_delta[qc]) : 0.f;
+          }
+          store_p_chunk(sPt, r, c * 4 + g, pv);
+          store_p_chunk(sdSt, r, c * 4 + g, dv);
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    mbar_wait(bar_o, (nq - 1) & 1);
+    tc_fence_after();
+    const long long HD = (long long)p.H * p.hd;
+    __nv_bfloat16* krow = p.dqkv + ((long long)b * p.N + kv) * p.ld_dqkv + HD + h * p.hd;
+    __nv_bfloat16* vrow = krow + HD;
+    for (int c = 0; c < p.n_o / 16; ++c) {
+      uint32_t o[16];
+      tc_ld16(tdV + lane_off + c * 16, o);
+      tc_wait_ld();
+      if (kv_ok) store_row16(vrow, c * 16, p.hd, o, 1.f);
+      tc_ld16(tdK + lane_off + c * 16, o);
+      tc_wait_ld();
+      if (kv_ok) store_row16(krow, c * 16, p.hd, o, p.scale);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// delta[b,h,i] = sum_d dout*out  (warp per row, bf16)
+__global__ void __launch_bounds__(128) attn_delta_tc_kernel(const __nv_bfloat16* __restrict__ out, long long ld_out,
+                                                             const __nv_bfloat16* __restrict__ dout, long long ld_dout,
+                                                             float* __restrict__ delta, int B, int N, int H, int hd) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);   // (b, i, h)
+  if (w >= (long long)B * N * H) return;
+  const int h = (int)(w % H);
+  const long long row = w / H;
+  const int b = (int)(row / N), i = (int)(row % N);
+  const __nv_bfloat16* o = out + row * ld_out + h * hd;
+  const __nv_bfloat16* d = dout + row * ld_dout + h * hd;
+  float s = 0.f;
+  for (int t = lane * 2; t < hd; t += 64) {
+    float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + t));
+    float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d + t));
+    s += a.x * c.x + a.y * c.y;
+  }
+  s = warp_sum(s);
+  if (lane == 0) delta[((long long)b * H + h) * N + i] = s;
+}
+
+// ---- host ---------------------------------------------------------------------------------------------
+struct Map4Key {
+  const void* ptr; int hd, slots, N, B; long long ld;
+  bool operator==(const Map4Key& o) const { return ptr == o.ptr && hd == o.hd && slots == o.slots && N == o.N && B == o.B && ld == o.ld; }
+};
+struct Map4Hash {
+  size_t operator()(const Map4Key& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.hd); mix(k.slots); mix(k.N); mix(k.B); mix((size_t)k.ld);
+    return h;
+  }
+};
+// 4-D bf16 map {hd, slots, N, B} over a [B*N, ld] row-major matrix whose row holds `slots` runs of hd elements
+static bool make_map4(CUtensorMap* out, const void* ptr, int hd, int slots, int N, int B, long long ld) {
+  static std::mutex mu;
+  static std::unordered_map<Map4Key, CUtensorMap, Map4Hash> cache;
+  Map4Key key{ptr, hd, slots, N, B, ld};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return true; }
+  }
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) { set_error("attention_tc: cuTensorMapEncodeTiled unavailable"); return false; }
+  cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)slots, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)hd * 2, (cuuint64_t)ld * 2, (cuuint64_t)N * ld * 2};
+  cuuint32_t box[4] = {64, 1, 128, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("attention_tc: cuTensorMapEncodeTiled failed (%d) hd=%d slots=%d N=%d B=%d ld=%lld", (int)r, hd, slots, N, B, ld); return false; }
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return true;
+}
+
+bool attention_tc_supported(const bfk_attention_args* a, bool bwd, const char** why) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  if (a->dtype != BFK_BF16) { *why = "bf16 only"; return false; }
+  if (a->hd % 8 != 0 || a->hd < 8 || a->hd > 128) { *why = "head_dim must be a multiple of 8 in [8,128]"; return false; }
+  if (a->ld_qkv % 8 != 0 || a->ld_out % 8 != 0 || !al16(a->qkv) || !al16(a->out)) { *why = "qkv/out must be 16-byte aligned"; return false; }
+  if (bwd && (a->ld_dout % 8 != 0 || a->ld_dqkv % 8 != 0 || !al16(a->dout) || !al16(a->dqkv))) { *why = "dout/dqkv must be 16-byte aligned"; return false; }
+  if (a->H > 65535 || a->B > 65535) { *why = "grid too large"; return false; }
+  if (!get_encode_tiled()) { *why = "driver entry point cuTensorMapEncodeTiled missing"; return false; }
+  return true;
+}
+
+static AttnTcParams make_params(const bfk_attention_args* a) {
+  AttnTcParams p;
+  p.B = a->B; p.N = a->N; p.H = a->H; p.hd = a->hd;
+  p.ksteps = (a->hd + 15) / 16;
+  p.n_o = p.ksteps * 16;
+  p.scale = a->scale;
+  p.row_mask = a->row_mask;
+  p.lse = a->lse;
+  p.delta = a->delta;
+  p.out = (__nv_bfloat16*)a->out; p.ld_out = a->ld_out;
+  p.dqkv = (__nv_bfloat16*)a->dqkv; p.ld_dqkv = a->ld_dqkv;
+  return p;
+}
+
+template <typename Kern>
+static int set_attr(Kern k, size_t smem, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("%s: cannot set smem %zu: %s", name, smem, cudaGetErrorString(e)); return BFK_E_CUDA; }
+  return BFK_OK;
+}
+
+int attention_fwd_tc(const bfk_attention_args* a, cudaStream_t s) {
+  CUtensorMap mq;
+  if (!make_map4(&mq, a->qkv, a->hd, 3 * a->H, a->N, a->B, a->ld_qkv)) return BFK_E_CUDA;
+  AttnTcParams p = make_params(a);
+  dim3 grid((a->N + 127) / 128, a->H, a->B);
+  if (a->hd <= 64) {
+    const size_t smem = 5 * AT_ATOM + 2 * AT_ATOM + 256;
+    if (int rc = set_attr(attn_fwd_tc_kernel<1>, smem, "attn_fwd_tc")) return rc;
+    attn_fwd_tc_kernel<1><<<grid, 160, smem, s>>>(mq, p);
+  } else {
+    const size_t smem = 5 * 2 * AT_ATOM + 2 * AT_ATOM + 256;
+    if (int rc = set_attr(attn_fwd_tc_kernel<2>, smem, "attn_fwd_tc")) return rc;
+    attn_fwd_tc_kernel<2><<<grid, 160, smem, s>>>(mq, p);
+  }
+  BFK_CHECK_LAUNCH("attention_fwd_tc");
+  return BFK_OK;
+}
+
+int attention_bwd_tc(const bfk_attention_args* a, cudaStream_t s) {
+  CUtensorMap mq, md;
+  if (!make_map4(&mq, a->qkv, a->hd, 3 * a->H, a->N, a->B, a->ld_qkv)) return BFK_E_CUDA;
+  if (!make_map4(&md, a->dout, a->hd, a->H, a->N, a->B, a->ld_dout)) return BFK_E_CUDA;
+  AttnTcParams p = make_params(a);
+  const long long rows = (long long)a->B * a->N * a->H;
+  attn_delta_tc_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>((const __nv_bfloat16*)a->out, a->ld_out, (const __nv_bfloat16*)a->dout,
+                                                                  a->ld_dout, a->delta, a->B, a->N, a->H, a->hd);
+  dim3 grid((a->N + 127) / 128, a->H, a->B);
+  if (a->hd <= 64) {
+    const size_t smem_q = 6 * AT_ATOM + 2 * AT_ATOM + 256, smem_kv = 6 * AT_ATOM + 4 * AT_ATOM + 2048;
+    if (int rc = set_attr(attn_bwd_dq_tc_kernel<1, 2>, smem_q, "attn_bwd_dq_tc")) return rc;
+    if (int rc = set_attr(attn_bwd_dkv_tc_kernel<1, 2>, smem_kv, "attn_bwd_dkv_tc")) return rc;
+    attn_bwd_dq_tc_kernel<1, 2><<<grid, 160, smem_q, s>>>(mq, md, p);
+    attn_bwd_dkv_tc_kernel<1, 2><<<grid, 160, smem_kv, s>>>(mq, md, p);
+  } else {
+    const size_t smem_q = 4 * 2 * AT_ATOM + 2 * AT_ATOM + 256, smem_kv = 4 * 2 * AT_ATOM + 4 * AT_ATOM + 2048;
+    if (int rc = set_attr(attn_bwd_dq_tc_kernel<2, 1>, smem_q, "attn_bwd_dq_tc")) return rc;
+    if (int rc = set_attr(attn_bwd_dkv_tc_kernel<2, 1>, smem_kv, "attn_bwd_dkv_tc")) return rc;
+    attn_bwd_dq_tc_kernel<2, 1><<<grid, 160, smem_q, s>>>(mq, md, p);
+    attn_bwd_dkv_tc_kernel<2, 1><<<grid, 160, smem_kv, s>>>(mq, md, p);
+  }
+  BFK_CHECK_LAUNCH("attention_bwd_tc");
+  return BFK_OK;
+}
+
 }  // namespace bfk
