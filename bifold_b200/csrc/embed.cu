@@ -41,31 +41,65 @@ __global__ void text_embed_kernel(const long long* __restrict__ ids, int L, int 
 }
 
 // ---- LoRA down projection: h[m, D+j] = sum_k drop(h[m,k]) Acat[j,k], j < 16 ------------------------
-// One warp per row; Acat (16 x D) staged in shared memory as fp32.
+// Acat is staged transposed in shared memory as fp32 rows of 20 floats (16 used; the pad makes the
+// float4 reads of consecutive k conflict-free).  One warp handles LR_ROWS rows per pass so every
+// shared-memory read of A is reused LR_ROWS times.
+constexpr int LR_ROWS = 4;
+constexpr int LR_PAD = 20;
+
+template <typename T>
+__device__ __forceinline__ void stage_acat(float* A_s, const T* __restrict__ Acat, int D) {
+  for (int i = threadIdx.x; i < 16 * D; i += blockDim.x) {
+    int j = i / D, k = i % D;
+    A_s[k * LR_PAD + j] = to_f32<T>(Acat[i]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) lora_down_kernel(T* __restrict__ h, long long ldh, int M, int D,
                                                         const T* __restrict__ Acat, float p_drop, uint64_t seed) {
-  extern __shared__ float A_s[];  // [16][D]
-  for (int i = threadIdx.x; i < 16 * D; i += blockDim.x) A_s[i] = to_f32<T>(Acat[i]);
+  extern __shared__ __align__(16) float A_s[];  // [D][LR_PAD]
+  stage_acat<T>(A_s, Acat, D);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
-    float acc[16] = {};
-    T* hr = h + (long long)row * ldh;
-    for (int k = lane; k < D; k += 32) {
-      float x = to_f32<T>(hr[k]);
-      if (p_drop > 0.f) x = hash_uniform(seed, row, k) < p_drop ? 0.f : x * keep_scale;
+  for (int row0 = (blockIdx.x * 8 + warp) * LR_ROWS; row0 < M; row0 += gridDim.x * 8 * LR_ROWS) {
+    float acc[LR_ROWS][16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = fmaf(x, A_s[j * D + k], acc[j]);
+    for (int r = 0; r < LR_ROWS; ++r)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[r][j] = 0.f;
+    for (int k = lane; k < D; k += 32) {
+      float x[LR_ROWS];
+#pragma unroll
+      for (int r = 0; r < LR_ROWS; ++r) {
+        const int row = row0 + r;
+        float v = row < M ? to_f32<T>(h[(long long)row * ldh + k]) : 0.f;
+        if (p_drop > 0.f) v = hash_uniform(seed, row, k) < p_drop ? 0.f : v * keep_scale;
+        x[r] = v;
+      }
+      const float4* a4 = reinterpret_cast<const float4*>(A_s + k * LR_PAD);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a = a4[q];
+#pragma unroll
+        for (int r = 0; r < LR_ROWS; ++r) {
+          acc[r][q * 4 + 0] = fmaf(x[r], a.x, acc[r][q * 4 + 0]);
+          acc[r][q * 4 + 1] = fmaf(x[r], a.y, acc[r][q * 4 + 1]);
+          acc[r][q * 4 + 2] = fmaf(x[r], a.z, acc[r][q * 4 + 2]);
+          acc[r][q * 4 + 3] = fmaf(x[r], a.w, acc[r][q * 4 + 3]);
+        }
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = warp_sum(acc[j]);
-    if (lane < 16) {
-      float v = 0.f;
+    for (int r = 0; r < LR_ROWS; ++r) {
+      float mine = 0.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) if (lane == j) v = acc[j];
-      hr[D + lane] = from_f32<T>(v);
+      for (int j = 0; j < 16; ++j) {
+        const float t = warp_sum(acc[r][j]);
+        if (lane == j) mine = t;
+      }
+      if (lane < 16 && row0 + r < M) h[(long long)(row0 + r) * ldh + D + lane] = from_f32<T>(mine);
     }
   }
 }
@@ -74,58 +108,94 @@ __global__ void __launch_bounds__(256) lora_down_kernel(T* __restrict__ h, long 
 template <typename T>
 __global__ void __launch_bounds__(256) lora_down_bwd_kernel(T* __restrict__ dh, long long ldh, int M, int D,
                                                             const T* __restrict__ Acat, float p_drop, uint64_t seed) {
-  extern __shared__ float A_s[];
-  for (int i = threadIdx.x; i < 16 * D; i += blockDim.x) A_s[i] = to_f32<T>(Acat[i]);
+  extern __shared__ __align__(16) float A_s[];
+  stage_acat<T>(A_s, Acat, D);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
-    T* hr = dh + (long long)row * ldh;
-    float du[16];
+  for (int row0 = (blockIdx.x * 8 + warp) * LR_ROWS; row0 < M; row0 += gridDim.x * 8 * LR_ROWS) {
+    float du[LR_ROWS][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) du[j] = to_f32<T>(hr[D + j]);
+    for (int r = 0; r < LR_ROWS; ++r)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) du[r][j] = row0 + r < M ? to_f32<T>(dh[(long long)(row0 + r) * ldh + D + j]) : 0.f;
     for (int k = lane; k < D; k += 32) {
-      float s = 0.f;
+      const float4* a4 = reinterpret_cast<const float4*>(A_s + k * LR_PAD);
+      float s[LR_ROWS];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) s = fmaf(du[j], A_s[j * D + k], s);
-      if (p_drop > 0.f) s = hash_uniform(seed, row, k) < p_drop ? 0.f : s * keep_scale;
-      hr[k] = from_f32<T>(to_f32<T>(hr[k]) + s);
+      for (int r = 0; r < LR_ROWS; ++r) s[r] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a = a4[q];
+#pragma unroll
+        for (int r = 0; r < LR_ROWS; ++r)
+          s[r] += du[r][q * 4] * a.x + du[r][q * 4 + 1] * a.y + du[r][q * 4 + 2] * a.z + du[r][q * 4 + 3] * a.w;
+      }
+#pragma unroll
+      for (int r = 0; r < LR_ROWS; ++r) {
+        const int row = row0 + r;
+        if (row < M) {
+          float v = s[r];
+          if (p_drop > 0.f) v = hash_uniform(seed, row, k) < p_drop ? 0.f : v * keep_scale;
+          T* e = dh + (long long)row * ldh + k;
+          *e = from_f32<T>(to_f32<T>(*e) + v);
+        }
+      }
     }
   }
 }
 
 // ---- tall-skinny Gram: out[i,j] = alpha * sum_m P[m,i] * drop(Q[m,j]) -------------------------------
-constexpr int SG_ROWS = 512;  // rows per first-stage block
+// stage 1: block = 128 threads x 2 adjacent columns, SG_ROWS rows (P rows staged in smem); stage 2 sums the
+// row-chunk partials in fixed order (deterministic).
+constexpr int SG_ROWS = 128;
+template <typename T> __device__ __forceinline__ float2 load2(const T* p);
+template <> __device__ __forceinline__ float2 load2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 load2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
 template <typename T>
 __global__ void __launch_bounds__(128) skinny_gram_stage1(const T* __restrict__ P, long long ldp, int ni,
                                                           const T* __restrict__ Q, long long ldq, int nj, int M,
-                                                          float p_drop, uint64_t seed, float* __restrict__ partials) {
-  // block: 128 threads = 128 columns j; loops over SG_ROWS rows; P rows staged in smem 32 at a time
-  __shared__ float P_s[32][16];
-  const int j = blockIdx.x * 128 + threadIdx.x;
+                                                          float p_drop, uint64_t seed, float* __restrict__ partials, int vec2) {
+  __shared__ __align__(16) float P_s[SG_ROWS][16];
+  const int j = (blockIdx.x * 128 + threadIdx.x) * 2;
   const int r0 = blockIdx.y * SG_ROWS, r1 = min(M, r0 + SG_ROWS);
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  float acc[16] = {};
-  for (int rb = r0; rb < r1; rb += 32) {
-    __syncthreads();
-    for (int t = threadIdx.x; t < 32 * 16; t += 128) {
-      int rr = t / 16, i = t % 16;
-      P_s[rr][i] = (rb + rr < r1 && i < ni) ? to_f32<T>(P[(long long)(rb + rr) * ldp + i]) : 0.f;
-    }
-    __syncthreads();
-    if (j < nj) {
-      const int re = min(32, r1 - rb);
-      for (int rr = 0; rr < re; ++rr) {
-        float q = to_f32<T>(Q[(long long)(rb + rr) * ldq + j]);
-        if (p_drop > 0.f) q = hash_uniform(seed, rb + rr, j) < p_drop ? 0.f : q * keep_scale;
+  for (int t = threadIdx.x; t < SG_ROWS * 16; t += 128) {
+    int rr = t / 16, i = t % 16;
+    P_s[rr][i] = (r0 + rr < r1 && i < ni) ? to_f32<T>(P[(long long)(r0 + rr) * ldp + i]) : 0.f;
+  }
+  __syncthreads();
+  float acc0[16] = {}, acc1[16] = {};
+  if (j < nj) {
+    const bool pair = vec2 && (j + 1 < nj);
+#pragma unroll 4
+    for (int rr = 0; rr < r1 - r0; ++rr) {
+      const T* qp = Q + (long long)(r0 + rr) * ldq + j;
+      float2 q;
+      if (pair) q = load2<T>(qp);
+      else { q.x = to_f32<T>(qp[0]); q.y = (j + 1 < nj) ? to_f32<T>(qp[1]) : 0.f; }
+      if (p_drop > 0.f) {
+        q.x = hash_uniform(seed, r0 + rr, j) < p_drop ? 0.f : q.x * keep_scale;
+        q.y = hash_uniform(seed, r0 + rr, j + 1) < p_drop ? 0.f : q.y * keep_scale;
+      }
+      const float4* p4 = reinterpret_cast<const float4*>(P_s[rr]);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = fmaf(P_s[rr][i], q, acc[i]);
+      for (int g = 0; g < 4; ++g) {
+        const float4 pv = p4[g];
+        acc0[g * 4 + 0] = fmaf(pv.x, q.x, acc0[g * 4 + 0]); acc1[g * 4 + 0] = fmaf(pv.x, q.y, acc1[g * 4 + 0]);
+        acc0[g * 4 + 1] = fmaf(pv.y, q.x, acc0[g * 4 + 1]); acc1[g * 4 + 1] = fmaf(pv.y, q.y, acc1[g * 4 + 1]);
+        acc0[g * 4 + 2] = fmaf(pv.z, q.x, acc0[g * 4 + 2]); acc1[g * 4 + 2] = fmaf(pv.z, q.y, acc1[g * 4 + 2]);
+        acc0[g * 4 + 3] = fmaf(pv.w, q.x, acc0[g * 4 + 3]); acc1[g * 4 + 3] = fmaf(pv.w, q.y, acc1[g * 4 + 3]);
       }
     }
-  }
-  if (j < nj) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) partials[((long long)blockIdx.y * 16 + i) * nj + j] = acc[i];
+    for (int i = 0; i < 16; ++i) {
+      float* o = partials + ((long long)blockIdx.y * 16 + i) * nj + j;
+      o[0] = acc0[i];
+      if (j + 1 < nj) o[1] = acc1[i];
+    }
   }
 }
 __global__ void skinny_gram_stage2(const float* __restrict__ partials, int nb, int ni, int nj, float alpha,
@@ -285,8 +355,8 @@ static int lora_smem(K kernel, size_t bytes) {
 extern "C" int32_t bfk_lora_down(void* h, int64_t ldh, int32_t dtype, int32_t M, int32_t D, const void* Acat,
                                  float dropout_p, uint64_t seed, bfk_stream_t s_) {
   BFK_CHECK_ARG(h && Acat && M > 0 && D > 0 && ldh >= D + 16, "bfk_lora_down: bad arguments");
-  size_t smem = (size_t)16 * D * sizeof(float);
-  int grid = std::min((M + 7) / 8, sm_count() * 4);
+  size_t smem = (size_t)LR_PAD * D * sizeof(float);
+  int grid = std::min((M + 8 * LR_ROWS - 1) / (8 * LR_ROWS), sm_count() * 3);
   if (dtype == BFK_BF16) {
     if (int rc = lora_smem(lora_down_kernel<__nv_bfloat16>, smem)) return rc;
     lora_down_kernel<__nv_bfloat16><<<grid, 256, smem, to_stream(s_)>>>((__nv_bfloat16*)h, ldh, M, D, (const __nv_bfloat16*)Acat, dropout_p, seed);
@@ -301,8 +371,8 @@ extern "C" int32_t bfk_lora_down(void* h, int64_t ldh, int32_t dtype, int32_t M,
 extern "C" int32_t bfk_lora_down_bwd(void* dh, int64_t ldh, int32_t dtype, int32_t M, int32_t D, const void* Acat,
                                      float dropout_p, uint64_t seed, bfk_stream_t s_) {
   BFK_CHECK_ARG(dh && Acat && M > 0 && D > 0 && ldh >= D + 16, "bfk_lora_down_bwd: bad arguments");
-  size_t smem = (size_t)16 * D * sizeof(float);
-  int grid = std::min((M + 7) / 8, sm_count() * 4);
+  size_t smem = (size_t)LR_PAD * D * sizeof(float);
+  int grid = std::min((M + 8 * LR_ROWS - 1) / (8 * LR_ROWS), sm_count() * 3);
   if (dtype == BFK_BF16) {
     if (int rc = lora_smem(lora_down_bwd_kernel<__nv_bfloat16>, smem)) return rc;
     lora_down_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, to_stream(s_)>>>((__nv_bfloat16*)dh, ldh, M, D, (const __nv_bfloat16*)Acat, dropout_p, seed);
@@ -325,12 +395,14 @@ extern "C" int32_t bfk_skinny_gram(const void* P, int64_t ldp, int32_t ni, const
                                    bfk_stream_t s_) {
   BFK_CHECK_ARG(P && Q && out && partials && ni > 0 && ni <= 16 && nj > 0 && M > 0, "bfk_skinny_gram: bad arguments");
   int nb = (M + SG_ROWS - 1) / SG_ROWS;
-  dim3 grid((nj + 127) / 128, nb);
+  dim3 grid((nj + 255) / 256, nb);
   cudaStream_t s = to_stream(s_);
+  const size_t es = dtype == BFK_BF16 ? 2 : 4;
+  const int vec2 = ((reinterpret_cast<uintptr_t>(Q) % (2 * es)) == 0 && ldq % 2 == 0) ? 1 : 0;
   if (dtype == BFK_BF16)
-    skinny_gram_stage1<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16*)P, ldp, ni, (const __nv_bfloat16*)Q, ldq, nj, M, dropout_p, seed, partials);
+    skinny_gram_stage1<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16*)P, ldp, ni, (const __nv_bfloat16*)Q, ldq, nj, M, dropout_p, seed, partials, vec2);
   else
-    skinny_gram_stage1<float><<<grid, 128, 0, s>>>((const float*)P, ldp, ni, (const float*)Q, ldq, nj, M, dropout_p, seed, partials);
+    skinny_gram_stage1<float><<<grid, 128, 0, s>>>((const float*)P, ldp, ni, (const float*)Q, ldq, nj, M, dropout_p, seed, partials, vec2);
   skinny_gram_stage2<<<(ni * nj + 127) / 128, 128, 0, s>>>(partials, nb, ni, nj, alpha, out, ldo, transpose_out);
   BFK_CHECK_LAUNCH("bfk_skinny_gram");
   return BFK_OK;

@@ -17,7 +17,8 @@ namespace bfk {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;   // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 template <int BN> struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
@@ -25,8 +26,128 @@ template <int BN> struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BN == 256 ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
 };
+
+// ---- fast epilogue math for bf16 outputs (the fp32 parity mode uses the exact functions of epilogue.cuh) ----
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k = 0.7978845608028654f, c = 0.044715f;
+  return 0.5f * x * (1.f + tanh_fast(k * (x + c * x * x * x)));
+}
+__device__ __forceinline__ float dgelu_tanh_fast(float x) {
+  const float k = 0.7978845608028654f, c = 0.044715f;
+  const float t = tanh_fast(k * (x + c * x * x * x));
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k * (1.f + 3.f * c * x * x);
+}
+
+// One 32-column chunk [nc, nc+32) of row m: global operands are fetched BEFORE the TMEM load is waited for,
+// bias comes from shared memory, all stores go last (no load is serialised behind a store).
+__device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, uint32_t taddr, const float* __restrict__ bias_s) {
+  const bool row_ok = m < ep.M;
+  const bool fast = ep.vec_ok && !ep.accumulate && (nc + 32 <= ep.N);
+  uint32_t r[32];
+  if (!fast) {
+    tc_ld32(taddr, r);
+    tc_wait_ld();
+    if (row_ok) {
+#pragma unroll
+      for (int t = 0; t < 32; ++t)
+        if (nc + t < ep.N) epi_store(ep, m, nc + t, __uint_as_float(r[t]));
+    }
+    return;
+  }
+  const bool dgelu = ep.act == BFK_ACT_DGELU_TANH || ep.act == BFK_ACT_DGELU_ERF;
+  float4 res[8];
+  uint4 hx[4];
+  if (row_ok && ep.residual) {
+    const int rm = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
+    const float4* rp = reinterpret_cast<const float4*>(ep.residual + (long long)rm * ep.ldr + nc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) res[i] = __ldg(rp + i);
+  }
+  if (row_ok && dgelu) {   // pre-activation, bf16 (aux dtype == operand dtype == bf16 on this path)
+    const uint4* hp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hx[i] = __ldg(hp + i);
+  }
+  tc_ld32(taddr, r);
+  tc_wait_ld();
+  if (!row_ok) return;
+  float v[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]) * ep.alpha;
+  if (ep.bias) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) v[t] += bias_s[t];
+  }
+  const bool out_bf16 = ep.out_dtype == BFK_BF16;
+  if (ep.act == BFK_ACT_GELU_TANH || ep.act == BFK_ACT_GELU_ERF) {
+    if (ep.aux) {
+      if (ep.aux_dtype == BFK_BF16) {
+        uint4* ap = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat162 h[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[i * 8 + 2 * t], v[i * 8 + 2 * t + 1]);
+          ap[i] = *reinterpret_cast<uint4*>(h);
+        }
+      } else {
+        float4* ap = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.aux) + (long long)m * ep.ld_aux + nc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ap[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+    if (ep.act == BFK_ACT_GELU_TANH) {
+      if (out_bf16) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] = gelu_tanh_fast(v[t]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] = gelu_tanh(v[t]);
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] = gelu_erf(v[t]);
+    }
+  } else if (dgelu) {
+    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(hx);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const float2 h = __bfloat1622float2(hp[t]);
+      if (ep.act == BFK_ACT_DGELU_TANH) {
+        v[2 * t] *= out_bf16 ? dgelu_tanh_fast(h.x) : dgelu_tanh(h.x);
+        v[2 * t + 1] *= out_bf16 ? dgelu_tanh_fast(h.y) : dgelu_tanh(h.y);
+      } else {
+        v[2 * t] *= dgelu_erf(h.x);
+        v[2 * t + 1] *= dgelu_erf(h.y);
+      }
+    }
+  }
+  if (ep.residual) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[4 * i] += res[i].x; v[4 * i + 1] += res[i].y; v[4 * i + 2] += res[i].z; v[4 * i + 3] += res[i].w; }
+  }
+  if (out_bf16) {
+    uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.D) + (long long)m * ep.ldd + nc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[i * 8 + 2 * t], v[i * 8 + 2 * t + 1]);
+      dp[i] = *reinterpret_cast<uint4*>(h);
+    }
+  } else {
+    float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.D) + (long long)m * ep.ldd + nc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+}
 
 template <int BN, bool AMN, bool BMN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -41,6 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  float* bias_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));   // [2][BN]
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -53,7 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -119,28 +241,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue warps (2..5): TMEM lane quarter = warp % 4 =====
-    const int quarter = warp & 3;
+    // ===== epilogue warps (2..9): TMEM lane quarter = warp % 4; the two warps of a quarter alternate chunks =====
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;   // 0..255
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * TC_BM, n0 = (tile % num_n) * BN;
+      float* bias_s = bias_smem + acc * BN;
+      if (ep.bias) {
+        for (int i = et; i < BN; i += 32 * TC_EPI_WARPS) bias_s[i] = (n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
+      }
+      named_bar_sync(1, 32 * TC_EPI_WARPS);   // bias visible; also orders reuse of the other buffer
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         if (n0 + c * 32 >= N) break;  // warp-uniform
-        uint32_t r[32];
-        tc_ld32(taddr + (uint32_t)(c * 32), r);
-        tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[j * 8 + t]);
-          epi_store8(ep, m, n0 + c * 32 + j * 8, v);
-        }
+        epi_chunk32(ep, m, n0 + c * 32, taddr + (uint32_t)(c * 32), bias_s + c * 32);
       }
       tc_fence_before();
       __syncwarp();

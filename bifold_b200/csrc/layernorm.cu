@@ -6,9 +6,9 @@
 namespace bfk {
 
 constexpr int LN_WARPS = 8;
-constexpr int LN_MAXC = 12;  // float4 chunks per lane: D <= 1536
+constexpr int LN_MAXC = 12;  // float4 chunks per lane: D <= 1536 (kernels are templated on the actual chunk count)
 
-template <typename TY>
+template <typename TY, int LN_MAXC>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(bfk_layernorm_fwd_args a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * LN_WARPS + warp;
@@ -85,7 +85,7 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
   reinterpret_cast<uint2*>(p)[c] = u;
 }
 
-template <typename TDY, typename TDX2, bool PARAM_GRADS>
+template <typename TDY, typename TDX2, bool PARAM_GRADS, int LN_MAXC>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(bfk_layernorm_bwd_args a, int rows_per_block) {
   __shared__ float red[PARAM_GRADS ? LN_WARPS : 1][PARAM_GRADS ? 132 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -165,17 +165,27 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(bfk_layernorm_bwd
   }
 }
 
-__global__ void ln_bwd_reduce(const float* __restrict__ partials, int nb, int D, float* __restrict__ dgamma,
-                              float* __restrict__ dbeta) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= 2 * D) return;
+// 32 columns x 8 row-slices per block; fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) ln_bwd_reduce(const float* __restrict__ partials, int nb, int D,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[8][33];
+  const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + col;
   float s = 0.f;
-  for (int b = 0; b < nb; ++b) s += partials[(long long)b * 2 * D + n];
-  if (n < D) dgamma[n] = s; else dbeta[n - D] = s;
+  if (n < 2 * D)
+    for (int b = slice; b < nb; b += 8) s += partials[(long long)b * 2 * D + n];
+  red[slice][col] = s;
+  __syncthreads();
+  if (slice == 0 && n < 2 * D) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][col];
+    if (n < D) dgamma[n] = t; else dbeta[n - D] = t;
+  }
 }
 
 static int ln_bwd_blocks(int M, int& rows_per_block) {
-  int target = sm_count() * 4;
+  int target = sm_count() * 2;
   rows_per_block = (M + target - 1) / target;
   rows_per_block = ((rows_per_block + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
   return (M + rows_per_block - 1) / rows_per_block;
@@ -190,8 +200,13 @@ extern "C" int32_t bfk_layernorm_fwd(const bfk_layernorm_fwd_args* a, bfk_stream
                 "bfk_layernorm_fwd: need D%%4==0, D<=%d, ld%%4==0 (D=%d)", 128 * LN_MAXC, a->D);
   cudaStream_t s = to_stream(s_);
   int grid = (a->M + LN_WARPS - 1) / LN_WARPS;
-  if (a->y_dtype == BFK_BF16) ln_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, s>>>(*a);
-  else ln_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, s>>>(*a);
+#define LN_FWD(NC)                                                                          \
+  do {                                                                                      \
+    if (a->y_dtype == BFK_BF16) ln_fwd_kernel<__nv_bfloat16, NC><<<grid, LN_WARPS * 32, 0, s>>>(*a); \
+    else ln_fwd_kernel<float, NC><<<grid, LN_WARPS * 32, 0, s>>>(*a);                         \
+  } while (0)
+  if (a->D <= 256) LN_FWD(2); else if (a->D <= 768) LN_FWD(6); else if (a->D <= 1152) LN_FWD(9); else LN_FWD(12);
+#undef LN_FWD
   BFK_CHECK_LAUNCH("bfk_layernorm_fwd");
   return BFK_OK;
 }
@@ -213,7 +228,13 @@ extern "C" int32_t bfk_layernorm_bwd(const bfk_layernorm_bwd_args* a, bfk_stream
   int rpb;
   int grid = ln_bwd_blocks(a->M, rpb);
   const bool dyb = a->dy_dtype == BFK_BF16, d2b = a->dx2 && a->dx2_dtype == BFK_BF16;
-#define LAUNCH(TDY, TDX2, PG) ln_bwd_kernel<TDY, TDX2, PG><<<grid, LN_WARPS * 32, 0, s>>>(*a, rpb)
+#define LAUNCH(TDY, TDX2, PG)                                                                      \
+  do {                                                                                             \
+    if (a->D <= 256) ln_bwd_kernel<TDY, TDX2, PG, 2><<<grid, LN_WARPS * 32, 0, s>>>(*a, rpb);        \
+    else if (a->D <= 768) ln_bwd_kernel<TDY, TDX2, PG, 6><<<grid, LN_WARPS * 32, 0, s>>>(*a, rpb);   \
+    else if (a->D <= 1152) ln_bwd_kernel<TDY, TDX2, PG, 9><<<grid, LN_WARPS * 32, 0, s>>>(*a, rpb);  \
+    else ln_bwd_kernel<TDY, TDX2, PG, 12><<<grid, LN_WARPS * 32, 0, s>>>(*a, rpb);                   \
+  } while (0)
   if (dyb) {
     if (d2b) { if (pg) LAUNCH(__nv_bfloat16, __nv_bfloat16, true); else LAUNCH(__nv_bfloat16, __nv_bfloat16, false); }
     else     { if (pg) LAUNCH(__nv_bfloat16, float, true); else LAUNCH(__nv_bfloat16, float, false); }
@@ -222,7 +243,7 @@ extern "C" int32_t bfk_layernorm_bwd(const bfk_layernorm_bwd_args* a, bfk_stream
     else     { if (pg) LAUNCH(float, float, true); else LAUNCH(float, float, false); }
   }
 #undef LAUNCH
-  if (pg) ln_bwd_reduce<<<(2 * a->D + 127) / 128, 128, 0, s>>>(a->partials, grid, a->D, a->dgamma, a->dbeta);
+  if (pg) ln_bwd_reduce<<<(2 * a->D + 31) / 32, 256, 0, s>>>(a->partials, grid, a->D, a->dgamma, a->dbeta);
   BFK_CHECK_LAUNCH("bfk_layernorm_bwd");
   return BFK_OK;
 }
