@@ -146,55 +146,103 @@ __global__ void __launch_bounds__(256) lora_down_bwd_kernel(T* __restrict__ dh, 
 }
 
 // ---- tall-skinny Gram: out[i,j] = alpha * sum_m P[m,i] * drop(Q[m,j]) -------------------------------
-// stage 1: block = 128 threads x 2 adjacent columns, SG_ROWS rows (P rows staged in smem); stage 2 sums the
-// row-chunk partials in fixed order (deterministic).
-constexpr int SG_ROWS = 128;
-template <typename T> __device__ __forceinline__ float2 load2(const T* p);
-template <> __device__ __forceinline__ float2 load2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
-template <> __device__ __forceinline__ float2 load2<__nv_bfloat16>(const __nv_bfloat16* p) {
-  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+// stage 1: block = 8 warps over SG_ROWS rows x (32 lanes * VC columns); every lane streams 16-byte
+// pieces of Q rows (8 loads in flight per warp), P rows are broadcast from shared memory, the 8 per-warp
+// register tiles are combined by a fixed smem tree; stage 2 sums the row-chunk partials in fixed order.
+constexpr int SG_ROWS = 256;
+template <typename T> struct SgVec;
+template <> struct SgVec<float> { static constexpr int VC = 4; };
+template <> struct SgVec<__nv_bfloat16> { static constexpr int VC = 8; };
+template <typename T>
+__device__ __forceinline__ void sg_load(const T* p, bool vec, int nvalid, float (&q)[SgVec<T>::VC]) {
+  constexpr int VC = SgVec<T>::VC;
+  if (vec && nvalid >= VC) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    if constexpr (sizeof(T) == 4) {
+      q[0] = __uint_as_float(u.x); q[1] = __uint_as_float(u.y); q[2] = __uint_as_float(u.z); q[3] = __uint_as_float(u.w);
+    } else {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { float2 f = __bfloat1622float2(h[t]); q[2 * t] = f.x; q[2 * t + 1] = f.y; }
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < VC; ++t) q[t] = t < nvalid ? to_f32<T>(p[t]) : 0.f;
+  }
 }
 template <typename T>
-__global__ void __launch_bounds__(128) skinny_gram_stage1(const T* __restrict__ P, long long ldp, int ni,
+__global__ void __launch_bounds__(256) skinny_gram_stage1(const T* __restrict__ P, long long ldp, int ni,
                                                           const T* __restrict__ Q, long long ldq, int nj, int M,
-                                                          float p_drop, uint64_t seed, float* __restrict__ partials, int vec2) {
-  __shared__ __align__(16) float P_s[SG_ROWS][16];
-  const int j = (blockIdx.x * 128 + threadIdx.x) * 2;
+                                                          float p_drop, uint64_t seed, float* __restrict__ partials, int vec) {
+  constexpr int VC = SgVec<T>::VC;
+  extern __shared__ __align__(16) float sg_smem[];
+  float* P_s = sg_smem;                      // [SG_ROWS][16]
+  float* red = sg_smem + SG_ROWS * 16;       // [4 warps][32 lanes][16*VC] tree-reduction scratch
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = (blockIdx.x * 32 + lane) * VC;
   const int r0 = blockIdx.y * SG_ROWS, r1 = min(M, r0 + SG_ROWS);
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  for (int t = threadIdx.x; t < SG_ROWS * 16; t += 128) {
+  for (int t = threadIdx.x; t < SG_ROWS * 16; t += 256) {
     int rr = t / 16, i = t % 16;
-    P_s[rr][i] = (r0 + rr < r1 && i < ni) ? to_f32<T>(P[(long long)(r0 + rr) * ldp + i]) : 0.f;
+    P_s[t] = (r0 + rr < r1 && i < ni) ? to_f32<T>(P[(long long)(r0 + rr) * ldp + i]) : 0.f;
   }
   __syncthreads();
-  float acc0[16] = {}, acc1[16] = {};
-  if (j < nj) {
-    const bool pair = vec2 && (j + 1 < nj);
+  float acc[16][VC];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+#pragma unroll
+    for (int t = 0; t < VC; ++t) acc[i][t] = 0.f;
+  const int nvalid = nj - j;   // <= 0: lane has no columns
+  if (nvalid > 0) {
 #pragma unroll 4
-    for (int rr = 0; rr < r1 - r0; ++rr) {
-      const T* qp = Q + (long long)(r0 + rr) * ldq + j;
-      float2 q;
-      if (pair) q = load2<T>(qp);
-      else { q.x = to_f32<T>(qp[0]); q.y = (j + 1 < nj) ? to_f32<T>(qp[1]) : 0.f; }
+    for (int rr = warp; rr < r1 - r0; rr += 8) {
+      float q[VC];
+      sg_load<T>(Q + (long long)(r0 + rr) * ldq + j, vec != 0, nvalid, q);
       if (p_drop > 0.f) {
-        q.x = hash_uniform(seed, r0 + rr, j) < p_drop ? 0.f : q.x * keep_scale;
-        q.y = hash_uniform(seed, r0 + rr, j + 1) < p_drop ? 0.f : q.y * keep_scale;
+#pragma unroll
+        for (int t = 0; t < VC; ++t) q[t] = hash_uniform(seed, r0 + rr, j + t) < p_drop ? 0.f : q[t] * keep_scale;
       }
-      const float4* p4 = reinterpret_cast<const float4*>(P_s[rr]);
+      const float4* p4 = reinterpret_cast<const float4*>(P_s + rr * 16);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const float4 pv = p4[g];
-        acc0[g * 4 + 0] = fmaf(pv.x, q.x, acc0[g * 4 + 0]); acc1[g * 4 + 0] = fmaf(pv.x, q.y, acc1[g * 4 + 0]);
-        acc0[g * 4 + 1] = fmaf(pv.y, q.x, acc0[g * 4 + 1]); acc1[g * 4 + 1] = fmaf(pv.y, q.y, acc1[g * 4 + 1]);
-        acc0[g * 4 + 2] = fmaf(pv.z, q.x, acc0[g * 4 + 2]); acc1[g * 4 + 2] = fmaf(pv.z, q.y, acc1[g * 4 + 2]);
-        acc0[g * 4 + 3] = fmaf(pv.w, q.x, acc0[g * 4 + 3]); acc1[g * 4 + 3] = fmaf(pv.w, q.y, acc1[g * 4 + 3]);
+#pragma unroll
+        for (int t = 0; t < VC; ++t) {
+          acc[g * 4 + 0][t] = fmaf(pv.x, q[t], acc[g * 4 + 0][t]);
+          acc[g * 4 + 1][t] = fmaf(pv.y, q[t], acc[g * 4 + 1][t]);
+          acc[g * 4 + 2][t] = fmaf(pv.z, q[t], acc[g * 4 + 2][t]);
+          acc[g * 4 + 3][t] = fmaf(pv.w, q[t], acc[g * 4 + 3][t]);
+        }
       }
     }
+  }
+  // fixed tree: warps 4-7 -> 0-3, warps 2-3 -> 0-1, warp 1 -> 0
+#pragma unroll
+  for (int stride = 4; stride >= 1; stride >>= 1) {
+    __syncthreads();
+    if (warp >= stride && warp < 2 * stride) {
+      float* dst = red + ((warp - stride) * 32 + lane) * (16 * VC);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+#pragma unroll
+        for (int t = 0; t < VC; ++t) dst[i * VC + t] = acc[i][t];
+    }
+    __syncthreads();
+    if (warp < stride) {
+      const float* src = red + (warp * 32 + lane) * (16 * VC);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+#pragma unroll
+        for (int t = 0; t < VC; ++t) acc[i][t] += src[i * VC + t];
+    }
+  }
+  if (warp == 0 && nvalid > 0) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       float* o = partials + ((long long)blockIdx.y * 16 + i) * nj + j;
-      o[0] = acc0[i];
-      if (j + 1 < nj) o[1] = acc1[i];
+#pragma unroll
+      for (int t = 0; t < VC; ++t)
+        if (t < nvalid) o[t] = acc[i][t];
     }
   }
 }
@@ -395,14 +443,19 @@ extern "C" int32_t bfk_skinny_gram(const void* P, int64_t ldp, int32_t ni, const
                                    bfk_stream_t s_) {
   BFK_CHECK_ARG(P && Q && out && partials && ni > 0 && ni <= 16 && nj > 0 && M > 0, "bfk_skinny_gram: bad arguments");
   int nb = (M + SG_ROWS - 1) / SG_ROWS;
-  dim3 grid((nj + 255) / 256, nb);
   cudaStream_t s = to_stream(s_);
   const size_t es = dtype == BFK_BF16 ? 2 : 4;
-  const int vec2 = ((reinterpret_cast<uintptr_t>(Q) % (2 * es)) == 0 && ldq % 2 == 0) ? 1 : 0;
-  if (dtype == BFK_BF16)
-    skinny_gram_stage1<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16*)P, ldp, ni, (const __nv_bfloat16*)Q, ldq, nj, M, dropout_p, seed, partials, vec2);
-  else
-    skinny_gram_stage1<float><<<grid, 128, 0, s>>>((const float*)P, ldp, ni, (const float*)Q, ldq, nj, M, dropout_p, seed, partials, vec2);
+  const int vc = (int)(16 / es);
+  const int vec = ((reinterpret_cast<uintptr_t>(Q) & 15u) == 0 && (ldq * es) % 16 == 0) ? 1 : 0;
+  dim3 grid((nj + 32 * vc - 1) / (32 * vc), nb);
+  const size_t smem = ((size_t)SG_ROWS * 16 + (size_t)4 * 32 * 16 * vc) * sizeof(float);
+  if (dtype == BFK_BF16) {
+    if (int rc = lora_smem(skinny_gram_stage1<__nv_bfloat16>, smem)) return rc;
+    skinny_gram_stage1<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)P, ldp, ni, (const __nv_bfloat16*)Q, ldq, nj, M, dropout_p, seed, partials, vec);
+  } else {
+    if (int rc = lora_smem(skinny_gram_stage1<float>, smem)) return rc;
+    skinny_gram_stage1<float><<<grid, 256, smem, s>>>((const float*)P, ldp, ni, (const float*)Q, ldq, nj, M, dropout_p, seed, partials, vec);
+  }
   skinny_gram_stage2<<<(ni * nj + 127) / 128, 128, 0, s>>>(partials, nb, ni, nj, alpha, out, ldo, transpose_out);
   BFK_CHECK_LAUNCH("bfk_skinny_gram");
   return BFK_OK;

@@ -1,0 +1,64 @@
+"""CPU, world_size 2 over gloo: the bucket planner and the overlapped gradient reducer of
+bifold_b200.ddp (the N>1 path of SURVEY.md §8e).  The CUDA kernels are not involved here."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from bifold_b200.ddp import GradReducer, plan_groups
+
+NAMES = ["siglip_model.model.text_model.encoder.layers.0.self_attn.q_proj.lora_A.siglip_adapter.weight",
+         "siglip_model.model.vision_model.encoder.layers.0.self_attn.q_proj.lora_B.siglip_adapter.weight",
+         "text_token", "image_token", "pick_place.fusion.token_type_embeddings.weight",
+         "pick_place.fusion.transformer_encoder.layers.0.0.norm.weight",
+         "pick_place.fusion.transformer_encoder.layers.0.0.fn.to_qkv.weight",
+         "pick_place.fusion.transformer_encoder.layers.1.0.norm.weight",
+         "pick_place.left_pick_decoder.decoder_net.0.weight", "pick_place.left_pick_decoder.decoder_net.0.bias",
+         "context_pos_embedding"]
+SIZES = [8 * 64, 64 * 8, 64, 64, 128, 64, 3 * 64 * 64, 64, 32 * 64, 30, 5 * 64]
+
+
+def test_plan_groups_covers_arena_once():
+    groups = plan_groups(NAMES, SIZES)
+    assert set(groups) == {"text", "vision", "tokens", "fusion.0", "fusion.1", "decoders"}
+    total = sum((s + 3) // 4 * 4 for s in SIZES)
+    covered = sorted(r for rs in groups.values() for r in rs)
+    pos = 0
+    for off, n in covered:
+        assert off == pos
+        pos += n
+    assert pos == total
+    assert len(groups["tokens"]) == 2          # tokens + type-embedding, then context_pos_embedding at the end
+    assert len(groups["decoders"]) == 1        # weight and (padded) bias merged into one range
+
+
+def _worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        red = GradReducer(NAMES, SIZES)
+        total = sum((s + 3) // 4 * 4 for s in SIZES)
+        torch.manual_seed(rank)
+        arena = torch.randn(total)
+        mine = arena.clone()
+        red.bind(arena)
+        for g in ("decoders", "fusion.1", "fusion.0", "tokens", "text", "vision"):   # backward order
+            red.on_ready(g)
+        red.wait()
+        others = [torch.empty(total) for _ in range(world)]
+        dist.all_gather(others, mine)
+        assert torch.allclose(arena, sum(others), atol=1e-6)
+        assert red.bytes_reduced == 4 * total
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_reducer_two_ranks_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port), nprocs=2, join=True)
