@@ -291,8 +291,12 @@ def main():
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM), one extra instrumented step ----
     roofline = None
-    if rank == 0 and not args.no_roofline:
-        roofline = gemm_roofline(eng, lambda: step(dev_sample, False))
+    if not args.no_roofline:
+        if rank == 0:
+            roofline = gemm_roofline(eng, lambda: step(dev_sample, False))
+        else:
+            step(dev_sample, False)      # the instrumented step contains the DDP collectives: every rank must run it
+            torch.cuda.synchronize()
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu_baseline = cpu_baseline_leg(args)
