@@ -26,7 +26,8 @@ class GemmArgs(C.Structure):
                 ("bias", vp), ("act", i32),
                 ("aux", vp), ("ld_aux", i64),
                 ("residual", vp), ("ldr", i64), ("res_row_mod", i32),
-                ("alpha", f32), ("accumulate", i32), ("backend", i32)]
+                ("alpha", f32), ("accumulate", i32), ("backend", i32),
+                ("workspace", vp), ("workspace_bytes", i64), ("split_k", i32)]
 
 
 class LayerNormFwdArgs(C.Structure):
@@ -39,7 +40,8 @@ class LayerNormBwdArgs(C.Structure):
                 ("x", vp), ("ldx", i64), ("mean", vp), ("rstd", vp), ("gamma", vp),
                 ("dres", vp), ("ld_dres", i64), ("dx", vp), ("ld_dx", i64),
                 ("dx2", vp), ("ld_dx2", i64), ("dx2_dtype", i32),
-                ("dgamma", vp), ("dbeta", vp), ("partials", vp)]
+                ("dgamma", vp), ("dbeta", vp), ("partials", vp),
+                ("dy2", vp), ("ld_dy2", i64), ("dy2_dropout_p", f32), ("dy2_seed", u64)]
 
 
 class AttentionArgs(C.Structure):
@@ -120,6 +122,7 @@ _PROTOS = {
     "bfk_text_embed": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "bfk_lora_down": (i32, [vp, i64, i32, i32, i32, vp, f32, u64, vp]),
     "bfk_lora_down_bwd": (i32, [vp, i64, i32, i32, i32, vp, f32, u64, vp]),
+    "bfk_dropout_copy": (i32, [vp, i64, vp, i64, i32, i32, i32, f32, u64, vp]),
     "bfk_skinny_gram_workspace_floats": (C.c_size_t, [i32, i32, i32]),
     "bfk_skinny_gram": (i32, [vp, i64, i32, vp, i64, i32, i32, i32, f32, vp, i64, i32, f32, u64, vp, vp]),
     "bfk_assemble_fwd": (i32, [C.POINTER(AssembleArgs), vp]),

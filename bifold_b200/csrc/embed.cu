@@ -145,6 +145,19 @@ __global__ void __launch_bounds__(256) lora_down_bwd_kernel(T* __restrict__ dh, 
   }
 }
 
+// ---- inverted-dropout copy (LoRA input dropout): dst = mask(seed,row,col) ? src/(1-p) : 0 -----------------
+template <typename T>
+__global__ void dropout_copy_kernel(const T* __restrict__ src, long long lds, T* __restrict__ dst, long long ldd, int M, int D,
+                                    float p_drop, uint64_t seed) {
+  const float keep_scale = 1.f / (1.f - p_drop);
+  const long long total = (long long)M * D;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int row = (int)(i / D), col = (int)(i % D);
+    const float v = to_f32<T>(src[(long long)row * lds + col]);
+    dst[(long long)row * ldd + col] = from_f32<T>(hash_uniform(seed, row, col) < p_drop ? 0.f : v * keep_scale);
+  }
+}
+
 // ---- tall-skinny Gram: out[i,j] = alpha * sum_m P[m,i] * drop(Q[m,j]) -------------------------------
 // stage 1: block = 8 warps over SG_ROWS rows x (32 lanes * VC columns); every lane streams 16-byte
 // pieces of Q rows (8 loads in flight per warp), P rows are broadcast from shared memory, the 8 per-warp
@@ -429,6 +442,16 @@ extern "C" int32_t bfk_lora_down_bwd(void* dh, int64_t ldh, int32_t dtype, int32
     lora_down_bwd_kernel<float><<<grid, 256, smem, to_stream(s_)>>>((float*)dh, ldh, M, D, (const float*)Acat, dropout_p, seed);
   }
   BFK_CHECK_LAUNCH("bfk_lora_down_bwd");
+  return BFK_OK;
+}
+
+extern "C" int32_t bfk_dropout_copy(const void* src, int64_t lds, void* dst, int64_t ldd, int32_t dtype, int32_t M, int32_t D,
+                                    float dropout_p, uint64_t seed, bfk_stream_t s_) {
+  BFK_CHECK_ARG(src && dst && M > 0 && D > 0 && dropout_p >= 0.f && dropout_p < 1.f, "bfk_dropout_copy: bad arguments");
+  int blocks = (int)std::min<long long>((long long)sm_count() * 16, ((long long)M * D + 255) / 256);
+  if (dtype == BFK_BF16) dropout_copy_kernel<__nv_bfloat16><<<blocks, 256, 0, to_stream(s_)>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, M, D, dropout_p, seed);
+  else dropout_copy_kernel<float><<<blocks, 256, 0, to_stream(s_)>>>((const float*)src, lds, (float*)dst, ldd, M, D, dropout_p, seed);
+  BFK_CHECK_LAUNCH("bfk_dropout_copy");
   return BFK_OK;
 }
 

@@ -45,6 +45,24 @@ __device__ __forceinline__ float dgelu_tanh_fast(float x) {
   return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k * (1.f + 3.f * c * x * x);
 }
 
+// erf by Abramowitz-Stegun 7.1.26 (|err| < 2e-7 + fast-exp error); e = exp(-x^2) is shared with the derivative
+__device__ __forceinline__ float erf_from_exp(float ax, float e) {
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  return 1.f - poly * e;
+}
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = x * 0.7071067811865476f, az = fabsf(z);
+  const float er = copysignf(erf_from_exp(az, __expf(-az * az)), z);
+  return 0.5f * x * (1.f + er);
+}
+__device__ __forceinline__ float dgelu_erf_fast(float x) {
+  const float z = x * 0.7071067811865476f, az = fabsf(z);
+  const float e = __expf(-az * az);
+  const float er = copysignf(erf_from_exp(az, e), z);
+  return 0.5f * (1.f + er) + x * 0.3989422804014327f * e;
+}
+
 // One 32-column chunk [nc, nc+32) of row m: global operands are fetched BEFORE the TMEM load is waited for,
 // bias comes from shared memory, all stores go last (no load is serialised behind a store).
 __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, uint32_t taddr, const float* __restrict__ bias_s) {
@@ -111,6 +129,9 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
 #pragma unroll
         for (int t = 0; t < 32; ++t) v[t] = gelu_tanh(v[t]);
       }
+    } else if (out_bf16) {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] = gelu_erf_fast(v[t]);
     } else {
 #pragma unroll
       for (int t = 0; t < 32; ++t) v[t] = gelu_erf(v[t]);
@@ -124,8 +145,8 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
         v[2 * t] *= out_bf16 ? dgelu_tanh_fast(h.x) : dgelu_tanh(h.x);
         v[2 * t + 1] *= out_bf16 ? dgelu_tanh_fast(h.y) : dgelu_tanh(h.y);
       } else {
-        v[2 * t] *= dgelu_erf(h.x);
-        v[2 * t + 1] *= dgelu_erf(h.y);
+        v[2 * t] *= out_bf16 ? dgelu_erf_fast(h.x) : dgelu_erf(h.x);
+        v[2 * t + 1] *= out_bf16 ? dgelu_erf_fast(h.y) : dgelu_erf(h.y);
       }
     }
   }
@@ -152,7 +173,7 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
 template <int BN, bool AMN, bool BMN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
-               EpiParams ep) {
+               EpiParams ep, int splits, long long split_stride) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -168,8 +189,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + TC_BM - 1) / TC_BM, num_n = (N + BN - 1) / BN;
-  const int tiles = num_m * num_n;
-  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int tiles = num_m * num_n * splits;          // work items: (output tile, K split)
+  const int num_kb_all = (K + TC_BK - 1) / TC_BK;
+  const int kb_per = (num_kb_all + splits - 1) / splits;
+  auto kb_range = [&](int item, int& kb0, int& kb1) {
+    const int sp = item % splits;
+    kb0 = sp * kb_per;
+    kb1 = min(num_kb_all, kb0 + kb_per);
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
@@ -192,9 +219,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < tiles; item += gridDim.x) {
+        const int tile = item / splits;
         const int m0 = (tile / num_n) * TC_BM, n0 = (tile % num_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int kb0, kb1;
+        kb_range(item, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
@@ -221,17 +251,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       constexpr uint32_t idesc = make_idesc(TC_BM, BN, AMN, BMN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < tiles; item += gridDim.x) {
+        int kb0, kb1;
+        kb_range(item, kb0, kb1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
-            tc_mma_bf16(tmem_d, operand_desc<AMN>(sa, k), operand_desc<BMN>(sb, k), idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_bf16(tmem_d, operand_desc<AMN>(sa, k), operand_desc<BMN>(sb, k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           tc_commit(empty_bar(stage));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -245,8 +277,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;   // 0..255
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < tiles; item += gridDim.x) {
+      const int tile = item / splits;
       const int m0 = (tile / num_n) * TC_BM, n0 = (tile % num_n) * BN;
+      EpiParams epl = ep;
+      if (splits > 1) epl.D = reinterpret_cast<float*>(ep.D) + (long long)(item % splits) * split_stride;   // fp32 partial
       float* bias_s = bias_smem + acc * BN;
       if (ep.bias) {
         for (int i = et; i < BN; i += 32 * TC_EPI_WARPS) bias_s[i] = (n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
@@ -259,7 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         if (n0 + c * 32 >= N) break;  // warp-uniform
-        epi_chunk32(ep, m, n0 + c * 32, taddr + (uint32_t)(c * 32), bias_s + c * 32);
+        epi_chunk32(epl, m, n0 + c * 32, taddr + (uint32_t)(c * 32), bias_s + c * 32);
       }
       tc_fence_before();
       __syncwarp();
@@ -343,6 +378,39 @@ bool gemm_tc_supported(const bfk_gemm_args* a, const char** why) {
   return true;
 }
 
+// D[m*ldd+n] = alpha * sum_s ws[s][m][n]   (fixed order => deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long split_stride, int M, int N, float alpha,
+                                     float* __restrict__ D, long long ldd, int accumulate) {
+  const long long total = (long long)M * N;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += ws[k * split_stride + i];
+    const int m = (int)(i / N), n = (int)(i % N);
+    float* d = D + (long long)m * ldd + n;
+    *d = accumulate ? (*d + alpha * s) : alpha * s;
+  }
+}
+
+// K splits for short-and-wide problems (wgrad: few output tiles, very long K) so every SM gets work.
+static int choose_splits(const bfk_gemm_args* a, int BN) {
+  if (a->split_k == 1 || !a->workspace) return 1;
+  const bool plain = !a->bias && a->act == BFK_ACT_NONE && !a->residual && a->out_dtype == BFK_F32;
+  if (!plain) return 1;
+  const int tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + BN - 1) / BN);
+  const int num_kb = (a->K + TC_BK - 1) / TC_BK;
+  int splits;
+  if (a->split_k > 1) splits = a->split_k;
+  else {
+    if (tiles * 2 > sm_count()) return 1;
+    splits = std::min(16, sm_count() / tiles);
+  }
+  splits = std::min(splits, std::max(1, num_kb / 4));
+  while (splits > 1 && (size_t)splits * a->M * a->N * 4 > (size_t)a->workspace_bytes) --splits;
+  // no empty split: ceil-div partition must leave work for the last one
+  while (splits > 1 && (splits - 1) * ((num_kb + splits - 1) / splits) >= num_kb) --splits;
+  return std::max(1, splits);
+}
+
 template <int BN, bool AMN, bool BMN>
 static int launch_tc(const bfk_gemm_args* a, cudaStream_t s) {
   using Cfg = TcCfg<BN>;
@@ -362,16 +430,28 @@ static int launch_tc(const bfk_gemm_args* a, cudaStream_t s) {
     if (e != cudaSuccess) { set_error("gemm_tc: cannot set smem %d: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return BFK_E_CUDA; }
     attr_set = true;
   }
-  const int tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + BN - 1) / BN);
+  const int splits = choose_splits(a, BN);
+  const long long split_stride = (long long)a->M * a->N;
+  if (splits > 1) {   // partial tiles go to the workspace as plain fp32 [splits][M][N]
+    ep.D = a->workspace; ep.ldd = a->N; ep.out_dtype = BFK_F32; ep.alpha = 1.f; ep.accumulate = 0;
+    ep.vec_ok = ((reinterpret_cast<uintptr_t>(a->workspace) & 15u) == 0 && (a->N % 4) == 0 && (split_stride % 4) == 0) ? 1 : 0;
+  }
+  const int tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + BN - 1) / BN) * splits;
   const int grid = std::min(tiles, sm_count());
-  gemm_tc_kernel<BN, AMN, BMN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, a->M, a->N, a->K, ep);
+  gemm_tc_kernel<BN, AMN, BMN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, a->M, a->N, a->K, ep, splits, split_stride);
+  if (splits > 1) {
+    const long long total = (long long)a->M * a->N;
+    const int rg = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
+    splitk_reduce_kernel<<<rg, 256, 0, s>>>((const float*)a->workspace, splits, split_stride, a->M, a->N, a->alpha, (float*)a->D, a->ldd,
+                                            a->accumulate);
+  }
   BFK_CHECK_LAUNCH("gemm_tc");
   return BFK_OK;
 }
 
 int gemm_tc(const bfk_gemm_args* a, cudaStream_t s) {
   const int w256 = ((a->N + 255) / 256) * 256 - a->N, w128 = ((a->N + 127) / 128) * 128 - a->N;
-  const bool bn256 = w256 <= w128;
+  const bool bn256 = w256 <= w128 && a->N > 128;
   const bool ta = a->trans_a != 0, tb = a->trans_b != 0;
 #define DISPATCH(BN)                                                  \
   do {                                                                \

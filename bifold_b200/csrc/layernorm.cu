@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(bfk_layernorm_bwd
     const float mean = a.mean[row], rstd = a.rstd[row];
     const float* x = a.x + (long long)row * a.ldx;
     const TDY* dy = reinterpret_cast<const TDY*>(a.dy) + (long long)row * a.ld_dy;
+    const TDY* dy2 = a.dy2 ? reinterpret_cast<const TDY*>(a.dy2) + (long long)row * a.ld_dy2 : nullptr;
+    const float keep2 = a.dy2_dropout_p > 0.f ? 1.f / (1.f - a.dy2_dropout_p) : 1.f;
     float4 gv[LN_MAXC], xh[LN_MAXC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -109,6 +111,16 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(bfk_layernorm_bwd
       int c = lane + 32 * i;
       if (c < nc) {
         float4 xv = load4<float>(x, c), d = load4<TDY>(dy, c), g = __ldg(g4 + c);
+        if (dy2) {
+          float4 e = load4<TDY>(dy2, c);
+          if (a.dy2_dropout_p > 0.f) {
+            e.x = hash_uniform(a.dy2_seed, row, 4 * c + 0) < a.dy2_dropout_p ? 0.f : e.x * keep2;
+            e.y = hash_uniform(a.dy2_seed, row, 4 * c + 1) < a.dy2_dropout_p ? 0.f : e.y * keep2;
+            e.z = hash_uniform(a.dy2_seed, row, 4 * c + 2) < a.dy2_dropout_p ? 0.f : e.z * keep2;
+            e.w = hash_uniform(a.dy2_seed, row, 4 * c + 3) < a.dy2_dropout_p ? 0.f : e.w * keep2;
+          }
+          d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
+        }
         xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
         if constexpr (PARAM_GRADS) {
           dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
@@ -220,7 +232,7 @@ extern "C" int32_t bfk_layernorm_bwd(const bfk_layernorm_bwd_args* a, bfk_stream
   using namespace bfk;
   BFK_CHECK_ARG(a && a->dy && a->x && a->mean && a->rstd && a->gamma && a->dx, "bfk_layernorm_bwd: null pointer");
   BFK_CHECK_ARG(a->M > 0 && a->D % 4 == 0 && a->D <= 128 * LN_MAXC && a->ldx % 4 == 0 && a->ld_dy % 4 == 0 &&
-                    a->ld_dx % 4 == 0 && (!a->dres || a->ld_dres % 4 == 0) && (!a->dx2 || a->ld_dx2 % 4 == 0),
+                    a->ld_dx % 4 == 0 && (!a->dres || a->ld_dres % 4 == 0) && (!a->dx2 || a->ld_dx2 % 4 == 0) && (!a->dy2 || a->ld_dy2 % 4 == 0),
                 "bfk_layernorm_bwd: need D%%4==0, D<=%d, ld%%4==0", 128 * LN_MAXC);
   const bool pg = a->dgamma != nullptr;
   BFK_CHECK_ARG(!pg || (a->dbeta && a->partials), "bfk_layernorm_bwd: dgamma needs dbeta and partials");

@@ -45,13 +45,23 @@ class Kernels:
         self.lib = K.load()
         self.launches = 0          # C-ABI calls issued (each is >= 1 kernel launch); bench.py reports it
         self.backend = K.BACKEND_AUTO
+        self._ws = None
+
+    def splitk_ws(self, device):
+        """fp32 scratch for split-K partial tiles (wgrad GEMMs); one buffer, reused stream-ordered."""
+        if self._ws is None or self._ws.device != device:
+            self._ws = torch.empty(16 * 1024 * 1024, device=device, dtype=torch.float32)   # 64 MB
+        return self._ws
 
     # -- GEMM ------------------------------------------------------------------------------------
     def gemm(self, A, B, D, M, N, Kd, lda, ldb, ldd, trans_a=False, trans_b=False, bias=None, act=K.ACT_NONE,
-             aux=None, ld_aux=0, residual=None, ldr=0, res_row_mod=0, alpha=1.0, accumulate=False, backend=None):
+             aux=None, ld_aux=0, residual=None, ldr=0, res_row_mod=0, alpha=1.0, accumulate=False, backend=None,
+             split_k=0):
+        ws = self.splitk_ws(A.device) if (trans_a and A.dtype == torch.bfloat16) or split_k > 1 else None
         a = K.GemmArgs(M, N, Kd, A.data_ptr(), lda, int(trans_a), B.data_ptr(), ldb, int(trans_b), _dt(A),
                        D.data_ptr(), ldd, _dt(D), K.ptr(bias), act, K.ptr(aux), ld_aux, K.ptr(residual), ldr,
-                       res_row_mod, alpha, int(accumulate), self.backend if backend is None else backend)
+                       res_row_mod, alpha, int(accumulate), self.backend if backend is None else backend,
+                       K.ptr(ws), ws.numel() * 4 if ws is not None else 0, split_k)
         assert _dt(A) == _dt(B)
         K.check(self.lib.bfk_gemm(C.byref(a), _stream()), "bfk_gemm")
         self.launches += 1
@@ -68,13 +78,15 @@ class Kernels:
         K.check(self.lib.bfk_layernorm_fwd(C.byref(a), _stream()), "bfk_layernorm_fwd")
         self.launches += 1
 
-    def layernorm_bwd(self, dy, ld_dy, x, M, D, mean, rstd, gamma, dres, dx, dx2=None, dgamma=None, dbeta=None):
+    def layernorm_bwd(self, dy, ld_dy, x, M, D, mean, rstd, gamma, dres, dx, dx2=None, dgamma=None, dbeta=None,
+                      dy2=None, ld_dy2=0, dy2_p=0.0, dy2_seed=0):
         ws = None
         if dgamma is not None:
             ws = torch.empty(self.lib.bfk_layernorm_bwd_workspace_floats(M, D), device=x.device, dtype=torch.float32)
         a = K.LayerNormBwdArgs(M, D, dy.data_ptr(), ld_dy, _dt(dy), x.data_ptr(), D, mean.data_ptr(), rstd.data_ptr(),
                                gamma.data_ptr(), K.ptr(dres), D, dx.data_ptr(), D, K.ptr(dx2), D,
-                               _dt(dx2) if dx2 is not None else 0, K.ptr(dgamma), K.ptr(dbeta), K.ptr(ws))
+                               _dt(dx2) if dx2 is not None else 0, K.ptr(dgamma), K.ptr(dbeta), K.ptr(ws),
+                               K.ptr(dy2), ld_dy2, dy2_p, dy2_seed)
         K.check(self.lib.bfk_layernorm_bwd(C.byref(a), _stream()), "bfk_layernorm_bwd")
         self.launches += 2 if dgamma is not None else 1
 
@@ -258,7 +270,18 @@ class Engine:
         mean1 = torch.empty(M, device=dev, dtype=torch.float32); rstd1 = torch.empty_like(mean1)
         k.layernorm_fwd(x, M, D, lw.ln1_w, lw.ln1_b, eps, h1, Dk, mean1, rstd1)
         p_drop = self.cfg.lora_dropout if (lw.Acat is not None and self.training) else 0.0
-        if lw.Acat is not None:
+        h1d = None
+        if lw.Acat is not None and T == torch.bfloat16:
+            # LoRA down-projection on the tensor cores: u = drop(h1) Acat^T written into the 16 extra K columns
+            lora_in, ld_in = h1, Dk
+            if p_drop > 0.0:
+                h1d = torch.empty(M, D, device=dev, dtype=T)
+                K.check(k.lib.bfk_dropout_copy(h1.data_ptr(), Dk, h1d.data_ptr(), D, _dt(h1), M, D, p_drop, lora_seed, _stream()),
+                        "bfk_dropout_copy")
+                k.launches += 1
+                lora_in, ld_in = h1d, D
+            k.gemm(lora_in, lw.Acat, h1[:, D:], M, 16, D, ld_in, D, Dk)
+        elif lw.Acat is not None:
             K.check(k.lib.bfk_lora_down(h1.data_ptr(), Dk, _dt(h1), M, D, lw.Acat.data_ptr(), p_drop, lora_seed, _stream()),
                     "bfk_lora_down")
             k.launches += 1
@@ -279,7 +302,7 @@ class Engine:
         k.gemm(a, lw.W2, x2, M, D, Mlp, Mlp, Mlp, D, bias=lw.b2, residual=x1, ldr=D)
         if save is not None:
             save.append(dict(x=x, h1=h1, mean1=mean1, rstd1=rstd1, qkv=qkv, ctx=ctx, lse=lse, x1=x1, h2=h2, mean2=mean2,
-                             rstd2=rstd2, pa=pa, a=a, p_drop=p_drop, seed=lora_seed))
+                             rstd2=rstd2, pa=pa, a=a, p_drop=p_drop, seed=lora_seed, h1d=h1d))
         return x2
 
     def _layer_bwd(self, dx2, dx2_T, sv, nseq, N, lw: LayerWeights, heads, eps, act, row_mask, grads, trainable):
@@ -323,13 +346,15 @@ class Engine:
         k.gemm(dqkv, lw.Wqkv, dh1, M, Dk, 3 * D, 3 * D, Dk, Dk, trans_b=True)
         if trainable:
             k.gemm(dqkv, sv["h1"], grads[n["Wqkv"]], 3 * D, D, M, 3 * D, Dk, D, trans_a=True, trans_b=True)
+        dy2 = None
         if lw.Acat is not None:
-            self._lora_bwd(sv, dqkv, dh1, M, lw, grads)
+            dy2 = self._lora_bwd(sv, dqkv, dh1, M, lw, grads)
         # LN1 + residual
         dx = torch.empty(M, D, device=dev, dtype=torch.float32)
         dx_T = torch.empty(M, D, device=dev, dtype=T) if T != torch.float32 else None
         k.layernorm_bwd(dh1, Dk, sv["x"], M, D, sv["mean1"], sv["rstd1"], lw.ln1_w, dx1, dx, dx_T,
-                        grads[n["ln1_w"]] if trainable else None, grads[n["ln1_b"]] if trainable else None)
+                        grads[n["ln1_w"]] if trainable else None, grads[n["ln1_b"]] if trainable else None,
+                        dy2=dy2, ld_dy2=D, dy2_p=sv["p_drop"] if dy2 is not None else 0.0, dy2_seed=sv["seed"])
         return dx, (dx_T if dx_T is not None else dx)
 
     def _lora_bwd(self, sv, dqkv, dh1, M, lw, grads):
@@ -339,8 +364,18 @@ class Engine:
         lib, st = k.lib, _stream()
         es = dqkv.element_size()
         h1, Dk = sv["h1"], lw.Dk
-        ws = torch.empty(max(lib.bfk_skinny_gram_workspace_floats(M, 16, D), 1), device=dqkv.device, dtype=torch.float32)
         n = lw.names
+        if self.T == torch.bfloat16:
+            # tensor-core path: split-K "wgrad" GEMMs for the factors, one K=16 GEMM for the dh1 contribution
+            x_in, ld_x = (sv["h1d"], D) if sv["h1d"] is not None else (h1, Dk)
+            for (Bn, ucol, qoff) in ((n["Bq"], 0, 0), (n["Bv"], 8, 2 * D)):
+                k.gemm(dqkv[:, qoff:], h1[:, D + ucol:], grads[Bn], D, r, M, 3 * D, Dk, r, trans_a=True, trans_b=True, alpha=s)
+            for (An, ucol) in ((n["Aq"], 0), (n["Av"], 8)):
+                k.gemm(dh1[:, D + ucol:], x_in, grads[An], r, D, M, Dk, ld_x, D, trans_a=True, trans_b=True)
+            dy2 = torch.empty(M, D, device=dqkv.device, dtype=self.T)
+            k.gemm(dh1[:, D:], lw.Acat, dy2, M, D, 16, Dk, D, D, trans_b=True)
+            return dy2
+        ws = torch.empty(max(lib.bfk_skinny_gram_workspace_floats(M, 16, D), 1), device=dqkv.device, dtype=torch.float32)
         # dB_q[d, i] = s * sum_m u_q[m,i] dq[m,d]   (u = h1[:, D:D+16]);  out stored transposed: [D, r]
         for (Bn, ucol, qoff) in ((n["Bq"], 0, 0), (n["Bv"], 8, 2 * D)):
             K.check(lib.bfk_skinny_gram(h1.data_ptr() + (D + ucol) * es, Dk, r, dqkv.data_ptr() + qoff * es, 3 * D, D,
@@ -352,6 +387,7 @@ class Engine:
         K.check(lib.bfk_lora_down_bwd(dh1.data_ptr(), Dk, _dt(dh1), M, D, lw.Acat.data_ptr(), sv["p_drop"], sv["seed"], st),
                 "bfk_lora_down_bwd")
         k.launches += 9
+        return None
 
     # ------------------------------------------------------------------------------------------------
     # towers

@@ -69,6 +69,8 @@ typedef struct {
   float alpha;
   int32_t accumulate;                /* D += ... (fp32 output only) */
   int32_t backend;
+  void* workspace; int64_t workspace_bytes; /* optional fp32 scratch enabling split-K (plain fp32-output GEMMs, e.g. wgrad) */
+  int32_t split_k;                          /* 0 = auto when a workspace is given, 1 = off, n = force n splits */
 } bfk_gemm_args;
 BFK_API int32_t bfk_gemm(const bfk_gemm_args* a, bfk_stream_t s);
 
@@ -102,6 +104,9 @@ typedef struct {
   void* dx2; int64_t ld_dx2; int32_t dx2_dtype; /* optional second copy of dx, or NULL */
   float* dgamma; float* dbeta;               /* [D] overwritten, or NULL (frozen LN) */
   float* partials;                           /* bfk_layernorm_bwd_workspace_floats(M,D) floats if dgamma */
+  const void* dy2; int64_t ld_dy2;           /* optional second upstream gradient (dy_dtype) added to dy under the
+                                                LoRA dropout mask: dy += keep(seed,m,k) ? dy2/(1-p) : 0 */
+  float dy2_dropout_p; uint64_t dy2_seed;
 } bfk_layernorm_bwd_args;
 BFK_API size_t bfk_layernorm_bwd_workspace_floats(int32_t M, int32_t D);
 BFK_API int32_t bfk_layernorm_bwd(const bfk_layernorm_bwd_args* a, bfk_stream_t s);
@@ -151,6 +156,9 @@ BFK_API int32_t bfk_lora_down(void* h, int64_t ldh, int32_t dtype, int32_t M, in
 /* backward of the above w.r.t. h:  dh[m,k] += mask(m,k) * sum_j dh[m, D+j] * Acat[j,k] */
 BFK_API int32_t bfk_lora_down_bwd(void* dh, int64_t ldh, int32_t dtype, int32_t M, int32_t D, const void* Acat,
                           float dropout_p, uint64_t seed, bfk_stream_t s);
+/* dst[m,k] = keep(seed,m,k) ? src[m,k]/(1-p) : 0 — the dropped LoRA input (same counter-based mask as above). */
+BFK_API int32_t bfk_dropout_copy(const void* src, int64_t lds, void* dst, int64_t ldd, int32_t dtype, int32_t M, int32_t D,
+                                 float dropout_p, uint64_t seed, bfk_stream_t s);
 /* Tall-skinny Gram product used for the LoRA weight gradients (deterministic split over rows):
  *   out[i, j] = alpha * sum_m P[m*ldp + i] * mask?(Q[m*ldq + j]),  i < ni (<=16), j < nj.
  * `partials`: bfk_skinny_gram_workspace_floats(M, ni, nj). */

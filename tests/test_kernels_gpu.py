@@ -53,6 +53,11 @@ GEMM_CASES = [
     (1000, 2304, 784, 0, 0, True, 0, False, 0, True),
     (2304, 768, 1048, 1, 1, False, 0, False, 0, False),
     (64, 16, 4304, 0, 0, False, 0, False, 0, False),
+    (768, 8, 4100, 1, 1, False, 0, False, 0, False),     # LoRA dB: split-K, N = 8
+    (8, 768, 4100, 1, 1, False, 0, False, 0, False),     # LoRA dA: split-K, M = 8
+    (300, 768, 16, 0, 1, False, 0, False, 0, True),      # LoRA dh contribution: K = 16
+    (300, 16, 768, 0, 0, False, 0, False, 0, True),      # LoRA down-projection: N = 16
+    (768, 768, 8200, 1, 1, False, 0, False, 0, False),   # wgrad, few tiles: split-K
 ]
 
 
