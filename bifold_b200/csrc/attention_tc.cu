@@ -72,6 +72,17 @@ __device__ __forceinline__ void store_row16(__nv_bfloat16* dst, int d0, int hd, 
   }
 }
 
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// width of key block j: full 128, or the valid tail rounded up to a multiple of 16 (MMA N / K granularity)
+__device__ __forceinline__ int kv_cols(int N, int j) {
+  const int rem = N - j * 128;
+  return rem >= 128 ? 128 : ((rem + 15) & ~15);
+}
+
 struct AttnSmem {
   uint32_t bar_q, bar_kv[2], bar_s, bar_p, bar_o, tmem_slot;
 };
@@ -109,7 +120,6 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_tc_kernel(const __grid_consta
 
   if (warp == 4) {
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc(128, 128, false, false);
       const uint32_t idesc_o = make_idesc(128, p.n_o, false, true);
       mbar_expect_tx(bar_q, TILE);
       load_tile<NA>(sQ, &map_qkv, bar_q, h, q0, b);
@@ -128,12 +138,13 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_tc_kernel(const __grid_consta
         mbar_wait(bar_kv0 + 8 * (j & 1), (j >> 1) & 1);
         tc_fence_after();
         const uint32_t k_t = sK + (j & 1) * TILE, v_t = sV + (j & 1) * TILE;
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tS, kmajor_desc(sQ, k), kmajor_desc(k_t, k), idesc_s, k > 0);
+        const int nc = kv_cols(p.N, j);
+        const uint32_t idesc_sj = make_idesc(128, nc, false, false);
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tS, kmajor_desc(sQ, k), kmajor_desc(k_t, k), idesc_sj, k > 0);
         tc_commit(bar_s);
         mbar_wait(bar_p, j & 1);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) tc_mma_bf16(tO, kmajor_desc(sP, k), mnmajor_desc(v_t, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < nc / 16; ++k) tc_mma_bf16(tO, kmajor_desc(sP, k), mnmajor_desc(v_t, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         tc_commit(bar_o);
       }
     }
@@ -142,44 +153,50 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_tc_kernel(const __grid_consta
     const int r = threadIdx.x, q = q0 + r;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const bool masked = p.row_mask && q < p.N && p.row_mask[(long long)b * p.N + q] == 0.f;
-    const float sl2 = p.scale * LOG2E;
-    float m_run = -INFINITY, l_run = 0.f;
+    // masked query row: every score equal => p == 1 for every key (scale 0, max 0)
+    const float sl2 = masked ? 0.f : p.scale * LOG2E;
+    float m_run = -INFINITY, l_run = 0.f;   // running max (scaled, log2 domain) and sum
     for (int j = 0; j < nblk; ++j) {
+      const int nc = kv_cols(p.N, j);            // columns computed for this block (multiple of 16)
+      const int nvalid = min(128, p.N - j * 128);  // real keys in this block
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
+      // pass 1: raw row max over the real keys
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < nc; c += 32) {
         uint32_t s[32];
-        tc_ld32(tS + lane_off + c * 32, s);
+        tc_ld32(tS + lane_off + c, s);
         tc_wait_ld();
+        const int lim = min(32, nvalid - c);   // only real keys enter the max
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const int col = j * 128 + c * 32 + t;
-          const float x = masked ? 0.f : __uint_as_float(s[t]) * sl2;
-          if (col < p.N) mx = fmaxf(mx, x);
-        }
+        for (int t = 0; t < 32; ++t)
+          if (t < lim) mx = fmaxf(mx, __uint_as_float(s[t]));
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f(m_run - m_new);
+      const float m_new = masked ? 0.f : fmaxf(m_run, mx * sl2);
+      const float alpha = ex2f(m_run - m_new);
       if (j > 0) { mbar_wait(bar_o, (j - 1) & 1); tc_fence_after(); }
       float rowsum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < nc; c += 32) {
         uint32_t s[32];
-        tc_ld32(tS + lane_off + c * 32, s);
+        tc_ld32(tS + lane_off + c, s);
         tc_wait_ld();
+        const int ng = min(4, (nc - c) >> 3);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float v[8];
+          if (g < ng) {
+            float v[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int col = j * 128 + c * 32 + g * 8 + t;
-            const float x = masked ? 0.f : __uint_as_float(s[g * 8 + t]) * sl2;
-            v[t] = col < p.N ? exp2f(x - m_new) : 0.f;
-            rowsum += v[t];
+            for (int t = 0; t < 8; ++t) v[t] = ex2f(fmaf(__uint_as_float(s[g * 8 + t]), sl2, -m_new));
+            if (c + g * 8 + 8 > nvalid) {   // tail: keys beyond the sequence get p = 0
+#pragma unroll
+              for (int t = 0; t < 8; ++t) if (c + g * 8 + t >= nvalid) v[t] = 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) rowsum += v[t];
+            store_p_chunk(sP, r, (c >> 3) + g, v);
           }
-          store_p_chunk(sP, r, c * 4 + g, v);
         }
       }
       l_run = l_run * alpha + rowsum;
@@ -253,7 +270,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
 
   if (warp == 4) {
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc(128, 128, false, false);
       const uint32_t idesc_q = make_idesc(128, p.n_o, false, true);
       auto issue_kv = [&](int j) {
         const int nb = j % NBUF;
@@ -272,13 +288,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
         mbar_wait(bar_kv0 + 8 * (j % NBUF), (j / NBUF) & 1);
         tc_fence_after();
         const uint32_t k_t = sK + (j % NBUF) * TILE, v_t = sV + (j % NBUF) * TILE;
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tS, kmajor_desc(sQ, k), kmajor_desc(k_t, k), idesc_s, k > 0);
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tdP, kmajor_desc(sdO, k), kmajor_desc(v_t, k), idesc_s, k > 0);
+        const int nc = kv_cols(p.N, j);
+        const uint32_t idesc_sj = make_idesc(128, nc, false, false);
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tS, kmajor_desc(sQ, k), kmajor_desc(k_t, k), idesc_sj, k > 0);
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tdP, kmajor_desc(sdO, k), kmajor_desc(v_t, k), idesc_sj, k > 0);
         tc_commit(bar_s);
         mbar_wait(bar_p, j & 1);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) tc_mma_bf16(tdQ, kmajor_desc(sdS, k), mnmajor_desc(k_t, k), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < nc / 16; ++k) tc_mma_bf16(tdQ, kmajor_desc(sdS, k), mnmajor_desc(k_t, k), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
         tc_commit(bar_o);
       }
     }
@@ -288,27 +305,32 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
     const bool live = q < p.N && !(p.row_mask && p.row_mask[(long long)b * p.N + q] == 0.f);
     const float sl2 = p.scale * LOG2E;
     const long long si = ((long long)b * p.H + h) * p.N + q;
-    const float lse2 = q < p.N ? p.lse[si] * LOG2E : 0.f, delta = q < p.N ? p.delta[si] : 0.f;
+    // non-live rows (masked query / beyond the sequence): lse = +inf => p == 0 => dS == 0
+    const float lse2 = live ? p.lse[si] * LOG2E : INFINITY, delta = live ? p.delta[si] : 0.f;
     for (int j = 0; j < nblk; ++j) {
+      const int nc = kv_cols(p.N, j);
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
       if (j > 0) { mbar_wait(bar_o, (j - 1) & 1); tc_fence_after(); }
+      // keys in [N, nc) have zero K rows: their dS values multiply zero rows in dQ += dS K, no masking needed
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < nc; c += 32) {
         uint32_t s[32], d[32];
-        tc_ld32(tS + lane_off + c * 32, s);
-        tc_ld32(tdP + lane_off + c * 32, d);
+        tc_ld32(tS + lane_off + c, s);
+        tc_ld32(tdP + lane_off + c, d);
         tc_wait_ld();
+        const int ng = min(4, (nc - c) >> 3);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float v[8];
+          if (g < ng) {
+            float v[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int col = j * 128 + c * 32 + g * 8 + t;
-            const float pr = exp2f(__uint_as_float(s[g * 8 + t]) * sl2 - lse2);
-            v[t] = (live && col < p.N) ? pr * (__uint_as_float(d[g * 8 + t]) - delta) : 0.f;
+            for (int t = 0; t < 8; ++t) {
+              const float pr = ex2f(fmaf(__uint_as_float(s[g * 8 + t]), sl2, -lse2));
+              v[t] = pr * (__uint_as_float(d[g * 8 + t]) - delta);
+            }
+            store_p_chunk(sdS, r, (c >> 3) + g, v);
           }
-          store_p_chunk(sdS, r, c * 4 + g, v);
         }
       }
       fence_async_smem();
@@ -344,9 +366,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid
   const uint32_t base = smem_u32(smem_raw);
   const uint32_t sK = base, sV = sK + TILE, sQ = sV + TILE, sdO = sQ + NBUF * TILE, sPt = sdO + NBUF * TILE, sdSt = sPt + 2 * AT_ATOM,
                  bars = sdSt + 2 * AT_ATOM;
-  float* s_lse2 = reinterpret_cast<float*>(smem_raw + (bars - base) + 64);   // per-query-column statistics
-  float* s_delta = s_lse2 + 128;
-  float* s_live = s_delta + 128;
+  float4* s_col = reinterpret_cast<float4*>(smem_raw + (bars - base) + 64);   // per-query-column {lse2, delta, scale2, live}
   const uint32_t bar_kv = bars, bar_q0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40, tmem_slot = bars + 48;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -371,7 +391,6 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid
 
   if (warp == 4) {
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc(128, 128, false, false);
       const uint32_t idesc_g = make_idesc(128, p.n_o, false, true);
       auto issue_q = [&](int i) {
         const int nb = i % NBUF;
@@ -390,15 +409,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid
         mbar_wait(bar_q0 + 8 * (i % NBUF), (i / NBUF) & 1);
         tc_fence_after();
         const uint32_t q_t = sQ + (i % NBUF) * TILE, do_t = sdO + (i % NBUF) * TILE;
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tSt, kmajor_desc(sK, k), kmajor_desc(q_t, k), idesc_s, k > 0);
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tdPt, kmajor_desc(sV, k), kmajor_desc(do_t, k), idesc_s, k > 0);
+        const int nc = kv_cols(p.N, i);
+        const uint32_t idesc_si = make_idesc(128, nc, false, false);
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tSt, kmajor_desc(sK, k), kmajor_desc(q_t, k), idesc_si, k > 0);
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tdPt, kmajor_desc(sV, k), kmajor_desc(do_t, k), idesc_si, k > 0);
         tc_commit(bar_s);
         mbar_wait(bar_p, i & 1);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) tc_mma_bf16(tdV, kmajor_desc(sPt, k), mnmajor_desc(do_t, k), idesc_g, (i > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) tc_mma_bf16(tdK, kmajor_desc(sdSt, k), mnmajor_desc(q_t, k), idesc_g, (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < nc / 16; ++k) tc_mma_bf16(tdV, kmajor_desc(sPt, k), mnmajor_desc(do_t, k), idesc_g, (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < nc / 16; ++k) tc_mma_bf16(tdK, kmajor_desc(sdSt, k), mnmajor_desc(q_t, k), idesc_g, (i > 0 || k > 0) ? 1u : 0u);
         tc_commit(bar_o);
       }
     }
@@ -406,43 +425,50 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid
     const int r = threadIdx.x, kv = j0 + r;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const float sl2 = p.scale * LOG2E;
-    const float inv_n = 1.f / (float)p.N;
+    const float log2n = log2f((float)p.N);
     const bool kv_ok = kv < p.N;
     for (int i = 0; i < nq; ++i) {
-      // per-query-column statistics of this block (thread t loads column t)
+      const int nc = kv_cols(p.N, i);
+      // per-query-column statistics of this block (thread t loads column t):
+      //   live query   : {lse*log2e, delta, scale*log2e, 1}   p = 2^(s*scale2 - lse2), dS = p (dP - delta)
+      //   masked query : {log2 N,    0,     0,           0}   p = 1/N,                 dS = 0
+      //   out of range : {+inf,      0,     0,           0}   p = 0
       named_bar_sync(1, 128);
       {
         const int q = i * 128 + r;
         const long long si = ((long long)b * p.H + h) * p.N + q;
-        const bool ok = q < p.N;
-        s_lse2[r] = ok ? p.lse[si] * LOG2E : INFINITY;   // +inf => p == 0 for out-of-range queries
-        s_delta[r] = ok ? p.delta[si] : 0.f;
-        s_live[r] = (ok && p.row_mask && p.row_mask[(long long)b * p.N + q] == 0.f) ? 0.f : 1.f;
+        float4 st = make_float4(INFINITY, 0.f, 0.f, 0.f);
+        if (q < p.N) {
+          const bool m = p.row_mask && p.row_mask[(long long)b * p.N + q] == 0.f;
+          st = m ? make_float4(log2n, 0.f, 0.f, 0.f) : make_float4(p.lse[si] * LOG2E, p.delta[si], sl2, 1.f);
+        }
+        s_col[r] = st;
       }
       named_bar_sync(1, 128);
       mbar_wait(bar_s, i & 1);
       tc_fence_after();
       if (i > 0) { mbar_wait(bar_o, (i - 1) & 1); tc_fence_after(); }
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < nc; c += 32) {
         uint32_t s[32], d[32];
-        tc_ld32(tSt + lane_off + c * 32, s);
-        tc_ld32(tdPt + lane_off + c * 32, d);
+        tc_ld32(tSt + lane_off + c, s);
+        tc_ld32(tdPt + lane_off + c, d);
         tc_wait_ld();
+        const int ng = min(4, (nc - c) >> 3);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float pv[8], dv[8];
+          if (g < ng) {
+            float pv[8], dv[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int qc = c * 32 + g * 8 + t;
-            const bool qlive = s_live[qc] != 0.f;
-            float pr = qlive ? exp2f(__uint_as_float(s[g * 8 + t]) * sl2 - s_lse2[qc]) : (s_lse2[qc] == INFINITY ? 0.f : inv_n);
-            if (!kv_ok) pr = 0.f;
-            pv[t] = pr;
-            dv[t] = qlive ? pr * (__uint_as_float(d[g * 8 + t]) - s_delta[qc]) : 0.f;
+            for (int t = 0; t < 8; ++t) {
+              const float4 st = s_col[c + g * 8 + t];
+              const float pr = ex2f(fmaf(__uint_as_float(s[g * 8 + t]), st.z, -st.x));
+              pv[t] = pr;
+              dv[t] = pr * st.w * (__uint_as_float(d[g * 8 + t]) - st.y);
+            }
+            store_p_chunk(sPt, r, (c >> 3) + g, pv);
+            store_p_chunk(sdSt, r, (c >> 3) + g, dv);
           }
-          store_p_chunk(sPt, r, c * 4 + g, pv);
-          store_p_chunk(sdSt, r, c * 4 + g, dv);
         }
       }
       fence_async_smem();
@@ -593,13 +619,13 @@ int attention_bwd_tc(const bfk_attention_args* a, cudaStream_t s) {
                                                                   a->ld_dout, a->delta, a->B, a->N, a->H, a->hd);
   dim3 grid((a->N + 127) / 128, a->H, a->B);
   if (a->hd <= 64) {
-    const size_t smem_q = 6 * AT_ATOM + 2 * AT_ATOM + 256, smem_kv = 6 * AT_ATOM + 4 * AT_ATOM + 2048;
+    const size_t smem_q = 6 * AT_ATOM + 2 * AT_ATOM + 256, smem_kv = 6 * AT_ATOM + 4 * AT_ATOM + 4096;
     if (int rc = set_attr(attn_bwd_dq_tc_kernel<1, 2>, smem_q, "attn_bwd_dq_tc")) return rc;
     if (int rc = set_attr(attn_bwd_dkv_tc_kernel<1, 2>, smem_kv, "attn_bwd_dkv_tc")) return rc;
     attn_bwd_dq_tc_kernel<1, 2><<<grid, 160, smem_q, s>>>(mq, md, p);
     attn_bwd_dkv_tc_kernel<1, 2><<<grid, 160, smem_kv, s>>>(mq, md, p);
   } else {
-    const size_t smem_q = 4 * 2 * AT_ATOM + 2 * AT_ATOM + 256, smem_kv = 4 * 2 * AT_ATOM + 4 * AT_ATOM + 2048;
+    const size_t smem_q = 4 * 2 * AT_ATOM + 2 * AT_ATOM + 256, smem_kv = 4 * 2 * AT_ATOM + 4 * AT_ATOM + 4096;
     if (int rc = set_attr(attn_bwd_dq_tc_kernel<2, 1>, smem_q, "attn_bwd_dq_tc")) return rc;
     if (int rc = set_attr(attn_bwd_dkv_tc_kernel<2, 1>, smem_kv, "attn_bwd_dkv_tc")) return rc;
     attn_bwd_dq_tc_kernel<2, 1><<<grid, 160, smem_q, s>>>(mq, md, p);

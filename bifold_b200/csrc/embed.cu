@@ -146,10 +146,30 @@ __global__ void __launch_bounds__(256) lora_down_bwd_kernel(T* __restrict__ dh, 
 }
 
 // ---- inverted-dropout copy (LoRA input dropout): dst = mask(seed,row,col) ? src/(1-p) : 0 -----------------
+// 8 elements (16 bytes of bf16) per thread when the layout allows it.
 template <typename T>
 __global__ void dropout_copy_kernel(const T* __restrict__ src, long long lds, T* __restrict__ dst, long long ldd, int M, int D,
-                                    float p_drop, uint64_t seed) {
+                                    float p_drop, uint64_t seed, int vec) {
   const float keep_scale = 1.f / (1.f - p_drop);
+  if (vec) {
+    const int dv = D / 8;
+    const long long total = (long long)M * dv;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+      const int row = (int)(i / dv), col = (int)(i % dv) * 8;
+      const uint4 u = *reinterpret_cast<const uint4*>(src + (long long)row * lds + col);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+      __nv_bfloat162 o[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = __bfloat1622float2(h[t]);
+        f.x = hash_uniform(seed, row, col + 2 * t) < p_drop ? 0.f : f.x * keep_scale;
+        f.y = hash_uniform(seed, row, col + 2 * t + 1) < p_drop ? 0.f : f.y * keep_scale;
+        o[t] = __floats2bfloat162_rn(f.x, f.y);
+      }
+      *reinterpret_cast<uint4*>(dst + (long long)row * ldd + col) = *reinterpret_cast<uint4*>(o);
+    }
+    return;
+  }
   const long long total = (long long)M * D;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int row = (int)(i / D), col = (int)(i % D);
@@ -448,9 +468,11 @@ extern "C" int32_t bfk_lora_down_bwd(void* dh, int64_t ldh, int32_t dtype, int32
 extern "C" int32_t bfk_dropout_copy(const void* src, int64_t lds, void* dst, int64_t ldd, int32_t dtype, int32_t M, int32_t D,
                                     float dropout_p, uint64_t seed, bfk_stream_t s_) {
   BFK_CHECK_ARG(src && dst && M > 0 && D > 0 && dropout_p >= 0.f && dropout_p < 1.f, "bfk_dropout_copy: bad arguments");
-  int blocks = (int)std::min<long long>((long long)sm_count() * 16, ((long long)M * D + 255) / 256);
-  if (dtype == BFK_BF16) dropout_copy_kernel<__nv_bfloat16><<<blocks, 256, 0, to_stream(s_)>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, M, D, dropout_p, seed);
-  else dropout_copy_kernel<float><<<blocks, 256, 0, to_stream(s_)>>>((const float*)src, lds, (float*)dst, ldd, M, D, dropout_p, seed);
+  const int vec = (dtype == BFK_BF16 && D % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) ? 1 : 0;
+  int blocks = (int)std::min<long long>((long long)sm_count() * 16, ((long long)M * D / (vec ? 8 : 1) + 255) / 256);
+  if (dtype == BFK_BF16) dropout_copy_kernel<__nv_bfloat16><<<blocks, 256, 0, to_stream(s_)>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, M, D, dropout_p, seed, vec);
+  else dropout_copy_kernel<float><<<blocks, 256, 0, to_stream(s_)>>>((const float*)src, lds, (float*)dst, ldd, M, D, dropout_p, seed, 0);
   BFK_CHECK_LAUNCH("bfk_dropout_copy");
   return BFK_OK;
 }

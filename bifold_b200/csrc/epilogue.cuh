@@ -14,7 +14,7 @@ struct EpiParams {
   const float* residual; long long ldr; int res_row_mod;
   float alpha;
   int accumulate;
-  int vec_ok;  // host-verified: D/aux/residual/bias pointers and leading dims allow 16-byte vector access
+  int vec_ok;  // host-verified: D/aux/residual/bias pointers and leading dims allow 32-byte vector access
 };
 
 __device__ __forceinline__ float epi_value(const EpiParams& p, int m, int n, float acc) {
@@ -129,12 +129,12 @@ inline bool epi_from_args(const bfk_gemm_args* a, EpiParams& p) {
   p.aux_dtype = (a->act == BFK_ACT_DGELU_TANH || a->act == BFK_ACT_DGELU_ERF) ? a->in_dtype : a->out_dtype;
   p.residual = a->residual; p.ldr = a->ldr; p.res_row_mod = a->res_row_mod;
   p.alpha = a->alpha; p.accumulate = a->accumulate;
-  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
   size_t es = a->out_dtype == BFK_BF16 ? 2 : 4, as = p.aux_dtype == BFK_BF16 ? 2 : 4;
-  bool ok = al16(a->D) && (a->ldd * es) % 16 == 0;
-  if (a->bias) ok = ok && al16(a->bias);
-  if (a->aux) ok = ok && al16(a->aux) && (a->ld_aux * as) % 16 == 0;
-  if (a->residual) ok = ok && al16(a->residual) && (a->ldr * 4) % 16 == 0;
+  bool ok = al32(a->D) && (a->ldd * es) % 32 == 0;
+  if (a->bias) ok = ok && al32(a->bias);
+  if (a->aux) ok = ok && al32(a->aux) && (a->ld_aux * as) % 32 == 0;
+  if (a->residual) ok = ok && al32(a->residual) && (a->ldr * 4) % 32 == 0;
   p.vec_ok = ok ? 1 : 0;
   return true;
 }

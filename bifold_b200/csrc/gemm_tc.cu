@@ -63,6 +63,26 @@ __device__ __forceinline__ float dgelu_erf_fast(float x) {
   return 0.5f * (1.f + er) + x * 0.3989422804014327f * e;
 }
 
+// 256-bit global accesses (LDG.256 / STG.256): one full 32-byte sector per thread and instruction
+struct alignas(32) V8 { uint32_t w[8]; };
+__device__ __forceinline__ V8 ldg256(const void* p) {
+  V8 v;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg256(void* p, const V8& v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]),
+               "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7])
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 // One 32-column chunk [nc, nc+32) of row m: global operands are fetched BEFORE the TMEM load is waited for,
 // bias comes from shared memory, all stores go last (no load is serialised behind a store).
 __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, uint32_t taddr, const float* __restrict__ bias_s) {
@@ -80,18 +100,18 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
     return;
   }
   const bool dgelu = ep.act == BFK_ACT_DGELU_TANH || ep.act == BFK_ACT_DGELU_ERF;
-  float4 res[8];
-  uint4 hx[4];
+  V8 res[4];
+  V8 hx[2];
   if (row_ok && ep.residual) {
     const int rm = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
-    const float4* rp = reinterpret_cast<const float4*>(ep.residual + (long long)rm * ep.ldr + nc);
+    const float* rp = ep.residual + (long long)rm * ep.ldr + nc;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) res[i] = __ldg(rp + i);
+    for (int i = 0; i < 4; ++i) res[i] = ldg256(rp + 8 * i);
   }
   if (row_ok && dgelu) {   // pre-activation, bf16 (aux dtype == operand dtype == bf16 on this path)
-    const uint4* hp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc);
+    const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) hx[i] = __ldg(hp + i);
+    for (int i = 0; i < 2; ++i) hx[i] = ldg256(hp + 16 * i);
   }
   tc_ld32(taddr, r);
   tc_wait_ld();
@@ -107,18 +127,23 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
   if (ep.act == BFK_ACT_GELU_TANH || ep.act == BFK_ACT_GELU_ERF) {
     if (ep.aux) {
       if (ep.aux_dtype == BFK_BF16) {
-        uint4* ap = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc);
+        __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __nv_bfloat162 h[4];
+        for (int i = 0; i < 2; ++i) {
+          V8 o;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[i * 8 + 2 * t], v[i * 8 + 2 * t + 1]);
-          ap[i] = *reinterpret_cast<uint4*>(h);
+          for (int t = 0; t < 8; ++t) o.w[t] = pack_bf16(v[i * 16 + 2 * t], v[i * 16 + 2 * t + 1]);
+          stg256(ap + 16 * i, o);
         }
       } else {
-        float4* ap = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.aux) + (long long)m * ep.ld_aux + nc);
+        float* ap = reinterpret_cast<float*>(ep.aux) + (long long)m * ep.ld_aux + nc;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ap[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int i = 0; i < 4; ++i) {
+          V8 o;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) o.w[t] = __float_as_uint(v[i * 8 + t]);
+          stg256(ap + 8 * i, o);
+        }
       }
     }
     if (ep.act == BFK_ACT_GELU_TANH) {
@@ -137,10 +162,10 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
       for (int t = 0; t < 32; ++t) v[t] = gelu_erf(v[t]);
     }
   } else if (dgelu) {
-    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(hx);
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
-      const float2 h = __bfloat1622float2(hp[t]);
+      const uint32_t hw = hx[t >> 3].w[t & 7];
+      const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw));
       if (ep.act == BFK_ACT_DGELU_TANH) {
         v[2 * t] *= out_bf16 ? dgelu_tanh_fast(h.x) : dgelu_tanh(h.x);
         v[2 * t + 1] *= out_bf16 ? dgelu_tanh_fast(h.y) : dgelu_tanh(h.y);
@@ -152,22 +177,40 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
   }
   if (ep.residual) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { v[4 * i] += res[i].x; v[4 * i + 1] += res[i].y; v[4 * i + 2] += res[i].z; v[4 * i + 3] += res[i].w; }
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[i * 8 + t] += __uint_as_float(res[i].w[t]);
   }
   if (out_bf16) {
-    uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.D) + (long long)m * ep.ldd + nc);
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(ep.D) + (long long)m * ep.ldd + nc;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 h[4];
+    for (int i = 0; i < 2; ++i) {
+      V8 o;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[i * 8 + 2 * t], v[i * 8 + 2 * t + 1]);
-      dp[i] = *reinterpret_cast<uint4*>(h);
+      for (int t = 0; t < 8; ++t) o.w[t] = pack_bf16(v[i * 16 + 2 * t], v[i * 16 + 2 * t + 1]);
+      stg256(dp + 16 * i, o);
     }
   } else {
-    float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.D) + (long long)m * ep.ldd + nc);
+    float* dp = reinterpret_cast<float*>(ep.D) + (long long)m * ep.ldd + nc;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    for (int i = 0; i < 4; ++i) {
+      V8 o;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o.w[t] = __float_as_uint(v[i * 8 + t]);
+      stg256(dp + 8 * i, o);
+    }
   }
+}
+
+// L2 prefetch of the operands the epilogue of (row m, chunk nc) will read (next work item of this CTA)
+__device__ __forceinline__ void epi_prefetch(const EpiParams& ep, int m, int nc) {
+  if (m >= ep.M || nc + 32 > ep.N) return;
+  if (ep.residual) {
+    const int rm = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
+    prefetch_l2(ep.residual + (long long)rm * ep.ldr + nc);
+  }
+  if (ep.act == BFK_ACT_DGELU_TANH || ep.act == BFK_ACT_DGELU_ERF)
+    prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc);
 }
 
 template <int BN, bool AMN, bool BMN>
@@ -287,6 +330,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int i = et; i < BN; i += 32 * TC_EPI_WARPS) bias_s[i] = (n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
       }
       named_bar_sync(1, 32 * TC_EPI_WARPS);   // bias visible; also orders reuse of the other buffer
+      if (ep.vec_ok && item + (int)gridDim.x < tiles) {   // warm L2 with what the NEXT item's epilogue will read
+        const int ntile = (item + (int)gridDim.x) / splits;
+        const int nm = (ntile / num_n) * TC_BM + quarter * 32 + lane, nn0 = (ntile % num_n) * BN;
+        for (int c = half; c < BN / 32; c += 2) epi_prefetch(ep, nm, nn0 + c * 32);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
@@ -434,7 +482,7 @@ static int launch_tc(const bfk_gemm_args* a, cudaStream_t s) {
   const long long split_stride = (long long)a->M * a->N;
   if (splits > 1) {   // partial tiles go to the workspace as plain fp32 [splits][M][N]
     ep.D = a->workspace; ep.ldd = a->N; ep.out_dtype = BFK_F32; ep.alpha = 1.f; ep.accumulate = 0;
-    ep.vec_ok = ((reinterpret_cast<uintptr_t>(a->workspace) & 15u) == 0 && (a->N % 4) == 0 && (split_stride % 4) == 0) ? 1 : 0;
+    ep.vec_ok = ((reinterpret_cast<uintptr_t>(a->workspace) & 31u) == 0 && (a->N % 8) == 0 && (split_stride % 8) == 0) ? 1 : 0;
   }
   const int tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + BN - 1) / BN) * splits;
   const int grid = std::min(tiles, sm_count());

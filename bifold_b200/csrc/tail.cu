@@ -24,9 +24,17 @@ __device__ __forceinline__ unsigned long long pack_key(float v, uint32_t idx) {
 // out[c] = sum_r v[r] * W[r*C + c]   (thread per column)
 __device__ void vecmat(const float* __restrict__ v_s, const float* __restrict__ W, int R, int C, float* __restrict__ out_s) {
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int r = 0; r < R; ++r) s = fmaf(v_s[r], W[(long long)r * C + c], s);
-    out_s[c] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // 4 independent chains, 8 loads in flight
+    int r = 0;
+#pragma unroll 2
+    for (; r + 4 <= R; r += 4) {
+      s0 = fmaf(v_s[r], W[(long long)r * C + c], s0);
+      s1 = fmaf(v_s[r + 1], W[(long long)(r + 1) * C + c], s1);
+      s2 = fmaf(v_s[r + 2], W[(long long)(r + 2) * C + c], s2);
+      s3 = fmaf(v_s[r + 3], W[(long long)(r + 3) * C + c], s3);
+    }
+    for (; r < R; ++r) s0 = fmaf(v_s[r], W[(long long)r * C + c], s0);
+    out_s[c] = (s0 + s1) + (s2 + s3);
   }
 }
 // out[r] = sum_c W[r*C + c] * g[c] + extra * bias[r]   (warp per row)
@@ -54,9 +62,9 @@ __device__ float block_dot(const float* __restrict__ a_s, const float* __restric
 }
 
 // grid: heads; smem: 5*D floats
-__global__ void __launch_bounds__(512) collapse_fwd_kernel(bfk_decoder_collapse_args a) {
+__global__ void __launch_bounds__(1024) collapse_fwd_kernel(bfk_decoder_collapse_args a) {
   extern __shared__ float sm[];
-  __shared__ float red[16];
+  __shared__ float red[32];
   const int h = blockIdx.x, D = a.D, c1 = D / 2, c2 = D / 4;
   float *v5 = sm, *v4 = sm + D, *v3 = sm + 2 * D, *v2 = sm + 3 * D, *we = sm + 4 * D;
   const float* const* W = a.W + h * 5;
@@ -86,7 +94,7 @@ __device__ void outer(float* __restrict__ dW, const float* __restrict__ u_s, con
 }
 
 // grid: heads; smem: 7*D floats
-__global__ void __launch_bounds__(512) collapse_bwd_kernel(bfk_decoder_collapse_args a) {
+__global__ void __launch_bounds__(1024) collapse_bwd_kernel(bfk_decoder_collapse_args a) {
   extern __shared__ float sm[];
   const int h = blockIdx.x, D = a.D, c1 = D / 2, c2 = D / 4;
   float *v2 = sm, *v3 = sm + D, *v4 = sm + 2 * D, *v5 = sm + 3 * D, *ga = sm + 4 * D, *gb = sm + 5 * D;
@@ -574,13 +582,13 @@ static int opt_in_smem(K kernel, size_t bytes, const char* name) {
 
 extern "C" int32_t bfk_decoder_collapse_fwd(const bfk_decoder_collapse_args* a, bfk_stream_t s_) {
   BFK_CHECK_ARG(a && a->W && a->b && a->w_eff && a->b_eff && a->chain && a->heads > 0 && a->D >= 4, "bfk_decoder_collapse_fwd: bad arguments");
-  collapse_fwd_kernel<<<a->heads, 512, 5 * a->D * sizeof(float), to_stream(s_)>>>(*a);
+  collapse_fwd_kernel<<<a->heads, 1024, 5 * a->D * sizeof(float), to_stream(s_)>>>(*a);
   BFK_CHECK_LAUNCH("bfk_decoder_collapse_fwd");
   return BFK_OK;
 }
 extern "C" int32_t bfk_decoder_collapse_bwd(const bfk_decoder_collapse_args* a, bfk_stream_t s_) {
   BFK_CHECK_ARG(a && a->W && a->b && a->chain && a->d_w_eff && a->d_b_eff && a->dW && a->db, "bfk_decoder_collapse_bwd: bad arguments");
-  collapse_bwd_kernel<<<a->heads, 512, 6 * a->D * sizeof(float), to_stream(s_)>>>(*a);
+  collapse_bwd_kernel<<<a->heads, 1024, 6 * a->D * sizeof(float), to_stream(s_)>>>(*a);
   BFK_CHECK_LAUNCH("bfk_decoder_collapse_bwd");
   return BFK_OK;
 }

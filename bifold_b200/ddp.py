@@ -20,11 +20,11 @@ import torch.distributed as dist
 
 
 def plan_groups(names: List[str], sizes: List[int]) -> Dict[str, List[Tuple[int, int]]]:
-    """Arena ranges (offset, length in floats; parameters padded to 4 floats) of every gradient group."""
+    """Arena ranges (offset, length in floats; parameters padded to 8 floats) of every gradient group."""
     groups: Dict[str, List[Tuple[int, int]]] = {}
     off = 0
     for n, s in zip(names, sizes):
-        padded = (s + 3) // 4 * 4
+        padded = (s + 7) // 8 * 8
         if "_decoder." in n:
             g = "decoders"
         elif ".transformer_encoder.layers." in n:

@@ -581,7 +581,7 @@ class Engine:
         sizes = [self.params[n].numel() for n in names]
         offs, tot = [], 0
         for s in sizes:
-            offs.append(tot); tot += (s + 3) // 4 * 4
+            offs.append(tot); tot += (s + 7) // 8 * 8
         arena = torch.empty(tot, device=dev, dtype=torch.float32)
         grads = {n: arena[o:o + s].view(self.params[n].shape) for n, o, s in zip(names, offs, sizes)}
         self.last_arena = arena

@@ -39,7 +39,7 @@ class FusedAdam(torch.optim.Optimizer):
         offs, tot = [], 0
         for p in ps:
             offs.append(tot)
-            tot += (p.numel() + 3) // 4 * 4
+            tot += (p.numel() + 7) // 8 * 8
         flat = torch.zeros(tot, device=dev, dtype=torch.float32)
         m, v = torch.zeros_like(flat), torch.zeros_like(flat)
         step = 0

@@ -24,7 +24,7 @@ SIZES = [8 * 64, 64 * 8, 64, 64, 128, 64, 3 * 64 * 64, 64, 32 * 64, 30, 5 * 64]
 def test_plan_groups_covers_arena_once():
     groups = plan_groups(NAMES, SIZES)
     assert set(groups) == {"text", "vision", "tokens", "fusion.0", "fusion.1", "decoders"}
-    total = sum((s + 3) // 4 * 4 for s in SIZES)
+    total = sum((s + 7) // 8 * 8 for s in SIZES)
     covered = sorted(r for rs in groups.values() for r in rs)
     pos = 0
     for off, n in covered:
@@ -40,7 +40,7 @@ def _worker(rank, world, port):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         red = GradReducer(NAMES, SIZES)
-        total = sum((s + 3) // 4 * 4 for s in SIZES)
+        total = sum((s + 7) // 8 * 8 for s in SIZES)
         torch.manual_seed(rank)
         arena = torch.randn(total)
         mine = arena.clone()
