@@ -77,16 +77,24 @@ int gemm_simt(const bfk_gemm_args* a, cudaStream_t s) {
 }
 
 // ---- column sums (bias gradients) --------------------------------------------------------------
-constexpr int CS_ROWS = 256;  // rows per first-stage block
+constexpr int CS_ROWS = 128;  // rows per first-stage block
 
 template <typename T>
 __global__ void colsum_stage1(const T* __restrict__ X, int M, int N, long long ld, float* __restrict__ partials) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   int r0 = blockIdx.y * CS_ROWS, r1 = min(M, r0 + CS_ROWS);
-  float s = 0.f;
-  for (int r = r0; r < r1; ++r) s += to_f32<T>(X[(long long)r * ld + n]);
-  partials[(long long)blockIdx.y * N + n] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // independent chains keep several loads in flight
+  int r = r0;
+#pragma unroll 2
+  for (; r + 4 <= r1; r += 4) {
+    s0 += to_f32<T>(X[(long long)r * ld + n]);
+    s1 += to_f32<T>(X[(long long)(r + 1) * ld + n]);
+    s2 += to_f32<T>(X[(long long)(r + 2) * ld + n]);
+    s3 += to_f32<T>(X[(long long)(r + 3) * ld + n]);
+  }
+  for (; r < r1; ++r) s0 += to_f32<T>(X[(long long)r * ld + n]);
+  partials[(long long)blockIdx.y * N + n] = (s0 + s1) + (s2 + s3);
 }
 __global__ void colsum_stage2(const float* __restrict__ partials, int nb, int N, float* __restrict__ out) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;

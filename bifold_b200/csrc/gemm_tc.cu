@@ -67,13 +67,13 @@ __device__ __forceinline__ float dgelu_erf_fast(float x) {
 struct alignas(32) V8 { uint32_t w[8]; };
 __device__ __forceinline__ V8 ldg256(const void* p) {
   V8 v;
-  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
                : "l"(p));
   return v;
 }
 __device__ __forceinline__ void stg256(void* p, const V8& v) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]),
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]),
                "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7])
                : "memory");
 }
@@ -83,39 +83,43 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// One 32-column chunk [nc, nc+32) of row m: global operands are fetched BEFORE the TMEM load is waited for,
-// bias comes from shared memory, all stores go last (no load is serialised behind a store).
-__device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, uint32_t taddr, const float* __restrict__ bias_s) {
-  const bool row_ok = m < ep.M;
-  const bool fast = ep.vec_ok && !ep.accumulate && (nc + 32 <= ep.N);
-  uint32_t r[32];
-  if (!fast) {
-    tc_ld32(taddr, r);
-    tc_wait_ld();
-    if (row_ok) {
-#pragma unroll
-      for (int t = 0; t < 32; ++t)
-        if (nc + t < ep.N) epi_store(ep, m, nc + t, __uint_as_float(r[t]));
-    }
-    return;
-  }
-  const bool dgelu = ep.act == BFK_ACT_DGELU_TANH || ep.act == BFK_ACT_DGELU_ERF;
-  V8 res[4];
-  V8 hx[2];
-  if (row_ok && ep.residual) {
+// Global operands of one 32-column chunk of one row (fp32 residual: 128 B, or bf16 pre-activation: 64 B)
+struct EpiOperands { V8 w[4]; };
+
+__device__ __forceinline__ bool epi_fast(const EpiParams& ep, int nc) {
+  return ep.vec_ok && !ep.accumulate && (nc + 32 <= ep.N);
+}
+// Issue the global loads of chunk [nc, nc+32) of row m (nothing waits on them here).
+__device__ __forceinline__ void epi_load(const EpiParams& ep, int m, int nc, EpiOperands& o) {
+  if (m >= ep.M || !epi_fast(ep, nc)) return;
+  if (ep.residual) {
     const int rm = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
     const float* rp = ep.residual + (long long)rm * ep.ldr + nc;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) res[i] = ldg256(rp + 8 * i);
-  }
-  if (row_ok && dgelu) {   // pre-activation, bf16 (aux dtype == operand dtype == bf16 on this path)
+    for (int i = 0; i < 4; ++i) o.w[i] = ldg256(rp + 8 * i);
+  } else if (ep.act == BFK_ACT_DGELU_TANH || ep.act == BFK_ACT_DGELU_ERF) {
     const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) hx[i] = ldg256(hp + 16 * i);
+    for (int i = 0; i < 2; ++i) o.w[i] = ldg256(hp + 16 * i);
   }
+}
+
+// One 32-column chunk [nc, nc+32) of row m: TMEM -> registers -> fused epilogue -> global.  `o` holds the
+// operands loaded earlier by epi_load (software-pipelined one chunk ahead); bias comes from shared memory.
+__device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, uint32_t taddr, const float* __restrict__ bias_s,
+                                            const EpiOperands& o) {
+  const bool row_ok = m < ep.M;
+  uint32_t r[32];
   tc_ld32(taddr, r);
   tc_wait_ld();
   if (!row_ok) return;
+  if (!epi_fast(ep, nc)) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t)
+      if (nc + t < ep.N) epi_store(ep, m, nc + t, __uint_as_float(r[t]));
+    return;
+  }
+  const bool dgelu = ep.act == BFK_ACT_DGELU_TANH || ep.act == BFK_ACT_DGELU_ERF;
   float v[32];
 #pragma unroll
   for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]) * ep.alpha;
@@ -130,19 +134,19 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
         __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          V8 o;
+          V8 q;
 #pragma unroll
-          for (int t = 0; t < 8; ++t) o.w[t] = pack_bf16(v[i * 16 + 2 * t], v[i * 16 + 2 * t + 1]);
-          stg256(ap + 16 * i, o);
+          for (int t = 0; t < 8; ++t) q.w[t] = pack_bf16(v[i * 16 + 2 * t], v[i * 16 + 2 * t + 1]);
+          stg256(ap + 16 * i, q);
         }
       } else {
         float* ap = reinterpret_cast<float*>(ep.aux) + (long long)m * ep.ld_aux + nc;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          V8 o;
+          V8 q;
 #pragma unroll
-          for (int t = 0; t < 8; ++t) o.w[t] = __float_as_uint(v[i * 8 + t]);
-          stg256(ap + 8 * i, o);
+          for (int t = 0; t < 8; ++t) q.w[t] = __float_as_uint(v[i * 8 + t]);
+          stg256(ap + 8 * i, q);
         }
       }
     }
@@ -162,42 +166,53 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
       for (int t = 0; t < 32; ++t) v[t] = gelu_erf(v[t]);
     }
   } else if (dgelu) {
+    float h[32];
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
-      const uint32_t hw = hx[t >> 3].w[t & 7];
-      const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw));
-      if (ep.act == BFK_ACT_DGELU_TANH) {
-        v[2 * t] *= out_bf16 ? dgelu_tanh_fast(h.x) : dgelu_tanh(h.x);
-        v[2 * t + 1] *= out_bf16 ? dgelu_tanh_fast(h.y) : dgelu_tanh(h.y);
+      const uint32_t hw = o.w[t >> 3].w[t & 7];
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw));
+      h[2 * t] = f.x; h[2 * t + 1] = f.y;
+    }
+    // one uniform branch per variant (a per-element select would execute the exact AND the fast path)
+    if (ep.act == BFK_ACT_DGELU_TANH) {
+      if (out_bf16) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] *= dgelu_tanh_fast(h[t]);
       } else {
-        v[2 * t] *= out_bf16 ? dgelu_erf_fast(h.x) : dgelu_erf(h.x);
-        v[2 * t + 1] *= out_bf16 ? dgelu_erf_fast(h.y) : dgelu_erf(h.y);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] *= dgelu_tanh(h[t]);
       }
+    } else if (out_bf16) {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] *= dgelu_erf_fast(h[t]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] *= dgelu_erf(h[t]);
     }
   }
   if (ep.residual) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int t = 0; t < 8; ++t) v[i * 8 + t] += __uint_as_float(res[i].w[t]);
+      for (int t = 0; t < 8; ++t) v[i * 8 + t] += __uint_as_float(o.w[i].w[t]);
   }
   if (out_bf16) {
     __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(ep.D) + (long long)m * ep.ldd + nc;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      V8 o;
+      V8 q;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) o.w[t] = pack_bf16(v[i * 16 + 2 * t], v[i * 16 + 2 * t + 1]);
-      stg256(dp + 16 * i, o);
+      for (int t = 0; t < 8; ++t) q.w[t] = pack_bf16(v[i * 16 + 2 * t], v[i * 16 + 2 * t + 1]);
+      stg256(dp + 16 * i, q);
     }
   } else {
     float* dp = reinterpret_cast<float*>(ep.D) + (long long)m * ep.ldd + nc;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      V8 o;
+      V8 q;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) o.w[t] = __float_as_uint(v[i * 8 + t]);
-      stg256(dp + 8 * i, o);
+      for (int t = 0; t < 8; ++t) q.w[t] = __float_as_uint(v[i * 8 + t]);
+      stg256(dp + 8 * i, q);
     }
   }
 }
@@ -335,14 +350,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int nm = (ntile / num_n) * TC_BM + quarter * 32 + lane, nn0 = (ntile % num_n) * BN;
         for (int c = half; c < BN / 32; c += 2) epi_prefetch(ep, nm, nn0 + c * 32);
       }
+      const int m = m0 + quarter * 32 + lane;
+      EpiOperands cur, nxt;
+      if (n0 + half * 32 < N) epi_load(epl, m, n0 + half * 32, cur);   // first chunk's operands: issued before the wait
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int m = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         if (n0 + c * 32 >= N) break;  // warp-uniform
-        epi_chunk32(epl, m, n0 + c * 32, taddr + (uint32_t)(c * 32), bias_s + c * 32);
+        if (c + 2 < BN / 32 && n0 + (c + 2) * 32 < N) epi_load(epl, m, n0 + (c + 2) * 32, nxt);   // one chunk ahead
+        epi_chunk32(epl, m, n0 + c * 32, taddr + (uint32_t)(c * 32), bias_s + c * 32, cur);
+        cur = nxt;
       }
       tc_fence_before();
       __syncwarp();
