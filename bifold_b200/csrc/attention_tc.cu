@@ -20,6 +20,8 @@
 
 namespace bfk {
 
+constexpr int AT_ROW_WARPS = 8;                 // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int AT_THREADS = 32 * AT_ROW_WARPS + 32;  // + control warp (TMA, tcgen05.mma issue, TMEM alloc)
 constexpr uint32_t AT_ATOM = 128 * 128;  // one 128-row x 128-byte swizzle atom column
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
@@ -91,7 +93,7 @@ struct AttnSmem {
 // forward
 // =====================================================================================================
 template <int NA>
-__global__ void __launch_bounds__(160, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnTcParams p) {
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t TILE = NA * AT_ATOM;
   const uint32_t base = smem_u32(smem_raw);
@@ -104,11 +106,11 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_tc_kernel(const __grid_consta
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
     mbar_init(bar_q, 1); mbar_init(bar_kv0, 1); mbar_init(bar_kv0 + 8, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_p, 32 * AT_ROW_WARPS); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
-  if (warp == 4) {
+  if (warp == AT_ROW_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tmem_slot) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_tc_kernel(const __grid_consta
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
   const uint32_t tS = tmem, tO = tmem + 128;
 
-  if (warp == 4) {
+  if (warp == AT_ROW_WARPS) {
     if (lane == 0) {
       const uint32_t idesc_o = make_idesc(128, p.n_o, false, true);
       mbar_expect_tx(bar_q, TILE);
@@ -149,38 +151,53 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_tc_kernel(const __grid_consta
       }
     }
   } else {
-    // ---- row threads: thread r owns query row q0 + r (TMEM lane r) ----
-    const int r = threadIdx.x, q = q0 + r;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    // ---- row threads: quarter = warp % 4 owns TMEM lanes / query rows [32q, 32q+32); the two warps of a quarter
+    //      (half 0 / 1) take alternating 32-column chunks and exchange row max / row sum through `xch` ----
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane, q = q0 + r;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    float* xch = reinterpret_cast<float*>(smem_raw + (bars + 64 - base));   // [128]
+    const bool quarter_live = q0 + quarter * 32 < p.N;      // warp-uniform: any real query row in this quarter?
     const bool masked = p.row_mask && q < p.N && p.row_mask[(long long)b * p.N + q] == 0.f;
     // masked query row: every score equal => p == 1 for every key (scale 0, max 0)
     const float sl2 = masked ? 0.f : p.scale * LOG2E;
-    float m_run = -INFINITY, l_run = 0.f;   // running max (scaled, log2 domain) and sum
+    float m_run = -INFINITY, l_run = 0.f;   // running max (scaled, log2 domain) and this warp's partial row sum
     for (int j = 0; j < nblk; ++j) {
-      const int nc = kv_cols(p.N, j);            // columns computed for this block (multiple of 16)
+      const int nc = kv_cols(p.N, j);              // columns computed for this block (multiple of 16)
       const int nvalid = min(128, p.N - j * 128);  // real keys in this block
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      // pass 1: raw row max over the real keys
+      if (!quarter_live) {                         // rows beyond the sequence: stay in lock-step, do nothing
+        if (j > 0) mbar_wait(bar_o, (j - 1) & 1);
+        mbar_arrive(bar_p);
+        continue;
+      }
+      // pass 1: raw row max over the real keys of this warp's chunks
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < nc; c += 32) {
-        uint32_t s[32];
-        tc_ld32(tS + lane_off + c, s);
+      for (int c = half * 32; c < nc; c += 64) {
+        uint32_t sreg[32];
+        tc_ld32(tS + lane_off + c, sreg);
         tc_wait_ld();
-        const int lim = min(32, nvalid - c);   // only real keys enter the max
+        const int lim = min(32, nvalid - c);
 #pragma unroll
         for (int t = 0; t < 32; ++t)
-          if (t < lim) mx = fmaxf(mx, __uint_as_float(s[t]));
+          if (t < lim) mx = fmaxf(mx, __uint_as_float(sreg[t]));
       }
+      // combine the two halves of the row: half 1 -> half 0 -> half 1
+      if (half == 1) xch[r] = mx;
+      named_bar_sync(1 + quarter, 64);
+      if (half == 0) { mx = fmaxf(mx, xch[r]); xch[r] = mx; }
+      named_bar_sync(1 + quarter, 64);
+      if (half == 1) mx = xch[r];
       const float m_new = masked ? 0.f : fmaxf(m_run, mx * sl2);
       const float alpha = ex2f(m_run - m_new);
       if (j > 0) { mbar_wait(bar_o, (j - 1) & 1); tc_fence_after(); }
       float rowsum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < nc; c += 32) {
-        uint32_t s[32];
-        tc_ld32(tS + lane_off + c, s);
+      for (int c = half * 32; c < nc; c += 64) {
+        uint32_t sreg[32];
+        tc_ld32(tS + lane_off + c, sreg);
         tc_wait_ld();
         const int ng = min(4, (nc - c) >> 3);
 #pragma unroll
@@ -188,7 +205,7 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_tc_kernel(const __grid_consta
           if (g < ng) {
             float v[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = ex2f(fmaf(__uint_as_float(s[g * 8 + t]), sl2, -m_new));
+            for (int t = 0; t < 8; ++t) v[t] = ex2f(fmaf(__uint_as_float(sreg[g * 8 + t]), sl2, -m_new));
             if (c + g * 8 + 8 > nvalid) {   // tail: keys beyond the sequence get p = 0
 #pragma unroll
               for (int t = 0; t < 8; ++t) if (c + g * 8 + t >= nvalid) v[t] = 0.f;
@@ -202,7 +219,7 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_tc_kernel(const __grid_consta
       l_run = l_run * alpha + rowsum;
       m_run = m_new;
       if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {
-        for (int c = 0; c < p.n_o / 16; ++c) {
+        for (int c = half; c < p.n_o / 16; c += 2) {   // the two halves rescale alternating 16-column chunks of O
           uint32_t o[16];
           tc_ld16(tO + lane_off + c * 16, o);
           tc_wait_ld();
@@ -218,19 +235,27 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_tc_kernel(const __grid_consta
     }
     mbar_wait(bar_o, (nblk - 1) & 1);
     tc_fence_after();
-    const float inv = 1.f / l_run;
-    __nv_bfloat16* orow = p.out + ((long long)b * p.N + q) * p.ld_out + h * p.hd;
-    for (int c = 0; c < p.n_o / 16; ++c) {
-      uint32_t o[16];
-      tc_ld16(tO + lane_off + c * 16, o);
-      tc_wait_ld();
-      if (q < p.N) store_row16(orow, c * 16, p.hd, o, inv);
+    if (quarter_live) {
+      // total row sum = sum of the two halves' partial sums (same rescaling history)
+      if (half == 1) xch[r] = l_run;
+      named_bar_sync(1 + quarter, 64);
+      if (half == 0) { l_run += xch[r]; xch[r] = l_run; }
+      named_bar_sync(1 + quarter, 64);
+      if (half == 1) l_run = xch[r];
+      const float inv = 1.f / l_run;
+      __nv_bfloat16* orow = p.out + ((long long)b * p.N + q) * p.ld_out + h * p.hd;
+      for (int c = half; c < p.n_o / 16; c += 2) {
+        uint32_t o[16];
+        tc_ld16(tO + lane_off + c * 16, o);
+        tc_wait_ld();
+        if (q < p.N) store_row16(orow, c * 16, p.hd, o, inv);
+      }
+      if (half == 0 && q < p.N && p.lse) p.lse[((long long)b * p.H + h) * p.N + q] = m_run * LN2 + logf(l_run);
     }
-    if (q < p.N && p.lse) p.lse[((long long)b * p.H + h) * p.N + q] = m_run * LN2 + logf(l_run);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == AT_ROW_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
   }
@@ -240,7 +265,7 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_tc_kernel(const __grid_consta
 // backward: dQ
 // =====================================================================================================
 template <int NA, int NBUF>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t TILE = NA * AT_ATOM;
@@ -254,11 +279,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
     mbar_init(bar_q, 1); mbar_init(bar_kv0, 1); mbar_init(bar_kv0 + 8, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_p, 32 * AT_ROW_WARPS); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
-  if (warp == 4) {
+  if (warp == AT_ROW_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -268,7 +293,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
   const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
 
-  if (warp == 4) {
+  if (warp == AT_ROW_WARPS) {
     if (lane == 0) {
       const uint32_t idesc_q = make_idesc(128, p.n_o, false, true);
       auto issue_kv = [&](int j) {
@@ -300,8 +325,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
       }
     }
   } else {
-    const int r = threadIdx.x, q = q0 + r;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane, q = q0 + r;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const bool quarter_live = q0 + quarter * 32 < p.N;
     const bool live = q < p.N && !(p.row_mask && p.row_mask[(long long)b * p.N + q] == 0.f);
     const float sl2 = p.scale * LOG2E;
     const long long si = ((long long)b * p.H + h) * p.N + q;
@@ -312,24 +339,27 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
       if (j > 0) { mbar_wait(bar_o, (j - 1) & 1); tc_fence_after(); }
-      // keys in [N, nc) have zero K rows: their dS values multiply zero rows in dQ += dS K, no masking needed
+      // keys in [N, nc) have zero K rows: their dS values multiply zero rows in dQ += dS K, no masking needed.
+      // Quarters without any real query row skip the math (their dS rows only feed dQ rows that are never stored).
+      if (quarter_live) {
 #pragma unroll 1
-      for (int c = 0; c < nc; c += 32) {
-        uint32_t s[32], d[32];
-        tc_ld32(tS + lane_off + c, s);
-        tc_ld32(tdP + lane_off + c, d);
-        tc_wait_ld();
-        const int ng = min(4, (nc - c) >> 3);
+        for (int c = half * 32; c < nc; c += 64) {
+          uint32_t sreg[32], d[32];
+          tc_ld32(tS + lane_off + c, sreg);
+          tc_ld32(tdP + lane_off + c, d);
+          tc_wait_ld();
+          const int ng = min(4, (nc - c) >> 3);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g < ng) {
-            float v[8];
+          for (int g = 0; g < 4; ++g) {
+            if (g < ng) {
+              float v[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const float pr = ex2f(fmaf(__uint_as_float(s[g * 8 + t]), sl2, -lse2));
-              v[t] = pr * (__uint_as_float(d[g * 8 + t]) - delta);
+              for (int t = 0; t < 8; ++t) {
+                const float pr = ex2f(fmaf(__uint_as_float(sreg[g * 8 + t]), sl2, -lse2));
+                v[t] = pr * (__uint_as_float(d[g * 8 + t]) - delta);
+              }
+              store_p_chunk(sdS, r, (c >> 3) + g, v);
             }
-            store_p_chunk(sdS, r, (c >> 3) + g, v);
           }
         }
       }
@@ -340,7 +370,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
     mbar_wait(bar_o, (nblk - 1) & 1);
     tc_fence_after();
     __nv_bfloat16* drow = p.dqkv + ((long long)b * p.N + q) * p.ld_dqkv + h * p.hd;
-    for (int c = 0; c < p.n_o / 16; ++c) {
+    for (int c = half; c < p.n_o / 16; c += 2) {
       uint32_t o[16];
       tc_ld16(tdQ + lane_off + c * 16, o);
       tc_wait_ld();
@@ -349,7 +379,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == AT_ROW_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
@@ -359,7 +389,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
 // backward: dK, dV
 // =====================================================================================================
 template <int NA, int NBUF>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t TILE = NA * AT_ATOM;
@@ -375,11 +405,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
     mbar_init(bar_kv, 1); mbar_init(bar_q0, 1); mbar_init(bar_q0 + 8, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_p, 32 * AT_ROW_WARPS); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
-  if (warp == 4) {
+  if (warp == AT_ROW_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -389,7 +419,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
   const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 384;
 
-  if (warp == 4) {
+  if (warp == AT_ROW_WARPS) {
     if (lane == 0) {
       const uint32_t idesc_g = make_idesc(128, p.n_o, false, true);
       auto issue_q = [&](int i) {
@@ -422,19 +452,21 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid
       }
     }
   } else {
-    const int r = threadIdx.x, kv = j0 + r;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane, kv = j0 + r;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * LOG2E;
     const float log2n = log2f((float)p.N);
     const bool kv_ok = kv < p.N;
+    const bool quarter_live = j0 + quarter * 32 < p.N;     // any real key row in this quarter?
     for (int i = 0; i < nq; ++i) {
       const int nc = kv_cols(p.N, i);
-      // per-query-column statistics of this block (thread t loads column t):
+      // per-query-column statistics of this block (half 0: thread r loads column r):
       //   live query   : {lse*log2e, delta, scale*log2e, 1}   p = 2^(s*scale2 - lse2), dS = p (dP - delta)
       //   masked query : {log2 N,    0,     0,           0}   p = 1/N,                 dS = 0
       //   out of range : {+inf,      0,     0,           0}   p = 0
-      named_bar_sync(1, 128);
-      {
+      named_bar_sync(1, 32 * AT_ROW_WARPS);
+      if (half == 0) {
         const int q = i * 128 + r;
         const long long si = ((long long)b * p.H + h) * p.N + q;
         float4 st = make_float4(INFINITY, 0.f, 0.f, 0.f);
@@ -444,30 +476,32 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid
         }
         s_col[r] = st;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 32 * AT_ROW_WARPS);
       mbar_wait(bar_s, i & 1);
       tc_fence_after();
       if (i > 0) { mbar_wait(bar_o, (i - 1) & 1); tc_fence_after(); }
+      if (quarter_live) {
 #pragma unroll 1
-      for (int c = 0; c < nc; c += 32) {
-        uint32_t s[32], d[32];
-        tc_ld32(tSt + lane_off + c, s);
-        tc_ld32(tdPt + lane_off + c, d);
-        tc_wait_ld();
-        const int ng = min(4, (nc - c) >> 3);
+        for (int c = half * 32; c < nc; c += 64) {
+          uint32_t sreg[32], d[32];
+          tc_ld32(tSt + lane_off + c, sreg);
+          tc_ld32(tdPt + lane_off + c, d);
+          tc_wait_ld();
+          const int ng = min(4, (nc - c) >> 3);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g < ng) {
-            float pv[8], dv[8];
+          for (int g = 0; g < 4; ++g) {
+            if (g < ng) {
+              float pv[8], dv[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const float4 st = s_col[c + g * 8 + t];
-              const float pr = ex2f(fmaf(__uint_as_float(s[g * 8 + t]), st.z, -st.x));
-              pv[t] = pr;
-              dv[t] = pr * st.w * (__uint_as_float(d[g * 8 + t]) - st.y);
+              for (int t = 0; t < 8; ++t) {
+                const float4 st = s_col[c + g * 8 + t];
+                const float pr = ex2f(fmaf(__uint_as_float(sreg[g * 8 + t]), st.z, -st.x));
+                pv[t] = pr;
+                dv[t] = pr * st.w * (__uint_as_float(d[g * 8 + t]) - st.y);
+              }
+              store_p_chunk(sPt, r, (c >> 3) + g, pv);
+              store_p_chunk(sdSt, r, (c >> 3) + g, dv);
             }
-            store_p_chunk(sPt, r, (c >> 3) + g, pv);
-            store_p_chunk(sdSt, r, (c >> 3) + g, dv);
           }
         }
       }
@@ -480,19 +514,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid
     const long long HD = (long long)p.H * p.hd;
     __nv_bfloat16* krow = p.dqkv + ((long long)b * p.N + kv) * p.ld_dqkv + HD + h * p.hd;
     __nv_bfloat16* vrow = krow + HD;
-    for (int c = 0; c < p.n_o / 16; ++c) {
+    for (int c = 0; c < p.n_o / 16; ++c) {   // half 0 stores dV, half 1 stores dK
       uint32_t o[16];
-      tc_ld16(tdV + lane_off + c * 16, o);
+      tc_ld16((half == 0 ? tdV : tdK) + lane_off + c * 16, o);
       tc_wait_ld();
-      if (kv_ok) store_row16(vrow, c * 16, p.hd, o, 1.f);
-      tc_ld16(tdK + lane_off + c * 16, o);
-      tc_wait_ld();
-      if (kv_ok) store_row16(krow, c * 16, p.hd, o, p.scale);
+      if (kv_ok) store_row16(half == 0 ? vrow : krow, c * 16, p.hd, o, half == 0 ? 1.f : p.scale);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == AT_ROW_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
@@ -597,13 +628,13 @@ int attention_fwd_tc(const bfk_attention_args* a, cudaStream_t s) {
   AttnTcParams p = make_params(a);
   dim3 grid((a->N + 127) / 128, a->H, a->B);
   if (a->hd <= 64) {
-    const size_t smem = 5 * AT_ATOM + 2 * AT_ATOM + 256;
+    const size_t smem = 5 * AT_ATOM + 2 * AT_ATOM + 576;   // 2 CTAs/SM: (233472 - 2*1024)/2 = 115712 >= 115264
     if (int rc = set_attr(attn_fwd_tc_kernel<1>, smem, "attn_fwd_tc")) return rc;
-    attn_fwd_tc_kernel<1><<<grid, 160, smem, s>>>(mq, p);
+    attn_fwd_tc_kernel<1><<<grid, AT_THREADS, smem, s>>>(mq, p);
   } else {
-    const size_t smem = 5 * 2 * AT_ATOM + 2 * AT_ATOM + 256;
+    const size_t smem = 5 * 2 * AT_ATOM + 2 * AT_ATOM + 576;
     if (int rc = set_attr(attn_fwd_tc_kernel<2>, smem, "attn_fwd_tc")) return rc;
-    attn_fwd_tc_kernel<2><<<grid, 160, smem, s>>>(mq, p);
+    attn_fwd_tc_kernel<2><<<grid, AT_THREADS, smem, s>>>(mq, p);
   }
   BFK_CHECK_LAUNCH("attention_fwd_tc");
   return BFK_OK;
@@ -622,14 +653,14 @@ int attention_bwd_tc(const bfk_attention_args* a, cudaStream_t s) {
     const size_t smem_q = 6 * AT_ATOM + 2 * AT_ATOM + 256, smem_kv = 6 * AT_ATOM + 4 * AT_ATOM + 4096;
     if (int rc = set_attr(attn_bwd_dq_tc_kernel<1, 2>, smem_q, "attn_bwd_dq_tc")) return rc;
     if (int rc = set_attr(attn_bwd_dkv_tc_kernel<1, 2>, smem_kv, "attn_bwd_dkv_tc")) return rc;
-    attn_bwd_dq_tc_kernel<1, 2><<<grid, 160, smem_q, s>>>(mq, md, p);
-    attn_bwd_dkv_tc_kernel<1, 2><<<grid, 160, smem_kv, s>>>(mq, md, p);
+    attn_bwd_dq_tc_kernel<1, 2><<<grid, AT_THREADS, smem_q, s>>>(mq, md, p);
+    attn_bwd_dkv_tc_kernel<1, 2><<<grid, AT_THREADS, smem_kv, s>>>(mq, md, p);
   } else {
     const size_t smem_q = 4 * 2 * AT_ATOM + 2 * AT_ATOM + 256, smem_kv = 4 * 2 * AT_ATOM + 4 * AT_ATOM + 4096;
     if (int rc = set_attr(attn_bwd_dq_tc_kernel<2, 1>, smem_q, "attn_bwd_dq_tc")) return rc;
     if (int rc = set_attr(attn_bwd_dkv_tc_kernel<2, 1>, smem_kv, "attn_bwd_dkv_tc")) return rc;
-    attn_bwd_dq_tc_kernel<2, 1><<<grid, 160, smem_q, s>>>(mq, md, p);
-    attn_bwd_dkv_tc_kernel<2, 1><<<grid, 160, smem_kv, s>>>(mq, md, p);
+    attn_bwd_dq_tc_kernel<2, 1><<<grid, AT_THREADS, smem_q, s>>>(mq, md, p);
+    attn_bwd_dkv_tc_kernel<2, 1><<<grid, AT_THREADS, smem_kv, s>>>(mq, md, p);
   }
   BFK_CHECK_LAUNCH("attention_bwd_tc");
   return BFK_OK;
