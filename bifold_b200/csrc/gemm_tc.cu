@@ -228,7 +228,7 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& ep, int m, int nc)
     prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc);
 }
 
-template <int BN, bool AMN, bool BMN>
+template <int BN, bool AMN, bool BMN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
                EpiParams ep, int splits, long long split_stride) {
@@ -247,7 +247,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + TC_BM - 1) / TC_BM, num_n = (N + BN - 1) / BN;
-  const int tiles = num_m * num_n * splits;          // work items: (output tile, K split)
+  // CL = 2: the two CTAs of a cluster work in lock-step on vertically adjacent output tiles (same n-block) and
+  // share the B operand: each loads one half of the B tile and multicasts it to both (halves the B traffic from L2).
+  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+  const int num_mp = (num_m + CL - 1) / CL;
+  const int tiles = num_mp * num_n * splits;         // work items per cluster: (row-pair, n-block, K split)
   const int num_kb_all = (K + TC_BK - 1) / TC_BK;
   const int kb_per = (num_kb_all + splits - 1) / splits;
   auto kb_range = [&](int item, int& kb0, int& kb1) {
@@ -259,7 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -270,6 +275,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -277,9 +283,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0;
-      for (int item = blockIdx.x; item < tiles; item += gridDim.x) {
+      for (int item = cid; item < tiles; item += ncl) {
         const int tile = item / splits;
-        const int m0 = (tile / num_n) * TC_BM, n0 = (tile % num_n) * BN;
+        const int m0 = ((tile / num_n) * CL + crank) * TC_BM, n0 = (tile % num_n) * BN;
         int kb0, kb1;
         kb_range(item, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -293,11 +299,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < TC_BM / 64; ++i) tma_load_2d(sa + i * 8192, &tma_a, full_bar(stage), m0 + 64 * i, k0);
           }
-          if constexpr (!BMN) {
-            tma_load_2d(sb, &tma_b, full_bar(stage), k0, n0);
-          } else {
+          if constexpr (CL == 1) {
+            if constexpr (!BMN) {
+              tma_load_2d(sb, &tma_b, full_bar(stage), k0, n0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &tma_b, full_bar(stage), n0 + 64 * i, k0);
+              for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &tma_b, full_bar(stage), n0 + 64 * i, k0);
+            }
+          } else {   // this CTA's half of B, multicast to both CTAs of the cluster
+            if constexpr (!BMN) {
+              tma_load_2d_mc(sb + crank * (Cfg::B_BYTES / 2), &tma_b, full_bar(stage), k0, n0 + crank * (BN / 2), (uint16_t)0x3);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i) {
+                const int bi = crank * (BN / 128) + i;
+                tma_load_2d_mc(sb + bi * 8192, &tma_b, full_bar(stage), n0 + 64 * bi, k0, (uint16_t)0x3);
+              }
+            }
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -309,7 +327,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       constexpr uint32_t idesc = make_idesc(TC_BM, BN, AMN, BMN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < tiles; item += gridDim.x) {
+      for (int item = cid; item < tiles; item += ncl) {
         int kb0, kb1;
         kb_range(item, kb0, kb1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -322,7 +340,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
             tc_mma_bf16(tmem_d, operand_desc<AMN>(sa, k), operand_desc<BMN>(sb, k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          tc_commit(empty_bar(stage));
+          if constexpr (CL == 1) tc_commit(empty_bar(stage));
+          else tc_commit_mc(empty_bar(stage), (uint16_t)0x3);   // the slot is free in BOTH CTAs' eyes only when both consumed it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
         tc_commit(tfull_bar(acc));
@@ -335,9 +354,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;   // 0..255
     int acc = 0; uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < tiles; item += gridDim.x) {
+    for (int item = cid; item < tiles; item += ncl) {
       const int tile = item / splits;
-      const int m0 = (tile / num_n) * TC_BM, n0 = (tile % num_n) * BN;
+      const int m0 = ((tile / num_n) * CL + crank) * TC_BM, n0 = (tile % num_n) * BN;
       EpiParams epl = ep;
       if (splits > 1) epl.D = reinterpret_cast<float*>(ep.D) + (long long)(item % splits) * split_stride;   // fp32 partial
       float* bias_s = bias_smem + acc * BN;
@@ -345,9 +364,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int i = et; i < BN; i += 32 * TC_EPI_WARPS) bias_s[i] = (n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
       }
       named_bar_sync(1, 32 * TC_EPI_WARPS);   // bias visible; also orders reuse of the other buffer
-      if (ep.vec_ok && item + (int)gridDim.x < tiles) {   // warm L2 with what the NEXT item's epilogue will read
-        const int ntile = (item + (int)gridDim.x) / splits;
-        const int nm = (ntile / num_n) * TC_BM + quarter * 32 + lane, nn0 = (ntile % num_n) * BN;
+      if (ep.vec_ok && item + ncl < tiles) {   // warm L2 with what the NEXT item's epilogue will read
+        const int ntile = (item + ncl) / splits;
+        const int nm = ((ntile / num_n) * CL + crank) * TC_BM + quarter * 32 + lane, nn0 = (ntile % num_n) * BN;
         for (int c = half; c < BN / 32; c += 2) epi_prefetch(ep, nm, nn0 + c * 32);
       }
       const int m = m0 + quarter * 32 + lane;
@@ -372,6 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) cluster_sync_all();   // nobody exits while the peer may still multicast into / signal this CTA
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
@@ -478,34 +498,49 @@ static int choose_splits(const bfk_gemm_args* a, int BN) {
   return std::max(1, splits);
 }
 
-template <int BN, bool AMN, bool BMN>
-static int launch_tc(const bfk_gemm_args* a, cudaStream_t s) {
+static bool cluster_enabled() {
+  static int v = -1;
+  // Off by default: measured on B200 (profiles/r01_gemm_cluster_multicast.txt) the cluster-of-2 B multicast is
+  // correct but not faster -- L2 already de-duplicates neighbouring unicast requests at this cluster size.
+  if (v < 0) { const char* e = getenv("BFK_GEMM_CLUSTER"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+template <int BN, bool AMN, bool BMN, int CL>
+static int launch_tc_cl(const bfk_gemm_args* a, cudaStream_t s, int splits) {
   using Cfg = TcCfg<BN>;
   CUtensorMap ma, mb;
   bool ok;
   if (!AMN) ok = make_map(&ma, a->A, a->K, a->M, a->lda, TC_BK, TC_BM);
   else      ok = make_map(&ma, a->A, a->M, a->K, a->lda, 64, TC_BK);
   if (!ok) return BFK_E_CUDA;
-  if (!BMN) ok = make_map(&mb, a->B, a->K, a->N, a->ldb, TC_BK, BN);
+  if (!BMN) ok = make_map(&mb, a->B, a->K, a->N, a->ldb, TC_BK, BN / CL);
   else      ok = make_map(&mb, a->B, a->N, a->K, a->ldb, 64, TC_BK);
   if (!ok) return BFK_E_CUDA;
   EpiParams ep;
   epi_from_args(a, ep);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AMN, BMN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("gemm_tc: cannot set smem %d: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return BFK_E_CUDA; }
     attr_set = true;
   }
-  const int splits = choose_splits(a, BN);
   const long long split_stride = (long long)a->M * a->N;
   if (splits > 1) {   // partial tiles go to the workspace as plain fp32 [splits][M][N]
     ep.D = a->workspace; ep.ldd = a->N; ep.out_dtype = BFK_F32; ep.alpha = 1.f; ep.accumulate = 0;
     ep.vec_ok = ((reinterpret_cast<uintptr_t>(a->workspace) & 31u) == 0 && (a->N % 8) == 0 && (split_stride % 8) == 0) ? 1 : 0;
   }
-  const int tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + BN - 1) / BN) * splits;
-  const int grid = std::min(tiles, sm_count());
-  gemm_tc_kernel<BN, AMN, BMN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, a->M, a->N, a->K, ep, splits, split_stride);
+  const int num_m = (a->M + TC_BM - 1) / TC_BM, num_n = (a->N + BN - 1) / BN;
+  const int items = ((num_m + CL - 1) / CL) * num_n * splits;
+  const int grid = CL * std::min(items, sm_count() / CL);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AMN, BMN, CL>, ma, mb, a->M, a->N, a->K, ep, splits, split_stride);
+  if (le != cudaSuccess) { set_error("gemm_tc: launch failed: %s", cudaGetErrorString(le)); return BFK_E_CUDA; }
   if (splits > 1) {
     const long long total = (long long)a->M * a->N;
     const int rg = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
@@ -514,6 +549,16 @@ static int launch_tc(const bfk_gemm_args* a, cudaStream_t s) {
   }
   BFK_CHECK_LAUNCH("gemm_tc");
   return BFK_OK;
+}
+
+template <int BN, bool AMN, bool BMN>
+static int launch_tc(const bfk_gemm_args* a, cudaStream_t s) {
+  const int splits = choose_splits(a, BN);
+  const int num_m = (a->M + TC_BM - 1) / TC_BM, num_n = (a->N + BN - 1) / BN;
+  // cluster-of-2 B multicast pays off when every SM has work anyway; tiny problems keep single CTAs
+  if (cluster_enabled() && splits == 1 && num_m >= 2 && num_m * num_n >= sm_count() / 2)
+    return launch_tc_cl<BN, AMN, BMN, 2>(a, s, splits);
+  return launch_tc_cl<BN, AMN, BMN, 1>(a, s, splits);
 }
 
 int gemm_tc(const bfk_gemm_args* a, cudaStream_t s) {
