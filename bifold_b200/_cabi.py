@@ -89,7 +89,7 @@ class HeatmapBwdArgs(C.Structure):
     _fields_ = [("B", i32), ("heads", i32), ("g", i32), ("mode", i32),
                 ("heat", vp), ("target", vp), ("target_mask", vp), ("mask_heads", u32),
                 ("gscale", vp), ("gscale_mul", f32), ("gscale_has_total", i32),
-                ("dheat", vp), ("tap_start", vp), ("tap_w", vp), ("dgrid", vp)]
+                ("dheat", vp), ("tap_start", vp), ("tap_w", vp), ("dgrid", vp), ("partials", vp)]
 
 
 class ActionArgs(C.Structure):
@@ -135,6 +135,7 @@ _PROTOS = {
     "bfk_upsample16_taps": (i32, [i32, vp, vp]),
     "bfk_heatmap_bands": (i32, [i32]),
     "bfk_heatmap_fwd": (i32, [C.POINTER(HeatmapFwdArgs), vp]),
+    "bfk_heatmap_bwd_workspace_floats": (C.c_size_t, [i32, i32, i32]),
     "bfk_heatmap_bwd": (i32, [C.POINTER(HeatmapBwdArgs), vp]),
     "bfk_bce_prob": (i32, [vp, vp, vp, i64, vp, vp, vp]),
     "bfk_bce_prob_bwd": (i32, [vp, vp, vp, i64, vp, vp, vp]),

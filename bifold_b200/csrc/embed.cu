@@ -385,12 +385,12 @@ __global__ void assemble_bwd_type_stage1(bfk_assemble_bwd_args a, float* __restr
   const long long total = (long long)a.B * rn;
   const long long per = (total + AS_SPLIT - 1) / AS_SPLIT;
   const long long t0 = per * blockIdx.z, t1 = min(total, t0 + per);
-  float s = 0.f;
-  for (long long t = t0; t < t1; ++t) {
-    int b = (int)(t / rn), r = rlo + (int)(t % rn);
-    s += a.dX[((long long)b * Nf + r) * a.D + d];
-  }
-  partials[((long long)type * AS_SPLIT + blockIdx.z) * a.D + d] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // independent chains: several loads in flight
+  auto at = [&](long long t) { int b = (int)(t / rn), r = rlo + (int)(t % rn); return a.dX[((long long)b * Nf + r) * a.D + d]; };
+  long long t = t0;
+  for (; t + 4 <= t1; t += 4) { s0 += at(t); s1 += at(t + 1); s2 += at(t + 2); s3 += at(t + 3); }
+  for (; t < t1; ++t) s0 += at(t);
+  partials[((long long)type * AS_SPLIT + blockIdx.z) * a.D + d] = (s0 + s1) + (s2 + s3);
 }
 __global__ void assemble_bwd_type_stage2(const float* __restrict__ partials, int D, float* __restrict__ d_type_emb) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;

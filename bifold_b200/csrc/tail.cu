@@ -20,6 +20,15 @@ __device__ __forceinline__ unsigned long long pack_key(float v, uint32_t idx) {
   return ((unsigned long long)f2ord(v) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
 }
 
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {   // read-once data: do not keep it in L1
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream4(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // ---- collapsed decoder ---------------------------------------------------------------------------
 // out[c] = sum_r v[r] * W[r*C + c]   (thread per column)
 __device__ void vecmat(const float* __restrict__ v_s, const float* __restrict__ W, int R, int C, float* __restrict__ out_s) {
@@ -135,32 +144,35 @@ __global__ void __launch_bounds__(1024) collapse_bwd_kernel(bfk_decoder_collapse
 }
 
 // ---- head projection -------------------------------------------------------------------------------
-// warp per token; w_eff staged in smem.  grid: ceil(B*Np/8)
+constexpr int HP_TOK_PER_WARP = 4;
+// warp per token (HP_TOK_PER_WARP tokens in sequence); w_eff staged in smem.  grid: ceil(B*Np/(8*HP_TOK_PER_WARP))
 __global__ void __launch_bounds__(256) head_project_fwd_kernel(bfk_head_project_args a) {
-  extern __shared__ float w_s[];  // [heads][D]
+  extern __shared__ __align__(16) float w_s[];  // [heads][D]
   for (int i = threadIdx.x; i < a.heads * a.D; i += blockDim.x) w_s[i] = a.w_eff[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long tok = (long long)blockIdx.x * 8 + warp;
-  if (tok >= (long long)a.B * a.Np) return;
-  const int b = (int)(tok / a.Np), n = (int)(tok % a.Np);
-  const float4* x4 = reinterpret_cast<const float4*>(a.X + (long long)b * a.x_batch_stride + (long long)(a.row0 + n) * a.D);
-  float acc[8] = {};
-  for (int c = lane; c < a.D / 4; c += 32) {
-    float4 x = x4[c];
+  for (int it = 0; it < HP_TOK_PER_WARP; ++it) {   // the staged w_eff is reused for several tokens
+    const long long tok = ((long long)blockIdx.x * HP_TOK_PER_WARP + it) * 8 + warp;
+    if (tok >= (long long)a.B * a.Np) return;
+    const int b = (int)(tok / a.Np), n = (int)(tok % a.Np);
+    const float* xr = a.X + (long long)b * a.x_batch_stride + (long long)(a.row0 + n) * a.D;
+    float acc[8] = {};
+    for (int c = lane; c < a.D / 4; c += 32) {
+      const float4 x = ldg_stream4(xr + 4 * c);
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        if (h < a.heads) {
+          const float4 w = *reinterpret_cast<const float4*>(w_s + h * a.D + c * 4);
+          acc[h] += x.x * w.x + x.y * w.y + x.z * w.z + x.w * w.w;
+        }
+      }
+    }
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
       if (h < a.heads) {
-        const float* w = w_s + h * a.D + c * 4;
-        acc[h] += x.x * w[0] + x.y * w[1] + x.z * w[2] + x.w * w[3];
+        float s = warp_sum(acc[h]);
+        if (lane == 0) a.grid[((long long)b * a.heads + h) * a.Np + n] = s + a.b_eff[h];
       }
-    }
-  }
-#pragma unroll
-  for (int h = 0; h < 8; ++h) {
-    if (h < a.heads) {
-      float s = warp_sum(acc[h]);
-      if (lane == 0) a.grid[((long long)b * a.heads + h) * a.Np + n] = s + a.b_eff[h];
     }
   }
 }
@@ -248,27 +260,33 @@ __global__ void __launch_bounds__(256) head_project_bwd_db_kernel(bfk_head_proje
 constexpr int HM_ROWS = 32;  // output rows per CTA
 constexpr int HM_THREADS = 256;
 constexpr int HM_MAXIN = HM_ROWS / 16 + 4;  // input rows feeding a band
+constexpr int HM_BATCH = 8;  // float4 items per thread whose loads are issued together
 
-// grid: (bands, heads, B).  smem: grid g*g + tmp HM_MAXIN*W floats
+
+// grid: (bands, heads, B).  smem: taps (start + 3 weights per output index), grid g*g, tmp HM_MAXIN*W floats
 __global__ void __launch_bounds__(HM_THREADS) heatmap_fwd_kernel(bfk_heatmap_fwd_args a) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   __shared__ float red_f[HM_THREADS / 32];
   __shared__ unsigned long long red_k[HM_THREADS / 32];
   const int g = a.g, W = 16 * g, H = W;
   const int band = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int y0 = band * HM_ROWS, y1 = min(H, y0 + HM_ROWS);
-  float* grid_s = sm;               // [g][g]
-  float* tmp_s = sm + ((g * g + 3) & ~3);  // [HM_MAXIN][W], 16-byte aligned
+  float* tmp_s = sm;                                   // [HM_MAXIN][W], 16-byte aligned
+  float* tapw_s = tmp_s + HM_MAXIN * W;                // [W][3]
+  int* taps_s = reinterpret_cast<int*>(tapw_s + 3 * W);   // [W]
+  float* grid_s = reinterpret_cast<float*>(taps_s + W);   // [g][g]
   const float* gsrc = a.grid + ((long long)b * a.heads + h) * g * g;
   for (int i = threadIdx.x; i < g * g; i += HM_THREADS) grid_s[i] = gsrc[i];
-  const int i_lo = a.tap_start[y0];
-  const int i_hi = min(g, a.tap_start[y1 - 1] + 3);  // exclusive
+  for (int i = threadIdx.x; i < W; i += HM_THREADS) taps_s[i] = a.tap_start[i];
+  for (int i = threadIdx.x; i < 3 * W; i += HM_THREADS) tapw_s[i] = a.tap_w[i];
   __syncthreads();
+  const int i_lo = taps_s[y0];
+  const int i_hi = min(g, taps_s[y1 - 1] + 3);  // exclusive
   // horizontal pass for the needed input rows
   for (int t = threadIdx.x; t < (i_hi - i_lo) * W; t += HM_THREADS) {
     int ii = t / W, x = t % W;
-    int js = a.tap_start[x];
-    const float* w = a.tap_w + 3 * x;
+    int js = taps_s[x];
+    const float* w = tapw_s + 3 * x;
     const float* row = grid_s + (i_lo + ii) * g;
     float v = w[0] * row[js];
     if (js + 1 < g) v = fmaf(w[1], row[js + 1], v);
@@ -284,41 +302,61 @@ __global__ void __launch_bounds__(HM_THREADS) heatmap_fwd_kernel(bfk_heatmap_fwd
   float best = -INFINITY;
   uint32_t best_idx = 0xFFFFFFFFu;
   const int W4 = W / 4;
-  for (int t = threadIdx.x; t < (y1 - y0) * W4; t += HM_THREADS) {
-    const int y = y0 + t / W4, x = (t % W4) * 4;
-    const int is = a.tap_start[y] - i_lo;
-    const float* wy = a.tap_w + 3 * y;
-    float4 r0 = *reinterpret_cast<const float4*>(tmp_s + is * W + x);
-    float4 z = make_float4(wy[0] * r0.x, wy[0] * r0.y, wy[0] * r0.z, wy[0] * r0.w);
-    if (is + 1 < i_hi - i_lo) {
-      float4 r1 = *reinterpret_cast<const float4*>(tmp_s + (is + 1) * W + x);
-      z.x = fmaf(wy[1], r1.x, z.x); z.y = fmaf(wy[1], r1.y, z.y); z.z = fmaf(wy[1], r1.z, z.z); z.w = fmaf(wy[1], r1.w, z.w);
-    }
-    if (is + 2 < i_hi - i_lo) {
-      float4 r2 = *reinterpret_cast<const float4*>(tmp_s + (is + 2) * W + x);
-      z.x = fmaf(wy[2], r2.x, z.x); z.y = fmaf(wy[2], r2.y, z.y); z.z = fmaf(wy[2], r2.z, z.z); z.w = fmaf(wy[2], r2.w, z.w);
-    }
-    float4 p = make_float4(1.f / (1.f + expf(-z.x)), 1.f / (1.f + expf(-z.y)), 1.f / (1.f + expf(-z.z)), 1.f / (1.f + expf(-z.w)));
-    const long long off = (long long)y * W + x;
-    *reinterpret_cast<float4*>(heat + off) = p;
+  const int n_items = (y1 - y0) * W4;
+  for (int t0 = threadIdx.x; t0 < n_items; t0 += HM_THREADS * HM_BATCH) {
+    // issue every target load of the batch before any of them is consumed
+    float4 tv[HM_BATCH];
     if (has_t) {
-      float4 tv = __ldg(reinterpret_cast<const float4*>(tgt + off));
-      if (tmask) {
-        float4 mv = __ldg(reinterpret_cast<const float4*>(tmask + off));
-        tv.x *= mv.x; tv.y *= mv.y; tv.z *= mv.z; tv.w *= mv.w;
+#pragma unroll
+      for (int k = 0; k < HM_BATCH; ++k) {
+        const int t = t0 + k * HM_THREADS;
+        if (t < n_items) {
+          const long long off = (long long)(y0 + t / W4) * W + (t % W4) * 4;
+          tv[k] = ldg_stream4(tgt + off);
+          if (tmask) {
+            const float4 mv = ldg_stream4(tmask + off);
+            tv[k].x *= mv.x; tv[k].y *= mv.y; tv[k].z *= mv.z; tv[k].w *= mv.w;
+          }
+        }
       }
-      // nn.BCELoss: -(t*max(log p,-100) + (1-t)*max(log1p(-p),-100))
-      loss -= tv.x * fmaxf(logf(p.x), -100.f) + (1.f - tv.x) * fmaxf(log1pf(-p.x), -100.f);
-      loss -= tv.y * fmaxf(logf(p.y), -100.f) + (1.f - tv.y) * fmaxf(log1pf(-p.y), -100.f);
-      loss -= tv.z * fmaxf(logf(p.z), -100.f) + (1.f - tv.z) * fmaxf(log1pf(-p.z), -100.f);
-      loss -= tv.w * fmaxf(logf(p.w), -100.f) + (1.f - tv.w) * fmaxf(log1pf(-p.w), -100.f);
     }
-    if (a.argmax_key) {
-      const uint32_t idx = (uint32_t)off;
-      if (p.x > best) { best = p.x; best_idx = idx; }
-      if (p.y > best) { best = p.y; best_idx = idx + 1; }
-      if (p.z > best) { best = p.z; best_idx = idx + 2; }
-      if (p.w > best) { best = p.w; best_idx = idx + 3; }
+#pragma unroll
+    for (int k = 0; k < HM_BATCH; ++k) {
+      const int t = t0 + k * HM_THREADS;
+      if (t >= n_items) break;
+      const int y = y0 + t / W4, x = (t % W4) * 4;
+      const int is = taps_s[y] - i_lo;
+      const float* wy = tapw_s + 3 * y;
+      float4 r0 = *reinterpret_cast<const float4*>(tmp_s + is * W + x);
+      float4 z = make_float4(wy[0] * r0.x, wy[0] * r0.y, wy[0] * r0.z, wy[0] * r0.w);
+      if (is + 1 < i_hi - i_lo) {
+        float4 r1 = *reinterpret_cast<const float4*>(tmp_s + (is + 1) * W + x);
+        z.x = fmaf(wy[1], r1.x, z.x); z.y = fmaf(wy[1], r1.y, z.y); z.z = fmaf(wy[1], r1.z, z.z); z.w = fmaf(wy[1], r1.w, z.w);
+      }
+      if (is + 2 < i_hi - i_lo) {
+        float4 r2 = *reinterpret_cast<const float4*>(tmp_s + (is + 2) * W + x);
+        z.x = fmaf(wy[2], r2.x, z.x); z.y = fmaf(wy[2], r2.y, z.y); z.z = fmaf(wy[2], r2.z, z.z); z.w = fmaf(wy[2], r2.w, z.w);
+      }
+      // sigmoid with ex2/rcp (rel. error ~3e-7); the BCE below is evaluated from this rounded p, like torch does
+      float4 p = make_float4(__fdividef(1.f, 1.f + __expf(-z.x)), __fdividef(1.f, 1.f + __expf(-z.y)),
+                             __fdividef(1.f, 1.f + __expf(-z.z)), __fdividef(1.f, 1.f + __expf(-z.w)));
+      const long long off = (long long)y * W + x;
+      stg_stream4(heat + off, p);
+      if (has_t) {
+        // 1 - p is exact near p = 1 (Sterbenz) and rounds to 1 for tiny p (|error| <= 6e-8): __logf(1 - p) is
+        // log1p(-p) to ~1e-7 absolute; log(0) = -inf hits the -100 clamp exactly like torch
+        loss -= tv[k].x * fmaxf(__logf(p.x), -100.f) + (1.f - tv[k].x) * fmaxf(__logf(1.f - p.x), -100.f);
+        loss -= tv[k].y * fmaxf(__logf(p.y), -100.f) + (1.f - tv[k].y) * fmaxf(__logf(1.f - p.y), -100.f);
+        loss -= tv[k].z * fmaxf(__logf(p.z), -100.f) + (1.f - tv[k].z) * fmaxf(__logf(1.f - p.z), -100.f);
+        loss -= tv[k].w * fmaxf(__logf(p.w), -100.f) + (1.f - tv[k].w) * fmaxf(__logf(1.f - p.w), -100.f);
+      }
+      if (a.argmax_key) {
+        const uint32_t idx = (uint32_t)off;
+        if (p.x > best) { best = p.x; best_idx = idx; }
+        if (p.y > best) { best = p.y; best_idx = idx + 1; }
+        if (p.z > best) { best = p.z; best_idx = idx + 2; }
+        if (p.w > best) { best = p.w; best_idx = idx + 3; }
+      }
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -375,22 +413,20 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restr
 }
 
 // ---- heatmap backward: dlogit -> dgrid through the transposed composite upsample -----------------------
-// grid: (heads, B); smem: Ct[g][W] + tmp2[H][g]
-__global__ void __launch_bounds__(256) heatmap_bwd_kernel(bfk_heatmap_bwd_args a) {
-  extern __shared__ float sm[];
-  const int g = a.g, W = 16 * g, H = W;
-  const int h = blockIdx.x, b = blockIdx.y;
-  float* Ct = sm;              // [g][W]   Ct[j][x] = weight of input j on output x
-  float* tmp2 = sm + g * W;    // [H][g]
-  for (int i = threadIdx.x; i < g * W; i += blockDim.x) Ct[i] = 0.f;
-  __syncthreads();
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    int js = a.tap_start[x];
-#pragma unroll
-    for (int t = 0; t < 3; ++t)
-      if (js + t < g) Ct[(js + t) * W + x] = a.tap_w[3 * x + t];
-  }
-  __syncthreads();
+// Stage 1, grid (bands, heads, B): a CTA streams HM_ROWS rows of (heat, target | dheat) once (float4, coalesced),
+// folds them vertically into the <= HM_MAXIN grid rows they touch (registers), then horizontally into grid
+// columns (shared memory) and writes one partial [HM_MAXIN][g] block.  Stage 2 sums the bands of a map in
+// fixed order (deterministic).  HBM-bound: reads heads*H*W*4 B (x2 with targets) per sample.
+constexpr int HB_THREADS = 256;
+__global__ void __launch_bounds__(HB_THREADS) heatmap_bwd_stage1(bfk_heatmap_bwd_args a, float* __restrict__ partials) {
+  extern __shared__ __align__(16) float sm[];
+  const int g = a.g, W = 16 * g, H = W, W4 = W / 4;
+  const int band = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int y0 = band * HM_ROWS, y1 = min(H, y0 + HM_ROWS);
+  const int i_lo = a.tap_start[y0];
+  const int groups = HB_THREADS / W4;                 // row groups working in parallel (>= 2 for W <= 448)
+  const int grp = threadIdx.x / W4, x4 = threadIdx.x % W4;
+  float* tmp = sm;                                     // [groups][HM_MAXIN][W]
   const float* heat = a.heat + ((long long)h * a.B + b) * H * W;
   const float* tgt = nullptr; const float* tmask = nullptr; const float* dheat = nullptr;
   float gs = 0.f;
@@ -401,47 +437,96 @@ __global__ void __launch_bounds__(256) heatmap_bwd_kernel(bfk_heatmap_bwd_args a
   } else {
     dheat = a.dheat[h] ? a.dheat[h] + (long long)b * H * W : nullptr;
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  constexpr int MAXX = 14;  // W <= 448
-  for (int y = warp; y < H; y += nw) {
-    float d[MAXX];
+  float4 acc[HM_MAXIN];
 #pragma unroll
-    for (int k = 0; k < MAXX; ++k) {
-      int x = lane + 32 * k;
-      float v = 0.f;
-      if (x < W) {
-        float p = heat[(long long)y * W + x];
-        if (a.mode == 0) {
-          float t = tgt[(long long)y * W + x];
-          if (tmask) t *= tmask[(long long)y * W + x];
-          v = gs * (p - t);
-        } else if (dheat) {
-          v = dheat[(long long)y * W + x] * p * (1.f - p);
+  for (int ii = 0; ii < HM_MAXIN; ++ii) acc[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (grp < groups) {
+    constexpr int RB = 4;   // rows whose loads are issued together
+    for (int yb = y0 + grp; yb < y1; yb += groups * RB) {
+      float4 pv[RB], qv[RB];
+#pragma unroll
+      for (int k = 0; k < RB; ++k) {
+        const int y = yb + k * groups;
+        if (y < y1) {
+          const long long off = (long long)y * W + x4 * 4;
+          pv[k] = ldg_stream4(heat + off);
+          if (a.mode == 0) {
+            qv[k] = ldg_stream4(tgt + off);
+            if (tmask) {
+              const float4 m = ldg_stream4(tmask + off);
+              qv[k].x *= m.x; qv[k].y *= m.y; qv[k].z *= m.z; qv[k].w *= m.w;
+            }
+          } else if (dheat) {
+            qv[k] = ldg_stream4(dheat + off);
+          }
         }
       }
-      d[k] = v;
-    }
-    for (int j = 0; j < g; ++j) {
-      float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < MAXX; ++k) {
-        int x = lane + 32 * k;
-        if (x < W) s = fmaf(Ct[j * W + x], d[k], s);
+      for (int k = 0; k < RB; ++k) {
+      const int y = yb + k * groups;
+      if (y >= y1) break;
+      const float4 p = pv[k];
+      float4 d;
+      if (a.mode == 0) {
+        const float4 t = qv[k];
+        d = make_float4(gs * (p.x - t.x), gs * (p.y - t.y), gs * (p.z - t.z), gs * (p.w - t.w));
+      } else if (dheat) {
+        const float4 u = qv[k];
+        d = make_float4(u.x * p.x * (1.f - p.x), u.y * p.y * (1.f - p.y), u.z * p.z * (1.f - p.z), u.w * p.w * (1.f - p.w));
+      } else {
+        d = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      s = warp_sum(s);
-      if (lane == 0) tmp2[y * g + j] = s;
+      const int is = a.tap_start[y] - i_lo;              // warp-uniform
+      const float w0 = a.tap_w[3 * y], w1 = a.tap_w[3 * y + 1], w2 = a.tap_w[3 * y + 2];
+#pragma unroll
+      for (int ii = 0; ii < HM_MAXIN; ++ii) {
+        const float c = ii == is ? w0 : (ii == is + 1 ? w1 : (ii == is + 2 ? w2 : 0.f));
+        acc[ii].x = fmaf(c, d.x, acc[ii].x); acc[ii].y = fmaf(c, d.y, acc[ii].y);
+        acc[ii].z = fmaf(c, d.z, acc[ii].z); acc[ii].w = fmaf(c, d.w, acc[ii].w);
+      }
+      }
     }
+#pragma unroll
+    for (int ii = 0; ii < HM_MAXIN; ++ii)
+      *reinterpret_cast<float4*>(tmp + ((long long)(grp * HM_MAXIN + ii)) * W + x4 * 4) = acc[ii];
   }
   __syncthreads();
+  // combine the row groups (fixed order) into group 0
+  for (int t = threadIdx.x; t < HM_MAXIN * W; t += HB_THREADS) {
+    float v = tmp[t];
+    for (int gq = 1; gq < groups; ++gq) v += tmp[(long long)gq * HM_MAXIN * W + t];
+    tmp[t] = v;
+  }
+  __syncthreads();
+  // horizontal fold: out[ii][j] = sum_x Cx[x][j] * tmp[ii][x];  x in the support of j
+  float* out = partials + ((((long long)b * a.heads + h) * gridDim.x + band) * HM_MAXIN) * g;
+  for (int t = threadIdx.x; t < HM_MAXIN * g; t += HB_THREADS) {
+    const int ii = t / g, j = t % g;
+    const int xlo = max(0, 16 * j - 32), xhi = min(W, 16 * j + 48);
+    float sacc = 0.f;
+    for (int x = xlo; x < xhi; ++x) {
+      const int k = j - a.tap_start[x];
+      if (k >= 0 && k < 3) sacc = fmaf(a.tap_w[3 * x + k], tmp[ii * W + x], sacc);
+    }
+    out[t] = sacc;
+  }
+}
+// grid (heads, B): dgrid[b,h,i,j] = sum over bands of the partial rows that map to grid row i
+__global__ void heatmap_bwd_stage2(bfk_heatmap_bwd_args a, const float* __restrict__ partials, int bands) {
+  const int g = a.g, H = 16 * g;
+  const int h = blockIdx.x, b = blockIdx.y;
   float* out = a.dgrid + ((long long)b * a.heads + h) * g * g;
   for (int t = threadIdx.x; t < g * g; t += blockDim.x) {
-    int i = t / g, j = t % g;
+    const int i = t / g, j = t % g;
     float s = 0.f;
-    // rows y whose taps include input row i: Ct is symmetric in role (same 1-D operator)
-    int ylo = max(0, 16 * i - 32), yhi = min(H, 16 * i + 48);
-    for (int y = ylo; y < yhi; ++y) s = fmaf(Ct[i * W + y], tmp2[y * g + j], s);
+    for (int band = 0; band < bands; ++band) {
+      const int i_lo = a.tap_start[band * HM_ROWS];
+      const int ii = i - i_lo;
+      if (ii >= 0 && ii < HM_MAXIN) s += partials[((((long long)b * a.heads + h) * bands + band) * HM_MAXIN + ii) * g + j];
+    }
     out[t] = s;
   }
+  (void)H;
 }
 
 // ---- standalone BCE on probabilities ---------------------------------------------------------------------
@@ -598,7 +683,7 @@ extern "C" int32_t bfk_head_project_fwd(const bfk_head_project_args* a, bfk_stre
   size_t smem = (size_t)a->heads * a->D * sizeof(float);
   if (int rc = opt_in_smem(head_project_fwd_kernel, smem, "head_project_fwd")) return rc;
   long long toks = (long long)a->B * a->Np;
-  head_project_fwd_kernel<<<(unsigned)((toks + 7) / 8), 256, smem, to_stream(s_)>>>(*a);
+  head_project_fwd_kernel<<<(unsigned)((toks + 8 * HP_TOK_PER_WARP - 1) / (8 * HP_TOK_PER_WARP)), 256, smem, to_stream(s_)>>>(*a);
   BFK_CHECK_LAUNCH("bfk_head_project_fwd");
   return BFK_OK;
 }
@@ -659,9 +744,7 @@ extern "C" int32_t bfk_heatmap_fwd(const bfk_heatmap_fwd_args* a, bfk_stream_t s
   cudaStream_t s = to_stream(s_);
   const int W = 16 * a->g, bands = bfk_heatmap_bands(a->g);
   if (a->argmax_key) cudaMemsetAsync(a->argmax_key, 0, sizeof(unsigned long long) * a->heads * a->B, s);
-  size_t smem = ((size_t)a->g * a->g + (size_t)HM_MAXIN * W) * sizeof(float);
-  // keep tmp_s 16-byte aligned: g*g floats may not be a multiple of 4
-  smem += 16;
+  size_t smem = ((size_t)HM_MAXIN * W + 3 * (size_t)W + (size_t)W + (size_t)a->g * a->g) * sizeof(float);
   if (int rc = opt_in_smem(heatmap_fwd_kernel, smem, "heatmap_fwd")) return rc;
   bfk_heatmap_fwd_args k = *a;
   heatmap_fwd_kernel<<<dim3(bands, a->heads, a->B), HM_THREADS, smem, s>>>(k);
@@ -673,13 +756,21 @@ extern "C" int32_t bfk_heatmap_fwd(const bfk_heatmap_fwd_args* a, bfk_stream_t s
   return BFK_OK;
 }
 
+extern "C" size_t bfk_heatmap_bwd_workspace_floats(int32_t B, int32_t heads, int32_t g) {
+  return (size_t)B * heads * bfk_heatmap_bands(g) * HM_MAXIN * g;
+}
+
 extern "C" int32_t bfk_heatmap_bwd(const bfk_heatmap_bwd_args* a, bfk_stream_t s_) {
-  BFK_CHECK_ARG(a && a->heat && a->tap_start && a->tap_w && a->dgrid && a->g > 0 && 16 * a->g <= 448, "bfk_heatmap_bwd: bad arguments (W <= 448)");
+  BFK_CHECK_ARG(a && a->heat && a->tap_start && a->tap_w && a->dgrid && a->partials && a->g > 0 && 16 * a->g <= 448,
+                "bfk_heatmap_bwd: bad arguments (W <= 448, partials required)");
   BFK_CHECK_ARG(a->mode == 0 ? (a->target && a->gscale) : (a->dheat != nullptr), "bfk_heatmap_bwd: mode inputs missing");
-  const int W = 16 * a->g;
-  size_t smem = ((size_t)a->g * W + (size_t)W * a->g) * sizeof(float);
-  if (int rc = opt_in_smem(heatmap_bwd_kernel, smem, "heatmap_bwd")) return rc;
-  heatmap_bwd_kernel<<<dim3(a->heads, a->B), 256, smem, to_stream(s_)>>>(*a);
+  const int W = 16 * a->g, bands = bfk_heatmap_bands(a->g);
+  const int groups = HB_THREADS / (W / 4);
+  size_t smem = (size_t)groups * HM_MAXIN * W * sizeof(float);
+  if (int rc = opt_in_smem(heatmap_bwd_stage1, smem, "heatmap_bwd")) return rc;
+  cudaStream_t s = to_stream(s_);
+  heatmap_bwd_stage1<<<dim3(bands, a->heads, a->B), HB_THREADS, smem, s>>>(*a, a->partials);
+  heatmap_bwd_stage2<<<dim3(a->heads, a->B), 256, 0, s>>>(*a, a->partials, bands);
   BFK_CHECK_LAUNCH("bfk_heatmap_bwd");
   return BFK_OK;
 }

@@ -590,11 +590,12 @@ class Engine:
 
         # ---- tail backward: dlogit -> dgrid -> (dX, d w_eff) -> decoder weights ----
         dgrid = torch.empty(B, heads, Np, device=dev, dtype=torch.float32)
+        hws = torch.empty(lib.bfk_heatmap_bwd_workspace_floats(B, heads, g), device=dev, dtype=torch.float32)
         first = True
         if dloss is not None:
             gscale = dloss.contiguous()     # [heads + 1]: per-head grads then the grad of their sum
             ba = K.HeatmapBwdArgs(B, heads, g, 0, tail["heat"].data_ptr(), tail["tptr"].data_ptr(), None, 0, gscale.data_ptr(),
-                                  1.0 / float(B * H * H), 1, None, ts.data_ptr(), tw.data_ptr(), dgrid.data_ptr())
+                                  1.0 / float(B * H * H), 1, None, ts.data_ptr(), tw.data_ptr(), dgrid.data_ptr(), hws.data_ptr())
             K.check(lib.bfk_heatmap_bwd(C.byref(ba), st), "bfk_heatmap_bwd")
             first = False
         if dheat is not None:
@@ -602,7 +603,7 @@ class Engine:
             dptr = self._ptr_table([dheat[h].data_ptr() for h in range(heads)])
             tgt = dgrid if first else torch.empty_like(dgrid)
             ba = K.HeatmapBwdArgs(B, heads, g, 1, tail["heat"].data_ptr(), None, None, 0, None, 1.0, 0, dptr.data_ptr(),
-                                  ts.data_ptr(), tw.data_ptr(), tgt.data_ptr())
+                                  ts.data_ptr(), tw.data_ptr(), tgt.data_ptr(), hws.data_ptr())
             K.check(lib.bfk_heatmap_bwd(C.byref(ba), st), "bfk_heatmap_bwd")
             if not first:
                 dgrid.add_(tgt)   # both a fused-loss and a heatmap gradient (rare): tiny [B,heads,Np] add

@@ -265,7 +265,9 @@ typedef struct {
   const float* const* dheat;         /* DEVICE array [heads] of (B,H,W) pointers (mode 1); NULL entry = zero */
   const int32_t* tap_start; const float* tap_w;
   float* dgrid;                      /* [B, heads, g*g] */
+  float* partials;                   /* bfk_heatmap_bwd_workspace_floats(B, heads, g) floats */
 } bfk_heatmap_bwd_args;
+BFK_API size_t bfk_heatmap_bwd_workspace_floats(int32_t B, int32_t heads, int32_t g);
 BFK_API int32_t bfk_heatmap_bwd(const bfk_heatmap_bwd_args* a, bfk_stream_t s);
 
 /* Standalone nn.BCELoss on probabilities (used when the caller only has heatmaps):
