@@ -260,10 +260,10 @@ __global__ void __launch_bounds__(256) head_project_bwd_db_kernel(bfk_head_proje
 constexpr int HM_ROWS = 32;  // output rows per CTA
 constexpr int HM_THREADS = 256;
 constexpr int HM_MAXIN = HM_ROWS / 16 + 4;  // input rows feeding a band
-constexpr int HM_BATCH = 8;  // float4 items per thread whose loads are issued together
 
 
 // grid: (bands, heads, B).  smem: taps (start + 3 weights per output index), grid g*g, tmp HM_MAXIN*W floats
+template <bool STREAM>
 __global__ void __launch_bounds__(HM_THREADS) heatmap_fwd_kernel(bfk_heatmap_fwd_args a) {
   extern __shared__ __align__(16) float sm[];
   __shared__ float red_f[HM_THREADS / 32];
@@ -276,14 +276,14 @@ __global__ void __launch_bounds__(HM_THREADS) heatmap_fwd_kernel(bfk_heatmap_fwd
   int* taps_s = reinterpret_cast<int*>(tapw_s + 3 * W);   // [W]
   float* grid_s = reinterpret_cast<float*>(taps_s + W);   // [g][g]
   const float* gsrc = a.grid + ((long long)b * a.heads + h) * g * g;
-  for (int i = threadIdx.x; i < g * g; i += HM_THREADS) grid_s[i] = gsrc[i];
-  for (int i = threadIdx.x; i < W; i += HM_THREADS) taps_s[i] = a.tap_start[i];
-  for (int i = threadIdx.x; i < 3 * W; i += HM_THREADS) tapw_s[i] = a.tap_w[i];
+  for (int i = threadIdx.x; i < g * g; i += blockDim.x) grid_s[i] = gsrc[i];
+  for (int i = threadIdx.x; i < W; i += blockDim.x) taps_s[i] = a.tap_start[i];
+  for (int i = threadIdx.x; i < 3 * W; i += blockDim.x) tapw_s[i] = a.tap_w[i];
   __syncthreads();
   const int i_lo = taps_s[y0];
   const int i_hi = min(g, taps_s[y1 - 1] + 3);  // exclusive
   // horizontal pass for the needed input rows
-  for (int t = threadIdx.x; t < (i_hi - i_lo) * W; t += HM_THREADS) {
+  for (int t = threadIdx.x; t < (i_hi - i_lo) * W; t += blockDim.x) {
     int ii = t / W, x = t % W;
     int js = taps_s[x];
     const float* w = tapw_s + 3 * x;
@@ -301,54 +301,47 @@ __global__ void __launch_bounds__(HM_THREADS) heatmap_fwd_kernel(bfk_heatmap_fwd
   float loss = 0.f;
   float best = -INFINITY;
   uint32_t best_idx = 0xFFFFFFFFu;
+  // thread -> fixed float4 column, rows y0+grp, y0+grp+groups, ... (no integer division in the loop)
   const int W4 = W / 4;
-  const int n_items = (y1 - y0) * W4;
-  for (int t0 = threadIdx.x; t0 < n_items; t0 += HM_THREADS * HM_BATCH) {
-    // issue every target load of the batch before any of them is consumed
-    float4 tv[HM_BATCH];
-    if (has_t) {
-#pragma unroll
-      for (int k = 0; k < HM_BATCH; ++k) {
-        const int t = t0 + k * HM_THREADS;
-        if (t < n_items) {
-          const long long off = (long long)(y0 + t / W4) * W + (t % W4) * 4;
-          tv[k] = ldg_stream4(tgt + off);
-          if (tmask) {
-            const float4 mv = ldg_stream4(tmask + off);
-            tv[k].x *= mv.x; tv[k].y *= mv.y; tv[k].z *= mv.z; tv[k].w *= mv.w;
-          }
+  const int groups = HM_THREADS / W4;
+  const int grp = threadIdx.x / W4, x = (threadIdx.x % W4) * 4;
+  const int nin = i_hi - i_lo;
+  if (grp < groups) {
+    for (int y = y0 + grp; y < y1; y += groups) {
+      const long long off = (long long)y * W + x;
+      float4 tv;
+      if (has_t) {
+        tv = STREAM ? ldg_stream4(tgt + off) : __ldg(reinterpret_cast<const float4*>(tgt + off));
+        if (tmask) {
+          const float4 mv = __ldg(reinterpret_cast<const float4*>(tmask + off));
+          tv.x *= mv.x; tv.y *= mv.y; tv.z *= mv.z; tv.w *= mv.w;
         }
       }
-    }
-#pragma unroll
-    for (int k = 0; k < HM_BATCH; ++k) {
-      const int t = t0 + k * HM_THREADS;
-      if (t >= n_items) break;
-      const int y = y0 + t / W4, x = (t % W4) * 4;
       const int is = taps_s[y] - i_lo;
       const float* wy = tapw_s + 3 * y;
       float4 r0 = *reinterpret_cast<const float4*>(tmp_s + is * W + x);
       float4 z = make_float4(wy[0] * r0.x, wy[0] * r0.y, wy[0] * r0.z, wy[0] * r0.w);
-      if (is + 1 < i_hi - i_lo) {
+      if (is + 1 < nin) {
         float4 r1 = *reinterpret_cast<const float4*>(tmp_s + (is + 1) * W + x);
         z.x = fmaf(wy[1], r1.x, z.x); z.y = fmaf(wy[1], r1.y, z.y); z.z = fmaf(wy[1], r1.z, z.z); z.w = fmaf(wy[1], r1.w, z.w);
       }
-      if (is + 2 < i_hi - i_lo) {
+      if (is + 2 < nin) {
         float4 r2 = *reinterpret_cast<const float4*>(tmp_s + (is + 2) * W + x);
         z.x = fmaf(wy[2], r2.x, z.x); z.y = fmaf(wy[2], r2.y, z.y); z.z = fmaf(wy[2], r2.z, z.z); z.w = fmaf(wy[2], r2.w, z.w);
       }
       // sigmoid with ex2/rcp (rel. error ~3e-7); the BCE below is evaluated from this rounded p, like torch does
       float4 p = make_float4(__fdividef(1.f, 1.f + __expf(-z.x)), __fdividef(1.f, 1.f + __expf(-z.y)),
                              __fdividef(1.f, 1.f + __expf(-z.z)), __fdividef(1.f, 1.f + __expf(-z.w)));
-      const long long off = (long long)y * W + x;
-      stg_stream4(heat + off, p);
+      if (STREAM) stg_stream4(heat + off, p); else *reinterpret_cast<float4*>(heat + off) = p;
       if (has_t) {
-        // 1 - p is exact near p = 1 (Sterbenz) and rounds to 1 for tiny p (|error| <= 6e-8): __logf(1 - p) is
-        // log1p(-p) to ~1e-7 absolute; log(0) = -inf hits the -100 clamp exactly like torch
-        loss -= tv[k].x * fmaxf(__logf(p.x), -100.f) + (1.f - tv[k].x) * fmaxf(__logf(1.f - p.x), -100.f);
-        loss -= tv[k].y * fmaxf(__logf(p.y), -100.f) + (1.f - tv[k].y) * fmaxf(__logf(1.f - p.y), -100.f);
-        loss -= tv[k].z * fmaxf(__logf(p.z), -100.f) + (1.f - tv[k].z) * fmaxf(__logf(1.f - p.z), -100.f);
-        loss -= tv[k].w * fmaxf(__logf(p.w), -100.f) + (1.f - tv[k].w) * fmaxf(__logf(1.f - p.w), -100.f);
+        // log2 domain (one MUFU each); ln2 and the -100 clamp are applied as -100/ln2 here and *ln2 at the end.
+        // 1 - p is exact near p = 1 (Sterbenz) and rounds to 1 for tiny p (|error| <= 6e-8); log(0) = -inf hits the
+        // clamp exactly like torch's max(log, -100)
+        const float cl = -144.26950408889634f;   // -100 / ln 2
+        loss -= tv.x * fmaxf(__log2f(p.x), cl) + (1.f - tv.x) * fmaxf(__log2f(1.f - p.x), cl);
+        loss -= tv.y * fmaxf(__log2f(p.y), cl) + (1.f - tv.y) * fmaxf(__log2f(1.f - p.y), cl);
+        loss -= tv.z * fmaxf(__log2f(p.z), cl) + (1.f - tv.z) * fmaxf(__log2f(1.f - p.z), cl);
+        loss -= tv.w * fmaxf(__log2f(p.w), cl) + (1.f - tv.w) * fmaxf(__log2f(1.f - p.w), cl);
       }
       if (a.argmax_key) {
         const uint32_t idx = (uint32_t)off;
@@ -359,6 +352,7 @@ __global__ void __launch_bounds__(HM_THREADS) heatmap_fwd_kernel(bfk_heatmap_fwd
       }
     }
   }
+  loss *= 0.6931471805599453f;   // back to natural log
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (has_t) {
     loss = warp_sum(loss);
@@ -377,12 +371,12 @@ __global__ void __launch_bounds__(HM_THREADS) heatmap_fwd_kernel(bfk_heatmap_fwd
   if (threadIdx.x == 0) {
     if (has_t) {
       float s = 0.f;
-      for (int w = 0; w < HM_THREADS / 32; ++w) s += red_f[w];
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red_f[w];
       a.partials[((long long)h * a.B + b) * gridDim.x + band] = s;
     }
     if (a.argmax_key) {
       unsigned long long k = 0ull;
-      for (int w = 0; w < HM_THREADS / 32; ++w) k = red_k[w] > k ? red_k[w] : k;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) k = red_k[w] > k ? red_k[w] : k;
       atomicMax(a.argmax_key + (long long)h * a.B + b, k);
     }
   }
@@ -441,7 +435,7 @@ __global__ void __launch_bounds__(HB_THREADS) heatmap_bwd_stage1(bfk_heatmap_bwd
 #pragma unroll
   for (int ii = 0; ii < HM_MAXIN; ++ii) acc[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (grp < groups) {
-    constexpr int RB = 4;   // rows whose loads are issued together
+    constexpr int RB = 2;   // rows whose loads are issued together
     for (int yb = y0 + grp; yb < y1; yb += groups * RB) {
       float4 pv[RB], qv[RB];
 #pragma unroll
@@ -476,14 +470,22 @@ __global__ void __launch_bounds__(HB_THREADS) heatmap_bwd_stage1(bfk_heatmap_bwd
       } else {
         d = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const int is = a.tap_start[y] - i_lo;              // warp-uniform
+      const int is = a.tap_start[y] - i_lo;              // uniform across the CTA for a given y: no divergence
       const float w0 = a.tap_w[3 * y], w1 = a.tap_w[3 * y + 1], w2 = a.tap_w[3 * y + 2];
-#pragma unroll
-      for (int ii = 0; ii < HM_MAXIN; ++ii) {
-        const float c = ii == is ? w0 : (ii == is + 1 ? w1 : (ii == is + 2 ? w2 : 0.f));
-        acc[ii].x = fmaf(c, d.x, acc[ii].x); acc[ii].y = fmaf(c, d.y, acc[ii].y);
-        acc[ii].z = fmaf(c, d.z, acc[ii].z); acc[ii].w = fmaf(c, d.w, acc[ii].w);
+#define BFK_ACC3(I)                                                                                              \
+      acc[I].x = fmaf(w0, d.x, acc[I].x); acc[I].y = fmaf(w0, d.y, acc[I].y);                                    \
+      acc[I].z = fmaf(w0, d.z, acc[I].z); acc[I].w = fmaf(w0, d.w, acc[I].w);                                    \
+      acc[I + 1].x = fmaf(w1, d.x, acc[I + 1].x); acc[I + 1].y = fmaf(w1, d.y, acc[I + 1].y);                    \
+      acc[I + 1].z = fmaf(w1, d.z, acc[I + 1].z); acc[I + 1].w = fmaf(w1, d.w, acc[I + 1].w);                    \
+      acc[I + 2].x = fmaf(w2, d.x, acc[I + 2].x); acc[I + 2].y = fmaf(w2, d.y, acc[I + 2].y);                    \
+      acc[I + 2].z = fmaf(w2, d.z, acc[I + 2].z); acc[I + 2].w = fmaf(w2, d.w, acc[I + 2].w);
+      switch (is) {   // taps beyond the grid carry weight 0 and land in accumulator rows that stage 2 never reads
+        case 0: BFK_ACC3(0) break;
+        case 1: BFK_ACC3(1) break;
+        case 2: BFK_ACC3(2) break;
+        default: BFK_ACC3(3) break;
       }
+#undef BFK_ACC3
       }
     }
 #pragma unroll
@@ -745,9 +747,13 @@ extern "C" int32_t bfk_heatmap_fwd(const bfk_heatmap_fwd_args* a, bfk_stream_t s
   const int W = 16 * a->g, bands = bfk_heatmap_bands(a->g);
   if (a->argmax_key) cudaMemsetAsync(a->argmax_key, 0, sizeof(unsigned long long) * a->heads * a->B, s);
   size_t smem = ((size_t)HM_MAXIN * W + 3 * (size_t)W + (size_t)W + (size_t)a->g * a->g) * sizeof(float);
-  if (int rc = opt_in_smem(heatmap_fwd_kernel, smem, "heatmap_fwd")) return rc;
   bfk_heatmap_fwd_args k = *a;
-  heatmap_fwd_kernel<<<dim3(bands, a->heads, a->B), HM_THREADS, smem, s>>>(k);
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("BFK_HM_VARIANT"); variant = e ? atoi(e) : 0; }
+  dim3 grid(bands, a->heads, a->B);
+  const int threads = ((HM_THREADS / (W / 4)) * (W / 4) + 31) / 32 * 32;   // whole rows of float4 columns (+ idle lanes to a full warp)
+  if (variant == 1) heatmap_fwd_kernel<true><<<grid, threads, smem, s>>>(k);    // streaming (L1 no-allocate) accesses
+  else heatmap_fwd_kernel<false><<<grid, threads, smem, s>>>(k);
   if (a->target) {
     float inv = 1.f / ((float)a->B * (float)W * (float)W);
     loss_finalize_kernel<<<1, 256, 0, s>>>(a->partials, a->heads, a->B * bands, inv, a->loss, 1);
