@@ -297,6 +297,9 @@ def main():
         else:
             step(dev_sample, False)      # the instrumented step contains the DDP collectives: every rank must run it
             torch.cuda.synchronize()
+    tail = None
+    if rank == 0 and not args.no_roofline:
+        tail = tail_roofline(B, args.image_size // 16, dev)
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu_baseline = cpu_baseline_leg(args)
@@ -312,7 +315,7 @@ def main():
                 "model_flops_per_sample": tr_flops if train else fw_flops,
                 "model_tflops_per_gpu": (tr_flops if train else fw_flops) * B / (per_step / 1e3) / 1e12,
                 "model_frac_of_bf16_peak": (tr_flops if train else fw_flops) * B / (per_step / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
-                "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "roofline": roofline, "roofline_tail": tail, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -360,6 +363,43 @@ def gemm_roofline(eng, step_fn):
     return {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::f16, TMA-fed, TMEM accumulators)", "achieved": ach,
             "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "launches": len(recs),
             "gemm_ms_per_step": ms, "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"}
+
+
+def tail_roofline(B, g, dev):
+    """HBM roofline of the fused heatmap tail kernel (x16 upsample + sigmoid + BCE + argmax) at the bench batch:
+    algorithmic bytes = heads*B*H*W*4 written + as much target read (+ the tiny grid), CUDA events, L2 flushed."""
+    import ctypes as C
+    import torch
+    from bifold_b200 import _cabi as K
+    lib = K.load()
+    heads, H = 4, 16 * g
+    grid = torch.randn(B, heads, g * g, device=dev)
+    ts_h = torch.empty(H, dtype=torch.int32); tw_h = torch.empty(H, 3)
+    K.check(lib.bfk_upsample16_taps(g, ts_h.data_ptr(), tw_h.data_ptr()))
+    ts, tw = ts_h.to(dev), tw_h.to(dev)
+    heat = torch.empty(heads, B, H, H, device=dev)
+    targets = [torch.rand(B, H, H, device=dev) for _ in range(heads)]
+    tptr = torch.tensor([t.data_ptr() for t in targets], dtype=torch.int64).to(dev)
+    loss = torch.empty(heads + 1, device=dev); key = torch.empty(heads * B, device=dev, dtype=torch.int64)
+    part = torch.empty(heads * B * lib.bfk_heatmap_bands(g), device=dev)
+    fa = K.HeatmapFwdArgs(B, heads, g, grid.data_ptr(), ts.data_ptr(), tw.data_ptr(), heat.data_ptr(), tptr.data_ptr(), None, 0,
+                          loss.data_ptr(), key.data_ptr(), part.data_ptr())
+    flush = torch.empty(192 * 1024 * 1024, device=dev, dtype=torch.uint8)
+    st = torch.cuda.current_stream().cuda_stream
+    ts_ms = []
+    for it in range(8):
+        flush.sum()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); K.check(lib.bfk_heatmap_fwd(C.byref(fa), st)); e1.record(); torch.cuda.synchronize()
+        if it >= 3:
+            ts_ms.append(e0.elapsed_time(e1))
+    ms = sorted(ts_ms)[len(ts_ms) // 2]
+    by = heads * B * H * H * 4 * 2 + grid.numel() * 4
+    peaks = load_peaks()
+    ach = by / ms / 1e6
+    return {"bound": "hbm", "kernel": "heatmap_fwd_kernel (x16 upsample + sigmoid + BCE + argmax)", "achieved": ach,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "bytes_per_launch": by,
+            "us_per_launch": ms * 1e3, "peak_source": peaks["source"], "note": "see profiles/r01_tail_roofline.txt for B=512 and the other tail kernels"}
 
 
 def cpu_baseline_leg(args):
