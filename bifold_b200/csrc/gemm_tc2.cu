@@ -1,0 +1,236 @@
+// tcgen05 GEMM, CTA-pair variant (cta_group::2): a cluster of two CTAs computes one 256 x 256 output tile.
+//
+//   * CTA r of the pair owns rows [128 r, 128 r + 128) of the tile (its TMEM holds them, all 256 columns) and
+//     stages only HALF of the B tile (128 of the 256 n-rows): 32 KB per 64-wide K block instead of 48 KB, i.e.
+//     1.5x the arithmetic intensity per byte pulled from L2 and 6 pipeline stages instead of 4.
+//   * both CTAs issue their own TMA loads (cta_group::2 form, completing on the LEADER's mbarrier);
+//     only the leader (cluster rank 0) issues tcgen05.mma.cta_group::2 (UMMA 256 x 256 x 16);
+//     tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs;
+//     both CTAs' epilogue warps release the accumulator on the leader's barrier (remote arrive).
+//   * same fused epilogue as gemm_tc.cu (tc_epilogue.cuh).
+// Opt-in from gemm_tc.cu (BFK_GEMM_2CTA).
+#include "tc_epilogue.cuh"
+
+namespace bfk {
+
+bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer);
+
+constexpr int T2_STAGES = 6;
+constexpr int T2_A_BYTES = 128 * 64 * 2, T2_B_BYTES = 128 * 64 * 2;
+constexpr int T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
+constexpr int T2_BN = 256;
+constexpr int T2_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 256 + 2 * T2_BN * 4;
+
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+// the data lands in THIS CTA's smem, the transaction bytes complete on the barrier at `cluster_bar` (the leader's)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
+template <bool AMN, bool BMN>
+__global__ void __launch_bounds__(T2_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K, EpiParams ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + T2_STAGES * T2_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (T2_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * T2_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * T2_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * T2_STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* bias_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));   // [2][256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int num_mp = (M + 255) / 256, num_n = (N + T2_BN - 1) / T2_BN;
+  const int items = num_mp * num_n;
+  const int num_kb = (K + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own 128 rows of A, own 128 n-rows of B =====
+      int stage = 0; uint32_t phase = 0;
+      for (int item = cid; item < items; item += ncl) {
+        const int m0 = (item / num_n) * 256 + crank * 128, nb0 = (item % num_n) * T2_BN + crank * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t lead_full = map_to_cta(full_bar(stage), 0);
+          mbar_expect_tx_cluster(lead_full, T2_STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * T2_STAGE_BYTES, sb = sa + T2_A_BYTES;
+          const int k0 = kb * 64;
+          if constexpr (!AMN) {
+            tma_load_2d_2sm(sa, &tma_a, lead_full, k0, m0);
+          } else {
+            tma_load_2d_2sm(sa, &tma_a, lead_full, m0, k0);
+            tma_load_2d_2sm(sa + 8192, &tma_a, lead_full, m0 + 64, k0);
+          }
+          if constexpr (!BMN) {
+            tma_load_2d_2sm(sb, &tma_b, lead_full, k0, nb0);
+          } else {
+            tma_load_2d_2sm(sb, &tma_b, lead_full, nb0, k0);
+            tma_load_2d_2sm(sb + 8192, &tma_b, lead_full, nb0 + 64, k0);
+          }
+          if (++stage == T2_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0) {
+      // ===== MMA issuer (leader CTA only): UMMA 256 x 256 x 16 over both CTAs' smem / TMEM =====
+      constexpr uint32_t idesc = make_idesc(256, T2_BN, AMN, BMN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = cid; item < items; item += ncl) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * T2_BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * T2_STAGE_BYTES, sb = sa + T2_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16_2sm(tmem_d, operand_desc<AMN>(sa, k), operand_desc<BMN>(sb, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit_2sm_mc(empty_bar(stage), (uint16_t)0x3);
+          if (++stage == T2_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_2sm_mc(tfull_bar(acc), (uint16_t)0x3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): own 128 rows x 256 columns =====
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = cid; item < items; item += ncl) {
+      const int m0 = (item / num_n) * 256 + crank * 128, n0 = (item % num_n) * T2_BN;
+      float* bias_s = bias_smem + acc * T2_BN;
+      if (ep.bias) {
+        for (int i = et; i < T2_BN; i += 32 * TC_EPI_WARPS) bias_s[i] = (n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
+      }
+      named_bar_sync(1, 32 * TC_EPI_WARPS);
+      if (ep.vec_ok && item + ncl < items) {
+        const int nit = item + ncl;
+        const int nm = (nit / num_n) * 256 + crank * 128 + quarter * 32 + lane, nn0 = (nit % num_n) * T2_BN;
+        for (int c = half; c < T2_BN / 32; c += 2) epi_prefetch(ep, nm, nn0 + c * 32);
+      }
+      const int m = m0 + quarter * 32 + lane;
+      EpiOperands cur, nxt;
+      if (n0 + half * 32 < N) epi_load(ep, m, n0 + half * 32, cur);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * T2_BN);
+#pragma unroll 1
+      for (int c = half; c < T2_BN / 32; c += 2) {
+        if (n0 + c * 32 >= N) break;
+        if (c + 2 < T2_BN / 32 && n0 + (c + 2) * 32 < N) epi_load(ep, m, n0 + (c + 2) * 32, nxt);
+        epi_chunk32(ep, m, n0 + c * 32, taddr + (uint32_t)(c * 32), bias_s + c * 32, cur);
+        cur = nxt;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(acc), 0));   // the leader's MMA thread waits for both CTAs
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+template <bool AMN, bool BMN>
+static int launch_tc2(const bfk_gemm_args* a, cudaStream_t s) {
+  CUtensorMap ma, mb;
+  bool ok;
+  if (!AMN) ok = make_map(&ma, a->A, a->K, a->M, a->lda, 64, 128);
+  else      ok = make_map(&ma, a->A, a->M, a->K, a->lda, 64, 64);
+  if (!ok) return BFK_E_CUDA;
+  if (!BMN) ok = make_map(&mb, a->B, a->K, a->N, a->ldb, 64, 128);
+  else      ok = make_map(&mb, a->B, a->N, a->K, a->ldb, 64, 64);
+  if (!ok) return BFK_E_CUDA;
+  EpiParams ep;
+  epi_from_args(a, ep);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("gemm_tc2: cannot set smem %d: %s", T2_SMEM_BYTES, cudaGetErrorString(e)); return BFK_E_CUDA; }
+    attr_set = true;
+  }
+  const int items = ((a->M + 255) / 256) * ((a->N + T2_BN - 1) / T2_BN);
+  const int grid = 2 * std::min(items, sm_count() / 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T2_THREADS); cfg.dynamicSmemBytes = T2_SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<AMN, BMN>, ma, mb, a->M, a->N, a->K, ep);
+  if (le != cudaSuccess) { set_error("gemm_tc2: launch failed: %s", cudaGetErrorString(le)); return BFK_E_CUDA; }
+  BFK_CHECK_LAUNCH("gemm_tc2");
+  return BFK_OK;
+}
+
+int gemm_tc2(const bfk_gemm_args* a, cudaStream_t s) {
+  const bool ta = a->trans_a != 0, tb = a->trans_b != 0;
+  if (!ta && !tb) return launch_tc2<false, false>(a, s);
+  if (!ta && tb) return launch_tc2<false, true>(a, s);
+  if (ta && tb) return launch_tc2<true, true>(a, s);
+  return launch_tc2<true, false>(a, s);
+}
+
+}  // namespace bfk

@@ -1,0 +1,211 @@
+// Epilogue of the tcgen05 GEMM kernels (gemm_tc.cu, gemm_tc2.cu): TMEM -> registers -> fused bias / GELU / dGELU /
+// residual -> global, 32 columns of one row at a time, global operands software-pipelined one chunk ahead.
+#pragma once
+#include "epilogue.cuh"
+#include "tc_common.cuh"
+
+namespace bfk {
+
+constexpr int TC_EPI_WARPS = 8;   // two warps per TMEM lane quarter, alternating 32-column chunks
+
+// ---- fast epilogue math for bf16 outputs (the fp32 parity mode uses the exact functions of epilogue.cuh) ----
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k = 0.7978845608028654f, c = 0.044715f;
+  return 0.5f * x * (1.f + tanh_fast(k * (x + c * x * x * x)));
+}
+__device__ __forceinline__ float dgelu_tanh_fast(float x) {
+  const float k = 0.7978845608028654f, c = 0.044715f;
+  const float t = tanh_fast(k * (x + c * x * x * x));
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k * (1.f + 3.f * c * x * x);
+}
+
+// erf by Abramowitz-Stegun 7.1.26 (|err| < 2e-7 + fast-exp error); e = exp(-x^2) is shared with the derivative
+__device__ __forceinline__ float erf_from_exp(float ax, float e) {
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  return 1.f - poly * e;
+}
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = x * 0.7071067811865476f, az = fabsf(z);
+  const float er = copysignf(erf_from_exp(az, __expf(-az * az)), z);
+  return 0.5f * x * (1.f + er);
+}
+__device__ __forceinline__ float dgelu_erf_fast(float x) {
+  const float z = x * 0.7071067811865476f, az = fabsf(z);
+  const float e = __expf(-az * az);
+  const float er = copysignf(erf_from_exp(az, e), z);
+  return 0.5f * (1.f + er) + x * 0.3989422804014327f * e;
+}
+
+// 256-bit global accesses (LDG.256 / STG.256): one full 32-byte sector per thread and instruction
+struct alignas(32) V8 { uint32_t w[8]; };
+__device__ __forceinline__ V8 ldg256(const void* p) {
+  V8 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg256(void* p, const V8& v) {
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]),
+               "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7])
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Global operands of one 32-column chunk of one row (fp32 residual: 128 B, or bf16 pre-activation: 64 B)
+struct EpiOperands { V8 w[4]; };
+
+__device__ __forceinline__ bool epi_fast(const EpiParams& ep, int nc) {
+  return ep.vec_ok && !ep.accumulate && (nc + 32 <= ep.N);
+}
+// Issue the global loads of chunk [nc, nc+32) of row m (nothing waits on them here).
+__device__ __forceinline__ void epi_load(const EpiParams& ep, int m, int nc, EpiOperands& o) {
+  if (m >= ep.M || !epi_fast(ep, nc)) return;
+  if (ep.residual) {
+    const int rm = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
+    const float* rp = ep.residual + (long long)rm * ep.ldr + nc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.w[i] = ldg256(rp + 8 * i);
+  } else if (ep.act == BFK_ACT_DGELU_TANH || ep.act == BFK_ACT_DGELU_ERF) {
+    const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) o.w[i] = ldg256(hp + 16 * i);
+  }
+}
+
+// One 32-column chunk [nc, nc+32) of row m: TMEM -> registers -> fused epilogue -> global.  `o` holds the
+// operands loaded earlier by epi_load (software-pipelined one chunk ahead); bias comes from shared memory.
+__device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, uint32_t taddr, const float* __restrict__ bias_s,
+                                            const EpiOperands& o) {
+  const bool row_ok = m < ep.M;
+  uint32_t r[32];
+  tc_ld32(taddr, r);
+  tc_wait_ld();
+  if (!row_ok) return;
+  if (!epi_fast(ep, nc)) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t)
+      if (nc + t < ep.N) epi_store(ep, m, nc + t, __uint_as_float(r[t]));
+    return;
+  }
+  const bool dgelu = ep.act == BFK_ACT_DGELU_TANH || ep.act == BFK_ACT_DGELU_ERF;
+  float v[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]) * ep.alpha;
+  if (ep.bias) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) v[t] += bias_s[t];
+  }
+  const bool out_bf16 = ep.out_dtype == BFK_BF16;
+  if (ep.act == BFK_ACT_GELU_TANH || ep.act == BFK_ACT_GELU_ERF) {
+    if (ep.aux) {
+      if (ep.aux_dtype == BFK_BF16) {
+        __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          V8 q;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) q.w[t] = pack_bf16(v[i * 16 + 2 * t], v[i * 16 + 2 * t + 1]);
+          stg256(ap + 16 * i, q);
+        }
+      } else {
+        float* ap = reinterpret_cast<float*>(ep.aux) + (long long)m * ep.ld_aux + nc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          V8 q;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) q.w[t] = __float_as_uint(v[i * 8 + t]);
+          stg256(ap + 8 * i, q);
+        }
+      }
+    }
+    if (ep.act == BFK_ACT_GELU_TANH) {
+      if (out_bf16) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] = gelu_tanh_fast(v[t]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] = gelu_tanh(v[t]);
+      }
+    } else if (out_bf16) {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] = gelu_erf_fast(v[t]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] = gelu_erf(v[t]);
+    }
+  } else if (dgelu) {
+    float h[32];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const uint32_t hw = o.w[t >> 3].w[t & 7];
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw));
+      h[2 * t] = f.x; h[2 * t + 1] = f.y;
+    }
+    // one uniform branch per variant (a per-element select would execute the exact AND the fast path)
+    if (ep.act == BFK_ACT_DGELU_TANH) {
+      if (out_bf16) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] *= dgelu_tanh_fast(h[t]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] *= dgelu_tanh(h[t]);
+      }
+    } else if (out_bf16) {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] *= dgelu_erf_fast(h[t]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] *= dgelu_erf(h[t]);
+    }
+  }
+  if (ep.residual) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[i * 8 + t] += __uint_as_float(o.w[i].w[t]);
+  }
+  if (out_bf16) {
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(ep.D) + (long long)m * ep.ldd + nc;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      V8 q;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) q.w[t] = pack_bf16(v[i * 16 + 2 * t], v[i * 16 + 2 * t + 1]);
+      stg256(dp + 16 * i, q);
+    }
+  } else {
+    float* dp = reinterpret_cast<float*>(ep.D) + (long long)m * ep.ldd + nc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      V8 q;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) q.w[t] = __float_as_uint(v[i * 8 + t]);
+      stg256(dp + 8 * i, q);
+    }
+  }
+}
+
+// L2 prefetch of the operands the epilogue of (row m, chunk nc) will read (next work item of this CTA)
+__device__ __forceinline__ void epi_prefetch(const EpiParams& ep, int m, int nc) {
+  if (m >= ep.M || nc + 32 > ep.N) return;
+  if (ep.residual) {
+    const int rm = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
+    prefetch_l2(ep.residual + (long long)rm * ep.ldr + nc);
+  }
+  if (ep.act == BFK_ACT_DGELU_TANH || ep.act == BFK_ACT_DGELU_ERF)
+    prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc);
+}
+
+
+}  // namespace bfk
