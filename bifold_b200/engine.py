@@ -16,6 +16,8 @@ Data layout in HBM
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import math
 from typing import Dict, List, Optional
@@ -49,9 +51,12 @@ class Kernels:
 
     def splitk_ws(self, device):
         """fp32 scratch for split-K partial tiles (wgrad GEMMs); one buffer, reused stream-ordered."""
-        if self._ws is None or self._ws.device != device:
-            self._ws = torch.empty(16 * 1024 * 1024, device=device, dtype=torch.float32)   # 64 MB
-        return self._ws
+        key = (device, torch.cuda.current_stream().cuda_stream)   # concurrent streams must not share partial tiles
+        if self._ws is None:
+            self._ws = {}
+        if key not in self._ws:
+            self._ws[key] = torch.empty(16 * 1024 * 1024, device=device, dtype=torch.float32)   # 64 MB
+        return self._ws[key]
 
     # -- GEMM ------------------------------------------------------------------------------------
     def gemm(self, A, B, D, M, N, Kd, lda, ldb, ldd, trans_a=False, trans_b=False, bias=None, act=K.ACT_NONE,
@@ -137,6 +142,8 @@ class Engine:
         self.step_seed = 0
         self.tw_prefix = "siglip_model.model." if cfg.lora else "siglip_model."
         self.grad_ready_hook = None   # DDP: called as hook(name_list) when a group of grads is final
+        self.overlap_towers = os.environ.get("BFK_OVERLAP_TOWERS", "1") != "0"    # text tower on a side stream, concurrent with the vision tower (fwd and bwd)
+        self._side = None
 
     # ------------------------------------------------------------------------------------------------
     # weight preparation
@@ -474,8 +481,23 @@ class Engine:
             images = torch.cat((rgb, sample["rgb_context"].reshape(B * T_ctx, *rgb.shape[1:])), dim=0).contiguous()
         else:
             images = rgb.contiguous()
-        vis = self._vision_fwd(images.float(), vsave)            # [(B + B*T)*Np, D]
-        txt = self._text_fwd(sample["instruction"].contiguous(), tsave)   # [B*L, D]
+        ids = sample["instruction"].contiguous()
+        if self.overlap_towers:
+            # the towers are independent until the token assembly: the small text-tower kernels (M = B*64 rows)
+            # fill SMs the vision-tower kernels leave idle
+            main = torch.cuda.current_stream()
+            if self._side is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(device=dev)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                txt = self._text_fwd(ids, tsave)                  # [B*L, D]
+            vis = self._vision_fwd(images.float(), vsave)         # [(B + B*T)*Np, D]
+            main.wait_stream(self._side)
+            txt.record_stream(main)
+            ids.record_stream(self._side)
+        else:
+            vis = self._vision_fwd(images.float(), vsave)
+            txt = self._text_fwd(ids, tsave)
 
         Nf = cfg.fusion_len(T_ctx)
         X = torch.empty(B * Nf, D, device=dev, dtype=torch.float32)
@@ -658,10 +680,22 @@ class Engine:
         # ---- towers (only LoRA factors are trainable; gradients flow through the frozen base) ----
         if need_tower:
             tp, vp = self.tw_prefix + "text_model", self.tw_prefix + "vision_model"
-            self._tower_bwd(dtxt, ctx["tsave"], self.text_layers, B, L, tp + ".final_layer_norm.weight", grads)
-            if self.grad_ready_hook:
-                self.grad_ready_hook("text")
-            self._tower_bwd(dvis, ctx["vsave"], self.vis_layers, B + B * T_ctx, Np, vp + ".post_layernorm.weight", grads)
+            if self.overlap_towers and self._side is not None:
+                main = torch.cuda.current_stream()
+                self._side.wait_stream(main)
+                dtxt.record_stream(self._side)
+                arena.record_stream(self._side)
+                with torch.cuda.stream(self._side):
+                    self._tower_bwd(dtxt, ctx["tsave"], self.text_layers, B, L, tp + ".final_layer_norm.weight", grads)
+                    if self.grad_ready_hook:
+                        self.grad_ready_hook("text")
+                self._tower_bwd(dvis, ctx["vsave"], self.vis_layers, B + B * T_ctx, Np, vp + ".post_layernorm.weight", grads)
+                main.wait_stream(self._side)
+            else:
+                self._tower_bwd(dtxt, ctx["tsave"], self.text_layers, B, L, tp + ".final_layer_norm.weight", grads)
+                if self.grad_ready_hook:
+                    self.grad_ready_hook("text")
+                self._tower_bwd(dvis, ctx["vsave"], self.vis_layers, B + B * T_ctx, Np, vp + ".post_layernorm.weight", grads)
             if self.grad_ready_hook:
                 self.grad_ready_hook("vision")
         return grads
