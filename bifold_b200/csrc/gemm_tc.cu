@@ -30,7 +30,7 @@ template <int BN> struct TcCfg {
 template <int BN, bool AMN, bool BMN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
-               EpiParams ep, int splits, long long split_stride) {
+               EpiParams ep, int splits, long long split_stride, int dbg) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -87,6 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int m0 = ((tile / num_n) * CL + crank) * TC_BM, n0 = (tile % num_n) * BN;
         int kb0, kb1;
         kb_range(item, kb0, kb1);
+        if (dbg & 2) continue;   // diagnostic: epilogue only
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
@@ -132,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1 && !(dbg & 2); ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
@@ -176,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
-        if (n0 + c * 32 >= N) break;  // warp-uniform
+        if (n0 + c * 32 >= N || (dbg & 1)) break;  // warp-uniform  (dbg & 1: diagnostic, main loop only)
         if (c + 2 < BN / 32 && n0 + (c + 2) * 32 < N) epi_load(epl, m, n0 + (c + 2) * 32, nxt);   // one chunk ahead
         epi_chunk32(epl, m, n0 + c * 32, taddr + (uint32_t)(c * 32), bias_s + c * 32, cur);
         cur = nxt;
@@ -300,7 +301,9 @@ static int choose_splits(const bfk_gemm_args* a, int BN) {
 int gemm_tc2(const bfk_gemm_args* a, cudaStream_t s);   // CTA-pair (cta_group::2) variant, gemm_tc2.cu
 static bool pair_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("BFK_GEMM_2CTA"); v = (e && e[0] == '1') ? 1 : 0; }
+  // On by default: the 256x256 pair tile needs 32 KB of operands per SM and K block instead of 48 KB; measured on
+  // B200 (profiles/r01_gemm_vs_cublas.txt) it is 2-14% faster than the single-CTA kernel on the policy's big shapes.
+  if (v < 0) { const char* e = getenv("BFK_GEMM_2CTA"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
 static bool cluster_enabled() {
@@ -309,6 +312,12 @@ static bool cluster_enabled() {
   // correct but not faster -- L2 already de-duplicates neighbouring unicast requests at this cluster size.
   if (v < 0) { const char* e = getenv("BFK_GEMM_CLUSTER"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
+}
+
+static int gemm_dbg() {   // BFK_GEMM_DBG: 1 = skip the epilogue body, 2 = skip TMA + MMA (measurement only; results are garbage)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BFK_GEMM_DBG"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
 template <int BN, bool AMN, bool BMN, int CL>
@@ -344,7 +353,7 @@ static int launch_tc_cl(const bfk_gemm_args* a, cudaStream_t s, int splits) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AMN, BMN, CL>, ma, mb, a->M, a->N, a->K, ep, splits, split_stride);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AMN, BMN, CL>, ma, mb, a->M, a->N, a->K, ep, splits, split_stride, gemm_dbg());
   if (le != cudaSuccess) { set_error("gemm_tc: launch failed: %s", cudaGetErrorString(le)); return BFK_E_CUDA; }
   if (splits > 1) {
     const long long total = (long long)a->M * a->N;

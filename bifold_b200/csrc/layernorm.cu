@@ -85,8 +85,21 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
   reinterpret_cast<uint2*>(p)[c] = u;
 }
 
+// raw (as stored) 4-element chunk: loads are issued in one batch per operand with no control flow in between, so a
+// warp has every byte of its row in flight at once; conversion happens afterwards
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { using type = float4; };
+template <> struct Raw4<__nv_bfloat16> { using type = uint2; };
+__device__ __forceinline__ float4 cvt4(float4 v) { return v; }
+__device__ __forceinline__ float4 cvt4(uint2 u) {
+  float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x));
+  float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
 template <typename TDY, typename TDX2, bool PARAM_GRADS, int LN_MAXC>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(bfk_layernorm_bwd_args a, int rows_per_block) {
+__global__ void __launch_bounds__(LN_WARPS * 32, (PARAM_GRADS || LN_MAXC > 6) ? 1 : 2) ln_bwd_kernel(bfk_layernorm_bwd_args a, int rows_per_block) {
+  using RawDY = typename Raw4<TDY>::type;
   __shared__ float red[PARAM_GRADS ? LN_WARPS : 1][PARAM_GRADS ? 132 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nc = a.D >> 2;
@@ -98,21 +111,39 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(bfk_layernorm_bwd
   }
   const int r_begin = blockIdx.x * rows_per_block;
   const int r_end = min(a.M, r_begin + rows_per_block);
+  const float keep2 = a.dy2_dropout_p > 0.f ? 1.f / (1.f - a.dy2_dropout_p) : 1.f;
   for (int row = r_begin + warp; row < r_end; row += LN_WARPS) {
+    const float4* x4 = reinterpret_cast<const float4*>(a.x + (long long)row * a.ldx);
+    const RawDY* dy = reinterpret_cast<const RawDY*>(reinterpret_cast<const TDY*>(a.dy) + (long long)row * a.ld_dy);
+    const RawDY* dy2 = a.dy2 ? reinterpret_cast<const RawDY*>(reinterpret_cast<const TDY*>(a.dy2) + (long long)row * a.ld_dy2) : nullptr;
+    const float4* dres = a.dres ? reinterpret_cast<const float4*>(a.dres + (long long)row * a.ld_dres) : nullptr;
+    // ---- load phase: every operand of the row, back to back ----
+    float4 xv[LN_MAXC], rv[LN_MAXC];
+    RawDY dv[LN_MAXC], ev[LN_MAXC];
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) if (lane + 32 * i < nc) xv[i] = x4[lane + 32 * i];
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) if (lane + 32 * i < nc) dv[i] = dy[lane + 32 * i];
+    if (dy2) {
+#pragma unroll
+      for (int i = 0; i < LN_MAXC; ++i) if (lane + 32 * i < nc) ev[i] = dy2[lane + 32 * i];
+    }
+    if (dres) {
+#pragma unroll
+      for (int i = 0; i < LN_MAXC; ++i) if (lane + 32 * i < nc) rv[i] = dres[lane + 32 * i];
+    }
     const float mean = a.mean[row], rstd = a.rstd[row];
-    const float* x = a.x + (long long)row * a.ldx;
-    const TDY* dy = reinterpret_cast<const TDY*>(a.dy) + (long long)row * a.ld_dy;
-    const TDY* dy2 = a.dy2 ? reinterpret_cast<const TDY*>(a.dy2) + (long long)row * a.ld_dy2 : nullptr;
-    const float keep2 = a.dy2_dropout_p > 0.f ? 1.f / (1.f - a.dy2_dropout_p) : 1.f;
-    float4 gv[LN_MAXC], xh[LN_MAXC];
+    // ---- statistics ----
+    float4 gv[LN_MAXC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {
-      int c = lane + 32 * i;
+      const int c = lane + 32 * i;
       if (c < nc) {
-        float4 xv = load4<float>(x, c), d = load4<TDY>(dy, c), g = __ldg(g4 + c);
+        float4 d = cvt4(dv[i]);
+        const float4 g = __ldg(g4 + c);
         if (dy2) {
-          float4 e = load4<TDY>(dy2, c);
+          float4 e = cvt4(ev[i]);
           if (a.dy2_dropout_p > 0.f) {
             e.x = hash_uniform(a.dy2_seed, row, 4 * c + 0) < a.dy2_dropout_p ? 0.f : e.x * keep2;
             e.y = hash_uniform(a.dy2_seed, row, 4 * c + 1) < a.dy2_dropout_p ? 0.f : e.y * keep2;
@@ -121,30 +152,27 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(bfk_layernorm_bwd
           }
           d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
         }
-        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        // xv becomes x-hat in place
+        xv[i] = make_float4((xv[i].x - mean) * rstd, (xv[i].y - mean) * rstd, (xv[i].z - mean) * rstd, (xv[i].w - mean) * rstd);
         if constexpr (PARAM_GRADS) {
-          dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+          dg[i].x += d.x * xv[i].x; dg[i].y += d.y * xv[i].y; dg[i].z += d.z * xv[i].z; dg[i].w += d.w * xv[i].w;
           db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
         }
         gv[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
         s1 += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
-        s2 += (gv[i].x * xh[i].x + gv[i].y * xh[i].y) + (gv[i].z * xh[i].z + gv[i].w * xh[i].w);
+        s2 += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
       }
     }
     const float c1 = warp_sum(s1) / (float)a.D, c2 = warp_sum(s2) / (float)a.D;
     float* dx = a.dx + (long long)row * a.ld_dx;
-    const float* dres = a.dres ? a.dres + (long long)row * a.ld_dres : nullptr;
     TDX2* dx2 = a.dx2 ? reinterpret_cast<TDX2*>(a.dx2) + (long long)row * a.ld_dx2 : nullptr;
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {
-      int c = lane + 32 * i;
+      const int c = lane + 32 * i;
       if (c < nc) {
-        float4 o = make_float4(rstd * (gv[i].x - c1 - xh[i].x * c2), rstd * (gv[i].y - c1 - xh[i].y * c2),
-                               rstd * (gv[i].z - c1 - xh[i].z * c2), rstd * (gv[i].w - c1 - xh[i].w * c2));
-        if (dres) {
-          float4 r = load4<float>(dres, c);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
+        float4 o = make_float4(rstd * (gv[i].x - c1 - xv[i].x * c2), rstd * (gv[i].y - c1 - xv[i].y * c2),
+                               rstd * (gv[i].z - c1 - xv[i].z * c2), rstd * (gv[i].w - c1 - xv[i].w * c2));
+        if (dres) { o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w; }
         store4<float>(dx, c, o);
         if (dx2) store4<TDX2>(dx2, c, o);
       }
@@ -196,7 +224,11 @@ __global__ void __launch_bounds__(256) ln_bwd_reduce(const float* __restrict__ p
   }
 }
 
-static int ln_bwd_blocks(int M, int& rows_per_block) {
+static int ln_bwd_blocks(int M, int& rows_per_block, bool param_grads = true) {
+  if (!param_grads) {   // no per-block partial sums to amortise: one row per warp, blocks scheduled dynamically
+    rows_per_block = LN_WARPS;
+    return (M + LN_WARPS - 1) / LN_WARPS;
+  }
   int target = sm_count() * 2;
   rows_per_block = (M + target - 1) / target;
   rows_per_block = ((rows_per_block + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
@@ -238,7 +270,7 @@ extern "C" int32_t bfk_layernorm_bwd(const bfk_layernorm_bwd_args* a, bfk_stream
   BFK_CHECK_ARG(!pg || (a->dbeta && a->partials), "bfk_layernorm_bwd: dgamma needs dbeta and partials");
   cudaStream_t s = to_stream(s_);
   int rpb;
-  int grid = ln_bwd_blocks(a->M, rpb);
+  int grid = ln_bwd_blocks(a->M, rpb, pg);
   const bool dyb = a->dy_dtype == BFK_BF16, d2b = a->dx2 && a->dx2_dtype == BFK_BF16;
 #define LAUNCH(TDY, TDX2, PG)                                                                      \
   do {                                                                                             \
