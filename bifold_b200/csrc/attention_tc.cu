@@ -38,17 +38,18 @@ struct AttnTcParams {
 };
 
 // K-major operand (rows x head_dim or rows x 128 keys), atoms stacked every AT_ATOM bytes; k-th UMMA_K slice
-__device__ __forceinline__ uint64_t kmajor_desc(uint32_t tile, int k) {
-  return make_sdesc(tile + (uint32_t)(k >> 2) * AT_ATOM + (uint32_t)(k & 3) * 32u, 16, 1024);
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t tile, int k, uint32_t atom = AT_ATOM) {
+  return make_sdesc(tile + (uint32_t)(k >> 2) * atom + (uint32_t)(k & 3) * 32u, 16, 1024);
 }
 // MN-major view of a [128 rows][NA*64 cols] tile: reduction over rows (slice k = rows 16k..16k+15), MN = columns
-__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t tile, int k) {
-  return make_sdesc(tile + (uint32_t)k * 2048u, AT_ATOM, 1024);
+__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t tile, int k, uint32_t atom = AT_ATOM) {
+  return make_sdesc(tile + (uint32_t)k * 2048u, atom, 1024);
 }
 template <int NA>
-__device__ __forceinline__ void load_tile(uint32_t dst, const CUtensorMap* map, uint32_t bar, int slot, int row0, int b) {
+__device__ __forceinline__ void load_tile(uint32_t dst, const CUtensorMap* map, uint32_t bar, int slot, int row0, int b,
+                                          uint32_t atom = AT_ATOM) {
 #pragma unroll
-  for (int a = 0; a < NA; ++a) tma_load_4d(dst + a * AT_ATOM, map, bar, 64 * a, slot, row0, b);
+  for (int a = 0; a < NA; ++a) tma_load_4d(dst + a * atom, map, bar, 64 * a, slot, row0, b);
 }
 // write 8 bf16 (one 16-byte chunk `c16` of 16 per 128-key row) of row r into a K-major swizzled [128 x 128] tile
 __device__ __forceinline__ void store_p_chunk(uint32_t tile, int r, int c16, const float (&v)[8]) {
@@ -80,9 +81,9 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 // width of key block j: full 128, or the valid tail rounded up to a multiple of 16 (MMA N / K granularity)
-__device__ __forceinline__ int kv_cols(int N, int j) {
-  const int rem = N - j * 128;
-  return rem >= 128 ? 128 : ((rem + 15) & ~15);
+__device__ __forceinline__ int kv_cols(int N, int j, int bw = 128) {
+  const int rem = N - j * bw;
+  return rem >= bw ? bw : ((rem + 15) & ~15);
 }
 
 struct AttnSmem {
@@ -98,14 +99,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
   constexpr uint32_t TILE = NA * AT_ATOM;
   const uint32_t base = smem_u32(smem_raw);
   const uint32_t sQ = base, sK = sQ + TILE, sV = sK + 2 * TILE, sP = sV + 2 * TILE, bars = sP + 2 * AT_ATOM;
-  const uint32_t bar_q = bars, bar_kv0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40, tmem_slot = bars + 48;
+  const uint32_t bar_q = bars, bar_k0 = bars + 8, bar_v0 = bars + 24, bar_s = bars + 40, bar_p = bars + 48, bar_o = bars + 56,
+                 tmem_slot = bars + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nblk = (p.N + 127) / 128;
 
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
-    mbar_init(bar_q, 1); mbar_init(bar_kv0, 1); mbar_init(bar_kv0 + 8, 1);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_k0, 1); mbar_init(bar_k0 + 8, 1); mbar_init(bar_v0, 1); mbar_init(bar_v0 + 8, 1);
     mbar_init(bar_s, 1); mbar_init(bar_p, 32 * AT_ROW_WARPS); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
@@ -122,32 +125,41 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
 
   if (warp == AT_ROW_WARPS) {
     if (lane == 0) {
+      // Issue order: ... P V(j) | S(j+1) -> commit(bar_s) ...; tcgen05 ops of one thread complete in order, so
+      // bar_s(j+1) also tells the row warps that P V(j) is done (P tile free, O safe to rescale).
       const uint32_t idesc_o = make_idesc(128, p.n_o, false, true);
+      auto issue_k = [&](int j) {
+        mbar_expect_tx(bar_k0 + 8 * (j & 1), TILE);
+        load_tile<NA>(sK + (j & 1) * TILE, &map_qkv, bar_k0 + 8 * (j & 1), p.H + h, j * 128, b);
+      };
+      auto issue_v = [&](int j) {
+        mbar_expect_tx(bar_v0 + 8 * (j & 1), TILE);
+        load_tile<NA>(sV + (j & 1) * TILE, &map_qkv, bar_v0 + 8 * (j & 1), 2 * p.H + h, j * 128, b);
+      };
+      auto issue_s = [&](int j) {
+        mbar_wait(bar_k0 + 8 * (j & 1), (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t idesc_sj = make_idesc(128, kv_cols(p.N, j), false, false);
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tS, kmajor_desc(sQ, k), kmajor_desc(sK + (j & 1) * TILE, k), idesc_sj, k > 0);
+        tc_commit(bar_s);
+      };
       mbar_expect_tx(bar_q, TILE);
       load_tile<NA>(sQ, &map_qkv, bar_q, h, q0, b);
-      mbar_expect_tx(bar_kv0, 2 * TILE);
-      load_tile<NA>(sK, &map_qkv, bar_kv0, p.H + h, 0, b);
-      load_tile<NA>(sV, &map_qkv, bar_kv0, 2 * p.H + h, 0, b);
+      issue_k(0); issue_v(0);
+      if (nblk > 1) { issue_k(1); issue_v(1); }
+      mbar_wait(bar_q, 0);
+      issue_s(0);
       for (int j = 0; j < nblk; ++j) {
-        if (j > 0) mbar_wait(bar_o, (j - 1) & 1);
-        if (j + 1 < nblk) {
-          const int nb = (j + 1) & 1;
-          mbar_expect_tx(bar_kv0 + 8 * nb, 2 * TILE);
-          load_tile<NA>(sK + nb * TILE, &map_qkv, bar_kv0 + 8 * nb, p.H + h, (j + 1) * 128, b);
-          load_tile<NA>(sV + nb * TILE, &map_qkv, bar_kv0 + 8 * nb, 2 * p.H + h, (j + 1) * 128, b);
-        }
-        if (j == 0) mbar_wait(bar_q, 0);
-        mbar_wait(bar_kv0 + 8 * (j & 1), (j >> 1) & 1);
+        mbar_wait(bar_p, j & 1);     // P(j) in smem, S(j) read; S(j) done => K buffer j&1 free, P V(j-1) done => V buffer (j-1)&1 free
         tc_fence_after();
-        const uint32_t k_t = sK + (j & 1) * TILE, v_t = sV + (j & 1) * TILE;
+        if (j + 2 < nblk) issue_k(j + 2);
+        if (j >= 1 && j + 1 < nblk) issue_v(j + 1);
+        mbar_wait(bar_v0 + 8 * (j & 1), (j >> 1) & 1);
+        tc_fence_after();
         const int nc = kv_cols(p.N, j);
-        const uint32_t idesc_sj = make_idesc(128, nc, false, false);
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tS, kmajor_desc(sQ, k), kmajor_desc(k_t, k), idesc_sj, k > 0);
-        tc_commit(bar_s);
-        mbar_wait(bar_p, j & 1);
-        tc_fence_after();
-        for (int k = 0; k < nc / 16; ++k) tc_mma_bf16(tO, kmajor_desc(sP, k), mnmajor_desc(v_t, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-        tc_commit(bar_o);
+        for (int k = 0; k < nc / 16; ++k)
+          tc_mma_bf16(tO, kmajor_desc(sP, k), mnmajor_desc(sV + (j & 1) * TILE, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        if (j + 1 < nblk) issue_s(j + 1); else tc_commit(bar_o);
       }
     }
   } else {
@@ -156,7 +168,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
     const int quarter = warp & 3, half = warp >> 2;
     const int r = quarter * 32 + lane, q = q0 + r;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    float* xch = reinterpret_cast<float*>(smem_raw + (bars + 64 - base));   // [128]
+    float* xch = reinterpret_cast<float*>(smem_raw + (bars + 128 - base));   // [128]
     const bool quarter_live = q0 + quarter * 32 < p.N;      // warp-uniform: any real query row in this quarter?
     const bool masked = p.row_mask && q < p.N && p.row_mask[(long long)b * p.N + q] == 0.f;
     // masked query row: every score equal => p == 1 for every key (scale 0, max 0)
@@ -168,7 +180,6 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
       if (!quarter_live) {                         // rows beyond the sequence: stay in lock-step, do nothing
-        if (j > 0) mbar_wait(bar_o, (j - 1) & 1);
         mbar_arrive(bar_p);
         continue;
       }
@@ -192,7 +203,6 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
       if (half == 1) mx = xch[r];
       const float m_new = masked ? 0.f : fmaxf(m_run, mx * sl2);
       const float alpha = ex2f(m_run - m_new);
-      if (j > 0) { mbar_wait(bar_o, (j - 1) & 1); tc_fence_after(); }
       float rowsum = 0.f;
 #pragma unroll 1
       for (int c = half * 32; c < nc; c += 64) {
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
       tc_fence_before();
       mbar_arrive(bar_p);
     }
-    mbar_wait(bar_o, (nblk - 1) & 1);
+    mbar_wait(bar_o, 0);
     tc_fence_after();
     if (quarter_live) {
       // total row sum = sum of the two halves' partial sums (same rescaling history)
@@ -264,64 +274,77 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
 // =====================================================================================================
 // backward: dQ
 // =====================================================================================================
-template <int NA, int NBUF>
-__global__ void __launch_bounds__(AT_THREADS, 1)
-attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, AttnTcParams p) {
+// BW = key-block width.  BW = 64 keeps the TMEM footprint at 256 columns (S, dP: 64 each, dQ: up to 128), so two CTAs
+// share an SM and one's MMA / TMA / barrier latencies hide behind the other's softmax math.
+// Issue order of the control thread: ... dQ(j) | S(j+1), dP(j+1) -> commit(bar_s) ...  tcgen05 ops of one thread
+// complete in order, so bar_s(j+1) also tells the row warps that dQ(j) has finished reading the dS tile.
+template <int NA, int BW, int NBUF>
+__global__ void __launch_bounds__(AT_THREADS, NA == 1 && BW == 64 ? 2 : 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                      const __grid_constant__ CUtensorMap map_do, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr uint32_t TILE = NA * AT_ATOM;
+  constexpr uint32_t TILE = NA * AT_ATOM;             // Q, dO: 128 rows
+  constexpr uint32_t KATOM = BW * 128, KTILE = NA * KATOM;   // K, V blocks: BW rows
+  constexpr uint32_t DS_BYTES = (BW / 64) * AT_ATOM;  // dS: 128 rows x BW keys (bf16)
+  constexpr int TCOLS = (2 * BW + NA * 64) <= 256 ? 256 : 512;
   const uint32_t base = smem_u32(smem_raw);
-  const uint32_t sQ = base, sdO = sQ + TILE, sK = sdO + TILE, sV = sK + NBUF * TILE, sdS = sV + NBUF * TILE, bars = sdS + 2 * AT_ATOM;
-  const uint32_t bar_q = bars, bar_kv0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40, tmem_slot = bars + 48;
+  const uint32_t sQ = base, sdO = sQ + TILE, sK = sdO + TILE, sV = sK + NBUF * KTILE, sdS = sV + NBUF * KTILE, bars = sdS + DS_BYTES;
+  const uint32_t bar_q = bars, bar_kv0 = bars + 8, bar_s = bars + 40, bar_p = bars + 48, bar_o = bars + 56, tmem_slot = bars + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int nblk = (p.N + 127) / 128;
+  const int nblk = (p.N + BW - 1) / BW;
 
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
-    mbar_init(bar_q, 1); mbar_init(bar_kv0, 1); mbar_init(bar_kv0 + 8, 1);
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < NBUF; ++i) mbar_init(bar_kv0 + 8 * i, 1);
     mbar_init(bar_s, 1); mbar_init(bar_p, 32 * AT_ROW_WARPS); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
   if (warp == AT_ROW_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
-  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
+  const uint32_t tS = tmem, tdP = tmem + BW, tdQ = tmem + 2 * BW;
 
   if (warp == AT_ROW_WARPS) {
     if (lane == 0) {
       const uint32_t idesc_q = make_idesc(128, p.n_o, false, true);
       auto issue_kv = [&](int j) {
         const int nb = j % NBUF;
-        mbar_expect_tx(bar_kv0 + 8 * nb, 2 * TILE);
-        load_tile<NA>(sK + nb * TILE, &map_qkv, bar_kv0 + 8 * nb, p.H + h, j * 128, b);
-        load_tile<NA>(sV + nb * TILE, &map_qkv, bar_kv0 + 8 * nb, 2 * p.H + h, j * 128, b);
+        mbar_expect_tx(bar_kv0 + 8 * nb, 2 * KTILE);
+        load_tile<NA>(sK + nb * KTILE, &map_kv, bar_kv0 + 8 * nb, p.H + h, j * BW, b, KATOM);
+        load_tile<NA>(sV + nb * KTILE, &map_kv, bar_kv0 + 8 * nb, 2 * p.H + h, j * BW, b, KATOM);
       };
-      mbar_expect_tx(bar_q, 2 * TILE);
-      load_tile<NA>(sQ, &map_qkv, bar_q, h, q0, b);
-      load_tile<NA>(sdO, &map_do, bar_q, h, q0, b);
-      issue_kv(0);
-      for (int j = 0; j < nblk; ++j) {
-        if (j > 0) mbar_wait(bar_o, (j - 1) & 1);
-        if (NBUF == 2) { if (j + 1 < nblk) issue_kv(j + 1); } else { if (j > 0) issue_kv(j); }
-        if (j == 0) mbar_wait(bar_q, 0);
+      auto issue_s = [&](int j) {
         mbar_wait(bar_kv0 + 8 * (j % NBUF), (j / NBUF) & 1);
         tc_fence_after();
-        const uint32_t k_t = sK + (j % NBUF) * TILE, v_t = sV + (j % NBUF) * TILE;
-        const int nc = kv_cols(p.N, j);
-        const uint32_t idesc_sj = make_idesc(128, nc, false, false);
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tS, kmajor_desc(sQ, k), kmajor_desc(k_t, k), idesc_sj, k > 0);
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tdP, kmajor_desc(sdO, k), kmajor_desc(v_t, k), idesc_sj, k > 0);
+        const uint32_t k_t = sK + (j % NBUF) * KTILE, v_t = sV + (j % NBUF) * KTILE;
+        const uint32_t idesc_sj = make_idesc(128, kv_cols(p.N, j, BW), false, false);
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tS, kmajor_desc(sQ, k, AT_ATOM), kmajor_desc(k_t, k, KATOM), idesc_sj, k > 0);
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tdP, kmajor_desc(sdO, k, AT_ATOM), kmajor_desc(v_t, k, KATOM), idesc_sj, k > 0);
         tc_commit(bar_s);
-        mbar_wait(bar_p, j & 1);
+      };
+      mbar_expect_tx(bar_q, 2 * TILE);
+      load_tile<NA>(sQ, &map_q, bar_q, h, q0, b, AT_ATOM);
+      load_tile<NA>(sdO, &map_do, bar_q, h, q0, b, AT_ATOM);
+      for (int j = 0; j < NBUF - 1 && j < nblk; ++j) issue_kv(j);
+      mbar_wait(bar_q, 0);
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(bar_p, j & 1);      // dS(j) is in smem, S(j)/dP(j) have been read; S(j) done => block j-1 fully consumed
         tc_fence_after();
-        for (int k = 0; k < nc / 16; ++k) tc_mma_bf16(tdQ, kmajor_desc(sdS, k), mnmajor_desc(k_t, k), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
-        tc_commit(bar_o);
+        if (j + NBUF - 1 < nblk) issue_kv(j + NBUF - 1);   // into the buffer block j-1 used
+        const uint32_t k_t = sK + (j % NBUF) * KTILE;
+        const int nc = kv_cols(p.N, j, BW);
+        for (int k = 0; k < nc / 16; ++k)
+          tc_mma_bf16(tdQ, kmajor_desc(sdS, k, AT_ATOM), mnmajor_desc(k_t, k, KATOM), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+        if (j + 1 < nblk) issue_s(j + 1); else tc_commit(bar_o);
       }
     }
   } else {
@@ -335,10 +358,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
     // non-live rows (masked query / beyond the sequence): lse = +inf => p == 0 => dS == 0
     const float lse2 = live ? p.lse[si] * LOG2E : INFINITY, delta = live ? p.delta[si] : 0.f;
     for (int j = 0; j < nblk; ++j) {
-      const int nc = kv_cols(p.N, j);
+      const int nc = kv_cols(p.N, j, BW);
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      if (j > 0) { mbar_wait(bar_o, (j - 1) & 1); tc_fence_after(); }
       // keys in [N, nc) have zero K rows: their dS values multiply zero rows in dQ += dS K, no masking needed.
       // Quarters without any real query row skip the math (their dS rows only feed dQ rows that are never stored).
       if (quarter_live) {
@@ -367,7 +389,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
       tc_fence_before();
       mbar_arrive(bar_p);
     }
-    mbar_wait(bar_o, (nblk - 1) & 1);
+    mbar_wait(bar_o, 0);
     tc_fence_after();
     __nv_bfloat16* drow = p.dqkv + ((long long)b * p.N + q) * p.ld_dqkv + h * p.hd;
     for (int c = half; c < p.n_o / 16; c += 2) {
@@ -381,111 +403,133 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
   __syncthreads();
   if (warp == AT_ROW_WARPS) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TCOLS) : "memory");
   }
 }
 
 // =====================================================================================================
 // backward: dK, dV
 // =====================================================================================================
-template <int NA, int NBUF>
-__global__ void __launch_bounds__(AT_THREADS, 1)
-attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, AttnTcParams p) {
+// CTA = 128 key rows; loop over BW-wide query blocks (BW = 64: 256 TMEM columns, two CTAs per SM, same issue order as dQ).
+template <int NA, int BW, int NBUF>
+__global__ void __launch_bounds__(AT_THREADS, NA == 1 && BW == 64 ? 2 : 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
+                       const __grid_constant__ CUtensorMap map_do, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr uint32_t TILE = NA * AT_ATOM;
+  constexpr uint32_t TILE = NA * AT_ATOM;             // K, V: 128 rows
+  constexpr uint32_t QATOM = BW * 128, QTILE = NA * QATOM;   // Q, dO blocks: BW rows
+  constexpr uint32_t PT_BYTES = (BW / 64) * AT_ATOM;  // P^T, dS^T: 128 key rows x BW queries (bf16)
+  constexpr int TCOLS = (2 * BW + 2 * NA * 64) <= 256 ? 256 : 512;
   const uint32_t base = smem_u32(smem_raw);
-  const uint32_t sK = base, sV = sK + TILE, sQ = sV + TILE, sdO = sQ + NBUF * TILE, sPt = sdO + NBUF * TILE, sdSt = sPt + 2 * AT_ATOM,
-                 bars = sdSt + 2 * AT_ATOM;
-  float4* s_col = reinterpret_cast<float4*>(smem_raw + (bars - base) + 64);   // per-query-column {lse2, delta, scale2, live}
-  const uint32_t bar_kv = bars, bar_q0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40, tmem_slot = bars + 48;
+  const uint32_t sK = base, sV = sK + TILE, sQ = sV + TILE, sdO = sQ + NBUF * QTILE, sPt = sdO + NBUF * QTILE, sdSt = sPt + PT_BYTES,
+                 bars = sdSt + PT_BYTES;
+  const uint32_t bar_kv = bars, bar_q0 = bars + 8, bar_s = bars + 40, bar_p = bars + 48, bar_o = bars + 56, tmem_slot = bars + 64;
+  float2* s_col = reinterpret_cast<float2*>(smem_raw + (bars - base) + 128);          // per-query-column {lse2, delta}
+  uint32_t* s_live = reinterpret_cast<uint32_t*>(smem_raw + (bars - base) + 128 + BW * 8);   // live-query bits, BW/32 words
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int nq = (p.N + 127) / 128;
+  const int nq = (p.N + BW - 1) / BW;
 
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
-    mbar_init(bar_kv, 1); mbar_init(bar_q0, 1); mbar_init(bar_q0 + 8, 1);
+    mbar_init(bar_kv, 1);
+    for (int i = 0; i < NBUF; ++i) mbar_init(bar_q0 + 8 * i, 1);
     mbar_init(bar_s, 1); mbar_init(bar_p, 32 * AT_ROW_WARPS); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
   if (warp == AT_ROW_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
-  const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 384;
+  const uint32_t tSt = tmem, tdPt = tmem + BW, tdV = tmem + 2 * BW, tdK = tdV + NA * 64;
 
   if (warp == AT_ROW_WARPS) {
     if (lane == 0) {
       const uint32_t idesc_g = make_idesc(128, p.n_o, false, true);
       auto issue_q = [&](int i) {
         const int nb = i % NBUF;
-        mbar_expect_tx(bar_q0 + 8 * nb, 2 * TILE);
-        load_tile<NA>(sQ + nb * TILE, &map_qkv, bar_q0 + 8 * nb, h, i * 128, b);
-        load_tile<NA>(sdO + nb * TILE, &map_do, bar_q0 + 8 * nb, h, i * 128, b);
+        mbar_expect_tx(bar_q0 + 8 * nb, 2 * QTILE);
+        load_tile<NA>(sQ + nb * QTILE, &map_q, bar_q0 + 8 * nb, h, i * BW, b, QATOM);
+        load_tile<NA>(sdO + nb * QTILE, &map_do, bar_q0 + 8 * nb, h, i * BW, b, QATOM);
       };
-      mbar_expect_tx(bar_kv, 2 * TILE);
-      load_tile<NA>(sK, &map_qkv, bar_kv, p.H + h, j0, b);
-      load_tile<NA>(sV, &map_qkv, bar_kv, 2 * p.H + h, j0, b);
-      issue_q(0);
-      for (int i = 0; i < nq; ++i) {
-        if (i > 0) mbar_wait(bar_o, (i - 1) & 1);
-        if (NBUF == 2) { if (i + 1 < nq) issue_q(i + 1); } else { if (i > 0) issue_q(i); }
-        if (i == 0) mbar_wait(bar_kv, 0);
+      auto issue_s = [&](int i) {
         mbar_wait(bar_q0 + 8 * (i % NBUF), (i / NBUF) & 1);
         tc_fence_after();
-        const uint32_t q_t = sQ + (i % NBUF) * TILE, do_t = sdO + (i % NBUF) * TILE;
-        const int nc = kv_cols(p.N, i);
-        const uint32_t idesc_si = make_idesc(128, nc, false, false);
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tSt, kmajor_desc(sK, k), kmajor_desc(q_t, k), idesc_si, k > 0);
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tdPt, kmajor_desc(sV, k), kmajor_desc(do_t, k), idesc_si, k > 0);
+        const uint32_t q_t = sQ + (i % NBUF) * QTILE, do_t = sdO + (i % NBUF) * QTILE;
+        const uint32_t idesc_si = make_idesc(128, kv_cols(p.N, i, BW), false, false);
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tSt, kmajor_desc(sK, k, AT_ATOM), kmajor_desc(q_t, k, QATOM), idesc_si, k > 0);
+        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tdPt, kmajor_desc(sV, k, AT_ATOM), kmajor_desc(do_t, k, QATOM), idesc_si, k > 0);
         tc_commit(bar_s);
+      };
+      mbar_expect_tx(bar_kv, 2 * TILE);
+      load_tile<NA>(sK, &map_kv, bar_kv, p.H + h, j0, b, AT_ATOM);
+      load_tile<NA>(sV, &map_kv, bar_kv, 2 * p.H + h, j0, b, AT_ATOM);
+      for (int i = 0; i < NBUF - 1 && i < nq; ++i) issue_q(i);
+      mbar_wait(bar_kv, 0);
+      issue_s(0);
+      for (int i = 0; i < nq; ++i) {
         mbar_wait(bar_p, i & 1);
         tc_fence_after();
-        for (int k = 0; k < nc / 16; ++k) tc_mma_bf16(tdV, kmajor_desc(sPt, k), mnmajor_desc(do_t, k), idesc_g, (i > 0 || k > 0) ? 1u : 0u);
-        for (int k = 0; k < nc / 16; ++k) tc_mma_bf16(tdK, kmajor_desc(sdSt, k), mnmajor_desc(q_t, k), idesc_g, (i > 0 || k > 0) ? 1u : 0u);
-        tc_commit(bar_o);
+        if (i + NBUF - 1 < nq) issue_q(i + NBUF - 1);
+        const uint32_t q_t = sQ + (i % NBUF) * QTILE, do_t = sdO + (i % NBUF) * QTILE;
+        const int nc = kv_cols(p.N, i, BW);
+        for (int k = 0; k < nc / 16; ++k)
+          tc_mma_bf16(tdV, kmajor_desc(sPt, k, AT_ATOM), mnmajor_desc(do_t, k, QATOM), idesc_g, (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < nc / 16; ++k)
+          tc_mma_bf16(tdK, kmajor_desc(sdSt, k, AT_ATOM), mnmajor_desc(q_t, k, QATOM), idesc_g, (i > 0 || k > 0) ? 1u : 0u);
+        if (i + 1 < nq) issue_s(i + 1); else tc_commit(bar_o);
       }
     }
   } else {
     const int quarter = warp & 3, half = warp >> 2;
     const int r = quarter * 32 + lane, kv = j0 + r;
+    const int tid = threadIdx.x;                           // 0..255; threads [0, BW) fetch the per-query statistics
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * LOG2E;
     const float log2n = log2f((float)p.N);
     const bool kv_ok = kv < p.N;
     const bool quarter_live = j0 + quarter * 32 < p.N;     // any real key row in this quarter?
-    for (int i = 0; i < nq; ++i) {
-      const int nc = kv_cols(p.N, i);
-      // per-query-column statistics of this block (half 0: thread r loads column r):
-      //   live query   : {lse*log2e, delta, scale*log2e, 1}   p = 2^(s*scale2 - lse2), dS = p (dP - delta)
-      //   masked query : {log2 N,    0,     0,           0}   p = 1/N,                 dS = 0
-      //   out of range : {+inf,      0,     0,           0}   p = 0
-      named_bar_sync(1, 32 * AT_ROW_WARPS);
-      if (half == 0) {
-        const int q = i * 128 + r;
+    // per-query-column statistics:   live query  : {lse*log2e, delta}, live bit 1   p = 2^(s*scale2 - lse2), dS = p (dP - delta)
+    //                                masked query: {log2 N, 0},       live bit 0   p = 1/N,                 dS = 0
+    //                                out of range: {+inf, 0},         live bit 0   p = 0
+    auto fetch = [&](int i, float2& st, bool& lv) {
+      const int q = i * BW + tid;
+      st = make_float2(INFINITY, 0.f);
+      lv = false;
+      if (q < p.N) {
         const long long si = ((long long)b * p.H + h) * p.N + q;
-        float4 st = make_float4(INFINITY, 0.f, 0.f, 0.f);
-        if (q < p.N) {
-          const bool m = p.row_mask && p.row_mask[(long long)b * p.N + q] == 0.f;
-          st = m ? make_float4(log2n, 0.f, 0.f, 0.f) : make_float4(p.lse[si] * LOG2E, p.delta[si], sl2, 1.f);
-        }
-        s_col[r] = st;
+        const bool m = p.row_mask && p.row_mask[(long long)b * p.N + q] == 0.f;
+        if (m) st = make_float2(log2n, 0.f);
+        else { st = make_float2(p.lse[si] * LOG2E, p.delta[si]); lv = true; }
+      }
+    };
+    float2 st_next = make_float2(INFINITY, 0.f);
+    bool lv_next = false;
+    if (tid < BW) fetch(0, st_next, lv_next);
+    for (int i = 0; i < nq; ++i) {
+      const int nc = kv_cols(p.N, i, BW);
+      named_bar_sync(1, 32 * AT_ROW_WARPS);                // everybody is done with the previous block's statistics
+      if (tid < BW) {                                      // warp-uniform (BW is a multiple of 32)
+        s_col[tid] = st_next;
+        const uint32_t bits = __ballot_sync(0xffffffffu, lv_next);
+        if (lane == 0) s_live[tid >> 5] = bits;
+        if (i + 1 < nq) fetch(i + 1, st_next, lv_next);    // in flight while this block is processed
       }
       named_bar_sync(1, 32 * AT_ROW_WARPS);
       mbar_wait(bar_s, i & 1);
       tc_fence_after();
-      if (i > 0) { mbar_wait(bar_o, (i - 1) & 1); tc_fence_after(); }
       if (quarter_live) {
 #pragma unroll 1
         for (int c = half * 32; c < nc; c += 64) {
           uint32_t sreg[32], d[32];
           tc_ld32(tSt + lane_off + c, sreg);
           tc_ld32(tdPt + lane_off + c, d);
+          const uint32_t lbits = s_live[c >> 5];
           tc_wait_ld();
           const int ng = min(4, (nc - c) >> 3);
 #pragma unroll
@@ -494,10 +538,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid
               float pv[8], dv[8];
 #pragma unroll
               for (int t = 0; t < 8; ++t) {
-                const float4 st = s_col[c + g * 8 + t];
-                const float pr = ex2f(fmaf(__uint_as_float(sreg[g * 8 + t]), st.z, -st.x));
+                const float2 st = s_col[c + g * 8 + t];
+                const bool lv = (lbits >> (g * 8 + t)) & 1u;
+                const float pr = ex2f(fmaf(__uint_as_float(sreg[g * 8 + t]), lv ? sl2 : 0.f, -st.x));
                 pv[t] = pr;
-                dv[t] = pr * st.w * (__uint_as_float(d[g * 8 + t]) - st.y);
+                dv[t] = lv ? pr * (__uint_as_float(d[g * 8 + t]) - st.y) : 0.f;
               }
               store_p_chunk(sPt, r, (c >> 3) + g, pv);
               store_p_chunk(sdSt, r, (c >> 3) + g, dv);
@@ -509,7 +554,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid
       tc_fence_before();
       mbar_arrive(bar_p);
     }
-    mbar_wait(bar_o, (nq - 1) & 1);
+    mbar_wait(bar_o, 0);
     tc_fence_after();
     const long long HD = (long long)p.H * p.hd;
     __nv_bfloat16* krow = p.dqkv + ((long long)b * p.N + kv) * p.ld_dqkv + HD + h * p.hd;
@@ -525,50 +570,61 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid
   __syncthreads();
   if (warp == AT_ROW_WARPS) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TCOLS) : "memory");
   }
 }
 
-// delta[b,h,i] = sum_d dout*out  (warp per row, bf16)
-__global__ void __launch_bounds__(128) attn_delta_tc_kernel(const __nv_bfloat16* __restrict__ out, long long ld_out,
-                                                             const __nv_bfloat16* __restrict__ dout, long long ld_dout,
-                                                             float* __restrict__ delta, int B, int N, int H, int hd) {
-  const int lane = threadIdx.x & 31;
-  const long long w = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);   // (b, i, h)
-  if (w >= (long long)B * N * H) return;
-  const int h = (int)(w % H);
-  const long long row = w / H;
-  const int b = (int)(row / N), i = (int)(row % N);
-  const __nv_bfloat16* o = out + row * ld_out + h * hd;
-  const __nv_bfloat16* d = dout + row * ld_dout + h * hd;
+// delta[b,h,i] = sum_d dout*out.  One thread per 8-element (16-byte) chunk of a token row, whole rows per block
+// (coalesced row reads); the chunks of a head are then summed through shared memory.
+__global__ void __launch_bounds__(1024) attn_delta_tc_kernel(const __nv_bfloat16* __restrict__ out, long long ld_out,
+                                                              const __nv_bfloat16* __restrict__ dout, long long ld_dout,
+                                                              float* __restrict__ delta, int B, int N, int H, int hd, int rows_per_block) {
+  extern __shared__ float s_part[];
+  const int cph = hd >> 3, chunks = H * cph;            // chunks per head / per row
+  const int lr = threadIdx.x / chunks, ch = threadIdx.x % chunks;
+  const long long row = (long long)blockIdx.x * rows_per_block + lr;
+  const bool ok = lr < rows_per_block && row < (long long)B * N;
   float s = 0.f;
-  for (int t = lane * 2; t < hd; t += 64) {
-    float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + t));
-    float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d + t));
-    s += a.x * c.x + a.y * c.y;
+  if (ok) {
+    const uint4 a = *reinterpret_cast<const uint4*>(out + row * ld_out + ch * 8);
+    const uint4 c = *reinterpret_cast<const uint4*>(dout + row * ld_dout + ch * 8);
+    const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* cp = reinterpret_cast<const __nv_bfloat162*>(&c);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 x = __bfloat1622float2(ap[t]), y = __bfloat1622float2(cp[t]);
+      s += x.x * y.x + x.y * y.y;
+    }
   }
-  s = warp_sum(s);
-  if (lane == 0) delta[((long long)b * H + h) * N + i] = s;
+  s_part[threadIdx.x] = s;
+  __syncthreads();
+  if (ok && ch % cph == 0) {
+    float t = 0.f;
+    for (int k = 0; k < cph; ++k) t += s_part[threadIdx.x + k];
+    const int hh = ch / cph;
+    const int bb = (int)(row / N), i = (int)(row % N);
+    delta[((long long)bb * H + hh) * N + i] = t;
+  }
 }
 
 // ---- host ---------------------------------------------------------------------------------------------
 struct Map4Key {
-  const void* ptr; int hd, slots, N, B; long long ld;
-  bool operator==(const Map4Key& o) const { return ptr == o.ptr && hd == o.hd && slots == o.slots && N == o.N && B == o.B && ld == o.ld; }
+  const void* ptr; int hd, slots, N, B; long long ld; int rows;
+  bool operator==(const Map4Key& o) const { return ptr == o.ptr && hd == o.hd && slots == o.slots && N == o.N && B == o.B && ld == o.ld && rows == o.rows; }
 };
 struct Map4Hash {
   size_t operator()(const Map4Key& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     auto mix = [&](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.hd); mix(k.slots); mix(k.N); mix(k.B); mix((size_t)k.ld);
+    mix(k.hd); mix(k.slots); mix(k.N); mix(k.B); mix((size_t)k.ld); mix(k.rows);
     return h;
   }
 };
 // 4-D bf16 map {hd, slots, N, B} over a [B*N, ld] row-major matrix whose row holds `slots` runs of hd elements
-static bool make_map4(CUtensorMap* out, const void* ptr, int hd, int slots, int N, int B, long long ld) {
+static bool make_map4(CUtensorMap* out, const void* ptr, int hd, int slots, int N, int B, long long ld, int box_rows) {
   static std::mutex mu;
   static std::unordered_map<Map4Key, CUtensorMap, Map4Hash> cache;
-  Map4Key key{ptr, hd, slots, N, B, ld};
+  Map4Key key{ptr, hd, slots, N, B, ld, box_rows};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -578,7 +634,7 @@ static bool make_map4(CUtensorMap* out, const void* ptr, int hd, int slots, int 
   if (!enc) { set_error("attention_tc: cuTensorMapEncodeTiled unavailable"); return false; }
   cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)slots, (cuuint64_t)N, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)hd * 2, (cuuint64_t)ld * 2, (cuuint64_t)N * ld * 2};
-  cuuint32_t box[4] = {64, 1, 128, 1};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -622,17 +678,23 @@ static int set_attr(Kern k, size_t smem, const char* name) {
   return BFK_OK;
 }
 
+static int bwd_block_width() {   // BFK_ATTN_BW=128 selects the one-CTA-per-SM 128-wide variant (measurement only)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BFK_ATTN_BW"); v = (e && atoi(e) == 128) ? 128 : 64; }
+  return v;
+}
+
 int attention_fwd_tc(const bfk_attention_args* a, cudaStream_t s) {
   CUtensorMap mq;
-  if (!make_map4(&mq, a->qkv, a->hd, 3 * a->H, a->N, a->B, a->ld_qkv)) return BFK_E_CUDA;
+  if (!make_map4(&mq, a->qkv, a->hd, 3 * a->H, a->N, a->B, a->ld_qkv, 128)) return BFK_E_CUDA;
   AttnTcParams p = make_params(a);
   dim3 grid((a->N + 127) / 128, a->H, a->B);
   if (a->hd <= 64) {
-    const size_t smem = 5 * AT_ATOM + 2 * AT_ATOM + 576;   // 2 CTAs/SM: (233472 - 2*1024)/2 = 115712 >= 115264
+    const size_t smem = 5 * AT_ATOM + 2 * AT_ATOM + 640;   // 2 CTAs/SM: (233472 - 2*1024)/2 = 115712 >= 115328
     if (int rc = set_attr(attn_fwd_tc_kernel<1>, smem, "attn_fwd_tc")) return rc;
     attn_fwd_tc_kernel<1><<<grid, AT_THREADS, smem, s>>>(mq, p);
   } else {
-    const size_t smem = 5 * 2 * AT_ATOM + 2 * AT_ATOM + 576;
+    const size_t smem = 5 * 2 * AT_ATOM + 2 * AT_ATOM + 640;
     if (int rc = set_attr(attn_fwd_tc_kernel<2>, smem, "attn_fwd_tc")) return rc;
     attn_fwd_tc_kernel<2><<<grid, AT_THREADS, smem, s>>>(mq, p);
   }
@@ -640,28 +702,39 @@ int attention_fwd_tc(const bfk_attention_args* a, cudaStream_t s) {
   return BFK_OK;
 }
 
-int attention_bwd_tc(const bfk_attention_args* a, cudaStream_t s) {
-  CUtensorMap mq, md;
-  if (!make_map4(&mq, a->qkv, a->hd, 3 * a->H, a->N, a->B, a->ld_qkv)) return BFK_E_CUDA;
-  if (!make_map4(&md, a->dout, a->hd, a->H, a->N, a->B, a->ld_dout)) return BFK_E_CUDA;
-  AttnTcParams p = make_params(a);
-  const long long rows = (long long)a->B * a->N * a->H;
-  attn_delta_tc_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>((const __nv_bfloat16*)a->out, a->ld_out, (const __nv_bfloat16*)a->dout,
-                                                                  a->ld_dout, a->delta, a->B, a->N, a->H, a->hd);
+template <int NA, int BW, int NBUF>
+static int launch_bwd(const bfk_attention_args* a, const AttnTcParams& p, cudaStream_t s) {
+  CUtensorMap mq128, mqb, md128, mdb;
+  if (!make_map4(&mq128, a->qkv, a->hd, 3 * a->H, a->N, a->B, a->ld_qkv, 128)) return BFK_E_CUDA;
+  if (!make_map4(&mqb, a->qkv, a->hd, 3 * a->H, a->N, a->B, a->ld_qkv, BW)) return BFK_E_CUDA;
+  if (!make_map4(&md128, a->dout, a->hd, a->H, a->N, a->B, a->ld_dout, 128)) return BFK_E_CUDA;
+  if (!make_map4(&mdb, a->dout, a->hd, a->H, a->N, a->B, a->ld_dout, BW)) return BFK_E_CUDA;
+  constexpr size_t TILE = NA * AT_ATOM, BTILE = NA * BW * 128, STAGE = (BW / 64) * AT_ATOM;
+  // NA == 1, BW == 64: 98560 and 115472 bytes -- two CTAs per SM ((233472 - 2*1024)/2 = 115712)
+  const size_t smem_q = 2 * TILE + 2 * NBUF * BTILE + STAGE + 256;
+  const size_t smem_kv = 2 * TILE + 2 * NBUF * BTILE + 2 * STAGE + 128 + BW * 8 + 16;
+  if (int rc = set_attr(attn_bwd_dq_tc_kernel<NA, BW, NBUF>, smem_q, "attn_bwd_dq_tc")) return rc;
+  if (int rc = set_attr(attn_bwd_dkv_tc_kernel<NA, BW, NBUF>, smem_kv, "attn_bwd_dkv_tc")) return rc;
   dim3 grid((a->N + 127) / 128, a->H, a->B);
-  if (a->hd <= 64) {
-    const size_t smem_q = 6 * AT_ATOM + 2 * AT_ATOM + 256, smem_kv = 6 * AT_ATOM + 4 * AT_ATOM + 4096;
-    if (int rc = set_attr(attn_bwd_dq_tc_kernel<1, 2>, smem_q, "attn_bwd_dq_tc")) return rc;
-    if (int rc = set_attr(attn_bwd_dkv_tc_kernel<1, 2>, smem_kv, "attn_bwd_dkv_tc")) return rc;
-    attn_bwd_dq_tc_kernel<1, 2><<<grid, AT_THREADS, smem_q, s>>>(mq, md, p);
-    attn_bwd_dkv_tc_kernel<1, 2><<<grid, AT_THREADS, smem_kv, s>>>(mq, md, p);
-  } else {
-    const size_t smem_q = 4 * 2 * AT_ATOM + 2 * AT_ATOM + 256, smem_kv = 4 * 2 * AT_ATOM + 4 * AT_ATOM + 4096;
-    if (int rc = set_attr(attn_bwd_dq_tc_kernel<2, 1>, smem_q, "attn_bwd_dq_tc")) return rc;
-    if (int rc = set_attr(attn_bwd_dkv_tc_kernel<2, 1>, smem_kv, "attn_bwd_dkv_tc")) return rc;
-    attn_bwd_dq_tc_kernel<2, 1><<<grid, AT_THREADS, smem_q, s>>>(mq, md, p);
-    attn_bwd_dkv_tc_kernel<2, 1><<<grid, AT_THREADS, smem_kv, s>>>(mq, md, p);
+  attn_bwd_dq_tc_kernel<NA, BW, NBUF><<<grid, AT_THREADS, smem_q, s>>>(mq128, mqb, md128, p);
+  attn_bwd_dkv_tc_kernel<NA, BW, NBUF><<<grid, AT_THREADS, smem_kv, s>>>(mq128, mqb, mdb, p);
+  return BFK_OK;
+}
+
+int attention_bwd_tc(const bfk_attention_args* a, cudaStream_t s) {
+  AttnTcParams p = make_params(a);
+  {
+    const int chunks = a->H * (a->hd / 8);
+    if (chunks > 1024) { set_error("attention_bwd_tc: H*hd/8 = %d exceeds 1024", chunks); return BFK_E_UNSUPPORTED; }
+    const int rpb = std::max(1, 256 / chunks);
+    const long long rows = (long long)a->B * a->N;
+    attn_delta_tc_kernel<<<(unsigned)((rows + rpb - 1) / rpb), chunks * rpb, chunks * rpb * sizeof(float), s>>>(
+        (const __nv_bfloat16*)a->out, a->ld_out, (const __nv_bfloat16*)a->dout, a->ld_dout, a->delta, a->B, a->N, a->H, a->hd, rpb);
   }
+  int rc;
+  if (a->hd <= 64) rc = bwd_block_width() == 64 ? launch_bwd<1, 64, 3>(a, p, s) : launch_bwd<1, 128, 2>(a, p, s);
+  else rc = launch_bwd<2, 64, 3>(a, p, s);   // 128-wide blocks with two head-dim atoms do not fit in shared memory
+  if (rc) return rc;
   BFK_CHECK_LAUNCH("attention_bwd_tc");
   return BFK_OK;
 }
