@@ -269,19 +269,38 @@ def main():
     torch.cuda.profiler.stop()
     clocks = sampler.stop()
     launches = (eng.k.launches - l0) + (optim.launches - o0)
+    # host time to ENQUEUE one step (no synchronisation inside): how far the launch queue runs ahead of the GPU
+    import time as _time
+    torch.cuda.synchronize()
+    _t0 = _time.perf_counter()
+    step(dev_sample, False)                 # one step: the launch queue (~1k entries) never fills, so this is host time only
+    host_enqueue_ms = (_time.perf_counter() - _t0) * 1e3
+    torch.cuda.synchronize()
     # ---- end-to-end through the public API with HOST (pinned) buffers: `e2e` ----
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
-    def e2e_step():
-        s = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        step(s, True)
+    # Every step copies its inputs from pinned host memory and reads its result (loss / action table) back.  The
+    # copies go through the package's input pipeline (bifold_b200.data): batch i+1 moves on a copy stream while
+    # batch i is computed, the loss comes back through pinned memory one step late.  All `steps` copies and reads
+    # happen inside the timed region (the first copy is fully exposed).
+    from bifold_b200.data import DevicePrefetcher, ScalarReader
+
+    def e2e_run(n):
+        pf = DevicePrefetcher((host for _ in range(n)), dev)
+        rd = ScalarReader(dev)
+        for s in pf:
+            r = step(s, False)
+            if train:
+                rd.push(r)
+        vals = rd.drain()
+        assert pf.bytes_copied == n * h2d and (not train or len(vals) == n)
+        return vals
 
     if args.skip_e2e:
         ms_e2e = ms_dev
     else:
-        for _ in range(2):
-            e2e_step()
-        ms_e2e = timed(e2e_step, args.steps)
+        e2e_run(2)
+        ms_e2e = timed(lambda: e2e_run(args.steps), 1)
     d2h = 4 if train else 4 * B * 2 * 4
     per_step = ms_dev / args.steps
     value = B * world / (per_step / 1e3)
@@ -311,7 +330,7 @@ def main():
                 "dtype": args.precision, "data": "synthetic", "config": workload_config(args, B, world),
                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks,
+                "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks,
                 "model_flops_per_sample": tr_flops if train else fw_flops,
                 "model_tflops_per_gpu": (tr_flops if train else fw_flops) * B / (per_step / 1e3) / 1e12,
                 "model_frac_of_bf16_peak": (tr_flops if train else fw_flops) * B / (per_step / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],

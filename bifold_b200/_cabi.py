@@ -32,7 +32,8 @@ class GemmArgs(C.Structure):
 
 class LayerNormFwdArgs(C.Structure):
     _fields_ = [("M", i32), ("D", i32), ("x", vp), ("ldx", i64), ("gamma", vp), ("beta", vp), ("eps", f32),
-                ("y", vp), ("ldy", i64), ("y_dtype", i32), ("mean", vp), ("rstd", vp)]
+                ("y", vp), ("ldy", i64), ("y_dtype", i32), ("mean", vp), ("rstd", vp),
+                ("y2", vp), ("ldy2", i64), ("y2_dropout_p", f32), ("y2_seed", u64)]
 
 
 class LayerNormBwdArgs(C.Structure):
@@ -99,6 +100,13 @@ class ActionArgs(C.Structure):
                 ("out_xy", vp), ("out_conf", vp)]
 
 
+class LoraGradsArgs(C.Structure):
+    _fields_ = [("M", i32), ("D", i32), ("r", i32),
+                ("dqkv", vp), ("ld_dqkv", i64), ("u", vp), ("ld_u", i64), ("du", vp), ("ld_du", i64), ("x", vp), ("ld_x", i64),
+                ("scale", f32), ("dBq", vp), ("dBv", vp), ("dAq", vp), ("dAv", vp),
+                ("workspace", vp), ("workspace_bytes", i64)]
+
+
 class AdamWArgs(C.Structure):
     _fields_ = [("n", i64), ("p", vp), ("g", vp), ("m", vp), ("v", vp), ("shadow_bf16", vp),
                 ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("weight_decay", f32),
@@ -123,6 +131,8 @@ _PROTOS = {
     "bfk_lora_down": (i32, [vp, i64, i32, i32, i32, vp, f32, u64, vp]),
     "bfk_lora_down_bwd": (i32, [vp, i64, i32, i32, i32, vp, f32, u64, vp]),
     "bfk_dropout_copy": (i32, [vp, i64, vp, i64, i32, i32, i32, f32, u64, vp]),
+    "bfk_lora_grads_workspace_bytes": (C.c_size_t, [i32]),
+    "bfk_lora_grads": (i32, [C.POINTER(LoraGradsArgs), vp]),
     "bfk_skinny_gram_workspace_floats": (C.c_size_t, [i32, i32, i32]),
     "bfk_skinny_gram": (i32, [vp, i64, i32, vp, i64, i32, i32, i32, f32, vp, i64, i32, f32, u64, vp, vp]),
     "bfk_assemble_fwd": (i32, [C.POINTER(AssembleArgs), vp]),

@@ -93,17 +93,23 @@ struct AttnSmem {
 // =====================================================================================================
 // forward
 // =====================================================================================================
-template <int NA>
-__global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, AttnTcParams p) {
+// BW = key-block width.  BW = 64: 128 TMEM columns and 64 KB of shared memory per CTA (three CTAs per SM), and each
+// row warp owns exactly one 32-column chunk of S per step.
+template <int NA, int BW>
+__global__ void __launch_bounds__(AT_THREADS, (NA == 1 && BW == 64) ? 3 : 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv, AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr uint32_t TILE = NA * AT_ATOM;
+  constexpr uint32_t TILE = NA * AT_ATOM;                    // Q: 128 rows
+  constexpr uint32_t KATOM = BW * 128, KTILE = NA * KATOM;   // K, V blocks: BW rows
+  constexpr uint32_t P_BYTES = (BW / 64) * AT_ATOM;          // P: 128 rows x BW keys (bf16)
+  constexpr int TCOLS = (BW + NA * 64) <= 128 ? 128 : 256;
   const uint32_t base = smem_u32(smem_raw);
-  const uint32_t sQ = base, sK = sQ + TILE, sV = sK + 2 * TILE, sP = sV + 2 * TILE, bars = sP + 2 * AT_ATOM;
+  const uint32_t sQ = base, sK = sQ + TILE, sV = sK + 2 * KTILE, sP = sV + 2 * KTILE, bars = sP + P_BYTES;
   const uint32_t bar_q = bars, bar_k0 = bars + 8, bar_v0 = bars + 24, bar_s = bars + 40, bar_p = bars + 48, bar_o = bars + 56,
                  tmem_slot = bars + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int nblk = (p.N + 127) / 128;
+  const int nblk = (p.N + BW - 1) / BW;
 
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
@@ -114,14 +120,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
     fence_async_smem();
   }
   if (warp == AT_ROW_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
-  const uint32_t tS = tmem, tO = tmem + 128;
+  const uint32_t tS = tmem, tO = tmem + BW;
 
   if (warp == AT_ROW_WARPS) {
     if (lane == 0) {
@@ -129,18 +135,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
       // bar_s(j+1) also tells the row warps that P V(j) is done (P tile free, O safe to rescale).
       const uint32_t idesc_o = make_idesc(128, p.n_o, false, true);
       auto issue_k = [&](int j) {
-        mbar_expect_tx(bar_k0 + 8 * (j & 1), TILE);
-        load_tile<NA>(sK + (j & 1) * TILE, &map_qkv, bar_k0 + 8 * (j & 1), p.H + h, j * 128, b);
+        mbar_expect_tx(bar_k0 + 8 * (j & 1), KTILE);
+        load_tile<NA>(sK + (j & 1) * KTILE, &map_kv, bar_k0 + 8 * (j & 1), p.H + h, j * BW, b, KATOM);
       };
       auto issue_v = [&](int j) {
-        mbar_expect_tx(bar_v0 + 8 * (j & 1), TILE);
-        load_tile<NA>(sV + (j & 1) * TILE, &map_qkv, bar_v0 + 8 * (j & 1), 2 * p.H + h, j * 128, b);
+        mbar_expect_tx(bar_v0 + 8 * (j & 1), KTILE);
+        load_tile<NA>(sV + (j & 1) * KTILE, &map_kv, bar_v0 + 8 * (j & 1), 2 * p.H + h, j * BW, b, KATOM);
       };
       auto issue_s = [&](int j) {
         mbar_wait(bar_k0 + 8 * (j & 1), (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t idesc_sj = make_idesc(128, kv_cols(p.N, j), false, false);
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tS, kmajor_desc(sQ, k), kmajor_desc(sK + (j & 1) * TILE, k), idesc_sj, k > 0);
+        const uint32_t idesc_sj = make_idesc(128, kv_cols(p.N, j, BW), false, false);
+        for (int k = 0; k < p.ksteps; ++k)
+          tc_mma_bf16(tS, kmajor_desc(sQ, k), kmajor_desc(sK + (j & 1) * KTILE, k, KATOM), idesc_sj, k > 0);
         tc_commit(bar_s);
       };
       mbar_expect_tx(bar_q, TILE);
@@ -156,9 +163,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
         if (j >= 1 && j + 1 < nblk) issue_v(j + 1);
         mbar_wait(bar_v0 + 8 * (j & 1), (j >> 1) & 1);
         tc_fence_after();
-        const int nc = kv_cols(p.N, j);
+        const int nc = kv_cols(p.N, j, BW);
         for (int k = 0; k < nc / 16; ++k)
-          tc_mma_bf16(tO, kmajor_desc(sP, k), mnmajor_desc(sV + (j & 1) * TILE, k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          tc_mma_bf16(tO, kmajor_desc(sP, k), mnmajor_desc(sV + (j & 1) * KTILE, k, KATOM), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         if (j + 1 < nblk) issue_s(j + 1); else tc_commit(bar_o);
       }
     }
@@ -169,46 +176,34 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
     const int r = quarter * 32 + lane, q = q0 + r;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     float* xch = reinterpret_cast<float*>(smem_raw + (bars + 128 - base));   // [128]
+    __nv_bfloat16* xch16 = reinterpret_cast<__nv_bfloat16*>(xch);            // [2][128] view of the same 512 bytes
     const bool quarter_live = q0 + quarter * 32 < p.N;      // warp-uniform: any real query row in this quarter?
     const bool masked = p.row_mask && q < p.N && p.row_mask[(long long)b * p.N + q] == 0.f;
     // masked query row: every score equal => p == 1 for every key (scale 0, max 0)
     const float sl2 = masked ? 0.f : p.scale * LOG2E;
     float m_run = -INFINITY, l_run = 0.f;   // running max (scaled, log2 domain) and this warp's partial row sum
     for (int j = 0; j < nblk; ++j) {
-      const int nc = kv_cols(p.N, j);              // columns computed for this block (multiple of 16)
-      const int nvalid = min(128, p.N - j * 128);  // real keys in this block
+      const int nc = kv_cols(p.N, j, BW);          // columns computed for this block (multiple of 16)
+      const int nvalid = min(BW, p.N - j * BW);    // real keys in this block
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
       if (!quarter_live) {                         // rows beyond the sequence: stay in lock-step, do nothing
         mbar_arrive(bar_p);
         continue;
       }
-      // pass 1: raw row max over the real keys of this warp's chunks
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = half * 32; c < nc; c += 64) {
-        uint32_t sreg[32];
-        tc_ld32(tS + lane_off + c, sreg);
-        tc_wait_ld();
-        const int lim = min(32, nvalid - c);
-#pragma unroll
-        for (int t = 0; t < 32; ++t)
-          if (t < lim) mx = fmaxf(mx, __uint_as_float(sreg[t]));
-      }
-      // combine the two halves of the row: half 1 -> half 0 -> half 1
-      if (half == 1) xch[r] = mx;
-      named_bar_sync(1 + quarter, 64);
-      if (half == 0) { mx = fmaxf(mx, xch[r]); xch[r] = mx; }
-      named_bar_sync(1 + quarter, 64);
-      if (half == 1) mx = xch[r];
-      const float m_new = masked ? 0.f : fmaxf(m_run, mx * sl2);
-      const float alpha = ex2f(m_run - m_new);
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int c = half * 32; c < nc; c += 64) {
-        uint32_t sreg[32];
-        tc_ld32(tS + lane_off + c, sreg);
-        tc_wait_ld();
+      float mx = -INFINITY, rowsum = 0.f, m_new, alpha;
+      auto exchange_max = [&]() {
+        // The two halves of a row must subtract the SAME reference; it need not be the exact maximum (the result is
+        // invariant to it), so each half publishes its max rounded UP to bf16 and both take the larger one: one
+        // 64-thread barrier, 512 bytes of exchange space.
+        __nv_bfloat16 mb = __float2bfloat16_ru(mx);
+        xch16[half * 128 + r] = mb;
+        named_bar_sync(1 + quarter, 64);
+        mx = fmaxf(__bfloat162float(mb), __bfloat162float(xch16[(half ^ 1) * 128 + r]));
+        m_new = masked ? 0.f : fmaxf(m_run, mx * sl2);
+        alpha = ex2f(m_run - m_new);
+      };
+      auto pass2 = [&](const uint32_t (&sreg)[32], int c) {
         const int ng = min(4, (nc - c) >> 3);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -224,6 +219,27 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
             for (int t = 0; t < 8; ++t) rowsum += v[t];
             store_p_chunk(sP, r, (c >> 3) + g, v);
           }
+        }
+      };
+      {
+        // pass 1: raw row max over the real keys of this warp's chunks
+#pragma unroll 1
+        for (int c = half * 32; c < nc; c += 64) {
+          uint32_t sreg[32];
+          tc_ld32(tS + lane_off + c, sreg);
+          tc_wait_ld();
+          const int lim = min(32, nvalid - c);
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            if (t < lim) mx = fmaxf(mx, __uint_as_float(sreg[t]));
+        }
+        exchange_max();
+#pragma unroll 1
+        for (int c = half * 32; c < nc; c += 64) {
+          uint32_t sreg[32];
+          tc_ld32(tS + lane_off + c, sreg);
+          tc_wait_ld();
+          pass2(sreg, c);
         }
       }
       l_run = l_run * alpha + rowsum;
@@ -267,7 +283,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
   __syncthreads();
   if (warp == AT_ROW_WARPS) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TCOLS) : "memory");
   }
 }
 
@@ -276,8 +292,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
 // =====================================================================================================
 // BW = key-block width.  BW = 64 keeps the TMEM footprint at 256 columns (S, dP: 64 each, dQ: up to 128), so two CTAs
 // share an SM and one's MMA / TMA / barrier latencies hide behind the other's softmax math.
-// Issue order of the control thread: ... dQ(j) | S(j+1), dP(j+1) -> commit(bar_s) ...  tcgen05 ops of one thread
-// complete in order, so bar_s(j+1) also tells the row warps that dQ(j) has finished reading the dS tile.
+// Issue order of the control thread after the row warps hand over dS(j):  S(j+1), dP(j+1) -> commit(bar_s) | dQ(j) ->
+// commit(bar_dq).  The products the row warps wait for go first; dS is double-buffered so dQ(j) may still read buffer
+// j&1 while the rows fill buffer (j+1)&1 (tcgen05 ops of one thread complete in order: bar_s(j+2) implies dQ(j) done).
 template <int NA, int BW, int NBUF>
 __global__ void __launch_bounds__(AT_THREADS, NA == 1 && BW == 64 ? 2 : 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
@@ -288,8 +305,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   constexpr uint32_t DS_BYTES = (BW / 64) * AT_ATOM;  // dS: 128 rows x BW keys (bf16)
   constexpr int TCOLS = (2 * BW + NA * 64) <= 256 ? 256 : 512;
   const uint32_t base = smem_u32(smem_raw);
-  const uint32_t sQ = base, sdO = sQ + TILE, sK = sdO + TILE, sV = sK + NBUF * KTILE, sdS = sV + NBUF * KTILE, bars = sdS + DS_BYTES;
-  const uint32_t bar_q = bars, bar_kv0 = bars + 8, bar_s = bars + 40, bar_p = bars + 48, bar_o = bars + 56, tmem_slot = bars + 64;
+  const uint32_t sQ = base, sdO = sQ + TILE, sK = sdO + TILE, sV = sK + NBUF * KTILE, sdS = sV + NBUF * KTILE, bars = sdS + 2 * DS_BYTES;
+  const uint32_t bar_q = bars, bar_kv0 = bars + 8, bar_s = bars + 40, bar_p = bars + 48, bar_o = bars + 56, bar_dq = bars + 72, tmem_slot = bars + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nblk = (p.N + BW - 1) / BW;
@@ -298,7 +315,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (base & 1023u) __trap();
     mbar_init(bar_q, 1);
     for (int i = 0; i < NBUF; ++i) mbar_init(bar_kv0 + 8 * i, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_p, 32 * AT_ROW_WARPS); mbar_init(bar_o, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_p, 32 * AT_ROW_WARPS); mbar_init(bar_o, 1); mbar_init(bar_dq, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -333,18 +350,22 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       mbar_expect_tx(bar_q, 2 * TILE);
       load_tile<NA>(sQ, &map_q, bar_q, h, q0, b, AT_ATOM);
       load_tile<NA>(sdO, &map_do, bar_q, h, q0, b, AT_ATOM);
-      for (int j = 0; j < NBUF - 1 && j < nblk; ++j) issue_kv(j);
+      for (int j = 0; j < NBUF && j < nblk; ++j) issue_kv(j);
       mbar_wait(bar_q, 0);
       issue_s(0);
       for (int j = 0; j < nblk; ++j) {
-        mbar_wait(bar_p, j & 1);      // dS(j) is in smem, S(j)/dP(j) have been read; S(j) done => block j-1 fully consumed
+        mbar_wait(bar_p, j & 1);      // dS(j) is in smem buffer j&1, S(j)/dP(j) have been read
         tc_fence_after();
-        if (j + NBUF - 1 < nblk) issue_kv(j + NBUF - 1);   // into the buffer block j-1 used
-        const uint32_t k_t = sK + (j % NBUF) * KTILE;
+        if (j + 1 < nblk) issue_s(j + 1);
+        if (j >= 1) {                 // every bar_dq phase is consumed, in order, BEFORE the next one is committed
+          mbar_wait(bar_dq, (j - 1) & 1);
+          if (j + NBUF - 1 < nblk) issue_kv(j + NBUF - 1);   // dQ(j-1) done: refill the buffer block j-1 used
+        }
+        const uint32_t k_t = sK + (j % NBUF) * KTILE, ds_t = sdS + (j & 1) * DS_BYTES;
         const int nc = kv_cols(p.N, j, BW);
         for (int k = 0; k < nc / 16; ++k)
-          tc_mma_bf16(tdQ, kmajor_desc(sdS, k, AT_ATOM), mnmajor_desc(k_t, k, KATOM), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
-        if (j + 1 < nblk) issue_s(j + 1); else tc_commit(bar_o);
+          tc_mma_bf16(tdQ, kmajor_desc(ds_t, k, AT_ATOM), mnmajor_desc(k_t, k, KATOM), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+        if (j + 1 < nblk) tc_commit(bar_dq); else tc_commit(bar_o);
       }
     }
   } else {
@@ -380,7 +401,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 const float pr = ex2f(fmaf(__uint_as_float(sreg[g * 8 + t]), sl2, -lse2));
                 v[t] = pr * (__uint_as_float(d[g * 8 + t]) - delta);
               }
-              store_p_chunk(sdS, r, (c >> 3) + g, v);
+              store_p_chunk(sdS + (j & 1) * DS_BYTES, r, (c >> 3) + g, v);
             }
           }
         }
@@ -684,20 +705,31 @@ static int bwd_block_width() {   // BFK_ATTN_BW=128 selects the one-CTA-per-SM 1
   return v;
 }
 
-int attention_fwd_tc(const bfk_attention_args* a, cudaStream_t s) {
-  CUtensorMap mq;
+static int fwd_block_width() {   // BFK_ATTN_FWD_BW=128 selects the 128-wide variant (measurement only)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BFK_ATTN_FWD_BW"); v = (e && atoi(e) == 128) ? 128 : 64; }
+  return v;
+}
+
+template <int NA, int BW>
+static int launch_fwd(const bfk_attention_args* a, const AttnTcParams& p, cudaStream_t s) {
+  CUtensorMap mq, mk;
   if (!make_map4(&mq, a->qkv, a->hd, 3 * a->H, a->N, a->B, a->ld_qkv, 128)) return BFK_E_CUDA;
-  AttnTcParams p = make_params(a);
+  if (!make_map4(&mk, a->qkv, a->hd, 3 * a->H, a->N, a->B, a->ld_qkv, BW)) return BFK_E_CUDA;
+  // NA == 1: 66176 bytes (BW 64, three CTAs per SM) / 115328 bytes (BW 128, two CTAs per SM)
+  const size_t smem = NA * AT_ATOM + 4 * NA * BW * 128 + (BW / 64) * AT_ATOM + 640;
+  if (int rc = set_attr(attn_fwd_tc_kernel<NA, BW>, smem, "attn_fwd_tc")) return rc;
   dim3 grid((a->N + 127) / 128, a->H, a->B);
-  if (a->hd <= 64) {
-    const size_t smem = 5 * AT_ATOM + 2 * AT_ATOM + 640;   // 2 CTAs/SM: (233472 - 2*1024)/2 = 115712 >= 115328
-    if (int rc = set_attr(attn_fwd_tc_kernel<1>, smem, "attn_fwd_tc")) return rc;
-    attn_fwd_tc_kernel<1><<<grid, AT_THREADS, smem, s>>>(mq, p);
-  } else {
-    const size_t smem = 5 * 2 * AT_ATOM + 2 * AT_ATOM + 640;
-    if (int rc = set_attr(attn_fwd_tc_kernel<2>, smem, "attn_fwd_tc")) return rc;
-    attn_fwd_tc_kernel<2><<<grid, AT_THREADS, smem, s>>>(mq, p);
-  }
+  attn_fwd_tc_kernel<NA, BW><<<grid, AT_THREADS, smem, s>>>(mq, mk, p);
+  return BFK_OK;
+}
+
+int attention_fwd_tc(const bfk_attention_args* a, cudaStream_t s) {
+  AttnTcParams p = make_params(a);
+  int rc;
+  if (a->hd <= 64) rc = fwd_block_width() == 64 ? launch_fwd<1, 64>(a, p, s) : launch_fwd<1, 128>(a, p, s);
+  else rc = fwd_block_width() == 64 ? launch_fwd<2, 64>(a, p, s) : launch_fwd<2, 128>(a, p, s);
+  if (rc) return rc;
   BFK_CHECK_LAUNCH("attention_fwd_tc");
   return BFK_OK;
 }
@@ -710,8 +742,8 @@ static int launch_bwd(const bfk_attention_args* a, const AttnTcParams& p, cudaSt
   if (!make_map4(&md128, a->dout, a->hd, a->H, a->N, a->B, a->ld_dout, 128)) return BFK_E_CUDA;
   if (!make_map4(&mdb, a->dout, a->hd, a->H, a->N, a->B, a->ld_dout, BW)) return BFK_E_CUDA;
   constexpr size_t TILE = NA * AT_ATOM, BTILE = NA * BW * 128, STAGE = (BW / 64) * AT_ATOM;
-  // NA == 1, BW == 64: 98560 and 115472 bytes -- two CTAs per SM ((233472 - 2*1024)/2 = 115712)
-  const size_t smem_q = 2 * TILE + 2 * NBUF * BTILE + STAGE + 256;
+  // NA == 1, BW == 64: 114944 and 115344 bytes -- two CTAs per SM ((233472 - 2*1024)/2 = 115712)
+  const size_t smem_q = 2 * TILE + 2 * NBUF * BTILE + 2 * STAGE + 256;
   const size_t smem_kv = 2 * TILE + 2 * NBUF * BTILE + 2 * STAGE + 128 + BW * 8 + 16;
   if (int rc = set_attr(attn_bwd_dq_tc_kernel<NA, BW, NBUF>, smem_q, "attn_bwd_dq_tc")) return rc;
   if (int rc = set_attr(attn_bwd_dkv_tc_kernel<NA, BW, NBUF>, smem_kv, "attn_bwd_dkv_tc")) return rc;

@@ -96,12 +96,22 @@ __global__ void colsum_stage1(const T* __restrict__ X, int M, int N, long long l
   for (; r < r1; ++r) s0 += to_f32<T>(X[(long long)r * ld + n]);
   partials[(long long)blockIdx.y * N + n] = (s0 + s1) + (s2 + s3);
 }
-__global__ void colsum_stage2(const float* __restrict__ partials, int nb, int N, float* __restrict__ out) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// 32 columns x 8 row-slices per block; fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) colsum_stage2(const float* __restrict__ partials, int nb, int N, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + col;
   float s = 0.f;
-  for (int b = 0; b < nb; ++b) s += partials[(long long)b * N + n];
-  out[n] = s;
+  if (n < N)
+    for (int b = slice; b < nb; b += 8) s += partials[(long long)b * N + n];
+  red[slice][col] = s;
+  __syncthreads();
+  if (slice == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][col];
+    out[n] = t;
+  }
 }
 
 }  // namespace bfk
@@ -119,7 +129,7 @@ extern "C" int32_t bfk_colsum(const void* X, int32_t dtype, int32_t M, int32_t N
   dim3 grid((N + 127) / 128, nb);
   if (dtype == BFK_BF16) colsum_stage1<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16*)X, M, N, ld, partials);
   else colsum_stage1<float><<<grid, 128, 0, s>>>((const float*)X, M, N, ld, partials);
-  colsum_stage2<<<(N + 127) / 128, 128, 0, s>>>(partials, nb, N, out);
+  colsum_stage2<<<(N + 31) / 32, 256, 0, s>>>(partials, nb, N, out);
   BFK_CHECK_LAUNCH("bfk_colsum");
   return BFK_OK;
 }

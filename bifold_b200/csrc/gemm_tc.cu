@@ -320,8 +320,10 @@ static int gemm_dbg() {   // BFK_GEMM_DBG: 1 = skip the epilogue body, 2 = skip 
   return v;
 }
 
+// partial_only: leave the fp32 K-split partials [splits][M][N] in the workspace (even for splits == 1) and skip the
+// reduction -- the caller fuses it into its own kernel (bfk_lora_grads).
 template <int BN, bool AMN, bool BMN, int CL>
-static int launch_tc_cl(const bfk_gemm_args* a, cudaStream_t s, int splits) {
+static int launch_tc_cl(const bfk_gemm_args* a, cudaStream_t s, int splits, bool partial_only = false) {
   using Cfg = TcCfg<BN>;
   CUtensorMap ma, mb;
   bool ok;
@@ -340,7 +342,7 @@ static int launch_tc_cl(const bfk_gemm_args* a, cudaStream_t s, int splits) {
     attr_set = true;
   }
   const long long split_stride = (long long)a->M * a->N;
-  if (splits > 1) {   // partial tiles go to the workspace as plain fp32 [splits][M][N]
+  if (splits > 1 || partial_only) {   // partial tiles go to the workspace as plain fp32 [splits][M][N]
     ep.D = a->workspace; ep.ldd = a->N; ep.out_dtype = BFK_F32; ep.alpha = 1.f; ep.accumulate = 0;
     ep.vec_ok = ((reinterpret_cast<uintptr_t>(a->workspace) & 31u) == 0 && (a->N % 8) == 0 && (split_stride % 8) == 0) ? 1 : 0;
   }
@@ -355,7 +357,7 @@ static int launch_tc_cl(const bfk_gemm_args* a, cudaStream_t s, int splits) {
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AMN, BMN, CL>, ma, mb, a->M, a->N, a->K, ep, splits, split_stride, gemm_dbg());
   if (le != cudaSuccess) { set_error("gemm_tc: launch failed: %s", cudaGetErrorString(le)); return BFK_E_CUDA; }
-  if (splits > 1) {
+  if (splits > 1 && !partial_only) {
     const long long total = (long long)a->M * a->N;
     const int rg = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
     splitk_reduce_kernel<<<rg, 256, 0, s>>>((const float*)a->workspace, splits, split_stride, a->M, a->N, a->alpha, (float*)a->D, a->ldd,
@@ -366,8 +368,12 @@ static int launch_tc_cl(const bfk_gemm_args* a, cudaStream_t s, int splits) {
 }
 
 template <int BN, bool AMN, bool BMN>
-static int launch_tc(const bfk_gemm_args* a, cudaStream_t s) {
+static int launch_tc(const bfk_gemm_args* a, cudaStream_t s, int* partial_splits = nullptr) {
   const int splits = choose_splits(a, BN);
+  if (partial_splits) {
+    *partial_splits = splits;
+    return launch_tc_cl<BN, AMN, BMN, 1>(a, s, splits, true);
+  }
   const int num_m = (a->M + TC_BM - 1) / TC_BM, num_n = (a->N + BN - 1) / BN;
   if (pair_enabled() && BN == 256 && splits == 1 && a->M >= 256 && ((a->M + 255) / 256) * num_n >= sm_count() / 4)
     return gemm_tc2(a, s);
@@ -375,6 +381,12 @@ static int launch_tc(const bfk_gemm_args* a, cudaStream_t s) {
   if (cluster_enabled() && splits == 1 && num_m >= 2 && num_m * num_n >= sm_count() / 2)
     return launch_tc_cl<BN, AMN, BMN, 2>(a, s, splits);
   return launch_tc_cl<BN, AMN, BMN, 1>(a, s, splits);
+}
+
+// wgrad-shaped product (A and B both stored [K, rows]) whose K-split partials stay in a->workspace; *splits = count
+int gemm_tc_wgrad_partials(const bfk_gemm_args* a, cudaStream_t s, int* splits) {
+  if (a->N > 128) return launch_tc<256, true, true>(a, s, splits);
+  return launch_tc<128, true, true>(a, s, splits);
 }
 
 int gemm_tc(const bfk_gemm_args* a, cudaStream_t s) {

@@ -8,6 +8,28 @@ namespace bfk {
 constexpr int LN_WARPS = 8;
 constexpr int LN_MAXC = 12;  // float4 chunks per lane: D <= 1536 (kernels are templated on the actual chunk count)
 
+template <typename T> __device__ __forceinline__ float4 load4(const T* p, int c);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p, int c) {
+  return reinterpret_cast<const float4*>(p)[c];
+}
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p, int c) {
+  uint2 u = reinterpret_cast<const uint2*>(p)[c];
+  float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x));
+  float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, int c, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, int c, float4 v) {
+  reinterpret_cast<float4*>(p)[c] = v;
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, int c, float4 v) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&p0);
+  u.y = *reinterpret_cast<uint32_t*>(&p1);
+  reinterpret_cast<uint2*>(p)[c] = u;
+}
+
 template <typename TY, int LN_MAXC>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(bfk_layernorm_fwd_args a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -43,6 +65,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(bfk_layernorm_fwd
   const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
   const float4* b4 = reinterpret_cast<const float4*>(a.beta);
   TY* y = reinterpret_cast<TY*>(a.y) + (long long)row * a.ldy;
+  TY* y2 = a.y2 ? reinterpret_cast<TY*>(a.y2) + (long long)row * a.ldy2 : nullptr;
+  const float keep2 = a.y2_dropout_p > 0.f ? 1.f / (1.f - a.y2_dropout_p) : 1.f;
 #pragma unroll
   for (int i = 0; i < LN_MAXC; ++i) {
     int c = lane + 32 * i;
@@ -58,31 +82,21 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(bfk_layernorm_fwd
         u.x = *reinterpret_cast<uint32_t*>(&p0);
         u.y = *reinterpret_cast<uint32_t*>(&p1);
         reinterpret_cast<uint2*>(y)[c] = u;
+        // the dropped copy starts from the ROUNDED value (what a separate dropout pass over y would read)
+        const float2 r0 = __bfloat1622float2(p0), r1 = __bfloat1622float2(p1);
+        o0 = r0.x; o1 = r0.y; o2 = r1.x; o3 = r1.y;
+      }
+      if (y2) {
+        if (a.y2_dropout_p > 0.f) {
+          o0 = hash_uniform(a.y2_seed, row, 4 * c + 0) < a.y2_dropout_p ? 0.f : o0 * keep2;
+          o1 = hash_uniform(a.y2_seed, row, 4 * c + 1) < a.y2_dropout_p ? 0.f : o1 * keep2;
+          o2 = hash_uniform(a.y2_seed, row, 4 * c + 2) < a.y2_dropout_p ? 0.f : o2 * keep2;
+          o3 = hash_uniform(a.y2_seed, row, 4 * c + 3) < a.y2_dropout_p ? 0.f : o3 * keep2;
+        }
+        store4<TY>(y2, c, make_float4(o0, o1, o2, o3));
       }
     }
   }
-}
-
-template <typename T> __device__ __forceinline__ float4 load4(const T* p, int c);
-template <> __device__ __forceinline__ float4 load4<float>(const float* p, int c) {
-  return reinterpret_cast<const float4*>(p)[c];
-}
-template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p, int c) {
-  uint2 u = reinterpret_cast<const uint2*>(p)[c];
-  float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x));
-  float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-template <typename T> __device__ __forceinline__ void store4(T* p, int c, float4 v);
-template <> __device__ __forceinline__ void store4<float>(float* p, int c, float4 v) {
-  reinterpret_cast<float4*>(p)[c] = v;
-}
-template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, int c, float4 v) {
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
-  uint2 u;
-  u.x = *reinterpret_cast<uint32_t*>(&p0);
-  u.y = *reinterpret_cast<uint32_t*>(&p1);
-  reinterpret_cast<uint2*>(p)[c] = u;
 }
 
 // raw (as stored) 4-element chunk: loads are issued in one batch per operand with no control flow in between, so a
@@ -240,6 +254,7 @@ static int ln_bwd_blocks(int M, int& rows_per_block, bool param_grads = true) {
 extern "C" int32_t bfk_layernorm_fwd(const bfk_layernorm_fwd_args* a, bfk_stream_t s_) {
   using namespace bfk;
   BFK_CHECK_ARG(a && a->x && a->y && a->gamma && a->beta, "bfk_layernorm_fwd: null pointer");
+  BFK_CHECK_ARG(!a->y2 || a->ldy2 % 4 == 0, "bfk_layernorm_fwd: ldy2 %% 4 != 0");
   BFK_CHECK_ARG(a->M > 0 && a->D > 0 && a->D % 4 == 0 && a->D <= 128 * LN_MAXC && a->ldx % 4 == 0 && a->ldy % 4 == 0,
                 "bfk_layernorm_fwd: need D%%4==0, D<=%d, ld%%4==0 (D=%d)", 128 * LN_MAXC, a->D);
   cudaStream_t s = to_stream(s_);

@@ -59,6 +59,14 @@ class Kernels:
         return self._ws[key]
 
     # -- GEMM ------------------------------------------------------------------------------------
+    def lora_ws(self, device, D):
+        key = ("lora", device, torch.cuda.current_stream().cuda_stream)
+        if self._ws is None:
+            self._ws = {}
+        if key not in self._ws:
+            self._ws[key] = torch.empty(self.lib.bfk_lora_grads_workspace_bytes(D) // 4, device=device, dtype=torch.float32)
+        return self._ws[key]
+
     def gemm(self, A, B, D, M, N, Kd, lda, ldb, ldd, trans_a=False, trans_b=False, bias=None, act=K.ACT_NONE,
              aux=None, ld_aux=0, residual=None, ldr=0, res_row_mod=0, alpha=1.0, accumulate=False, backend=None,
              split_k=0):
@@ -77,9 +85,9 @@ class Kernels:
         self.launches += 2
 
     # -- LayerNorm ---------------------------------------------------------------------------------
-    def layernorm_fwd(self, x, M, D, gamma, beta, eps, y, ldy, mean=None, rstd=None):
+    def layernorm_fwd(self, x, M, D, gamma, beta, eps, y, ldy, mean=None, rstd=None, y2=None, ldy2=0, y2_p=0.0, y2_seed=0):
         a = K.LayerNormFwdArgs(M, D, x.data_ptr(), D, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(), ldy, _dt(y),
-                               K.ptr(mean), K.ptr(rstd))
+                               K.ptr(mean), K.ptr(rstd), K.ptr(y2), ldy2, y2_p, y2_seed)
         K.check(self.lib.bfk_layernorm_fwd(C.byref(a), _stream()), "bfk_layernorm_fwd")
         self.launches += 1
 
@@ -275,18 +283,14 @@ class Engine:
         Mlp = lw.W1.shape[0]
         h1 = torch.empty(M, Dk, device=dev, dtype=T)
         mean1 = torch.empty(M, device=dev, dtype=torch.float32); rstd1 = torch.empty_like(mean1)
-        k.layernorm_fwd(x, M, D, lw.ln1_w, lw.ln1_b, eps, h1, Dk, mean1, rstd1)
         p_drop = self.cfg.lora_dropout if (lw.Acat is not None and self.training) else 0.0
         h1d = None
+        if lw.Acat is not None and T == torch.bfloat16 and p_drop > 0.0:
+            h1d = torch.empty(M, D, device=dev, dtype=T)   # drop(h1): the LoRA branch input, written by the same LN pass
+        k.layernorm_fwd(x, M, D, lw.ln1_w, lw.ln1_b, eps, h1, Dk, mean1, rstd1, y2=h1d, ldy2=D, y2_p=p_drop, y2_seed=lora_seed)
         if lw.Acat is not None and T == torch.bfloat16:
             # LoRA down-projection on the tensor cores: u = drop(h1) Acat^T written into the 16 extra K columns
-            lora_in, ld_in = h1, Dk
-            if p_drop > 0.0:
-                h1d = torch.empty(M, D, device=dev, dtype=T)
-                K.check(k.lib.bfk_dropout_copy(h1.data_ptr(), Dk, h1d.data_ptr(), D, _dt(h1), M, D, p_drop, lora_seed, _stream()),
-                        "bfk_dropout_copy")
-                k.launches += 1
-                lora_in, ld_in = h1d, D
+            lora_in, ld_in = (h1d, D) if h1d is not None else (h1, Dk)
             k.gemm(lora_in, lw.Acat, h1[:, D:], M, 16, D, ld_in, D, Dk)
         elif lw.Acat is not None:
             K.check(k.lib.bfk_lora_down(h1.data_ptr(), Dk, _dt(h1), M, D, lw.Acat.data_ptr(), p_drop, lora_seed, _stream()),
@@ -375,10 +379,19 @@ class Engine:
         if self.T == torch.bfloat16:
             # tensor-core path: split-K "wgrad" GEMMs for the factors, one K=16 GEMM for the dh1 contribution
             x_in, ld_x = (sv["h1d"], D) if sv["h1d"] is not None else (h1, Dk)
-            for (Bn, ucol, qoff) in ((n["Bq"], 0, 0), (n["Bv"], 8, 2 * D)):
-                k.gemm(dqkv[:, qoff:], h1[:, D + ucol:], grads[Bn], D, r, M, 3 * D, Dk, r, trans_a=True, trans_b=True, alpha=s)
-            for (An, ucol) in ((n["Aq"], 0), (n["Av"], 8)):
-                k.gemm(dh1[:, D + ucol:], x_in, grads[An], r, D, M, Dk, ld_x, D, trans_a=True, trans_b=True)
+            if r <= 8 and D % 8 == 0:
+                # both B factors from one dqkv^T u product, both A factors from one du^T x product, one fused reduction
+                ws = k.lora_ws(dqkv.device, D)
+                a = K.LoraGradsArgs(M, D, r, dqkv.data_ptr(), 3 * D, h1.data_ptr() + D * es, Dk, dh1.data_ptr() + D * es, Dk,
+                                    x_in.data_ptr(), ld_x, s, grads[n["Bq"]].data_ptr(), grads[n["Bv"]].data_ptr(),
+                                    grads[n["Aq"]].data_ptr(), grads[n["Av"]].data_ptr(), ws.data_ptr(), ws.numel() * 4)
+                K.check(lib.bfk_lora_grads(C.byref(a), st), "bfk_lora_grads")
+                k.launches += 3
+            else:
+                for (Bn, ucol, qoff) in ((n["Bq"], 0, 0), (n["Bv"], 8, 2 * D)):
+                    k.gemm(dqkv[:, qoff:], h1[:, D + ucol:], grads[Bn], D, r, M, 3 * D, Dk, r, trans_a=True, trans_b=True, alpha=s)
+                for (An, ucol) in ((n["Aq"], 0), (n["Av"], 8)):
+                    k.gemm(dh1[:, D + ucol:], x_in, grads[An], r, D, M, Dk, ld_x, D, trans_a=True, trans_b=True)
             dy2 = torch.empty(M, D, device=dqkv.device, dtype=self.T)
             k.gemm(dh1[:, D:], lw.Acat, dy2, M, D, 16, Dk, D, D, trans_b=True)
             return dy2

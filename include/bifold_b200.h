@@ -91,6 +91,9 @@ typedef struct {
   const float* gamma; const float* beta; float eps;
   void* y; int64_t ldy; int32_t y_dtype;
   float* mean; float* rstd;          /* [M] saved for backward (may be NULL) */
+  /* optional second output (NULL = none), same dtype as y: y2 = dropout(y, p, seed) -- the LoRA-branch input
+   * (peft LoRA lora_dropout on the q_proj / v_proj inputs); same element hash as bfk_dropout_copy / bfk_layernorm_bwd.dy2 */
+  void* y2; int64_t ldy2; float y2_dropout_p; uint64_t y2_seed;
 } bfk_layernorm_fwd_args;
 BFK_API int32_t bfk_layernorm_fwd(const bfk_layernorm_fwd_args* a, bfk_stream_t s);
 
@@ -159,6 +162,27 @@ BFK_API int32_t bfk_lora_down_bwd(void* dh, int64_t ldh, int32_t dtype, int32_t 
 /* dst[m,k] = keep(seed,m,k) ? src[m,k]/(1-p) : 0 — the dropped LoRA input (same counter-based mask as above). */
 BFK_API int32_t bfk_dropout_copy(const void* src, int64_t lds, void* dst, int64_t ldd, int32_t dtype, int32_t M, int32_t D,
                                  float dropout_p, uint64_t seed, bfk_stream_t s);
+/* LoRA factor gradients of one tower layer on the tensor cores (bf16 operands), replacing the autograd of peft's
+ * lora_A / lora_B Linear pair on q_proj and v_proj (rank r <= 8, packed layout: q factors in columns 0..r-1, v factors
+ * in columns 8..8+r-1 of the 16-column blocks):
+ *   dBq[d, j] = scale * sum_m dqkv[m, d]      * u[m, j]          dBv[d, j] = scale * sum_m dqkv[m, 2D + d] * u[m, 8 + j]
+ *   dAq[j, c] =         sum_m du[m, j]        * x[m, c]          dAv[j, c] =         sum_m du[m, 8 + j]    * x[m, c]
+ * Two split-K GEMMs leave fp32 partials in `workspace` (bfk_lora_grads_workspace_bytes(D)), one kernel reduces them in a
+ * fixed order (deterministic) into the four fp32 outputs (overwritten). */
+typedef struct {
+  int32_t M, D, r;
+  const void* dqkv; int64_t ld_dqkv;  /* [M, 3D] bf16 gradient of the packed q|k|v projections */
+  const void* u;    int64_t ld_u;     /* [M, 16]  bf16 A drop(h) */
+  const void* du;   int64_t ld_du;    /* [M, 16]  bf16 gradient w.r.t. u */
+  const void* x;    int64_t ld_x;     /* [M, D]   bf16 drop(h), the LoRA branch input */
+  float scale;                        /* lora_alpha / r */
+  float* dBq; float* dBv;             /* [D, r] */
+  float* dAq; float* dAv;             /* [r, D] */
+  void* workspace; int64_t workspace_bytes;
+} bfk_lora_grads_args;
+BFK_API size_t bfk_lora_grads_workspace_bytes(int32_t D);
+BFK_API int32_t bfk_lora_grads(const bfk_lora_grads_args* a, bfk_stream_t s);
+
 /* Tall-skinny Gram product used for the LoRA weight gradients (deterministic split over rows):
  *   out[i, j] = alpha * sum_m P[m*ldp + i] * mask?(Q[m*ldq + j]),  i < ni (<=16), j < nj.
  * `partials`: bfk_skinny_gram_workspace_floats(M, ni, nj). */

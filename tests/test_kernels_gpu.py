@@ -135,6 +135,51 @@ def test_layernorm_fwd_bwd(kern, D, ydt):
     assert (dx_b - gx).abs().max().item() <= tol * gx.abs().max().item()
 
 
+def test_layernorm_fwd_fused_dropout_copy(kern):
+    """The optional second LN output equals bfk_dropout_copy applied to the first (same element hash)."""
+    from bifold_b200 import _cabi as K
+    M, D, p, seed = 333, 768, 0.1, 1234567
+    x = torch.randn(M, D, device="cuda")
+    gam = torch.randn(D, device="cuda"); bet = torch.randn(D, device="cuda")
+    y = torch.zeros(M, D + 16, device="cuda", dtype=torch.bfloat16)
+    y2 = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    kern.layernorm_fwd(x, M, D, gam, bet, 1e-6, y, D + 16, y2=y2, ldy2=D, y2_p=p, y2_seed=seed)
+    ref = torch.empty_like(y2)
+    K.check(kern.lib.bfk_dropout_copy(y.data_ptr(), D + 16, ref.data_ptr(), D, K.BF16, M, D, p, seed,
+                                      torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(y2, ref)
+    frac = (y2 == 0).float().mean().item()
+    assert 0.07 < frac < 0.13
+
+
+@pytest.mark.parametrize("M,D,r", [(1000, 64, 8), (12544, 768, 8), (777, 128, 4)])
+def test_lora_grads_fused(kern, M, D, r):
+    """bfk_lora_grads (two split-K tcgen05 GEMMs + one reduction) against fp32 matmuls of the same bf16 inputs."""
+    from bifold_b200 import _cabi as K
+    g = torch.Generator().manual_seed(M + D)
+    Dk = D + 16
+    dqkv = torch.randn(M, 3 * D, generator=g).cuda().bfloat16()
+    h1 = torch.randn(M, Dk, generator=g).cuda().bfloat16()      # u = h1[:, D:]
+    dh1 = torch.randn(M, Dk, generator=g).cuda().bfloat16()     # du = dh1[:, D:]
+    x = torch.randn(M, D, generator=g).cuda().bfloat16()
+    outs = [torch.full((D, r), float("nan"), device="cuda"), torch.full((D, r), float("nan"), device="cuda"),
+            torch.full((r, D), float("nan"), device="cuda"), torch.full((r, D), float("nan"), device="cuda")]
+    ws = torch.empty(kern.lib.bfk_lora_grads_workspace_bytes(D) // 4, device="cuda")
+    scale = 2.0
+    a = K.LoraGradsArgs(M, D, r, dqkv.data_ptr(), 3 * D, h1.data_ptr() + 2 * D, Dk, dh1.data_ptr() + 2 * D, Dk, x.data_ptr(), D,
+                        scale, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), ws.data_ptr(),
+                        ws.numel() * 4)
+    K.check(kern.lib.bfk_lora_grads(C.byref(a), torch.cuda.current_stream().cuda_stream), "bfk_lora_grads")
+    torch.cuda.synchronize()
+    u, du = h1[:, D:].float(), dh1[:, D:].float()
+    refs = [scale * dqkv[:, :D].float().t() @ u[:, :r], scale * dqkv[:, 2 * D:].float().t() @ u[:, 8:8 + r],
+            du[:, :r].t() @ x.float(), du[:, 8:8 + r].t() @ x.float()]
+    for o, ref in zip(outs, refs):
+        assert torch.isfinite(o).all()
+        assert (o - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+
+
 def _attn_ref(qkv, B, N, H, hd, mask, scale):
     q, k, v = qkv.float().view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
     dots = q @ k.transpose(-1, -2) * scale
