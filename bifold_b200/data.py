@@ -16,8 +16,9 @@ import torch
 class DevicePrefetcher:
     """Iterates device-resident batches; the copy of the next host batch overlaps the current step.
 
-    ``batches`` yields dicts of (ideally pinned) host tensors.  Exactly one host->device copy is issued
-    per yielded batch, one batch ahead of the consumer.
+    ``batches`` yields dicts of (ideally pinned) host tensors with fixed shapes.  Exactly one host->device copy
+    is issued per yielded batch, one batch ahead of the consumer, into one of two persistent device buffer sets
+    (no allocation in steady state).  A yielded batch is valid until the next ``__next__`` call returns.
     """
 
     def __init__(self, batches: Iterable[Dict[str, torch.Tensor]], device: torch.device):
@@ -25,41 +26,58 @@ class DevicePrefetcher:
         self.device = device
         self.copy_stream = torch.cuda.Stream(device=device)
         self.bytes_copied = 0
-        self._next: Optional[Dict[str, torch.Tensor]] = None
-        self._ready: Optional[torch.cuda.Event] = None
-        self._issue()
+        self._bufs: List[Optional[Dict[str, torch.Tensor]]] = [None, None]
+        self._free: List[Optional[torch.cuda.Event]] = [None, None]    # consumer finished enqueuing work on the slot
+        self._ready: List[Optional[torch.cuda.Event]] = [None, None]   # copy into the slot finished
+        self._i = 0            # index of the next batch to hand out
+        self._pending = self._issue(0)
 
-    def _issue(self):
+    def _issue(self, slot: int) -> bool:
         try:
             host = next(self.it)
         except StopIteration:
-            self._next, self._ready = None, None
-            return
+            return False
+        bufs = self._bufs[slot]
+        if bufs is None or any(torch.is_tensor(v) and (k not in bufs or bufs[k].shape != v.shape or bufs[k].dtype != v.dtype)
+                               for k, v in host.items()):
+            bufs = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items() if torch.is_tensor(v)}
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))   # allocation happened on the consumer's stream
         with torch.cuda.stream(self.copy_stream):
-            dev = {}
+            if self._free[slot] is not None:
+                self.copy_stream.wait_event(self._free[slot])
+            out = {}
             for k, v in host.items():
                 if torch.is_tensor(v):
-                    dev[k] = v.to(self.device, non_blocking=True)
+                    bufs[k].copy_(v, non_blocking=True)
                     self.bytes_copied += v.numel() * v.element_size()
+                    out[k] = bufs[k]
                 else:
-                    dev[k] = v
+                    out[k] = v
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        self._next, self._ready = dev, ev
+        self._bufs[slot] = bufs
+        self._out = getattr(self, "_out", [None, None])
+        self._out[slot] = out
+        self._ready[slot] = ev
+        return True
 
     def __iter__(self):
         return self
 
     def __next__(self) -> Dict[str, torch.Tensor]:
-        if self._next is None:
+        if not self._pending:
             raise StopIteration
-        batch, ev = self._next, self._ready
+        slot = self._i % 2
         cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(ev)
-        for v in batch.values():
-            if torch.is_tensor(v):
-                v.record_stream(cur)      # allocated on the copy stream, consumed on the compute stream
-        self._issue()                     # batch i+1 starts moving while batch i is computed
+        cur.wait_event(self._ready[slot])
+        batch = self._out[slot]
+        # everything the consumer enqueued for batch i-1 (the other slot) precedes this point on `cur`
+        other = 1 - slot
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._free[other] = ev
+        self._i += 1
+        self._pending = self._issue(other)     # batch i+1 starts moving while batch i is computed
         return batch
 
 
