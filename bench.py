@@ -367,11 +367,14 @@ def gemm_roofline(eng, step_fn):
         recs.append((2.0 * M * N * Kd, e0, e1, A.dtype == torch.bfloat16))
 
     k.gemm = timed_gemm
+    overlap = eng.overlap_towers
+    eng.overlap_towers = False      # one stream: no concurrent text-tower kernels inside the per-launch event windows
     try:
         step_fn()
         torch.cuda.synchronize()
     finally:
         k.gemm = orig
+        eng.overlap_towers = overlap
     fl = sum(r[0] for r in recs if r[3])
     ms = sum(r[1].elapsed_time(r[2]) for r in recs if r[3])
     peaks = load_peaks()

@@ -15,6 +15,19 @@ struct EpiParams {
   float alpha;
   int accumulate;
   int vec_ok;  // host-verified: D/aux/residual/bias pointers and leading dims allow 32-byte vector access
+  int mode;    // EpiMode: compile-time specialised tcgen05 epilogue for the hot combinations (tc_epilogue.cuh), 0 = generic
+};
+
+// Specialised epilogues of the tcgen05 kernels.  All require vec_ok, alpha == 1, no accumulate, N % 32 == 0.
+enum EpiMode : int {
+  EPI_GENERIC = 0,
+  EPI_STORE_BF16,        // D(bf16) = acc (+ bias)
+  EPI_STORE_F32,         // D(fp32) = acc (+ bias)
+  EPI_RES_F32,           // D(fp32) = acc (+ bias) + residual(fp32)
+  EPI_GELU_TANH_BF16,    // aux(bf16, optional) = acc + bias;  D(bf16) = gelu_tanh(acc + bias)
+  EPI_GELU_ERF_BF16,
+  EPI_DGELU_TANH_BF16,   // D(bf16) = acc * gelu_tanh'(aux(bf16))
+  EPI_DGELU_ERF_BF16,
 };
 
 __device__ __forceinline__ float epi_value(const EpiParams& p, int m, int n, float acc) {
@@ -136,6 +149,16 @@ inline bool epi_from_args(const bfk_gemm_args* a, EpiParams& p) {
   if (a->aux) ok = ok && al32(a->aux) && (a->ld_aux * as) % 32 == 0;
   if (a->residual) ok = ok && al32(a->residual) && (a->ldr * 4) % 32 == 0;
   p.vec_ok = ok ? 1 : 0;
+  p.mode = EPI_GENERIC;
+  if (ok && a->alpha == 1.f && !a->accumulate && a->N % 32 == 0) {
+    const bool bf = a->out_dtype == BFK_BF16;
+    if (a->act == BFK_ACT_NONE && !a->residual) p.mode = bf ? EPI_STORE_BF16 : EPI_STORE_F32;
+    else if (a->act == BFK_ACT_NONE && a->residual && !bf) p.mode = EPI_RES_F32;
+    else if (a->act == BFK_ACT_GELU_TANH && !a->residual && bf && p.aux_dtype == BFK_BF16) p.mode = EPI_GELU_TANH_BF16;
+    else if (a->act == BFK_ACT_GELU_ERF && !a->residual && bf && p.aux_dtype == BFK_BF16) p.mode = EPI_GELU_ERF_BF16;
+    else if (a->act == BFK_ACT_DGELU_TANH && !a->residual && !a->bias && bf && p.aux_dtype == BFK_BF16) p.mode = EPI_DGELU_TANH_BF16;
+    else if (a->act == BFK_ACT_DGELU_ERF && !a->residual && !a->bias && bf && p.aux_dtype == BFK_BF16) p.mode = EPI_DGELU_ERF_BF16;
+  }
   return true;
 }
 

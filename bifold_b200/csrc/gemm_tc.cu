@@ -160,9 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       EpiParams epl = ep;
       if (splits > 1) epl.D = reinterpret_cast<float*>(ep.D) + (long long)(item % splits) * split_stride;   // fp32 partial
       float* bias_s = bias_smem + acc * BN;
-      if (ep.bias) {
-        for (int i = et; i < BN; i += 32 * TC_EPI_WARPS) bias_s[i] = (n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
-      }
+      for (int i = et; i < BN; i += 32 * TC_EPI_WARPS) bias_s[i] = (ep.bias && n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
       named_bar_sync(1, 32 * TC_EPI_WARPS);   // bias visible; also orders reuse of the other buffer
       if (ep.vec_ok && item + ncl < tiles) {   // warm L2 with what the NEXT item's epilogue will read
         const int ntile = (item + ncl) / splits;
@@ -170,17 +168,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int c = half; c < BN / 32; c += 2) epi_prefetch(ep, nm, nn0 + c * 32);
       }
       const int m = m0 + quarter * 32 + lane;
-      EpiOperands cur, nxt;
-      if (n0 + half * 32 < N) epi_load(epl, m, n0 + half * 32, cur);   // first chunk's operands: issued before the wait
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      const bool skip = (dbg & 1) || (ep.vec_ok & 16);   // measurement only
+      {
+        EpiOperands cur, nxt;
+        if (n0 + half * 32 < N) epi_load(epl, m, n0 + half * 32, cur);   // first chunk's operands: issued before the wait
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        if (n0 + c * 32 >= N || (dbg & 1)) break;  // warp-uniform  (dbg & 1: diagnostic, main loop only)
-        if (c + 2 < BN / 32 && n0 + (c + 2) * 32 < N) epi_load(epl, m, n0 + (c + 2) * 32, nxt);   // one chunk ahead
-        epi_chunk32(epl, m, n0 + c * 32, taddr + (uint32_t)(c * 32), bias_s + c * 32, cur);
-        cur = nxt;
+        for (int c = half; c < BN / 32; c += 2) {
+          if (n0 + c * 32 >= N || skip) break;  // warp-uniform
+          if (c + 2 < BN / 32 && n0 + (c + 2) * 32 < N) epi_load(epl, m, n0 + (c + 2) * 32, nxt);   // one chunk ahead
+          epi_chunk32(epl, m, n0 + c * 32, taddr + (uint32_t)(c * 32), bias_s + c * 32, cur);
+          cur = nxt;
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -314,7 +315,7 @@ static bool cluster_enabled() {
   return v == 1;
 }
 
-static int gemm_dbg() {   // BFK_GEMM_DBG: 1 = skip the epilogue body, 2 = skip TMA + MMA (measurement only; results are garbage)
+int gemm_dbg() {   // BFK_GEMM_DBG: 1 = skip the epilogue body, 2 = skip TMA + MMA (measurement only; results are garbage)
   static int v = -1;
   if (v < 0) { const char* e = getenv("BFK_GEMM_DBG"); v = e ? atoi(e) : 0; }
   return v;
@@ -345,7 +346,9 @@ static int launch_tc_cl(const bfk_gemm_args* a, cudaStream_t s, int splits, bool
   if (splits > 1 || partial_only) {   // partial tiles go to the workspace as plain fp32 [splits][M][N]
     ep.D = a->workspace; ep.ldd = a->N; ep.out_dtype = BFK_F32; ep.alpha = 1.f; ep.accumulate = 0;
     ep.vec_ok = ((reinterpret_cast<uintptr_t>(a->workspace) & 31u) == 0 && (a->N % 8) == 0 && (split_stride % 8) == 0) ? 1 : 0;
+    ep.mode = (ep.vec_ok && a->N % 32 == 0) ? EPI_STORE_F32 : EPI_GENERIC;
   }
+  if (ep.vec_ok) ep.vec_ok |= gemm_dbg() & 28;
   const int num_m = (a->M + TC_BM - 1) / TC_BM, num_n = (a->N + BN - 1) / BN;
   const int items = ((num_m + CL - 1) / CL) * num_n * splits;
   const int grid = CL * std::min(items, sm_count() / CL);

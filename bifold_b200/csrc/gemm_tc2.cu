@@ -13,13 +13,13 @@
 
 namespace bfk {
 
+int gemm_dbg();   // gemm_tc.cu: BFK_GEMM_DBG measurement knobs (4 = no stores, 8 = no TMEM read, 16 = no epilogue body)
 bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer);
 
 constexpr int T2_STAGES = 6;
 constexpr int T2_A_BYTES = 128 * 64 * 2, T2_B_BYTES = 128 * 64 * 2;
 constexpr int T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
 constexpr int T2_BN = 256;
-constexpr int T2_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 256 + 2 * T2_BN * 4;
 
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta_rank) {
@@ -55,9 +55,12 @@ __device__ __forceinline__ void tc_commit_2sm_mc(uint32_t bar, uint16_t mask) {
                : "memory");
 }
 
-template <bool AMN, bool BMN>
-__global__ void __launch_bounds__(T2_THREADS, 1)
+// MODE: compile-time EpiMode.  EPI_GENERIC keeps every fused variant behind runtime flags (8 epilogue warps, 168
+// registers); a specialised MODE compiles only its own epilogue and runs 16 epilogue warps (launch bound 576 threads).
+template <bool AMN, bool BMN, int MODE>
+__global__ void __launch_bounds__(64 + 32 * epi_warps(MODE), 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K, EpiParams ep) {
+  constexpr int EW = epi_warps(MODE);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + T2_STAGES * T2_STAGE_BYTES;
@@ -80,7 +83,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
     for (int s = 0; s < T2_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * TC_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -148,34 +151,42 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       }
     }
   } else {
-    // ===== epilogue warps (both CTAs): own 128 rows x 256 columns =====
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    // ===== epilogue warps (both CTAs): own 128 rows x 256 columns; quarter = TMEM lane quarter, sub = warp within it =====
+    const int quarter = warp & 3, sub = (warp - 2) >> 2;
+    const int half = sub;   // generic path: two warps per quarter
     const int et = threadIdx.x - 64;
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = cid; item < items; item += ncl) {
       const int m0 = (item / num_n) * 256 + crank * 128, n0 = (item % num_n) * T2_BN;
       float* bias_s = bias_smem + acc * T2_BN;
-      if (ep.bias) {
-        for (int i = et; i < T2_BN; i += 32 * TC_EPI_WARPS) bias_s[i] = (n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
-      }
-      named_bar_sync(1, 32 * TC_EPI_WARPS);
+      for (int i = et; i < T2_BN; i += 32 * EW) bias_s[i] = (ep.bias && n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
+      named_bar_sync(1, 32 * EW);
       if (ep.vec_ok && item + ncl < items) {
         const int nit = item + ncl;
         const int nm = (nit / num_n) * 256 + crank * 128 + quarter * 32 + lane, nn0 = (nit % num_n) * T2_BN;
-        for (int c = half; c < T2_BN / 32; c += 2) epi_prefetch(ep, nm, nn0 + c * 32);
+        for (int c = sub; c < T2_BN / 32; c += EW / 4) epi_prefetch(ep, nm, nn0 + c * 32);
       }
       const int m = m0 + quarter * 32 + lane;
-      EpiOperands cur, nxt;
-      if (n0 + half * 32 < N) epi_load(ep, m, n0 + half * 32, cur);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * T2_BN);
+      const bool skip = (ep.vec_ok & 16) != 0;   // measurement only
+      if constexpr (MODE != EPI_GENERIC) {
+        EpiOps<MODE> ops;
+        epi_tile_preload<MODE>(ep, m, n0, sub, ops);           // first chunk's operands: in flight during the wait
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        if (!skip) epi_tile<MODE, (T2_BN / 32) / (EW / 4), EW / 4>(ep, m, n0, sub, taddr, bias_s, ops);
+      } else {
+        EpiOperands cur, nxt;
+        if (n0 + half * 32 < N) epi_load(ep, m, n0 + half * 32, cur);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = half; c < T2_BN / 32; c += 2) {
-        if (n0 + c * 32 >= N) break;
-        if (c + 2 < T2_BN / 32 && n0 + (c + 2) * 32 < N) epi_load(ep, m, n0 + (c + 2) * 32, nxt);
-        epi_chunk32(ep, m, n0 + c * 32, taddr + (uint32_t)(c * 32), bias_s + c * 32, cur);
-        cur = nxt;
+        for (int c = half; c < T2_BN / 32; c += 2) {
+          if (n0 + c * 32 >= N || skip) break;
+          if (c + 2 < T2_BN / 32 && n0 + (c + 2) * 32 < N) epi_load(ep, m, n0 + (c + 2) * 32, nxt);
+          epi_chunk32(ep, m, n0 + c * 32, taddr + (uint32_t)(c * 32), bias_s + c * 32, cur);
+          cur = nxt;
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -193,6 +204,31 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   }
 }
 
+template <bool AMN, bool BMN, int MODE>
+static int launch_tc2_mode(const bfk_gemm_args* a, cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const EpiParams& ep) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<AMN, BMN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("gemm_tc2: cannot set smem %d: %s", T2_SMEM_BYTES, cudaGetErrorString(e)); return BFK_E_CUDA; }
+    attr_set = true;
+  }
+  const int items = ((a->M + 255) / 256) * ((a->N + T2_BN - 1) / T2_BN);
+  const int grid = 2 * std::min(items, sm_count() / 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * epi_warps(MODE)); cfg.dynamicSmemBytes = T2_SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<AMN, BMN, MODE>, ma, mb, a->M, a->N, a->K, ep);
+  if (le != cudaSuccess) { set_error("gemm_tc2: launch failed: %s", cudaGetErrorString(le)); return BFK_E_CUDA; }
+  BFK_CHECK_LAUNCH("gemm_tc2");
+  return BFK_OK;
+}
+
+// Specialised epilogues are instantiated only for the operand layouts that use them:
+//   forward (A, B K-major): store bf16, bias + residual fp32, bias + GELU;   dgrad (B MN-major): store bf16, dGELU;
+//   wgrad (A, B MN-major): store fp32.
 template <bool AMN, bool BMN>
 static int launch_tc2(const bfk_gemm_args* a, cudaStream_t s) {
   CUtensorMap ma, mb;
@@ -205,24 +241,19 @@ static int launch_tc2(const bfk_gemm_args* a, cudaStream_t s) {
   if (!ok) return BFK_E_CUDA;
   EpiParams ep;
   epi_from_args(a, ep);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("gemm_tc2: cannot set smem %d: %s", T2_SMEM_BYTES, cudaGetErrorString(e)); return BFK_E_CUDA; }
-    attr_set = true;
+  if (gemm_dbg() & 32) ep.mode = EPI_GENERIC;     // measurement only: force the generic epilogue
+  if (ep.vec_ok) ep.vec_ok |= gemm_dbg() & 28;
+#define T2_CASE(MODE_) case MODE_: return launch_tc2_mode<AMN, BMN, MODE_>(a, s, ma, mb, ep)
+  if constexpr (!AMN && !BMN) {
+    switch (ep.mode) { T2_CASE(EPI_STORE_BF16); T2_CASE(EPI_RES_F32); T2_CASE(EPI_GELU_TANH_BF16); T2_CASE(EPI_GELU_ERF_BF16); default: break; }
+  } else if constexpr (!AMN && BMN) {
+    switch (ep.mode) { T2_CASE(EPI_STORE_BF16); T2_CASE(EPI_DGELU_TANH_BF16); T2_CASE(EPI_DGELU_ERF_BF16); default: break; }
+  } else if constexpr (AMN && BMN) {
+    switch (ep.mode) { T2_CASE(EPI_STORE_F32); default: break; }
   }
-  const int items = ((a->M + 255) / 256) * ((a->N + T2_BN - 1) / T2_BN);
-  const int grid = 2 * std::min(items, sm_count() / 2);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T2_THREADS); cfg.dynamicSmemBytes = T2_SMEM_BYTES; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<AMN, BMN>, ma, mb, a->M, a->N, a->K, ep);
-  if (le != cudaSuccess) { set_error("gemm_tc2: launch failed: %s", cudaGetErrorString(le)); return BFK_E_CUDA; }
-  BFK_CHECK_LAUNCH("gemm_tc2");
-  return BFK_OK;
+#undef T2_CASE
+  ep.mode = EPI_GENERIC;
+  return launch_tc2_mode<AMN, BMN, EPI_GENERIC>(a, s, ma, mb, ep);
 }
 
 int gemm_tc2(const bfk_gemm_args* a, cudaStream_t s) {

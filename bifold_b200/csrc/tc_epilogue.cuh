@@ -6,7 +6,10 @@
 
 namespace bfk {
 
-constexpr int TC_EPI_WARPS = 8;   // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int TC_EPI_WARPS = 8;   // generic epilogue: two warps per TMEM lane quarter, alternating 32-column chunks
+// Kernels compiled for one specialised EpiMode need far fewer registers and run four warps per lane quarter: the fused
+// epilogues are instruction-bound (GELU / dGELU cost 10-25 instructions per element), more warps = more issue slots used.
+__host__ __device__ constexpr int epi_warps(int mode) { return mode == EPI_GENERIC ? 8 : 16; }
 
 // ---- fast epilogue math for bf16 outputs (the fp32 parity mode uses the exact functions of epilogue.cuh) ----
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -66,7 +69,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 struct EpiOperands { V8 w[4]; };
 
 __device__ __forceinline__ bool epi_fast(const EpiParams& ep, int nc) {
-  return ep.vec_ok && !ep.accumulate && (nc + 32 <= ep.N);
+  return (ep.vec_ok & 1) && !ep.accumulate && (nc + 32 <= ep.N);
 }
 // Issue the global loads of chunk [nc, nc+32) of row m (nothing waits on them here).
 __device__ __forceinline__ void epi_load(const EpiParams& ep, int m, int nc, EpiOperands& o) {
@@ -89,8 +92,13 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
                                             const EpiOperands& o) {
   const bool row_ok = m < ep.M;
   uint32_t r[32];
-  tc_ld32(taddr, r);
-  tc_wait_ld();
+  if (!(ep.vec_ok & 8)) {          // bit 3 (BFK_GEMM_DBG=8, measurement only): skip the TMEM read
+    tc_ld32(taddr, r);
+    tc_wait_ld();
+  } else {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) r[t] = 0u;
+  }
   if (!row_ok) return;
   if (!epi_fast(ep, nc)) {
 #pragma unroll
@@ -175,6 +183,7 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
 #pragma unroll
       for (int t = 0; t < 8; ++t) v[i * 8 + t] += __uint_as_float(o.w[i].w[t]);
   }
+  if (ep.vec_ok & 4) return;       // bit 2 (BFK_GEMM_DBG=4, measurement only): skip the output stores
   if (out_bf16) {
     __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(ep.D) + (long long)m * ep.ldd + nc;
 #pragma unroll
@@ -192,6 +201,126 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
 #pragma unroll
       for (int t = 0; t < 8; ++t) q.w[t] = __float_as_uint(v[i * 8 + t]);
       stg256(dp + 8 * i, q);
+    }
+  }
+}
+
+// ---- specialised tile epilogues ----------------------------------------------------------------------------
+// One warp's share of a 128 x BN accumulator tile: row m (TMEM lane), chunks c = half, half + 2, ... of 32 columns.
+// MODE is a compile-time EpiMode, the chunk loop is fully unrolled: no per-chunk flag tests, no register copies
+// between code paths (the generic epi_chunk32 spends ~60% of its instructions on those), operands of the next chunk
+// are in flight while the current one is processed.  bias_s is this tile's bias in shared memory (zeros if none).
+// `sub` = this warp's index within its lane quarter, CS = warps per quarter: chunks c = sub, sub + CS, ...; NCH = chunks per warp.
+// The operands of the first chunk are loaded by epi_tile_preload BEFORE the caller waits for the accumulator.
+template <int MODE> struct EpiOps {
+  static constexpr bool RES = MODE == EPI_RES_F32;
+  static constexpr bool DG = MODE == EPI_DGELU_TANH_BF16 || MODE == EPI_DGELU_ERF_BF16;
+  static constexpr int NOP = RES ? 4 : (DG ? 2 : 1);       // 32-byte operand vectors per chunk
+  V8 a[NOP], b[NOP];
+};
+template <int MODE>
+__device__ __forceinline__ void epi_load_ops(const EpiParams& ep, int m, int nc, V8 (&op)[EpiOps<MODE>::NOP]) {
+  if constexpr (EpiOps<MODE>::RES) {
+    const float* rrow = ep.residual + (long long)(ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m) * ep.ldr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) op[i] = ldg256(rrow + nc + 8 * i);
+  } else if constexpr (EpiOps<MODE>::DG) {
+    const __nv_bfloat16* hrow = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) op[i] = ldg256(hrow + nc + 16 * i);
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void epi_tile_preload(const EpiParams& ep, int m, int n0, int sub, EpiOps<MODE>& ops) {
+  if constexpr (EpiOps<MODE>::RES || EpiOps<MODE>::DG) {
+    if (m < ep.M && n0 + sub * 32 < ep.N) epi_load_ops<MODE>(ep, m, n0 + sub * 32, ops.a);
+  }
+}
+
+template <int MODE, int NCH, int CS>
+__device__ __forceinline__ void epi_tile(const EpiParams& ep, int m, int n0, int sub, uint32_t taddr, const float* __restrict__ bias_s,
+                                         EpiOps<MODE>& ops) {
+  constexpr bool RES = MODE == EPI_RES_F32;
+  constexpr bool DG = MODE == EPI_DGELU_TANH_BF16 || MODE == EPI_DGELU_ERF_BF16;
+  constexpr bool GE = MODE == EPI_GELU_TANH_BF16 || MODE == EPI_GELU_ERF_BF16;
+  constexpr bool OUT_BF16 = MODE != EPI_STORE_F32 && MODE != EPI_RES_F32;
+  const bool row_ok = m < ep.M;
+  constexpr int NOP = EpiOps<MODE>::NOP;
+  // chunk i of this warp: columns [nc, nc + 32); `op` holds its operands, `nxt` receives those of chunk i + 1
+  auto chunk = [&](int i, V8 (&op)[NOP], V8 (&nxt)[NOP]) {
+    const int c = sub + CS * i, nc = n0 + c * 32;
+    if (nc >= ep.N) return;                                  // warp-uniform; N % 32 == 0, so chunks are never partial
+    if ((RES || DG) && i + 1 < NCH && row_ok && nc + CS * 32 < ep.N) epi_load_ops<MODE>(ep, m, nc + CS * 32, nxt);
+    uint32_t r[32];
+    tc_ld32(taddr + (uint32_t)(c * 32), r);
+    tc_wait_ld();
+    if (!row_ok) return;
+    float v[32];
+    if constexpr (DG) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const uint32_t hw = op[t >> 3].w[t & 7];
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw));
+        if constexpr (MODE == EPI_DGELU_TANH_BF16) {
+          v[2 * t] = __uint_as_float(r[2 * t]) * dgelu_tanh_fast(f.x);
+          v[2 * t + 1] = __uint_as_float(r[2 * t + 1]) * dgelu_tanh_fast(f.y);
+        } else {
+          v[2 * t] = __uint_as_float(r[2 * t]) * dgelu_erf_fast(f.x);
+          v[2 * t + 1] = __uint_as_float(r[2 * t + 1]) * dgelu_erf_fast(f.y);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]) + bias_s[c * 32 + t];
+    }
+    if constexpr (RES) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[q * 8 + t] += __uint_as_float(op[q].w[t]);
+    }
+    if constexpr (GE) {
+      if (ep.aux) {                                          // pre-activation for the backward pass
+        __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          V8 w;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) w.w[t] = pack_bf16(v[q * 16 + 2 * t], v[q * 16 + 2 * t + 1]);
+          stg256(ap + 16 * q, w);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] = MODE == EPI_GELU_TANH_BF16 ? gelu_tanh_fast(v[t]) : gelu_erf_fast(v[t]);
+    }
+    if constexpr (OUT_BF16) {
+      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(ep.D) + (long long)m * ep.ldd + nc;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        V8 w;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w.w[t] = pack_bf16(v[q * 16 + 2 * t], v[q * 16 + 2 * t + 1]);
+        stg256(dp + 16 * q, w);
+      }
+    } else {
+      float* dp = reinterpret_cast<float*>(ep.D) + (long long)m * ep.ldd + nc;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        V8 w;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w.w[t] = __float_as_uint(v[q * 8 + t]);
+        stg256(dp + 8 * q, w);
+      }
+    }
+  };
+  if constexpr (NCH == 1) {
+    chunk(0, ops.a, ops.b);
+  } else {
+    static_assert(NCH % 2 == 0, "chunks per warp must be 1 or even");
+#pragma unroll 1
+    for (int i = 0; i < NCH; i += 2) {                       // operand buffers alternate by name: no register copies
+      chunk(i, ops.a, ops.b);
+      chunk(i + 1, ops.b, ops.a);
     }
   }
 }
