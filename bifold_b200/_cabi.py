@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbifold_b200.so")
 F32, BF16 = 0, 1
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_DGELU_TANH, ACT_DGELU_ERF = 0, 1, 2, 3, 4
+ACT_GELU_TANH_GRAD, ACT_GELU_ERF_GRAD, ACT_MUL_AUX = 5, 6, 7
 
 vp, i32, i64, f32, u32, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint32, C.c_uint64
 

@@ -49,7 +49,9 @@ extern "C" int32_t bfk_gemm(const bfk_gemm_args* a, bfk_stream_t s_) {
   BFK_CHECK_ARG(a->in_dtype == BFK_F32 || a->in_dtype == BFK_BF16, "bfk_gemm: bad in_dtype");
   BFK_CHECK_ARG(a->out_dtype == BFK_F32 || a->out_dtype == BFK_BF16, "bfk_gemm: bad out_dtype");
   BFK_CHECK_ARG(!a->accumulate || a->out_dtype == BFK_F32, "bfk_gemm: accumulate needs fp32 output");
-  BFK_CHECK_ARG(!(a->act == BFK_ACT_DGELU_TANH || a->act == BFK_ACT_DGELU_ERF) || a->aux, "bfk_gemm: dGELU needs aux");
+  BFK_CHECK_ARG(a->act >= BFK_ACT_NONE && a->act <= BFK_ACT_MUL_AUX, "bfk_gemm: bad act %d", a->act);
+  BFK_CHECK_ARG(!(a->act == BFK_ACT_DGELU_TANH || a->act == BFK_ACT_DGELU_ERF || a->act == BFK_ACT_MUL_AUX ||
+                  a->act == BFK_ACT_GELU_TANH_GRAD || a->act == BFK_ACT_GELU_ERF_GRAD) || a->aux, "bfk_gemm: this act needs aux");
   cudaStream_t s = to_stream(s_);
   if (a->backend == BFK_BACKEND_SIMT || a->in_dtype == BFK_F32) {
     BFK_CHECK_ARG(a->backend != BFK_BACKEND_TCGEN05, "bfk_gemm: tcgen05 backend needs bf16 operands");

@@ -130,10 +130,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   const uint32_t tS = tmem, tO = tmem + BW;
 
   if (warp == AT_ROW_WARPS) {
-    if (lane == 0) {
+    if (elect_one()) {
       // Issue order: ... P V(j) | S(j+1) -> commit(bar_s) ...; tcgen05 ops of one thread complete in order, so
       // bar_s(j+1) also tells the row warps that P V(j) is done (P tile free, O safe to rescale).
+      // Descriptors are built once; inside the loops an operand advances by a constant (this thread's instruction
+      // stream is the critical path between the row warps' hand-over and the next S tile).
       const uint32_t idesc_o = make_idesc(128, p.n_o, false, true);
+      const uint64_t dq0 = kmajor_desc(sQ, 0), dk0 = kmajor_desc(sK, 0, KATOM), dp0 = kmajor_desc(sP, 0), dv0 = mnmajor_desc(sV, 0, KATOM);
       auto issue_k = [&](int j) {
         mbar_expect_tx(bar_k0 + 8 * (j & 1), KTILE);
         load_tile<NA>(sK + (j & 1) * KTILE, &map_kv, bar_k0 + 8 * (j & 1), p.H + h, j * BW, b, KATOM);
@@ -146,8 +149,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         mbar_wait(bar_k0 + 8 * (j & 1), (j >> 1) & 1);
         tc_fence_after();
         const uint32_t idesc_sj = make_idesc(128, kv_cols(p.N, j, BW), false, false);
-        for (int k = 0; k < p.ksteps; ++k)
-          tc_mma_bf16(tS, kmajor_desc(sQ, k), kmajor_desc(sK + (j & 1) * KTILE, k, KATOM), idesc_sj, k > 0);
+        uint64_t da = dq0, db = dk0 + (uint64_t)((j & 1) * (KTILE >> 4));
+        for (int k = 0; k < p.ksteps; ++k) {
+          tc_mma_bf16(tS, da, db, idesc_sj, k > 0);
+          da += 2; db += 2;                                         // next 16 elements of K: +32 bytes
+          if ((k & 3) == 3) { da += (AT_ATOM >> 4) - 8; db += (KATOM >> 4) - 8; }   // next 64-wide atom
+        }
         tc_commit(bar_s);
       };
       mbar_expect_tx(bar_q, TILE);
@@ -163,9 +170,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         if (j >= 1 && j + 1 < nblk) issue_v(j + 1);
         mbar_wait(bar_v0 + 8 * (j & 1), (j >> 1) & 1);
         tc_fence_after();
-        const int nc = kv_cols(p.N, j, BW);
-        for (int k = 0; k < nc / 16; ++k)
-          tc_mma_bf16(tO, kmajor_desc(sP, k), mnmajor_desc(sV + (j & 1) * KTILE, k, KATOM), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        const int nk = kv_cols(p.N, j, BW) >> 4;
+        uint64_t da = dp0, db = dv0 + (uint64_t)((j & 1) * (KTILE >> 4));
+        for (int k = 0; k < nk; ++k) {
+          tc_mma_bf16(tO, da, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          da += 2; db += 2048 >> 4;                                 // P: next 16 keys (+32 bytes); V: next 16 rows (+2048 bytes)
+          if ((k & 3) == 3) da += (AT_ATOM >> 4) - 8;
+        }
         if (j + 1 < nblk) issue_s(j + 1); else tc_commit(bar_o);
       }
     }
@@ -330,8 +341,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   const uint32_t tS = tmem, tdP = tmem + BW, tdQ = tmem + 2 * BW;
 
   if (warp == AT_ROW_WARPS) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_q = make_idesc(128, p.n_o, false, true);
+      // descriptors built once; an operand advances by a constant inside the loops (see the forward kernel)
+      const uint64_t dq0 = kmajor_desc(sQ, 0), ddo0 = kmajor_desc(sdO, 0), dk0 = kmajor_desc(sK, 0, KATOM), dv0 = kmajor_desc(sV, 0, KATOM),
+                     dds0 = kmajor_desc(sdS, 0), dkm0 = mnmajor_desc(sK, 0, KATOM);
       auto issue_kv = [&](int j) {
         const int nb = j % NBUF;
         mbar_expect_tx(bar_kv0 + 8 * nb, 2 * KTILE);
@@ -339,12 +353,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         load_tile<NA>(sV + nb * KTILE, &map_kv, bar_kv0 + 8 * nb, 2 * p.H + h, j * BW, b, KATOM);
       };
       auto issue_s = [&](int j) {
-        mbar_wait(bar_kv0 + 8 * (j % NBUF), (j / NBUF) & 1);
+        const int nb = j % NBUF;
+        mbar_wait(bar_kv0 + 8 * nb, (j / NBUF) & 1);
         tc_fence_after();
-        const uint32_t k_t = sK + (j % NBUF) * KTILE, v_t = sV + (j % NBUF) * KTILE;
         const uint32_t idesc_sj = make_idesc(128, kv_cols(p.N, j, BW), false, false);
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tS, kmajor_desc(sQ, k, AT_ATOM), kmajor_desc(k_t, k, KATOM), idesc_sj, k > 0);
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tdP, kmajor_desc(sdO, k, AT_ATOM), kmajor_desc(v_t, k, KATOM), idesc_sj, k > 0);
+        const uint64_t boff = (uint64_t)(nb * (KTILE >> 4));
+        uint64_t da = dq0, db = dk0 + boff;
+        for (int k = 0; k < p.ksteps; ++k) {
+          tc_mma_bf16(tS, da, db, idesc_sj, k > 0);
+          da += 2; db += 2;
+          if ((k & 3) == 3) { da += (AT_ATOM >> 4) - 8; db += (KATOM >> 4) - 8; }
+        }
+        da = ddo0; db = dv0 + boff;
+        for (int k = 0; k < p.ksteps; ++k) {
+          tc_mma_bf16(tdP, da, db, idesc_sj, k > 0);
+          da += 2; db += 2;
+          if ((k & 3) == 3) { da += (AT_ATOM >> 4) - 8; db += (KATOM >> 4) - 8; }
+        }
         tc_commit(bar_s);
       };
       mbar_expect_tx(bar_q, 2 * TILE);
@@ -361,10 +386,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           mbar_wait(bar_dq, (j - 1) & 1);
           if (j + NBUF - 1 < nblk) issue_kv(j + NBUF - 1);   // dQ(j-1) done: refill the buffer block j-1 used
         }
-        const uint32_t k_t = sK + (j % NBUF) * KTILE, ds_t = sdS + (j & 1) * DS_BYTES;
-        const int nc = kv_cols(p.N, j, BW);
-        for (int k = 0; k < nc / 16; ++k)
-          tc_mma_bf16(tdQ, kmajor_desc(ds_t, k, AT_ATOM), mnmajor_desc(k_t, k, KATOM), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+        const int nk = kv_cols(p.N, j, BW) >> 4;
+        uint64_t da = dds0 + (uint64_t)((j & 1) * (DS_BYTES >> 4)), db = dkm0 + (uint64_t)((j % NBUF) * (KTILE >> 4));
+        for (int k = 0; k < nk; ++k) {
+          tc_mma_bf16(tdQ, da, db, idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+          da += 2; db += 2048 >> 4;
+          if ((k & 3) == 3) da += (AT_ATOM >> 4) - 8;
+        }
         if (j + 1 < nblk) tc_commit(bar_dq); else tc_commit(bar_o);
       }
     }
@@ -470,8 +498,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
   const uint32_t tSt = tmem, tdPt = tmem + BW, tdV = tmem + 2 * BW, tdK = tdV + NA * 64;
 
   if (warp == AT_ROW_WARPS) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_g = make_idesc(128, p.n_o, false, true);
+      const uint64_t dk0 = kmajor_desc(sK, 0), dv0 = kmajor_desc(sV, 0), dq0 = kmajor_desc(sQ, 0, QATOM), ddo0 = kmajor_desc(sdO, 0, QATOM),
+                     dpt0 = kmajor_desc(sPt, 0), ddst0 = kmajor_desc(sdSt, 0), dqm0 = mnmajor_desc(sQ, 0, QATOM),
+                     ddom0 = mnmajor_desc(sdO, 0, QATOM);
       auto issue_q = [&](int i) {
         const int nb = i % NBUF;
         mbar_expect_tx(bar_q0 + 8 * nb, 2 * QTILE);
@@ -479,12 +510,23 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
         load_tile<NA>(sdO + nb * QTILE, &map_do, bar_q0 + 8 * nb, h, i * BW, b, QATOM);
       };
       auto issue_s = [&](int i) {
-        mbar_wait(bar_q0 + 8 * (i % NBUF), (i / NBUF) & 1);
+        const int nb = i % NBUF;
+        mbar_wait(bar_q0 + 8 * nb, (i / NBUF) & 1);
         tc_fence_after();
-        const uint32_t q_t = sQ + (i % NBUF) * QTILE, do_t = sdO + (i % NBUF) * QTILE;
         const uint32_t idesc_si = make_idesc(128, kv_cols(p.N, i, BW), false, false);
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tSt, kmajor_desc(sK, k, AT_ATOM), kmajor_desc(q_t, k, QATOM), idesc_si, k > 0);
-        for (int k = 0; k < p.ksteps; ++k) tc_mma_bf16(tdPt, kmajor_desc(sV, k, AT_ATOM), kmajor_desc(do_t, k, QATOM), idesc_si, k > 0);
+        const uint64_t boff = (uint64_t)(nb * (QTILE >> 4));
+        uint64_t da = dk0, db = dq0 + boff;
+        for (int k = 0; k < p.ksteps; ++k) {
+          tc_mma_bf16(tSt, da, db, idesc_si, k > 0);
+          da += 2; db += 2;
+          if ((k & 3) == 3) { da += (AT_ATOM >> 4) - 8; db += (QATOM >> 4) - 8; }
+        }
+        da = dv0; db = ddo0 + boff;
+        for (int k = 0; k < p.ksteps; ++k) {
+          tc_mma_bf16(tdPt, da, db, idesc_si, k > 0);
+          da += 2; db += 2;
+          if ((k & 3) == 3) { da += (AT_ATOM >> 4) - 8; db += (QATOM >> 4) - 8; }
+        }
         tc_commit(bar_s);
       };
       mbar_expect_tx(bar_kv, 2 * TILE);
@@ -497,12 +539,20 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
         mbar_wait(bar_p, i & 1);
         tc_fence_after();
         if (i + NBUF - 1 < nq) issue_q(i + NBUF - 1);
-        const uint32_t q_t = sQ + (i % NBUF) * QTILE, do_t = sdO + (i % NBUF) * QTILE;
-        const int nc = kv_cols(p.N, i, BW);
-        for (int k = 0; k < nc / 16; ++k)
-          tc_mma_bf16(tdV, kmajor_desc(sPt, k, AT_ATOM), mnmajor_desc(do_t, k, QATOM), idesc_g, (i > 0 || k > 0) ? 1u : 0u);
-        for (int k = 0; k < nc / 16; ++k)
-          tc_mma_bf16(tdK, kmajor_desc(sdSt, k, AT_ATOM), mnmajor_desc(q_t, k, QATOM), idesc_g, (i > 0 || k > 0) ? 1u : 0u);
+        const int nk = kv_cols(p.N, i, BW) >> 4;
+        const uint64_t boff = (uint64_t)((i % NBUF) * (QTILE >> 4));
+        uint64_t da = dpt0, db = ddom0 + boff;
+        for (int k = 0; k < nk; ++k) {
+          tc_mma_bf16(tdV, da, db, idesc_g, (i > 0 || k > 0) ? 1u : 0u);
+          da += 2; db += 2048 >> 4;
+          if ((k & 3) == 3) da += (AT_ATOM >> 4) - 8;
+        }
+        da = ddst0; db = dqm0 + boff;
+        for (int k = 0; k < nk; ++k) {
+          tc_mma_bf16(tdK, da, db, idesc_g, (i > 0 || k > 0) ? 1u : 0u);
+          da += 2; db += 2048 >> 4;
+          if ((k & 3) == 3) da += (AT_ATOM >> 4) - 8;
+        }
         if (i + 1 < nq) issue_s(i + 1); else tc_commit(bar_o);
       }
     }

@@ -28,21 +28,31 @@ enum EpiMode : int {
   EPI_GELU_ERF_BF16,
   EPI_DGELU_TANH_BF16,   // D(bf16) = acc * gelu_tanh'(aux(bf16))
   EPI_DGELU_ERF_BF16,
+  EPI_GELUG_TANH_BF16,   // v = acc + bias;  aux(bf16) = gelu_tanh'(v);  D(bf16) = gelu_tanh(v)
+  EPI_GELUG_ERF_BF16,
+  EPI_MULAUX_BF16,       // D(bf16) = acc * aux(bf16)
 };
+__host__ __device__ inline bool act_reads_aux(int act) { return act == BFK_ACT_DGELU_TANH || act == BFK_ACT_DGELU_ERF || act == BFK_ACT_MUL_AUX; }
+__host__ __device__ inline bool act_is_gelu_fwd(int act) {
+  return act == BFK_ACT_GELU_TANH || act == BFK_ACT_GELU_ERF || act == BFK_ACT_GELU_TANH_GRAD || act == BFK_ACT_GELU_ERF_GRAD;
+}
 
 __device__ __forceinline__ float epi_value(const EpiParams& p, int m, int n, float acc) {
   float v = acc * p.alpha;
   if (p.bias) v += __ldg(p.bias + n);
-  if (p.act == BFK_ACT_GELU_TANH || p.act == BFK_ACT_GELU_ERF) {
+  if (act_is_gelu_fwd(p.act)) {
+    const bool tanh_form = p.act == BFK_ACT_GELU_TANH || p.act == BFK_ACT_GELU_TANH_GRAD;
     if (p.aux) {
-      if (p.aux_dtype == BFK_BF16) ((__nv_bfloat16*)p.aux)[(long long)m * p.ld_aux + n] = __float2bfloat16_rn(v);
-      else ((float*)p.aux)[(long long)m * p.ld_aux + n] = v;
+      float sv = v;     // GELU_*: the pre-activation;  GELU_*_GRAD: the derivative at the pre-activation
+      if (p.act == BFK_ACT_GELU_TANH_GRAD || p.act == BFK_ACT_GELU_ERF_GRAD) sv = tanh_form ? dgelu_tanh(v) : dgelu_erf(v);
+      if (p.aux_dtype == BFK_BF16) ((__nv_bfloat16*)p.aux)[(long long)m * p.ld_aux + n] = __float2bfloat16_rn(sv);
+      else ((float*)p.aux)[(long long)m * p.ld_aux + n] = sv;
     }
-    v = (p.act == BFK_ACT_GELU_TANH) ? gelu_tanh(v) : gelu_erf(v);
-  } else if (p.act == BFK_ACT_DGELU_TANH || p.act == BFK_ACT_DGELU_ERF) {
+    v = tanh_form ? gelu_tanh(v) : gelu_erf(v);
+  } else if (act_reads_aux(p.act)) {
     float h = (p.aux_dtype == BFK_BF16) ? __bfloat162float(((const __nv_bfloat16*)p.aux)[(long long)m * p.ld_aux + n])
                                         : ((const float*)p.aux)[(long long)m * p.ld_aux + n];
-    v *= (p.act == BFK_ACT_DGELU_TANH) ? dgelu_tanh(h) : dgelu_erf(h);
+    v *= (p.act == BFK_ACT_MUL_AUX) ? h : ((p.act == BFK_ACT_DGELU_TANH) ? dgelu_tanh(h) : dgelu_erf(h));
   }
   if (p.residual) {
     int rm = p.res_row_mod > 0 ? (m % p.res_row_mod) : m;
@@ -65,7 +75,7 @@ __device__ __forceinline__ void epi_store(const EpiParams& p, int m, int n, floa
 // Vector path when the chunk is fully inside N and the host verified alignment.
 __device__ __forceinline__ void epi_store8(const EpiParams& p, int m, int n0, const float (&acc)[8]) {
   if (m >= p.M || n0 >= p.N) return;
-  if (!p.vec_ok || n0 + 8 > p.N) {
+  if (!p.vec_ok || n0 + 8 > p.N || p.act >= BFK_ACT_GELU_TANH_GRAD) {   // the GRAD / MUL_AUX acts only have the scalar form here
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (n0 + j < p.N) epi_store(p, m, n0 + j, acc[j]);
@@ -139,7 +149,7 @@ inline bool epi_from_args(const bfk_gemm_args* a, EpiParams& p) {
   p.D = a->D; p.ldd = a->ldd; p.out_dtype = a->out_dtype;
   p.bias = a->bias; p.act = a->act;
   p.aux = a->aux; p.ld_aux = a->ld_aux;
-  p.aux_dtype = (a->act == BFK_ACT_DGELU_TANH || a->act == BFK_ACT_DGELU_ERF) ? a->in_dtype : a->out_dtype;
+  p.aux_dtype = act_reads_aux(a->act) ? a->in_dtype : a->out_dtype;
   p.residual = a->residual; p.ldr = a->ldr; p.res_row_mod = a->res_row_mod;
   p.alpha = a->alpha; p.accumulate = a->accumulate;
   auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
@@ -158,6 +168,9 @@ inline bool epi_from_args(const bfk_gemm_args* a, EpiParams& p) {
     else if (a->act == BFK_ACT_GELU_ERF && !a->residual && bf && p.aux_dtype == BFK_BF16) p.mode = EPI_GELU_ERF_BF16;
     else if (a->act == BFK_ACT_DGELU_TANH && !a->residual && !a->bias && bf && p.aux_dtype == BFK_BF16) p.mode = EPI_DGELU_TANH_BF16;
     else if (a->act == BFK_ACT_DGELU_ERF && !a->residual && !a->bias && bf && p.aux_dtype == BFK_BF16) p.mode = EPI_DGELU_ERF_BF16;
+    else if (a->act == BFK_ACT_GELU_TANH_GRAD && !a->residual && bf && a->aux && p.aux_dtype == BFK_BF16) p.mode = EPI_GELUG_TANH_BF16;
+    else if (a->act == BFK_ACT_GELU_ERF_GRAD && !a->residual && bf && a->aux && p.aux_dtype == BFK_BF16) p.mode = EPI_GELUG_ERF_BF16;
+    else if (a->act == BFK_ACT_MUL_AUX && !a->residual && !a->bias && bf && p.aux_dtype == BFK_BF16) p.mode = EPI_MULAUX_BF16;
   }
   return true;
 }

@@ -79,7 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0;
       for (int item = cid; item < tiles; item += ncl) {
@@ -122,9 +122,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = make_idesc(TC_BM, BN, AMN, BMN);
+      constexpr int KSTEP_A = (AMN ? 2048 : 32) >> 4, KSTEP_B = (BMN ? 2048 : 32) >> 4;   // descriptor step per UMMA_K slice
+      const uint64_t da0 = operand_desc<AMN>(smem_base, 0), db0 = operand_desc<BMN>(smem_base + Cfg::A_BYTES, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int item = cid; item < tiles; item += ncl) {
@@ -136,10 +138,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int kb = kb0; kb < kb1 && !(dbg & 2); ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+          const uint64_t soff = (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));   // descriptors are built once (da0, db0)
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
-            tc_mma_bf16(tmem_d, operand_desc<AMN>(sa, k), operand_desc<BMN>(sb, k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16(tmem_d, da0 + soff + (uint64_t)(k * KSTEP_A), db0 + soff + (uint64_t)(k * KSTEP_B), idesc,
+                        (kb > kb0 || k > 0) ? 1u : 0u);
           if constexpr (CL == 1) tc_commit(empty_bar(stage));
           else tc_commit_mc(empty_bar(stage), (uint16_t)0x3);   // the slot is free in BOTH CTAs' eyes only when both consumed it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }

@@ -98,7 +98,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== TMA producer (both CTAs): own 128 rows of A, own 128 n-rows of B =====
       int stage = 0; uint32_t phase = 0;
       for (int item = cid; item < items; item += ncl) {
@@ -126,9 +126,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {
+    if (crank == 0 && elect_one()) {
       // ===== MMA issuer (leader CTA only): UMMA 256 x 256 x 16 over both CTAs' smem / TMEM =====
       constexpr uint32_t idesc = make_idesc(256, T2_BN, AMN, BMN);
+      constexpr int KSTEP_A = (AMN ? 2048 : 32) >> 4, KSTEP_B = (BMN ? 2048 : 32) >> 4;   // descriptor step per UMMA_K slice
+      const uint64_t da0 = operand_desc<AMN>(smem_base, 0), db0 = operand_desc<BMN>(smem_base + T2_A_BYTES, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int item = cid; item < items; item += ncl) {
@@ -138,10 +140,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * T2_STAGE_BYTES, sb = sa + T2_A_BYTES;
+          const uint64_t soff = (uint64_t)(stage * (T2_STAGE_BYTES >> 4));     // descriptors are built once (da0, db0)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma_bf16_2sm(tmem_d, operand_desc<AMN>(sa, k), operand_desc<BMN>(sb, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16_2sm(tmem_d, da0 + soff + (uint64_t)(k * KSTEP_A), db0 + soff + (uint64_t)(k * KSTEP_B), idesc,
+                            (kb > 0 || k > 0) ? 1u : 0u);
           tc_commit_2sm_mc(empty_bar(stage), (uint16_t)0x3);
           if (++stage == T2_STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -227,7 +230,8 @@ static int launch_tc2_mode(const bfk_gemm_args* a, cudaStream_t s, const CUtenso
 }
 
 // Specialised epilogues are instantiated only for the operand layouts that use them:
-//   forward (A, B K-major): store bf16, bias + residual fp32, bias + GELU;   dgrad (B MN-major): store bf16, dGELU;
+//   forward (A, B K-major): store bf16, bias + residual fp32, bias + GELU (+ derivative);   dgrad (B MN-major): store bf16,
+//   dGELU, multiply by aux;
 //   wgrad (A, B MN-major): store fp32.
 template <bool AMN, bool BMN>
 static int launch_tc2(const bfk_gemm_args* a, cudaStream_t s) {
@@ -245,9 +249,10 @@ static int launch_tc2(const bfk_gemm_args* a, cudaStream_t s) {
   if (ep.vec_ok) ep.vec_ok |= gemm_dbg() & 28;
 #define T2_CASE(MODE_) case MODE_: return launch_tc2_mode<AMN, BMN, MODE_>(a, s, ma, mb, ep)
   if constexpr (!AMN && !BMN) {
-    switch (ep.mode) { T2_CASE(EPI_STORE_BF16); T2_CASE(EPI_RES_F32); T2_CASE(EPI_GELU_TANH_BF16); T2_CASE(EPI_GELU_ERF_BF16); default: break; }
+    switch (ep.mode) { T2_CASE(EPI_STORE_BF16); T2_CASE(EPI_RES_F32); T2_CASE(EPI_GELU_TANH_BF16); T2_CASE(EPI_GELU_ERF_BF16);
+                       T2_CASE(EPI_GELUG_TANH_BF16); T2_CASE(EPI_GELUG_ERF_BF16); default: break; }
   } else if constexpr (!AMN && BMN) {
-    switch (ep.mode) { T2_CASE(EPI_STORE_BF16); T2_CASE(EPI_DGELU_TANH_BF16); T2_CASE(EPI_DGELU_ERF_BF16); default: break; }
+    switch (ep.mode) { T2_CASE(EPI_STORE_BF16); T2_CASE(EPI_DGELU_TANH_BF16); T2_CASE(EPI_DGELU_ERF_BF16); T2_CASE(EPI_MULAUX_BF16); default: break; }
   } else if constexpr (AMN && BMN) {
     switch (ep.mode) { T2_CASE(EPI_STORE_F32); default: break; }
   }

@@ -45,6 +45,24 @@ __device__ __forceinline__ float dgelu_erf_fast(float x) {
   return 0.5f * (1.f + er) + x * 0.3989422804014327f * e;
 }
 
+// value and derivative together (the GELU_*_GRAD forward epilogues): tanh / exp evaluated once
+__device__ __forceinline__ void gelu_tanh_both_fast(float x, float& g, float& d) {
+  const float k = 0.7978845608028654f, c = 0.044715f;
+  const float x2 = x * x;
+  const float t = tanh_fast(k * x * fmaf(c, x2, 1.f));
+  const float hp = fmaf(0.5f, t, 0.5f);
+  g = x * hp;
+  d = fmaf(0.5f * x * (1.f - t * t), k * fmaf(3.f * c, x2, 1.f), hp);
+}
+__device__ __forceinline__ void gelu_erf_both_fast(float x, float& g, float& d) {
+  const float z = x * 0.7071067811865476f, az = fabsf(z);
+  const float e = __expf(-az * az);
+  const float er = copysignf(erf_from_exp(az, e), z);
+  const float hp = fmaf(0.5f, er, 0.5f);
+  g = x * hp;
+  d = fmaf(x * 0.3989422804014327f, e, hp);
+}
+
 // 256-bit global accesses (LDG.256 / STG.256): one full 32-byte sector per thread and instruction
 struct alignas(32) V8 { uint32_t w[8]; };
 __device__ __forceinline__ V8 ldg256(const void* p) {
@@ -69,7 +87,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 struct EpiOperands { V8 w[4]; };
 
 __device__ __forceinline__ bool epi_fast(const EpiParams& ep, int nc) {
-  return (ep.vec_ok & 1) && !ep.accumulate && (nc + 32 <= ep.N);
+  return (ep.vec_ok & 1) && !ep.accumulate && (nc + 32 <= ep.N) && ep.act < BFK_ACT_GELU_TANH_GRAD;
 }
 // Issue the global loads of chunk [nc, nc+32) of row m (nothing waits on them here).
 __device__ __forceinline__ void epi_load(const EpiParams& ep, int m, int nc, EpiOperands& o) {
@@ -214,7 +232,7 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int nc, 
 // The operands of the first chunk are loaded by epi_tile_preload BEFORE the caller waits for the accumulator.
 template <int MODE> struct EpiOps {
   static constexpr bool RES = MODE == EPI_RES_F32;
-  static constexpr bool DG = MODE == EPI_DGELU_TANH_BF16 || MODE == EPI_DGELU_ERF_BF16;
+  static constexpr bool DG = MODE == EPI_DGELU_TANH_BF16 || MODE == EPI_DGELU_ERF_BF16 || MODE == EPI_MULAUX_BF16;
   static constexpr int NOP = RES ? 4 : (DG ? 2 : 1);       // 32-byte operand vectors per chunk
   V8 a[NOP], b[NOP];
 };
@@ -241,8 +259,9 @@ template <int MODE, int NCH, int CS>
 __device__ __forceinline__ void epi_tile(const EpiParams& ep, int m, int n0, int sub, uint32_t taddr, const float* __restrict__ bias_s,
                                          EpiOps<MODE>& ops) {
   constexpr bool RES = MODE == EPI_RES_F32;
-  constexpr bool DG = MODE == EPI_DGELU_TANH_BF16 || MODE == EPI_DGELU_ERF_BF16;
+  constexpr bool DG = EpiOps<MODE>::DG;
   constexpr bool GE = MODE == EPI_GELU_TANH_BF16 || MODE == EPI_GELU_ERF_BF16;
+  constexpr bool GG = MODE == EPI_GELUG_TANH_BF16 || MODE == EPI_GELUG_ERF_BF16;
   constexpr bool OUT_BF16 = MODE != EPI_STORE_F32 && MODE != EPI_RES_F32;
   const bool row_ok = m < ep.M;
   constexpr int NOP = EpiOps<MODE>::NOP;
@@ -261,7 +280,10 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, int m, int n0, int
       for (int t = 0; t < 16; ++t) {
         const uint32_t hw = op[t >> 3].w[t & 7];
         const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw));
-        if constexpr (MODE == EPI_DGELU_TANH_BF16) {
+        if constexpr (MODE == EPI_MULAUX_BF16) {
+          v[2 * t] = __uint_as_float(r[2 * t]) * f.x;
+          v[2 * t + 1] = __uint_as_float(r[2 * t + 1]) * f.y;
+        } else if constexpr (MODE == EPI_DGELU_TANH_BF16) {
           v[2 * t] = __uint_as_float(r[2 * t]) * dgelu_tanh_fast(f.x);
           v[2 * t + 1] = __uint_as_float(r[2 * t + 1]) * dgelu_tanh_fast(f.y);
         } else {
@@ -293,7 +315,29 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, int m, int n0, int
 #pragma unroll
       for (int t = 0; t < 32; ++t) v[t] = MODE == EPI_GELU_TANH_BF16 ? gelu_tanh_fast(v[t]) : gelu_erf_fast(v[t]);
     }
-    if constexpr (OUT_BF16) {
+    if constexpr (GG) {                                      // value -> D, derivative -> aux, 16 columns at a time
+      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(ep.D) + (long long)m * ep.ldd + nc;
+      __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        V8 wg, wd;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          float g0, d0, g1, d1;
+          if constexpr (MODE == EPI_GELUG_TANH_BF16) {
+            gelu_tanh_both_fast(v[q * 16 + 2 * t], g0, d0);
+            gelu_tanh_both_fast(v[q * 16 + 2 * t + 1], g1, d1);
+          } else {
+            gelu_erf_both_fast(v[q * 16 + 2 * t], g0, d0);
+            gelu_erf_both_fast(v[q * 16 + 2 * t + 1], g1, d1);
+          }
+          wg.w[t] = pack_bf16(g0, g1);
+          wd.w[t] = pack_bf16(d0, d1);
+        }
+        stg256(dp + 16 * q, wg);
+        stg256(ap + 16 * q, wd);
+      }
+    } else if constexpr (OUT_BF16) {
       __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(ep.D) + (long long)m * ep.ldd + nc;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -332,7 +376,7 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& ep, int m, int nc)
     const int rm = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
     prefetch_l2(ep.residual + (long long)rm * ep.ldr + nc);
   }
-  if (ep.act == BFK_ACT_DGELU_TANH || ep.act == BFK_ACT_DGELU_ERF)
+  if (act_reads_aux(ep.act))
     prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux + nc);
 }
 

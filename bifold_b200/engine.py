@@ -308,12 +308,16 @@ class Engine:
         k.layernorm_fwd(x1, M, D, lw.ln2_w, lw.ln2_b, eps, h2, D, mean2, rstd2)
         pa = torch.empty(M, Mlp, device=dev, dtype=T) if save is not None else None
         a = torch.empty(M, Mlp, device=dev, dtype=T)
-        k.gemm(h2, lw.W1, a, M, Mlp, D, D, D, Mlp, bias=lw.b1, act=act, aux=pa, ld_aux=Mlp)
+        # bf16 training: the fc1 epilogue stores gelu'(pre-activation) instead of the pre-activation, so the fc2 dgrad
+        # epilogue is a plain multiply (tanh / exp evaluated once per element instead of twice)
+        pa_is_grad = pa is not None and T == torch.bfloat16
+        act_f = act if not pa_is_grad else (K.ACT_GELU_TANH_GRAD if act == K.ACT_GELU_TANH else K.ACT_GELU_ERF_GRAD)
+        k.gemm(h2, lw.W1, a, M, Mlp, D, D, D, Mlp, bias=lw.b1, act=act_f, aux=pa, ld_aux=Mlp)
         x2 = torch.empty(M, D, device=dev, dtype=torch.float32)
         k.gemm(a, lw.W2, x2, M, D, Mlp, Mlp, Mlp, D, bias=lw.b2, residual=x1, ldr=D)
         if save is not None:
             save.append(dict(x=x, h1=h1, mean1=mean1, rstd1=rstd1, qkv=qkv, ctx=ctx, lse=lse, x1=x1, h2=h2, mean2=mean2,
-                             rstd2=rstd2, pa=pa, a=a, p_drop=p_drop, seed=lora_seed, h1d=h1d))
+                             rstd2=rstd2, pa=pa, a=a, p_drop=p_drop, seed=lora_seed, h1d=h1d, pa_is_grad=pa_is_grad))
         return x2
 
     def _layer_bwd(self, dx2, dx2_T, sv, nseq, N, lw: LayerWeights, heads, eps, act, row_mask, grads, trainable):
@@ -321,7 +325,7 @@ class Engine:
         k, D, T, dev = self.k, self.cfg.dim, self.T, dx2.device
         M, Dk, hd = nseq * N, lw.Dk, D // heads
         Mlp = lw.W1.shape[0]
-        dact = K.ACT_DGELU_TANH if act == K.ACT_GELU_TANH else K.ACT_DGELU_ERF
+        dact = K.ACT_MUL_AUX if sv.get("pa_is_grad") else (K.ACT_DGELU_TANH if act == K.ACT_GELU_TANH else K.ACT_DGELU_ERF)
         n = lw.names
         # fc2: x2 = a W2^T + b2 + x1
         dpa = torch.empty(M, Mlp, device=dev, dtype=T)

@@ -38,7 +38,12 @@ enum {
   BFK_ACT_GELU_TANH = 1,   /* HF:323-327 (gelu_pytorch_tanh)            */
   BFK_ACT_GELU_ERF = 2,    /* bifold/models/modules.py:23 (nn.GELU())   */
   BFK_ACT_DGELU_TANH = 3,  /* out = acc * gelu_tanh'(aux)  (backward)   */
-  BFK_ACT_DGELU_ERF = 4    /* out = acc * gelu_erf'(aux)   (backward)   */
+  BFK_ACT_DGELU_ERF = 4,   /* out = acc * gelu_erf'(aux)   (backward)   */
+  /* training pair that moves the derivative into the forward epilogue (tanh / exp are computed once):
+   *   forward : v = acc + bias;  out = gelu(v);  aux = gelu'(v)          backward: out = acc * aux */
+  BFK_ACT_GELU_TANH_GRAD = 5,
+  BFK_ACT_GELU_ERF_GRAD = 6,
+  BFK_ACT_MUL_AUX = 7
 };
 
 BFK_API int32_t bfk_version(void);
@@ -63,8 +68,8 @@ typedef struct {
   void* D; int64_t ldd; int32_t out_dtype;
   const float* bias;                 /* [N] fp32 or NULL */
   int32_t act;                       /* BFK_ACT_*  */
-  void* aux; int64_t ld_aux;         /* GELU_*: optional store of the pre-activation (out_dtype);
-                                        DGELU_*: pre-activation to read (in_dtype) */
+  void* aux; int64_t ld_aux;         /* GELU_*: optional store of the pre-activation (out_dtype); GELU_*_GRAD: store of
+                                        gelu'(pre-activation) (out_dtype); DGELU_* / MUL_AUX: tensor to read (in_dtype) */
   const float* residual; int64_t ldr; int32_t res_row_mod; /* fp32; row = res_row_mod ? m % res_row_mod : m */
   float alpha;
   int32_t accumulate;                /* D += ... (fp32 output only) */

@@ -89,6 +89,74 @@ def test_gemm(kern, case, dtype, backend):
         assert err2 <= tol * pre.abs().max().item(), f"pre-activation store: {err2:.3e}"
 
 
+SPECIAL_CASES = [
+    # ta, tb, bias, act, residual, out_bf16   (alpha = 1, N % 32 == 0, enough tiles for the CTA-pair kernel)
+    (0, 0, True, 0, False, True),      # EPI_STORE_BF16
+    (0, 1, False, 0, False, True),     # EPI_STORE_BF16, dgrad layout
+    (0, 0, True, 0, True, False),      # EPI_RES_F32
+    (0, 0, True, 1, False, True),      # EPI_GELU_TANH_BF16 (+ pre-activation)
+    (0, 0, True, 2, False, True),      # EPI_GELU_ERF_BF16
+    (0, 1, False, 3, False, True),     # EPI_DGELU_TANH_BF16
+    (0, 1, False, 4, False, True),     # EPI_DGELU_ERF_BF16
+    (0, 0, True, 5, False, True),      # EPI_GELUG_TANH_BF16: value + derivative
+    (0, 0, True, 6, False, True),      # EPI_GELUG_ERF_BF16
+    (0, 1, False, 7, False, True),     # EPI_MULAUX_BF16
+    (1, 1, False, 0, False, False),    # EPI_STORE_F32, wgrad layout
+]
+
+
+@pytest.mark.parametrize("case", SPECIAL_CASES)
+@pytest.mark.parametrize("shape", [(1280, 2048, 320), (1304, 2048, 328)])
+def test_gemm_specialised_epilogues(kern, case, shape):
+    """The compile-time specialised tcgen05 epilogues (alpha == 1, N % 32 == 0) against fp32 torch; M = 1304 leaves a
+    ragged last row block, K = 328 a ragged last K block."""
+    ta, tb, use_bias, act, use_res, out_bf16 = case
+    M, N, Kd = shape
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(1000 * act + 10 * ta + tb + M)
+    T = torch.bfloat16
+    A = (torch.randn((Kd, M) if ta else (M, Kd), generator=g) * 0.25).to(dev).to(T)
+    B = (torch.randn((Kd, N) if tb else (N, Kd), generator=g) * 0.25).to(dev).to(T)
+    bias = torch.randn(N, generator=g).to(dev) if use_bias else None
+    res = torch.randn(M, N, generator=g).to(dev) if use_res else None
+    reads_aux = act in (3, 4, 7)
+    aux_in = torch.randn(M, N, generator=g).to(dev).to(T) if reads_aux else None
+    out_T = torch.bfloat16 if out_bf16 else torch.float32
+    D = torch.full((M, N), float("nan"), device=dev, dtype=out_T)
+    aux = aux_in if reads_aux else (torch.full((M, N), float("nan"), device=dev, dtype=out_T) if act in (1, 2, 5, 6) else None)
+    kern.gemm(A, B, D, M, N, Kd, A.shape[1], B.shape[1], N, trans_a=bool(ta), trans_b=bool(tb), bias=bias, act=act,
+              aux=aux, ld_aux=N, residual=res, ldr=N, backend=2)
+    torch.cuda.synchronize()
+    a = A.float().t() if ta else A.float()
+    b = B.float() if tb else B.float().t()
+    pre = a @ b + (bias if bias is not None else 0)
+    tanh_form = act in (1, 3, 5)
+
+    def gelu_and_grad(h):
+        h = h.clone().requires_grad_(True)
+        y = F.gelu(h, approximate="tanh") if tanh_form else F.gelu(h)
+        (dg,) = torch.autograd.grad(y.sum(), h)
+        return y.detach(), dg
+
+    aux_ref = None
+    if act == 0:
+        ref = pre + (res if res is not None else 0)
+    elif act in (1, 2):
+        ref, aux_ref = gelu_and_grad(pre)[0], pre
+    elif act in (3, 4):
+        ref = pre * gelu_and_grad(aux_in.float())[1]
+    elif act in (5, 6):
+        ref, aux_ref = gelu_and_grad(pre)
+    else:
+        ref = pre * aux_in.float()
+    tol = 2e-2 if out_bf16 else 2e-3
+    err = (D.float() - ref).abs().max().item()
+    assert math.isfinite(err) and err <= tol * ref.abs().max().item(), f"{case} {shape}: err {err:.3e}"
+    if aux_ref is not None:
+        err2 = (aux.float() - aux_ref).abs().max().item()
+        assert math.isfinite(err2) and err2 <= tol * max(aux_ref.abs().max().item(), 1.0), f"{case} {shape}: aux err {err2:.3e}"
+
+
 def test_gemm_accumulate(kern):
     M, N, Kd = 130, 72, 40
     A = torch.randn(M, Kd, device="cuda"); B = torch.randn(N, Kd, device="cuda")

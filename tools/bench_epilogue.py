@@ -32,6 +32,10 @@ timeit("bias+gelu_tanh (no aux)", lambda: k.gemm(A, B, D16, M, N, Kd, Kd, Kd, N,
 timeit("trans_b plain", lambda: k.gemm(A, Bt, D16, M, N, Kd, Kd, N, N, trans_b=True))
 timeit("trans_b dgelu_tanh", lambda: k.gemm(A, Bt, D16, M, N, Kd, Kd, N, N, trans_b=True, act=K.ACT_DGELU_TANH, aux=pa, ld_aux=N))
 timeit("trans_b dgelu_erf", lambda: k.gemm(A, Bt, D16, M, N, Kd, Kd, N, N, trans_b=True, act=K.ACT_DGELU_ERF, aux=pa, ld_aux=N))
+aux2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+timeit("bias+gelu_tanh_grad (value+derivative)", lambda: k.gemm(A, B, D16, M, N, Kd, Kd, Kd, N, bias=bias, act=K.ACT_GELU_TANH_GRAD, aux=aux2, ld_aux=N))
+timeit("bias+gelu_erf_grad (value+derivative)", lambda: k.gemm(A, B, D16, M, N, Kd, Kd, Kd, N, bias=bias, act=K.ACT_GELU_ERF_GRAD, aux=aux2, ld_aux=N))
+timeit("trans_b mul_aux", lambda: k.gemm(A, Bt, D16, M, N, Kd, Kd, N, N, trans_b=True, act=K.ACT_MUL_AUX, aux=pa, ld_aux=N))
 timeit("plain dgelu_tanh (trans_b=0)", lambda: k.gemm(A, B, D16, M, N, Kd, Kd, Kd, N, act=K.ACT_DGELU_TANH, aux=pa, ld_aux=N))
 # residual fp32
 M2, N2 = 12544, 768
