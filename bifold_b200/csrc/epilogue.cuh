@@ -18,7 +18,8 @@ struct EpiParams {
   int mode;    // EpiMode: compile-time specialised tcgen05 epilogue for the hot combinations (tc_epilogue.cuh), 0 = generic
 };
 
-// Specialised epilogues of the tcgen05 kernels.  All require vec_ok, alpha == 1, no accumulate, N % 32 == 0.
+// Specialised epilogues of the tcgen05 kernels.  All require vec_ok, alpha == 1, no accumulate; all but the two plain
+// stores also N % 32 == 0.
 enum EpiMode : int {
   EPI_GENERIC = 0,
   EPI_STORE_BF16,        // D(bf16) = acc (+ bias)
@@ -160,9 +161,11 @@ inline bool epi_from_args(const bfk_gemm_args* a, EpiParams& p) {
   if (a->residual) ok = ok && al32(a->residual) && (a->ldr * 4) % 32 == 0;
   p.vec_ok = ok ? 1 : 0;
   p.mode = EPI_GENERIC;
-  if (ok && a->alpha == 1.f && !a->accumulate && a->N % 32 == 0) {
+  if (ok && a->alpha == 1.f && !a->accumulate && a->act == BFK_ACT_NONE && !a->residual) {
+    p.mode = a->out_dtype == BFK_BF16 ? EPI_STORE_BF16 : EPI_STORE_F32;   // plain stores also take a ragged last chunk
+  } else if (ok && a->alpha == 1.f && !a->accumulate && a->N % 32 == 0) {
     const bool bf = a->out_dtype == BFK_BF16;
-    if (a->act == BFK_ACT_NONE && !a->residual) p.mode = bf ? EPI_STORE_BF16 : EPI_STORE_F32;
+    if (false) {}
     else if (a->act == BFK_ACT_NONE && a->residual && !bf) p.mode = EPI_RES_F32;
     else if (a->act == BFK_ACT_GELU_TANH && !a->residual && bf && p.aux_dtype == BFK_BF16) p.mode = EPI_GELU_TANH_BF16;
     else if (a->act == BFK_ACT_GELU_ERF && !a->residual && bf && p.aux_dtype == BFK_BF16) p.mode = EPI_GELU_ERF_BF16;

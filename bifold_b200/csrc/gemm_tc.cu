@@ -16,7 +16,6 @@ namespace bfk {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 template <int BN> struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
@@ -27,11 +26,14 @@ template <int BN> struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
 };
 
-template <int BN, bool AMN, bool BMN, int CL>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// MODE: compile-time EpiMode (see gemm_tc2.cu): EPI_GENERIC = runtime-flag epilogue, 8 epilogue warps; a specialised
+// MODE compiles only its own epilogue and runs 16 epilogue warps.
+template <int BN, bool AMN, bool BMN, int CL, int MODE>
+__global__ void __launch_bounds__(64 + 32 * epi_warps(MODE), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
                EpiParams ep, int splits, long long split_stride, int dbg) {
   using Cfg = TcCfg<BN>;
+  constexpr int EW = epi_warps(MODE);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -64,7 +66,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -153,9 +155,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue warps (2..9): TMEM lane quarter = warp % 4; the two warps of a quarter alternate chunks =====
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64;   // 0..255
+    // ===== epilogue warps: TMEM lane quarter = warp % 4; the EW/4 warps of a quarter take every (EW/4)-th chunk =====
+    const int quarter = warp & 3, sub = (warp - 2) >> 2;
+    const int half = sub;   // generic path: two warps per quarter
+    const int et = threadIdx.x - 64;
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = cid; item < tiles; item += ncl) {
       const int tile = item / splits;
@@ -163,17 +166,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       EpiParams epl = ep;
       if (splits > 1) epl.D = reinterpret_cast<float*>(ep.D) + (long long)(item % splits) * split_stride;   // fp32 partial
       float* bias_s = bias_smem + acc * BN;
-      for (int i = et; i < BN; i += 32 * TC_EPI_WARPS) bias_s[i] = (ep.bias && n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
-      named_bar_sync(1, 32 * TC_EPI_WARPS);   // bias visible; also orders reuse of the other buffer
+      for (int i = et; i < BN; i += 32 * EW) bias_s[i] = (ep.bias && n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
+      named_bar_sync(1, 32 * EW);   // bias visible; also orders reuse of the other buffer
       if (ep.vec_ok && item + ncl < tiles) {   // warm L2 with what the NEXT item's epilogue will read
         const int ntile = (item + ncl) / splits;
         const int nm = ((ntile / num_n) * CL + crank) * TC_BM + quarter * 32 + lane, nn0 = (ntile % num_n) * BN;
-        for (int c = half; c < BN / 32; c += 2) epi_prefetch(ep, nm, nn0 + c * 32);
+        for (int c = sub; c < BN / 32; c += EW / 4) epi_prefetch(ep, nm, nn0 + c * 32);
       }
       const int m = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
       const bool skip = (dbg & 1) || (ep.vec_ok & 16);   // measurement only
-      {
+      if constexpr (MODE != EPI_GENERIC) {
+        EpiOps<MODE> ops;
+        epi_tile_preload<MODE>(epl, m, n0, sub, ops);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        if (!skip) epi_tile<MODE, (BN / 32) / (EW / 4), EW / 4>(epl, m, n0, sub, taddr, bias_s, ops);
+      } else {
         EpiOperands cur, nxt;
         if (n0 + half * 32 < N) epi_load(epl, m, n0 + half * 32, cur);   // first chunk's operands: issued before the wait
         mbar_wait(tfull_bar(acc), acc_phase);
@@ -324,6 +333,27 @@ int gemm_dbg() {   // BFK_GEMM_DBG: 1 = skip the epilogue body, 2 = skip TMA + M
   return v;
 }
 
+template <int BN, bool AMN, bool BMN, int CL, int MODE>
+static int launch_tc_mode(const bfk_gemm_args* a, cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const EpiParams& ep,
+                          int splits, long long split_stride, int grid) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AMN, BMN, CL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("gemm_tc: cannot set smem %d: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return BFK_E_CUDA; }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * epi_warps(MODE)); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AMN, BMN, CL, MODE>, ma, mb, a->M, a->N, a->K, ep, splits, split_stride, gemm_dbg());
+  if (le != cudaSuccess) { set_error("gemm_tc: launch failed: %s", cudaGetErrorString(le)); return BFK_E_CUDA; }
+  return BFK_OK;
+}
+
 // partial_only: leave the fp32 K-split partials [splits][M][N] in the workspace (even for splits == 1) and skip the
 // reduction -- the caller fuses it into its own kernel (bfk_lora_grads).
 template <int BN, bool AMN, bool BMN, int CL>
@@ -339,30 +369,25 @@ static int launch_tc_cl(const bfk_gemm_args* a, cudaStream_t s, int splits, bool
   if (!ok) return BFK_E_CUDA;
   EpiParams ep;
   epi_from_args(a, ep);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AMN, BMN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("gemm_tc: cannot set smem %d: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return BFK_E_CUDA; }
-    attr_set = true;
-  }
   const long long split_stride = (long long)a->M * a->N;
   if (splits > 1 || partial_only) {   // partial tiles go to the workspace as plain fp32 [splits][M][N]
     ep.D = a->workspace; ep.ldd = a->N; ep.out_dtype = BFK_F32; ep.alpha = 1.f; ep.accumulate = 0;
     ep.vec_ok = ((reinterpret_cast<uintptr_t>(a->workspace) & 31u) == 0 && (a->N % 8) == 0 && (split_stride % 8) == 0) ? 1 : 0;
-    ep.mode = (ep.vec_ok && a->N % 32 == 0) ? EPI_STORE_F32 : EPI_GENERIC;
+    ep.mode = ep.vec_ok ? EPI_STORE_F32 : EPI_GENERIC;
   }
+  if (gemm_dbg() & 32) ep.mode = EPI_GENERIC;     // measurement only: force the generic epilogue
   if (ep.vec_ok) ep.vec_ok |= gemm_dbg() & 28;
   const int num_m = (a->M + TC_BM - 1) / TC_BM, num_n = (a->N + BN - 1) / BN;
   const int items = ((num_m + CL - 1) / CL) * num_n * splits;
   const int grid = CL * std::min(items, sm_count() / CL);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AMN, BMN, CL>, ma, mb, a->M, a->N, a->K, ep, splits, split_stride, gemm_dbg());
-  if (le != cudaSuccess) { set_error("gemm_tc: launch failed: %s", cudaGetErrorString(le)); return BFK_E_CUDA; }
+  // specialised epilogues are instantiated only where the step uses them on this kernel: plain fp32 stores of the
+  // wgrad layout (split-K partials) and plain bf16 stores of the dgrad layout
+  constexpr bool HAS_F32 = CL == 1 && AMN && BMN, HAS_BF16 = CL == 1 && !AMN && BMN;
+  int rc;
+  if (HAS_F32 && ep.mode == EPI_STORE_F32) rc = launch_tc_mode<BN, AMN, BMN, CL, HAS_F32 ? EPI_STORE_F32 : EPI_GENERIC>(a, s, ma, mb, ep, splits, split_stride, grid);
+  else if (HAS_BF16 && ep.mode == EPI_STORE_BF16) rc = launch_tc_mode<BN, AMN, BMN, CL, HAS_BF16 ? EPI_STORE_BF16 : EPI_GENERIC>(a, s, ma, mb, ep, splits, split_stride, grid);
+  else { ep.mode = EPI_GENERIC; rc = launch_tc_mode<BN, AMN, BMN, CL, EPI_GENERIC>(a, s, ma, mb, ep, splits, split_stride, grid); }
+  if (rc) return rc;
   if (splits > 1 && !partial_only) {
     const long long total = (long long)a->M * a->N;
     const int rg = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
@@ -381,8 +406,6 @@ static int launch_tc(const bfk_gemm_args* a, cudaStream_t s, int* partial_splits
     return launch_tc_cl<BN, AMN, BMN, 1>(a, s, splits, true);
   }
   const int num_m = (a->M + TC_BM - 1) / TC_BM, num_n = (a->N + BN - 1) / BN;
-  if (pair_enabled() && BN == 256 && splits == 1 && a->M >= 256 && ((a->M + 255) / 256) * num_n >= sm_count() / 4)
-    return gemm_tc2(a, s);
   // cluster-of-2 B multicast pays off when every SM has work anyway; tiny problems keep single CTAs
   if (cluster_enabled() && splits == 1 && num_m >= 2 && num_m * num_n >= sm_count() / 2)
     return launch_tc_cl<BN, AMN, BMN, 2>(a, s, splits);
@@ -396,6 +419,11 @@ int gemm_tc_wgrad_partials(const bfk_gemm_args* a, cudaStream_t s, int* splits) 
 }
 
 int gemm_tc(const bfk_gemm_args* a, cudaStream_t s) {
+  // CTA-pair kernel (256 x 256 tiles) for every problem that fills the machine with them; a ragged last n-tile
+  // (N = 784: 16 live columns of 256) is cheaper there than 128-wide tiles on the single-CTA kernel
+  if (pair_enabled() && a->M >= 256 && a->N >= 512 && ((a->M + 255) / 256) * ((a->N + 255) / 256) >= sm_count() / 4 &&
+      choose_splits(a, 256) == 1)
+    return gemm_tc2(a, s);
   const int w256 = ((a->N + 255) / 256) * 256 - a->N, w128 = ((a->N + 127) / 128) * 128 - a->N;
   const bool bn256 = w256 <= w128 && a->N > 128;
   const bool ta = a->trans_a != 0, tb = a->trans_b != 0;

@@ -268,12 +268,25 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, int m, int n0, int
   // chunk i of this warp: columns [nc, nc + 32); `op` holds its operands, `nxt` receives those of chunk i + 1
   auto chunk = [&](int i, V8 (&op)[NOP], V8 (&nxt)[NOP]) {
     const int c = sub + CS * i, nc = n0 + c * 32;
-    if (nc >= ep.N) return;                                  // warp-uniform; N % 32 == 0, so chunks are never partial
+    if (nc >= ep.N) return;                                  // warp-uniform
     if ((RES || DG) && i + 1 < NCH && row_ok && nc + CS * 32 < ep.N) epi_load_ops<MODE>(ep, m, nc + CS * 32, nxt);
     uint32_t r[32];
     tc_ld32(taddr + (uint32_t)(c * 32), r);
     tc_wait_ld();
     if (!row_ok) return;
+    if constexpr (MODE == EPI_STORE_BF16 || MODE == EPI_STORE_F32) {
+      if (nc + 32 > ep.N) {                                  // ragged last chunk of the matrix: element-wise
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          if (nc + t < ep.N) {
+            const float x = __uint_as_float(r[t]) + bias_s[c * 32 + t];
+            if constexpr (MODE == EPI_STORE_BF16) reinterpret_cast<__nv_bfloat16*>(ep.D)[(long long)m * ep.ldd + nc + t] = __float2bfloat16_rn(x);
+            else reinterpret_cast<float*>(ep.D)[(long long)m * ep.ldd + nc + t] = x;
+          }
+        }
+        return;
+      }
+    }
     float v[32];
     if constexpr (DG) {
 #pragma unroll

@@ -26,3 +26,13 @@ for (M, N, Kd) in [(12544, 3072, 768), (12544, 768, 3072), (12544, 2304, 784), (
     if dbg == "0":
         Bt = B.t()
         timeit(f"cuBLAS {M}x{N}x{Kd} (torch.matmul)", lambda: torch.matmul(A, Bt, out=D16), fl)
+
+# QKV dgrad with the LoRA columns: M x 784 = dqkv[M x 2304] . Wext[2304 x 784] (B stored [K, N]); wgrad split-K
+M, N, Kd = 12544, 784, 2304
+A = torch.randn(M, Kd, device="cuda").bfloat16(); Bt = torch.randn(Kd, N, device="cuda").bfloat16()
+D16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+timeit(f"bfk dgrad N=784 {M}x{N}x{Kd} trans_b", lambda: k.gemm(A, Bt, D16, M, N, Kd, Kd, N, N, trans_b=True), 2 * M * N * Kd)
+M, N, Kd = 3072, 768, 16768
+At = torch.randn(Kd, M, device="cuda").bfloat16(); Bt = torch.randn(Kd, N, device="cuda").bfloat16()
+D32 = torch.empty(M, N, device="cuda")
+timeit(f"bfk wgrad {M}x{N}x{Kd} split-K", lambda: k.gemm(At, Bt, D32, M, N, Kd, M, N, N, trans_a=True, trans_b=True), 2 * M * N * Kd)
