@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: only the device-resident timed loop")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the captured whole-step CUDA graph")
     return ap.parse_args()
 
 
@@ -224,7 +225,7 @@ def main():
     train = args.mode == "train"
     model.train(train)
 
-    def step(sample, read_back):
+    def eager_step(sample, read_back):
         if train:
             eng.step_seed += 1
             out = model(sample)
@@ -235,6 +236,21 @@ def main():
             return loss.item() if read_back else loss
         action = model.get_action(sample)      # D2H of the (heads,B,2) pixel table happens inside
         return action
+
+    # Single-process training replays ONE captured CUDA graph per step (bifold_b200.graphs): the ~750 launches of the
+    # eager step cost ~14 ms of host time against ~23 ms of GPU work, so any host contention makes it launch-bound.
+    # Multi-GPU (the gradient all-reduce is not captured) and inference use the eager path.
+    use_graph = train and world == 1 and not args.no_graph
+    gstep = None
+    if use_graph:
+        from bifold_b200.graphs import GraphedTrainStep
+        gstep = GraphedTrainStep(model, loss_fn, optim, warmup=2)
+
+    def step(sample, read_back):
+        if gstep is not None:
+            loss = gstep(sample)
+            return loss.item() if read_back else loss
+        return eager_step(sample, read_back)
 
     def barrier():
         torch.cuda.synchronize()
@@ -269,6 +285,8 @@ def main():
     torch.cuda.profiler.stop()
     clocks = sampler.stop()
     launches = (eng.k.launches - l0) + (optim.launches - o0)
+    if gstep is not None and gstep.graph is not None:
+        launches = gstep.launches_per_replay * args.steps      # kernels inside the replayed graph (counted at capture)
     # host time to ENQUEUE one step (no synchronisation inside): how far the launch queue runs ahead of the GPU
     import time as _time
     torch.cuda.synchronize()
@@ -312,9 +330,9 @@ def main():
     roofline = None
     if not args.no_roofline:
         if rank == 0:
-            roofline = gemm_roofline(eng, lambda: step(dev_sample, False))
+            roofline = gemm_roofline(eng, lambda: eager_step(dev_sample, False))
         else:
-            step(dev_sample, False)      # the instrumented step contains the DDP collectives: every rank must run it
+            eager_step(dev_sample, False)      # the instrumented step contains the DDP collectives: every rank must run it
             torch.cuda.synchronize()
     tail = None
     if rank == 0 and not args.no_roofline:
@@ -330,7 +348,8 @@ def main():
                 "dtype": args.precision, "data": "synthetic", "config": workload_config(args, B, world),
                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks,
+                "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
+                "launch_mode": "whole-step CUDA graph replay" if (gstep is not None and gstep.graph is not None) else "eager", "clocks": clocks,
                 "model_flops_per_sample": tr_flops if train else fw_flops,
                 "model_tflops_per_gpu": (tr_flops if train else fw_flops) * B / (per_step / 1e3) / 1e12,
                 "model_frac_of_bf16_peak": (tr_flops if train else fw_flops) * B / (per_step / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],

@@ -34,7 +34,8 @@ class GemmArgs(C.Structure):
 class LayerNormFwdArgs(C.Structure):
     _fields_ = [("M", i32), ("D", i32), ("x", vp), ("ldx", i64), ("gamma", vp), ("beta", vp), ("eps", f32),
                 ("y", vp), ("ldy", i64), ("y_dtype", i32), ("mean", vp), ("rstd", vp),
-                ("y2", vp), ("ldy2", i64), ("y2_dropout_p", f32), ("y2_seed", u64)]
+                ("y2", vp), ("ldy2", i64), ("y2_dropout_p", f32), ("y2_seed", u64),
+                ("lora_a", vp), ("lora_u", vp), ("ld_u", i64), ("seed_ptr", vp)]
 
 
 class LayerNormBwdArgs(C.Structure):
@@ -43,7 +44,7 @@ class LayerNormBwdArgs(C.Structure):
                 ("dres", vp), ("ld_dres", i64), ("dx", vp), ("ld_dx", i64),
                 ("dx2", vp), ("ld_dx2", i64), ("dx2_dtype", i32),
                 ("dgamma", vp), ("dbeta", vp), ("partials", vp),
-                ("dy2", vp), ("ld_dy2", i64), ("dy2_dropout_p", f32), ("dy2_seed", u64)]
+                ("dy2", vp), ("ld_dy2", i64), ("dy2_dropout_p", f32), ("dy2_seed", u64), ("seed_ptr", vp)]
 
 
 class AttentionArgs(C.Structure):
@@ -108,10 +109,15 @@ class LoraGradsArgs(C.Structure):
                 ("workspace", vp), ("workspace_bytes", i64)]
 
 
+class CastSegment(C.Structure):
+    _fields_ = [("src", vp), ("dst", vp), ("ld_dst", i64), ("first_chunk", i64),
+                ("rows", i32), ("cols", i32), ("dst_dtype", i32), ("scale", f32)]
+
+
 class AdamWArgs(C.Structure):
     _fields_ = [("n", i64), ("p", vp), ("g", vp), ("m", vp), ("v", vp), ("shadow_bf16", vp),
                 ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("weight_decay", f32),
-                ("decoupled", i32), ("step", i32), ("grad_scale", f32)]
+                ("decoupled", i32), ("step", i32), ("grad_scale", f32), ("dyn", vp)]
 
 
 # name -> (restype, argtypes).  This table is also what tests/test_cabi_symbols.py checks against the header.
@@ -132,6 +138,8 @@ _PROTOS = {
     "bfk_lora_down": (i32, [vp, i64, i32, i32, i32, vp, f32, u64, vp]),
     "bfk_lora_down_bwd": (i32, [vp, i64, i32, i32, i32, vp, f32, u64, vp]),
     "bfk_dropout_copy": (i32, [vp, i64, vp, i64, i32, i32, i32, f32, u64, vp]),
+    "bfk_adamw_advance": (i32, [vp, vp, f32, f32, vp, vp]),
+    "bfk_multi_cast": (i32, [vp, i32, i64, vp]),
     "bfk_lora_grads_workspace_bytes": (C.c_size_t, [i32]),
     "bfk_lora_grads": (i32, [C.POINTER(LoraGradsArgs), vp]),
     "bfk_skinny_gram_workspace_floats": (C.c_size_t, [i32, i32, i32]),

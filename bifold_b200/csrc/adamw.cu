@@ -4,8 +4,16 @@
 
 namespace bfk {
 
+__global__ void adamw_advance_kernel(int32_t* step_dev, const float* lr_dev, float beta1, float beta2, float* dyn) {
+  const int step = ++(*step_dev);
+  dyn[0] = *lr_dev;
+  dyn[1] = (float)(1.0 - pow((double)beta1, (double)step));
+  dyn[2] = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+}
+
 __global__ void __launch_bounds__(256) adamw_kernel(bfk_adamw_args a, float bc1, float bc2_sqrt) {
   const long long n4 = a.n >> 2;
+  if (a.dyn) { a.lr = a.dyn[0]; bc1 = a.dyn[1]; bc2_sqrt = a.dyn[2]; }   // device-resident schedule (CUDA-graph replay)
   const float step_size = a.lr / bc1;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     float4 p = reinterpret_cast<float4*>(a.p)[i];
@@ -56,20 +64,67 @@ __global__ void cast_kernel(const float* __restrict__ src, T* __restrict__ dst, 
   }
 }
 
+__global__ void __launch_bounds__(256) multi_cast_kernel(const bfk_cast_segment* __restrict__ segs, int nseg, long long total_chunks) {
+  for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    int lo = 0, hi = nseg - 1;                    // last segment whose first_chunk <= chunk (block-uniform search)
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (segs[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const bfk_cast_segment sg = segs[lo];
+    const long long n = (long long)sg.rows * sg.cols;
+    const long long e0 = (chunk - sg.first_chunk) * 1024 + threadIdx.x * 4;
+    if (e0 >= n) continue;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (e0 + 4 <= n && (reinterpret_cast<uintptr_t>(sg.src + e0) & 15u) == 0) {
+      const float4 f = *reinterpret_cast<const float4*>(sg.src + e0);
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+      for (int j = 0; j < 4; ++j) if (e0 + j < n) v[j] = sg.src[e0 + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long e = e0 + j;
+      if (e < n) {
+        const long long r = e / sg.cols, c = e % sg.cols;
+        const float x = v[j] * sg.scale;
+        if (sg.dst_dtype == BFK_BF16) reinterpret_cast<__nv_bfloat16*>(sg.dst)[r * sg.ld_dst + c] = __float2bfloat16_rn(x);
+        else reinterpret_cast<float*>(sg.dst)[r * sg.ld_dst + c] = x;
+      }
+    }
+  }
+}
+
 }  // namespace bfk
 
 using namespace bfk;
 
+extern "C" int32_t bfk_multi_cast(const bfk_cast_segment* segs, int32_t nseg, int64_t total_chunks, bfk_stream_t s_) {
+  BFK_CHECK_ARG(segs && nseg > 0 && total_chunks > 0, "bfk_multi_cast: bad arguments");
+  const int blocks = (int)std::min<long long>((long long)sm_count() * 16, total_chunks);
+  multi_cast_kernel<<<blocks, 256, 0, to_stream(s_)>>>(segs, nseg, total_chunks);
+  BFK_CHECK_LAUNCH("bfk_multi_cast");
+  return BFK_OK;
+}
+
 extern "C" int32_t bfk_adamw(const bfk_adamw_args* a, bfk_stream_t s_) {
-  BFK_CHECK_ARG(a && a->p && a->g && a->m && a->v && a->n > 0 && a->step >= 1, "bfk_adamw: bad arguments");
+  BFK_CHECK_ARG(a && a->p && a->g && a->m && a->v && a->n > 0 && (a->step >= 1 || a->dyn), "bfk_adamw: bad arguments");
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   BFK_CHECK_ARG(al16(a->p) && al16(a->g) && al16(a->m) && al16(a->v) && (!a->shadow_bf16 || (reinterpret_cast<uintptr_t>(a->shadow_bf16) & 7u) == 0),
                 "bfk_adamw: buffers must be 16-byte aligned");
-  double bc1 = 1.0 - pow((double)a->beta1, (double)a->step);
-  double bc2 = 1.0 - pow((double)a->beta2, (double)a->step);
+  const int hstep = a->step >= 1 ? a->step : 1;
+  double bc1 = 1.0 - pow((double)a->beta1, (double)hstep);
+  double bc2 = 1.0 - pow((double)a->beta2, (double)hstep);
   int blocks = (int)std::min<long long>((long long)sm_count() * 8, ((a->n >> 2) + 255) / 256 + 1);
   adamw_kernel<<<blocks, 256, 0, to_stream(s_)>>>(*a, (float)bc1, (float)sqrt(bc2));
   BFK_CHECK_LAUNCH("bfk_adamw");
+  return BFK_OK;
+}
+
+extern "C" int32_t bfk_adamw_advance(int32_t* step_dev, const float* lr_dev, float beta1, float beta2, float* dyn, bfk_stream_t s_) {
+  BFK_CHECK_ARG(step_dev && lr_dev && dyn, "bfk_adamw_advance: null pointer");
+  adamw_advance_kernel<<<1, 1, 0, to_stream(s_)>>>(step_dev, lr_dev, beta1, beta2, dyn);
+  BFK_CHECK_LAUNCH("bfk_adamw_advance");
   return BFK_OK;
 }
 

@@ -30,7 +30,7 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
   reinterpret_cast<uint2*>(p)[c] = u;
 }
 
-template <typename TY, int LN_MAXC>
+template <typename TY, int LN_MAXC, bool LORA = false>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(bfk_layernorm_fwd_args a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * LN_WARPS + warp;
@@ -67,6 +67,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(bfk_layernorm_fwd
   TY* y = reinterpret_cast<TY*>(a.y) + (long long)row * a.ldy;
   TY* y2 = a.y2 ? reinterpret_cast<TY*>(a.y2) + (long long)row * a.ldy2 : nullptr;
   const float keep2 = a.y2_dropout_p > 0.f ? 1.f / (1.f - a.y2_dropout_p) : 1.f;
+  const uint64_t seed2 = a.y2_seed + (a.seed_ptr ? *a.seed_ptr : 0ull);
+  float lacc[LORA ? 16 : 1];
+  if constexpr (LORA) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) lacc[j] = 0.f;
+  }
 #pragma unroll
   for (int i = 0; i < LN_MAXC; ++i) {
     int c = lane + 32 * i;
@@ -88,14 +94,35 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(bfk_layernorm_fwd
       }
       if (y2) {
         if (a.y2_dropout_p > 0.f) {
-          o0 = hash_uniform(a.y2_seed, row, 4 * c + 0) < a.y2_dropout_p ? 0.f : o0 * keep2;
-          o1 = hash_uniform(a.y2_seed, row, 4 * c + 1) < a.y2_dropout_p ? 0.f : o1 * keep2;
-          o2 = hash_uniform(a.y2_seed, row, 4 * c + 2) < a.y2_dropout_p ? 0.f : o2 * keep2;
-          o3 = hash_uniform(a.y2_seed, row, 4 * c + 3) < a.y2_dropout_p ? 0.f : o3 * keep2;
+          o0 = hash_uniform(seed2, row, 4 * c + 0) < a.y2_dropout_p ? 0.f : o0 * keep2;
+          o1 = hash_uniform(seed2, row, 4 * c + 1) < a.y2_dropout_p ? 0.f : o1 * keep2;
+          o2 = hash_uniform(seed2, row, 4 * c + 2) < a.y2_dropout_p ? 0.f : o2 * keep2;
+          o3 = hash_uniform(seed2, row, 4 * c + 3) < a.y2_dropout_p ? 0.f : o3 * keep2;
         }
         store4<TY>(y2, c, make_float4(o0, o1, o2, o3));
       }
+      if constexpr (LORA) {
+        // u += drop(y) . A^T on the values as stored (bf16): what a GEMM over the stored rows would read
+        const float2 q0 = __bfloat1622float2(__floats2bfloat162_rn(o0, o1)), q1 = __bfloat1622float2(__floats2bfloat162_rn(o2, o3));
+        const uint2* A2 = reinterpret_cast<const uint2*>(a.lora_a) + c;     // row j starts at j * (D / 4)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint2 aw = __ldg(A2 + (long long)j * nc);
+          const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw.x));
+          const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw.y));
+          lacc[j] = fmaf(q0.x, a0.x, fmaf(q0.y, a0.y, fmaf(q1.x, a1.x, fmaf(q1.y, a1.y, lacc[j]))));
+        }
+      }
     }
+  }
+  if constexpr (LORA) {
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float t = warp_sum(lacc[j]);
+      if (lane == j) mine = t;
+    }
+    if (lane < 16) reinterpret_cast<__nv_bfloat16*>(a.lora_u)[(long long)row * a.ld_u + lane] = __float2bfloat16_rn(mine);
   }
 }
 
@@ -126,6 +153,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PARAM_GRADS || LN_MAXC > 6) ? 
   const int r_begin = blockIdx.x * rows_per_block;
   const int r_end = min(a.M, r_begin + rows_per_block);
   const float keep2 = a.dy2_dropout_p > 0.f ? 1.f / (1.f - a.dy2_dropout_p) : 1.f;
+  const uint64_t seed2 = a.dy2_seed + (a.seed_ptr ? *a.seed_ptr : 0ull);
   for (int row = r_begin + warp; row < r_end; row += LN_WARPS) {
     const float4* x4 = reinterpret_cast<const float4*>(a.x + (long long)row * a.ldx);
     const RawDY* dy = reinterpret_cast<const RawDY*>(reinterpret_cast<const TDY*>(a.dy) + (long long)row * a.ld_dy);
@@ -159,10 +187,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PARAM_GRADS || LN_MAXC > 6) ? 
         if (dy2) {
           float4 e = cvt4(ev[i]);
           if (a.dy2_dropout_p > 0.f) {
-            e.x = hash_uniform(a.dy2_seed, row, 4 * c + 0) < a.dy2_dropout_p ? 0.f : e.x * keep2;
-            e.y = hash_uniform(a.dy2_seed, row, 4 * c + 1) < a.dy2_dropout_p ? 0.f : e.y * keep2;
-            e.z = hash_uniform(a.dy2_seed, row, 4 * c + 2) < a.dy2_dropout_p ? 0.f : e.z * keep2;
-            e.w = hash_uniform(a.dy2_seed, row, 4 * c + 3) < a.dy2_dropout_p ? 0.f : e.w * keep2;
+            e.x = hash_uniform(seed2, row, 4 * c + 0) < a.dy2_dropout_p ? 0.f : e.x * keep2;
+            e.y = hash_uniform(seed2, row, 4 * c + 1) < a.dy2_dropout_p ? 0.f : e.y * keep2;
+            e.z = hash_uniform(seed2, row, 4 * c + 2) < a.dy2_dropout_p ? 0.f : e.z * keep2;
+            e.w = hash_uniform(seed2, row, 4 * c + 3) < a.dy2_dropout_p ? 0.f : e.w * keep2;
           }
           d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
         }
@@ -255,13 +283,16 @@ extern "C" int32_t bfk_layernorm_fwd(const bfk_layernorm_fwd_args* a, bfk_stream
   using namespace bfk;
   BFK_CHECK_ARG(a && a->x && a->y && a->gamma && a->beta, "bfk_layernorm_fwd: null pointer");
   BFK_CHECK_ARG(!a->y2 || a->ldy2 % 4 == 0, "bfk_layernorm_fwd: ldy2 %% 4 != 0");
+  BFK_CHECK_ARG(!a->lora_a || (a->y_dtype == BFK_BF16 && a->lora_u && (reinterpret_cast<uintptr_t>(a->lora_a) & 7u) == 0),
+                "bfk_layernorm_fwd: the fused LoRA down-projection needs bf16 y, lora_u and an 8-byte aligned lora_a");
   BFK_CHECK_ARG(a->M > 0 && a->D > 0 && a->D % 4 == 0 && a->D <= 128 * LN_MAXC && a->ldx % 4 == 0 && a->ldy % 4 == 0,
                 "bfk_layernorm_fwd: need D%%4==0, D<=%d, ld%%4==0 (D=%d)", 128 * LN_MAXC, a->D);
   cudaStream_t s = to_stream(s_);
   int grid = (a->M + LN_WARPS - 1) / LN_WARPS;
 #define LN_FWD(NC)                                                                          \
   do {                                                                                      \
-    if (a->y_dtype == BFK_BF16) ln_fwd_kernel<__nv_bfloat16, NC><<<grid, LN_WARPS * 32, 0, s>>>(*a); \
+    if (a->y_dtype == BFK_BF16 && a->lora_a) ln_fwd_kernel<__nv_bfloat16, NC, true><<<grid, LN_WARPS * 32, 0, s>>>(*a); \
+    else if (a->y_dtype == BFK_BF16) ln_fwd_kernel<__nv_bfloat16, NC><<<grid, LN_WARPS * 32, 0, s>>>(*a); \
     else ln_fwd_kernel<float, NC><<<grid, LN_WARPS * 32, 0, s>>>(*a);                         \
   } while (0)
   if (a->D <= 256) LN_FWD(2); else if (a->D <= 768) LN_FWD(6); else if (a->D <= 1152) LN_FWD(9); else LN_FWD(12);

@@ -48,6 +48,7 @@ class Kernels:
         self.launches = 0          # C-ABI calls issued (each is >= 1 kernel launch); bench.py reports it
         self.backend = K.BACKEND_AUTO
         self._ws = None
+        self.seed_dev = None   # device int64 counter added to every dropout seed (advanced inside captured CUDA graphs)
 
     def splitk_ws(self, device):
         """fp32 scratch for split-K partial tiles (wgrad GEMMs); one buffer, reused stream-ordered."""
@@ -85,9 +86,11 @@ class Kernels:
         self.launches += 2
 
     # -- LayerNorm ---------------------------------------------------------------------------------
-    def layernorm_fwd(self, x, M, D, gamma, beta, eps, y, ldy, mean=None, rstd=None, y2=None, ldy2=0, y2_p=0.0, y2_seed=0):
+    def layernorm_fwd(self, x, M, D, gamma, beta, eps, y, ldy, mean=None, rstd=None, y2=None, ldy2=0, y2_p=0.0, y2_seed=0,
+                      lora_a=None, lora_u=None, ld_u=0):
         a = K.LayerNormFwdArgs(M, D, x.data_ptr(), D, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(), ldy, _dt(y),
-                               K.ptr(mean), K.ptr(rstd), K.ptr(y2), ldy2, y2_p, y2_seed)
+                               K.ptr(mean), K.ptr(rstd), K.ptr(y2), ldy2, y2_p, y2_seed, K.ptr(lora_a), K.ptr(lora_u), ld_u,
+                               K.ptr(self.seed_dev) if y2_p > 0.0 else None)
         K.check(self.lib.bfk_layernorm_fwd(C.byref(a), _stream()), "bfk_layernorm_fwd")
         self.launches += 1
 
@@ -99,7 +102,7 @@ class Kernels:
         a = K.LayerNormBwdArgs(M, D, dy.data_ptr(), ld_dy, _dt(dy), x.data_ptr(), D, mean.data_ptr(), rstd.data_ptr(),
                                gamma.data_ptr(), K.ptr(dres), D, dx.data_ptr(), D, K.ptr(dx2), D,
                                _dt(dx2) if dx2 is not None else 0, K.ptr(dgamma), K.ptr(dbeta), K.ptr(ws),
-                               K.ptr(dy2), ld_dy2, dy2_p, dy2_seed)
+                               K.ptr(dy2), ld_dy2, dy2_p, dy2_seed, K.ptr(self.seed_dev) if dy2_p > 0.0 else None)
         K.check(self.lib.bfk_layernorm_bwd(C.byref(a), _stream()), "bfk_layernorm_bwd")
         self.launches += 2 if dgamma is not None else 1
 
@@ -152,6 +155,7 @@ class Engine:
         self.grad_ready_hook = None   # DDP: called as hook(name_list) when a group of grads is final
         self.overlap_towers = os.environ.get("BFK_OVERLAP_TOWERS", "1") != "0"    # text tower on a side stream, concurrent with the vision tower (fwd and bwd)
         self._side = None
+        self.fuse_lora_down = os.environ.get("BFK_FUSE_LORA_DOWN", "1") != "0"
 
     # ------------------------------------------------------------------------------------------------
     # weight preparation
@@ -194,16 +198,16 @@ class Engine:
         lw.W2, lw.b2 = self._shadow(self._p(prefix + ".mlp.fc2.weight")), self._p(prefix + ".mlp.fc2.bias")
         return lw
 
-    def _refresh_lora(self, lw: LayerWeights):
-        """Re-pack the trainable LoRA factors into the extended QKV weight and the down-projection."""
-        cfg, D, r = self.cfg, self.cfg.dim, self.cfg.r
+    def _lora_segments(self, lw: LayerWeights, segs):
+        """Trainable LoRA factors -> their slots in the extended QKV weight [W | (alpha/r) B] and the [A_q; A_v] pack."""
+        cfg, D, r, Dk = self.cfg, self.cfg.dim, self.cfg.r, lw.Dk
         s = cfg.lora_alpha / cfg.r
-        Bq, Bv = self._p(lw.names["Bq"]), self._p(lw.names["Bv"])
-        # Wqkv[0:D, D:D+r] = s*Bq ; Wqkv[2D:3D, D+8:D+8+r] = s*Bv   (tiny: torch copy, not on the activation path)
-        lw.Wqkv[0:D, D:D + r].copy_(Bq * s)
-        lw.Wqkv[2 * D:3 * D, D + 8:D + 8 + r].copy_(Bv * s)
-        lw.Acat[0:r].copy_(self._p(lw.names["Aq"]))
-        lw.Acat[8:8 + r].copy_(self._p(lw.names["Av"]))
+        es = lw.Wqkv.element_size()
+        n = lw.names
+        segs.append((self._p(n["Bq"]), lw.Wqkv.data_ptr() + D * es, D, r, Dk, s, lw.Wqkv.dtype))
+        segs.append((self._p(n["Bv"]), lw.Wqkv.data_ptr() + (2 * D * Dk + D + 8) * es, D, r, Dk, s, lw.Wqkv.dtype))
+        segs.append((self._p(n["Aq"]), lw.Acat.data_ptr(), r, D, D, 1.0, lw.Acat.dtype))
+        segs.append((self._p(n["Av"]), lw.Acat.data_ptr() + 8 * D * lw.Acat.element_size(), r, D, D, 1.0, lw.Acat.dtype))
 
     def _fusion_layer_weights(self, l: int) -> LayerWeights:
         D = self.cfg.dim
@@ -218,7 +222,7 @@ class Engine:
         lw.bqkv, lw.Acat = None, None
         return lw
 
-    def _refresh_fusion(self, lw: LayerWeights):
+    def _fusion_segments(self, lw: LayerWeights, segs):
         n = lw.names
         lw.ln1_w, lw.ln1_b, lw.ln2_w, lw.ln2_b = (self._p(n[k]) for k in ("ln1_w", "ln1_b", "ln2_w", "ln2_b"))
         lw.bo, lw.b1, lw.b2 = self._p(n["bo"]), self._p(n["b1"]), self._p(n["b2"])
@@ -231,7 +235,31 @@ class Engine:
                 if cur is None or cur.shape != w.shape:
                     cur = torch.empty_like(w, dtype=self.T)
                     setattr(lw, k, cur)
-                self.k.cast(w, cur, w.shape[0], w.shape[1], w.shape[1], w.shape[1])
+                segs.append((w, cur.data_ptr(), w.shape[0], w.shape[1], w.shape[1], 1.0, self.T))
+
+    def _refresh_trainable(self):
+        """ONE launch (bfk_multi_cast) re-derives every operand-dtype copy of the trainable weights."""
+        segs = []
+        if self.cfg.lora:
+            for lw in self.text_layers + self.vis_layers:
+                self._lora_segments(lw, segs)
+        for lw in self.fusion_layers:
+            self._fusion_segments(lw, segs)
+        if not segs:
+            return
+        key = tuple((w.data_ptr(), dst) for (w, dst, *_rest) in segs)
+        if getattr(self, "_seg_key", None) != key:
+            arr = (K.CastSegment * len(segs))()
+            chunk = 0
+            for i, (w, dst, rows, cols, ld, scale, dt) in enumerate(segs):
+                assert w.dtype == torch.float32 and w.is_contiguous()
+                arr[i] = K.CastSegment(w.data_ptr(), dst, ld, chunk, rows, cols, K.BF16 if dt == torch.bfloat16 else K.F32, scale)
+                chunk += (rows * cols + 1023) // 1024
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+            self._seg_host, self._seg_dev = host, host.to(self.device, non_blocking=True)
+            self._seg_key, self._seg_n, self._seg_chunks = key, len(segs), chunk
+        K.check(self.k.lib.bfk_multi_cast(self._seg_dev.data_ptr(), self._seg_n, self._seg_chunks, _stream()), "bfk_multi_cast")
+        self.k.launches += 1
 
     def prepare(self, device):
         """(Re)build operand-dtype shadows.  Frozen tower weights once; trainable ones when changed."""
@@ -239,6 +267,7 @@ class Engine:
         if self.device != device:
             self.device, self._frozen_ready, self._train_version = device, False, None
             self._taps, self._ptr_tables = {}, {}
+            self.k.seed_dev = torch.zeros(1, device=device, dtype=torch.int64)
         fver = sum(p._version + (p.data_ptr() % 1000003) for p in self.params.values() if not p.requires_grad)
         if fver != self._frozen_version:   # e.g. load_state_dict after a forward
             self._frozen_ready, self._frozen_version, self._train_version = False, fver, None
@@ -257,11 +286,7 @@ class Engine:
         version = sum(p._version for p in self.params.values() if p.requires_grad) + \
             sum(p.data_ptr() % 1000003 for p in self.params.values() if p.requires_grad)
         if version != self._train_version:
-            if cfg.lora:
-                for lw in self.text_layers + self.vis_layers:
-                    self._refresh_lora(lw)
-            for lw in self.fusion_layers:
-                self._refresh_fusion(lw)
+            self._refresh_trainable()
             self._train_version = version
 
     def taps(self, g: int):
@@ -287,9 +312,12 @@ class Engine:
         h1d = None
         if lw.Acat is not None and T == torch.bfloat16 and p_drop > 0.0:
             h1d = torch.empty(M, D, device=dev, dtype=T)   # drop(h1): the LoRA branch input, written by the same LN pass
-        k.layernorm_fwd(x, M, D, lw.ln1_w, lw.ln1_b, eps, h1, Dk, mean1, rstd1, y2=h1d, ldy2=D, y2_p=p_drop, y2_seed=lora_seed)
-        if lw.Acat is not None and T == torch.bfloat16:
-            # LoRA down-projection on the tensor cores: u = drop(h1) Acat^T written into the 16 extra K columns
+        lora_bf16 = lw.Acat is not None and T == torch.bfloat16
+        fuse_lora = lora_bf16 and self.fuse_lora_down
+        # bf16: the LayerNorm pass also computes the LoRA down-projection u = drop(h1) Acat^T into the 16 extra K columns
+        k.layernorm_fwd(x, M, D, lw.ln1_w, lw.ln1_b, eps, h1, Dk, mean1, rstd1, y2=h1d, ldy2=D, y2_p=p_drop, y2_seed=lora_seed,
+                        lora_a=lw.Acat if fuse_lora else None, lora_u=h1[:, D:] if fuse_lora else None, ld_u=Dk)
+        if lora_bf16 and not fuse_lora:      # measurement only: the same product as an N = 16 tensor-core GEMM
             lora_in, ld_in = (h1d, D) if h1d is not None else (h1, Dk)
             k.gemm(lora_in, lw.Acat, h1[:, D:], M, 16, D, ld_in, D, Dk)
         elif lw.Acat is not None:
@@ -562,8 +590,11 @@ class Engine:
         if t is None:
             if len(self._ptr_tables) > 256:
                 self._ptr_tables.clear()
-            t = torch.tensor(list(key), dtype=torch.int64).to(self.device)
+            host = torch.tensor(list(key), dtype=torch.int64).pin_memory()    # pinned: the upload is a legal graph node
+            t = host.to(self.device, non_blocking=True)
             self._ptr_tables[key] = t
+            self._ptr_hosts = getattr(self, "_ptr_hosts", [])
+            self._ptr_hosts.append(host)                                       # a captured copy re-reads it on every replay
         return t
 
     def _tail_fwd(self, x, B, Nf, targets, want_argmax, need_grad):

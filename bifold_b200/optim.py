@@ -28,6 +28,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.pre_step_hook = None      # DDP: wait for the gradient all-reduce
         self._flat = {}
         self.launches = 0
+        self.device_schedule = False   # step count / lr / bias corrections live on the device (CUDA-graph replay)
 
     def _flatten(self, gi, group):
         ps = [p for p in group["params"] if p.requires_grad]
@@ -58,12 +59,45 @@ class FusedAdam(torch.optim.Optimizer):
         self._flat[gi] = st
         return st
 
-    def _launch(self, n, p, g, m, v, group, step):
+    def _launch(self, n, p, g, m, v, group, step, dyn=None):
         b1, b2 = group["betas"]
         a = K.AdamWArgs(n, p, g, m, v, None, group["lr"], b1, b2, group["eps"], group["weight_decay"],
-                        int(group["decoupled"]), step, float(self.grad_scale))
+                        int(group["decoupled"]), step, float(self.grad_scale), K.ptr(dyn))
         K.check(K.load().bfk_adamw(C.byref(a), torch.cuda.current_stream().cuda_stream), "bfk_adamw")
         self.launches += 1
+
+    # ---- device-resident schedule: what a captured CUDA graph needs (the kernel arguments of a graph are frozen) ----
+    def enable_device_schedule(self):
+        """Keep the step counter, learning rate and bias corrections of every flat group in device memory:
+        ``bfk_adamw_advance`` (one thread) increments the counter and refreshes them right before ``bfk_adamw``,
+        which reads them instead of its by-value arguments.  Works eagerly and inside a captured graph."""
+        self.device_schedule = True
+
+    def _dev_state(self, st, group):
+        if "step_dev" not in st:
+            dev = st["p"].device
+            # created inside step(), after the host counter was incremented: the device counter holds the steps DONE
+            st["step_dev"] = torch.full((1,), int(st["step"]) - 1, device=dev, dtype=torch.int32)
+            st["lr_dev"] = torch.full((1,), float(group["lr"]), device=dev, dtype=torch.float32)
+            st["lr_host"] = float(group["lr"])
+            st["dyn"] = torch.zeros(3, device=dev, dtype=torch.float32)
+        return st
+
+    def sync_lr(self):
+        """Push host-side learning-rate changes (schedulers mutate param_groups) to the device copies; call before a
+        graph replay.  A no-op when nothing changed."""
+        for gi, group in enumerate(self.param_groups):
+            st = self._flat.get(gi)
+            if st is not None and "lr_dev" in st and st["lr_host"] != float(group["lr"]):
+                st["lr_dev"].fill_(float(group["lr"]))
+                st["lr_host"] = float(group["lr"])
+
+    def note_replayed_step(self):
+        """Host bookkeeping for a step that ran as a graph replay (the device counter advanced by itself)."""
+        for st in self._flat.values():
+            st["step"] += 1
+            for p in st["ps"]:
+                self.state[p]["step"] += 1
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -86,7 +120,16 @@ class FusedAdam(torch.optim.Optimizer):
             flat_ok = g0 is not None and g0.dtype == torch.float32 and all(
                 p.grad is not None and p.grad.is_contiguous() and p.grad.data_ptr() == g0.data_ptr() + 4 * o
                 for p, o in zip(ps, offs))
-            if flat_ok:
+            if flat_ok and self.device_schedule:
+                self._dev_state(st, group)
+                self.sync_lr()
+                b1, b2 = group["betas"]
+                K.check(K.load().bfk_adamw_advance(st["step_dev"].data_ptr(), st["lr_dev"].data_ptr(), b1, b2, st["dyn"].data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream), "bfk_adamw_advance")
+                self.launches += 1
+                self._launch(st["tot"], st["p"].data_ptr(), g0.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(), group, st["step"],
+                             dyn=st["dyn"])
+            elif flat_ok:
                 self._launch(st["tot"], st["p"].data_ptr(), g0.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(), group, st["step"])
             else:
                 for p, o in zip(ps, offs):
@@ -97,6 +140,8 @@ class FusedAdam(torch.optim.Optimizer):
                         g = g.clone()
                     self._launch(p.numel(), st["p"].data_ptr() + 4 * o, g.data_ptr(), st["m"].data_ptr() + 4 * o,
                                  st["v"].data_ptr() + 4 * o, group, st["step"])
+            # the kernels wrote through raw pointers: tell torch (and the engine's operand-copy cache) the values changed
+            torch._C._increment_version(ps)
         return loss
 
 

@@ -99,6 +99,13 @@ typedef struct {
   /* optional second output (NULL = none), same dtype as y: y2 = dropout(y, p, seed) -- the LoRA-branch input
    * (peft LoRA lora_dropout on the q_proj / v_proj inputs); same element hash as bfk_dropout_copy / bfk_layernorm_bwd.dy2 */
   void* y2; int64_t ldy2; float y2_dropout_p; uint64_t y2_seed;
+  /* optional fused LoRA down-projection (bf16 y only, NULL = none):  u[m, j] = sum_k drop(y)[m, k] * lora_a[j, k],
+   * j < 16 (q factors rows 0..r-1, v factors rows 8..8+r-1, unused rows zero) -- peft lora_A of q_proj / v_proj applied to
+   * the dropped LayerNorm output; u is normally the 16 extra K columns of the same row (u = y + D, ld_u = ldy) */
+  const void* lora_a; void* lora_u; int64_t ld_u;
+  /* optional DEVICE counter added to y2_seed when the kernel runs (NULL = 0): lets a captured CUDA graph draw a new
+   * dropout mask on every replay */
+  const uint64_t* seed_ptr;
 } bfk_layernorm_fwd_args;
 BFK_API int32_t bfk_layernorm_fwd(const bfk_layernorm_fwd_args* a, bfk_stream_t s);
 
@@ -115,6 +122,7 @@ typedef struct {
   const void* dy2; int64_t ld_dy2;           /* optional second upstream gradient (dy_dtype) added to dy under the
                                                 LoRA dropout mask: dy += keep(seed,m,k) ? dy2/(1-p) : 0 */
   float dy2_dropout_p; uint64_t dy2_seed;
+  const uint64_t* seed_ptr;          /* optional device counter added to dy2_seed (see bfk_layernorm_fwd_args) */
 } bfk_layernorm_bwd_args;
 BFK_API size_t bfk_layernorm_bwd_workspace_floats(int32_t M, int32_t D);
 BFK_API int32_t bfk_layernorm_bwd(const bfk_layernorm_bwd_args* a, bfk_stream_t s);
@@ -336,8 +344,25 @@ typedef struct {
   void* shadow_bf16;                 /* or NULL */
   float lr, beta1, beta2, eps, weight_decay; int32_t decoupled;
   int32_t step; float grad_scale;
+  /* optional DEVICE float[3] = {lr, 1 - beta1^step, sqrt(1 - beta2^step)} that overrides lr / step when the kernel runs
+   * (written by bfk_adamw_advance): the step count and learning rate of a captured CUDA graph advance on the device */
+  const float* dyn;
 } bfk_adamw_args;
 BFK_API int32_t bfk_adamw(const bfk_adamw_args* a, bfk_stream_t s);
+/* Multi-tensor strided cast: every segment copies a contiguous fp32 [rows, cols] matrix into dst[r * ld_dst + c] =
+ * scale * src[r * cols + c] (dst_dtype BFK_F32 / BFK_BF16).  One launch refreshes all operand-dtype copies of the trainable
+ * weights after an optimizer step (fusion weights -> bf16; LoRA factors -> the [W | (alpha/r) B] / [A_q; A_v] packs).
+ * `segs` is a DEVICE array; first_chunk = running sum of ceil(rows*cols / 1024) over the previous segments. */
+typedef struct {
+  const float* src; void* dst;
+  int64_t ld_dst, first_chunk;
+  int32_t rows, cols, dst_dtype;
+  float scale;
+} bfk_cast_segment;
+BFK_API int32_t bfk_multi_cast(const bfk_cast_segment* segs, int32_t nseg, int64_t total_chunks, bfk_stream_t s);
+
+/* ++*step_dev;  dyn = {*lr_dev, 1 - beta1^step, sqrt(1 - beta2^step)}  (one thread, double precision like the host path) */
+BFK_API int32_t bfk_adamw_advance(int32_t* step_dev, const float* lr_dev, float beta1, float beta2, float* dyn, bfk_stream_t s);
 /* fp32 -> bf16 cast (shadow weights), optional transpose of a [rows, cols] matrix. */
 BFK_API int32_t bfk_cast_bf16(const float* src, void* dst, int64_t n, bfk_stream_t s);
 BFK_API int32_t bfk_cast_f32_to(const float* src, void* dst, int32_t dst_dtype, int64_t rows, int64_t cols,

@@ -219,6 +219,19 @@ def test_layernorm_fwd_fused_dropout_copy(kern):
     assert torch.equal(y2, ref)
     frac = (y2 == 0).float().mean().item()
     assert 0.07 < frac < 0.13
+    # fused LoRA down-projection: u = drop(y) A^T into the 16 columns behind y (with and without dropout)
+    A = (torch.randn(16, D, device="cuda") * 0.1).bfloat16()
+    for p_drop in (p, 0.0):
+        yb = torch.zeros(M, D + 16, device="cuda", dtype=torch.bfloat16)
+        y2b = torch.empty(M, D, device="cuda", dtype=torch.bfloat16) if p_drop > 0 else None
+        kern.layernorm_fwd(x, M, D, gam, bet, 1e-6, yb, D + 16, y2=y2b, ldy2=D, y2_p=p_drop, y2_seed=seed,
+                           lora_a=A, lora_u=yb[:, D:], ld_u=D + 16)
+        torch.cuda.synchronize()
+        assert torch.equal(yb[:, :D], y[:, :D])
+        src = y2b if p_drop > 0 else yb[:, :D]
+        u_ref = src.float() @ A.float().t()
+        err = (yb[:, D:].float() - u_ref).abs().max().item()
+        assert err <= 1e-2 * u_ref.abs().max().item(), (p_drop, err)
 
 
 @pytest.mark.parametrize("M,D,r", [(1000, 64, 8), (12544, 768, 8), (777, 128, 4)])
