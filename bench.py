@@ -240,6 +240,10 @@ def main():
     # Single-process training replays ONE captured CUDA graph per step (bifold_b200.graphs): the ~750 launches of the
     # eager step cost ~14 ms of host time against ~23 ms of GPU work, so any host contention makes it launch-bound.
     # Multi-GPU (the gradient all-reduce is not captured) and inference use the eager path.
+    try:    # the extra instrumented eager step after the capture keeps old AccumulateGrad nodes alive: a benign warning
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+    except Exception:
+        pass
     use_graph = train and world == 1 and not args.no_graph
     gstep = None
     if use_graph:
@@ -370,6 +374,18 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def gemm_traffic():
+    """DRAM bytes (read + write) per launch of the dominant GEMM kernel, from the committed `ncu --set full` capture of
+    this bench command (profiles/r01_gemm_traffic.json, written by tools/ncu_traffic.py); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+            t = json.load(f)
+        return {"dram_bytes_per_launch": t["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": t["algorithmic_bytes_per_launch"],
+                "kernel": t["kernel"], "shape": t["shape"], "source": "profiles/r01_gemm_traffic.json (ncu --set full)"}
+    except Exception:
+        return None
+
+
 def gemm_roofline(eng, step_fn):
     """CUDA-event timing of every tcgen05 GEMM launch of one extra (untimed-for-the-headline) step, on the
     launching stream: achieved = sum(2*M*N*K) / sum(duration)."""
@@ -402,7 +418,7 @@ def gemm_roofline(eng, step_fn):
     ach = fl / (ms / 1e3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     return {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::f16, TMA-fed, TMEM accumulators)", "achieved": ach,
-            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "launches": len(recs),
+            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": gemm_traffic(), "launches": len(recs),
             "gemm_ms_per_step": ms, "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"}
 
 

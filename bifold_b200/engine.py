@@ -320,7 +320,7 @@ class Engine:
         if lora_bf16 and not fuse_lora:      # measurement only: the same product as an N = 16 tensor-core GEMM
             lora_in, ld_in = (h1d, D) if h1d is not None else (h1, Dk)
             k.gemm(lora_in, lw.Acat, h1[:, D:], M, 16, D, ld_in, D, Dk)
-        elif lw.Acat is not None:
+        elif lw.Acat is not None and not lora_bf16:      # fp32 parity mode: SIMT kernel
             K.check(k.lib.bfk_lora_down(h1.data_ptr(), Dk, _dt(h1), M, D, lw.Acat.data_ptr(), p_drop, lora_seed, _stream()),
                     "bfk_lora_down")
             k.launches += 1
