@@ -156,6 +156,8 @@ class Engine:
         self.overlap_towers = os.environ.get("BFK_OVERLAP_TOWERS", "1") != "0"    # text tower on a side stream, concurrent with the vision tower (fwd and bwd)
         self._side = None
         self.fuse_lora_down = os.environ.get("BFK_FUSE_LORA_DOWN", "1") != "0"
+        self.overlap_wgrad = os.environ.get("BFK_OVERLAP_WGRAD", "1") != "0"
+        self._wgrad_streams, self._wgrad_busy = {}, False
 
     # ------------------------------------------------------------------------------------------------
     # weight preparation
@@ -359,14 +361,18 @@ class Engine:
         dpa = torch.empty(M, Mlp, device=dev, dtype=T)
         k.gemm(dx2_T, lw.W2, dpa, M, Mlp, D, D, Mlp, Mlp, trans_b=True, act=dact, aux=sv["pa"], ld_aux=Mlp)
         if trainable:
-            k.gemm(dx2_T, sv["a"], grads[n["W2"]], D, Mlp, M, D, Mlp, Mlp, trans_a=True, trans_b=True)
-            k.colsum(dx2, M, D, D, grads[n["b2"]])
+            def wg_fc2():
+                k.gemm(dx2_T, sv["a"], grads[n["W2"]], D, Mlp, M, D, Mlp, Mlp, trans_a=True, trans_b=True)
+                k.colsum(dx2, M, D, D, grads[n["b2"]])
+            self._off_chain(wg_fc2, dx2_T, sv["a"], dx2)
         # fc1: pa = h2 W1^T + b1
         dh2 = torch.empty(M, D, device=dev, dtype=T)
         k.gemm(dpa, lw.W1, dh2, M, D, Mlp, Mlp, D, D, trans_b=True)
         if trainable:
-            k.gemm(dpa, sv["h2"], grads[n["W1"]], Mlp, D, M, Mlp, D, D, trans_a=True, trans_b=True)
-            k.colsum(dpa, M, Mlp, Mlp, grads[n["b1"]])
+            def wg_fc1(dpa=dpa):
+                k.gemm(dpa, sv["h2"], grads[n["W1"]], Mlp, D, M, Mlp, D, D, trans_a=True, trans_b=True)
+                k.colsum(dpa, M, Mlp, Mlp, grads[n["b1"]])
+            self._off_chain(wg_fc1, dpa, sv["h2"])
         del dpa
         # LN2 + residual
         dx1 = torch.empty(M, D, device=dev, dtype=torch.float32)
@@ -379,8 +385,10 @@ class Engine:
         dctx = dh2  # reuse buffer [M, D]
         k.gemm(dx1_T, lw.Wo, dctx, M, D, D, D, D, D, trans_b=True)
         if trainable:
-            k.gemm(dx1_T, sv["ctx"], grads[n["Wo"]], D, D, M, D, D, D, trans_a=True, trans_b=True)
-            k.colsum(dx1, M, D, D, grads[n["bo"]])
+            def wg_out():
+                k.gemm(dx1_T, sv["ctx"], grads[n["Wo"]], D, D, M, D, D, D, trans_a=True, trans_b=True)
+                k.colsum(dx1, M, D, D, grads[n["bo"]])
+            self._off_chain(wg_out, dx1_T, sv["ctx"], dx1)
         # attention
         dqkv = torch.empty(M, 3 * D, device=dev, dtype=T)
         k.attention_bwd(sv["qkv"], sv["ctx"], sv["lse"], dctx, dqkv, nseq, N, heads, hd, hd ** -0.5, row_mask)
@@ -388,7 +396,8 @@ class Engine:
         dh1 = torch.empty(M, Dk, device=dev, dtype=T)
         k.gemm(dqkv, lw.Wqkv, dh1, M, Dk, 3 * D, 3 * D, Dk, Dk, trans_b=True)
         if trainable:
-            k.gemm(dqkv, sv["h1"], grads[n["Wqkv"]], 3 * D, D, M, 3 * D, Dk, D, trans_a=True, trans_b=True)
+            self._off_chain(lambda: k.gemm(dqkv, sv["h1"], grads[n["Wqkv"]], 3 * D, D, M, 3 * D, Dk, D, trans_a=True, trans_b=True),
+                            dqkv, sv["h1"])
         dy2 = None
         if lw.Acat is not None:
             dy2 = self._lora_bwd(sv, dqkv, dh1, M, lw, grads)
@@ -399,6 +408,43 @@ class Engine:
                         grads[n["ln1_w"]] if trainable else None, grads[n["ln1_b"]] if trainable else None,
                         dy2=dy2, ld_dy2=D, dy2_p=sv["p_drop"] if dy2 is not None else 0.0, dy2_seed=sv["seed"])
         return dx, (dx_T if dx_T is not None else dx)
+
+    # Weight / bias gradients are leaves of the backward dependency chain: they run on a second stream (in a captured
+    # step: a parallel graph branch) and fill the SM time the chain's kernels leave idle (tails, short LayerNorm passes).
+    def _off_chain(self, fn, *inputs):
+        if not self.overlap_wgrad:
+            fn()
+            return
+        cur = torch.cuda.current_stream()
+        ws = self._wgrad_streams.get(cur.cuda_stream)
+        if ws is None:
+            ws = self._wgrad_streams[cur.cuda_stream] = torch.cuda.Stream(device=cur.device)
+        ws.wait_stream(cur)                       # everything the gradient reads has been enqueued on `cur`
+        with torch.cuda.stream(ws):
+            fn()
+        for t in inputs:
+            if t is not None:
+                t.record_stream(ws)
+        self._wgrad_busy = True
+
+    def _join_off_chain(self, hook_group=None):
+        """Make the current stream wait for the off-chain gradients; a DDP hook is announced once they are final."""
+        cur = torch.cuda.current_stream()
+        ws = self._wgrad_streams.get(cur.cuda_stream)
+        if ws is not None and self._wgrad_busy:
+            cur.wait_stream(ws)
+            self._wgrad_busy = False
+
+    def _hook_after_off_chain(self, group):
+        """Announce a gradient group whose members were written on the current stream AND the off-chain stream."""
+        cur = torch.cuda.current_stream()
+        ws = self._wgrad_streams.get(cur.cuda_stream)
+        if ws is None or not self._wgrad_busy:
+            self.grad_ready_hook(group)
+            return
+        ws.wait_stream(cur)
+        with torch.cuda.stream(ws):
+            self.grad_ready_hook(group)           # the hook orders the all-reduce behind the stream it is called on
 
     def _lora_bwd(self, sv, dqkv, dh1, M, lw, grads):
         """LoRA factor gradients and the rank-r contribution to dh1 (peft LoRA backward)."""
@@ -413,12 +459,15 @@ class Engine:
             x_in, ld_x = (sv["h1d"], D) if sv["h1d"] is not None else (h1, Dk)
             if r <= 8 and D % 8 == 0:
                 # both B factors from one dqkv^T u product, both A factors from one du^T x product, one fused reduction
-                ws = k.lora_ws(dqkv.device, D)
                 a = K.LoraGradsArgs(M, D, r, dqkv.data_ptr(), 3 * D, h1.data_ptr() + D * es, Dk, dh1.data_ptr() + D * es, Dk,
                                     x_in.data_ptr(), ld_x, s, grads[n["Bq"]].data_ptr(), grads[n["Bv"]].data_ptr(),
-                                    grads[n["Aq"]].data_ptr(), grads[n["Av"]].data_ptr(), ws.data_ptr(), ws.numel() * 4)
-                K.check(lib.bfk_lora_grads(C.byref(a), st), "bfk_lora_grads")
-                k.launches += 3
+                                    grads[n["Aq"]].data_ptr(), grads[n["Av"]].data_ptr(), None, 0)
+                def lora_grads(a=a):
+                    ws = k.lora_ws(dqkv.device, D)            # keyed by the stream the products run on
+                    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+                    K.check(lib.bfk_lora_grads(C.byref(a), _stream()), "bfk_lora_grads")
+                    k.launches += 3
+                self._off_chain(lora_grads, dqkv, h1, dh1, x_in)
             else:
                 for (Bn, ucol, qoff) in ((n["Bq"], 0, 0), (n["Bv"], 8, 2 * D)):
                     k.gemm(dqkv[:, qoff:], h1[:, D + ucol:], grads[Bn], D, r, M, 3 * D, Dk, r, trans_a=True, trans_b=True, alpha=s)
@@ -705,7 +754,8 @@ class Engine:
                                        ctx["mask"], grads, trainable=True)
             fsave[l] = None
             if self.grad_ready_hook:
-                self.grad_ready_hook(f"fusion.{l}")
+                self._hook_after_off_chain(f"fusion.{l}")
+        self._join_off_chain()
 
         # ---- assembly ----
         need_tower = cfg.lora
@@ -736,14 +786,16 @@ class Engine:
                 with torch.cuda.stream(self._side):
                     self._tower_bwd(dtxt, ctx["tsave"], self.text_layers, B, L, tp + ".final_layer_norm.weight", grads)
                     if self.grad_ready_hook:
-                        self.grad_ready_hook("text")
+                        self._hook_after_off_chain("text")
+                    self._join_off_chain()
                 self._tower_bwd(dvis, ctx["vsave"], self.vis_layers, B + B * T_ctx, Np, vp + ".post_layernorm.weight", grads)
                 main.wait_stream(self._side)
             else:
                 self._tower_bwd(dtxt, ctx["tsave"], self.text_layers, B, L, tp + ".final_layer_norm.weight", grads)
                 if self.grad_ready_hook:
-                    self.grad_ready_hook("text")
+                    self._hook_after_off_chain("text")
                 self._tower_bwd(dvis, ctx["vsave"], self.vis_layers, B + B * T_ctx, Np, vp + ".post_layernorm.weight", grads)
             if self.grad_ready_hook:
-                self.grad_ready_hook("vision")
+                self._hook_after_off_chain("vision")
+            self._join_off_chain()
         return grads
