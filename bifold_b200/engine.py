@@ -412,7 +412,9 @@ class Engine:
     # Weight / bias gradients are leaves of the backward dependency chain: they run on a second stream (in a captured
     # step: a parallel graph branch) and fill the SM time the chain's kernels leave idle (tails, short LayerNorm passes).
     def _off_chain(self, fn, *inputs):
-        if not self.overlap_wgrad:
+        # (multi-process runs keep the gradients on the chain: the all-reduce hooks order themselves behind ONE stream, and
+        #  the eager DDP step measured slower with a third compute stream competing with the NCCL kernels)
+        if not self.overlap_wgrad or self.grad_ready_hook is not None:
             fn()
             return
         cur = torch.cuda.current_stream()
