@@ -82,6 +82,26 @@ __global__ void __launch_bounds__(256) multi_cast_kernel(const bfk_cast_segment*
     } else {
       for (int j = 0; j < 4; ++j) if (e0 + j < n) v[j] = sg.src[e0 + j];
     }
+    if (e0 + 4 <= n && (sg.cols & 3) == 0 && (sg.ld_dst & 3) == 0) {   // the 4 elements share a row: one packed store
+      const long long r = e0 / sg.cols, c = e0 % sg.cols;
+      if (sg.dst_dtype == BFK_BF16) {
+        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(sg.dst) + r * sg.ld_dst + c;
+        if ((reinterpret_cast<uintptr_t>(d) & 7u) == 0) {
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0] * sg.scale, v[1] * sg.scale), p1 = __floats2bfloat162_rn(v[2] * sg.scale, v[3] * sg.scale);
+          uint2 u;
+          u.x = *reinterpret_cast<const uint32_t*>(&p0);
+          u.y = *reinterpret_cast<const uint32_t*>(&p1);
+          *reinterpret_cast<uint2*>(d) = u;
+          continue;
+        }
+      } else {
+        float* d = reinterpret_cast<float*>(sg.dst) + r * sg.ld_dst + c;
+        if ((reinterpret_cast<uintptr_t>(d) & 15u) == 0) {
+          *reinterpret_cast<float4*>(d) = make_float4(v[0] * sg.scale, v[1] * sg.scale, v[2] * sg.scale, v[3] * sg.scale);
+          continue;
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const long long e = e0 + j;

@@ -565,6 +565,7 @@ class Engine:
         dev = rgb.device
         self.training = training
         self.prepare(dev)
+        pre = self._collapse_fwd(dev, off_chain=True)     # needs only the decoder weights: overlaps the towers
         B, Np, L = rgb.shape[0], cfg.num_patches, cfg.text_len
         T_ctx = sample["rgb_context"].shape[1] if cfg.sequential else 0
         tower_grad = need_grad and cfg.lora
@@ -615,7 +616,7 @@ class Engine:
 
         # ---- heatmap tail ----
         heads = len(cfg.heads_out)
-        tail = self._tail_fwd(x, B, Nf, targets, want_argmax, need_grad)
+        tail = self._tail_fwd(x, B, Nf, targets, want_argmax, need_grad, pre=pre)
         if need_grad:
             ctx.update(vsave=vsave, tsave=tsave, fsave=fsave, mask=mask, xf=x, Nf=Nf, tail=tail, targets=targets,
                        heads=heads)
@@ -648,18 +649,44 @@ class Engine:
             self._ptr_hosts.append(host)                                       # a captured copy re-reads it on every replay
         return t
 
-    def _tail_fwd(self, x, B, Nf, targets, want_argmax, need_grad):
-        cfg, k, D, dev = self.cfg, self.k, self.cfg.dim, x.device
-        heads, Np, g = len(cfg.heads_out), cfg.num_patches, cfg.grid
-        H = 16 * g
-        lib, st = k.lib, _stream()
+    def _collapse_fwd(self, dev, off_chain=False):
+        """w_eff / b_eff of the linear decoders.  Depends on the decoder weights only, so with `off_chain` it runs on the
+        second stream at the START of the forward (four latency-bound CTAs, ~180 us) instead of on the critical path."""
+        cfg, k, D = self.cfg, self.k, self.cfg.dim
+        heads = len(cfg.heads_out)
         Wt, bt = self._decoder_ptr_tables()
         w_eff = torch.empty(heads, D, device=dev, dtype=torch.float32)
         b_eff = torch.empty(heads, device=dev, dtype=torch.float32)
         chain = torch.empty(heads, 4, D, device=dev, dtype=torch.float32)
         ca = K.DecoderCollapseArgs(heads, D, Wt.data_ptr(), bt.data_ptr(), w_eff.data_ptr(), b_eff.data_ptr(), chain.data_ptr(),
                                    None, None, None, None)
-        K.check(lib.bfk_decoder_collapse_fwd(C.byref(ca), st), "bfk_decoder_collapse_fwd")
+        ev = None
+        if off_chain and self.overlap_wgrad and self.grad_ready_hook is None:
+            cur = torch.cuda.current_stream()
+            ws = self._wgrad_streams.get(cur.cuda_stream)
+            if ws is None:
+                ws = self._wgrad_streams[cur.cuda_stream] = torch.cuda.Stream(device=cur.device)
+            ws.wait_stream(cur)
+            with torch.cuda.stream(ws):
+                K.check(k.lib.bfk_decoder_collapse_fwd(C.byref(ca), _stream()), "bfk_decoder_collapse_fwd")
+                ev = torch.cuda.Event()
+                ev.record()
+            for t in (w_eff, b_eff, chain):
+                t.record_stream(ws)
+        else:
+            K.check(k.lib.bfk_decoder_collapse_fwd(C.byref(ca), _stream()), "bfk_decoder_collapse_fwd")
+        return dict(w_eff=w_eff, b_eff=b_eff, chain=chain, tables=(Wt, bt), ev=ev)
+
+    def _tail_fwd(self, x, B, Nf, targets, want_argmax, need_grad, pre=None):
+        cfg, k, D, dev = self.cfg, self.k, self.cfg.dim, x.device
+        heads, Np, g = len(cfg.heads_out), cfg.num_patches, cfg.grid
+        H = 16 * g
+        lib, st = k.lib, _stream()
+        if pre is None:
+            pre = self._collapse_fwd(dev)
+        elif pre["ev"] is not None:
+            torch.cuda.current_stream().wait_event(pre["ev"])
+        w_eff, b_eff, chain, (Wt, bt) = pre["w_eff"], pre["b_eff"], pre["chain"], pre["tables"]
         grid = torch.empty(B, heads, Np, device=dev, dtype=torch.float32)
         row0 = Nf - Np
         pa = K.HeadProjectArgs(B, heads, Np, D, x.data_ptr(), Nf * D, row0, w_eff.data_ptr(), b_eff.data_ptr(), grid.data_ptr(),
@@ -743,7 +770,11 @@ class Engine:
         Wt, bt, dWt, dbt = self._decoder_ptr_tables(grads)
         ca = K.DecoderCollapseArgs(heads, D, Wt.data_ptr(), bt.data_ptr(), None, None, tail["chain"].data_ptr(),
                                    d_w_eff.data_ptr(), d_b_eff.data_ptr(), dWt.data_ptr(), dbt.data_ptr())
-        K.check(lib.bfk_decoder_collapse_bwd(C.byref(ca), st), "bfk_decoder_collapse_bwd")
+        chain_t = tail["chain"]
+
+        def collapse_bwd(ca=ca):      # weight gradients of the decoder chain: a leaf of the backward, off the chain
+            K.check(lib.bfk_decoder_collapse_bwd(C.byref(ca), _stream()), "bfk_decoder_collapse_bwd")
+        self._off_chain(collapse_bwd, d_w_eff, d_b_eff, chain_t)
         k.launches += 7
         if self.grad_ready_hook:
             self.grad_ready_hook("decoders")
