@@ -404,12 +404,17 @@ def gemm_roofline(eng, step_fn):
     k.gemm = timed_gemm
     overlap = eng.overlap_towers
     eng.overlap_towers = False      # one stream: no concurrent text-tower kernels inside the per-launch event windows
+    wgrad = eng.overlap_wgrad
+    eng.overlap_wgrad = False
     try:
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(0.03 * 1.9e9))   # ~30 ms head start for the host: the event windows then hold kernels only
         step_fn()
         torch.cuda.synchronize()
     finally:
         k.gemm = orig
         eng.overlap_towers = overlap
+        eng.overlap_wgrad = wgrad
     fl = sum(r[0] for r in recs if r[3])
     ms = sum(r[1].elapsed_time(r[2]) for r in recs if r[3])
     peaks = load_peaks()
