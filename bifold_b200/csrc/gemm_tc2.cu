@@ -55,6 +55,21 @@ __device__ __forceinline__ void tc_commit_2sm_mc(uint32_t bar, uint16_t mask) {
                : "memory");
 }
 
+// Work item -> (row-pair block, n block, MMA N of the tile).  When the last n block holds at most 128 live columns
+// (N = 784: 16) it becomes a THIN tile: the UMMA runs with N = live columns rounded up to 16 instead of 256, and all thin
+// tiles are enumerated after the full ones so the static round-robin over clusters stays balanced.
+struct T2Item { int mp, nb, ntile; };
+__device__ __forceinline__ T2Item t2_decode(int item, int num_mp, int num_n, int N) {
+  const int tail_w = N - (num_n - 1) * T2_BN;
+  const bool thin = tail_w <= 128 && num_n > 1;
+  const int nf = thin ? num_n - 1 : num_n;
+  const int full_items = num_mp * nf;
+  T2Item it;
+  if (item < full_items) { it.mp = item / nf; it.nb = item % nf; it.ntile = T2_BN; }
+  else { it.mp = item - full_items; it.nb = num_n - 1; it.ntile = (tail_w + 15) & ~15; }
+  return it;
+}
+
 // MODE: compile-time EpiMode.  EPI_GENERIC keeps every fused variant behind runtime flags (8 epilogue warps, 168
 // registers); a specialised MODE compiles only its own epilogue and runs 16 epilogue warps (launch bound 576 threads).
 template <bool AMN, bool BMN, int MODE>
@@ -102,7 +117,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       // ===== TMA producer (both CTAs): own 128 rows of A, own 128 n-rows of B =====
       int stage = 0; uint32_t phase = 0;
       for (int item = cid; item < items; item += ncl) {
-        const int m0 = (item / num_n) * 256 + crank * 128, nb0 = (item % num_n) * T2_BN + crank * 128;
+        const T2Item it = t2_decode(item, num_mp, num_n, N);
+        const int m0 = it.mp * 256 + crank * 128, nb0 = it.nb * T2_BN + crank * (it.ntile >> 1);   // this CTA's half of the B rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t lead_full = map_to_cta(full_bar(stage), 0);
@@ -128,12 +144,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   } else if (warp == 1) {
     if (crank == 0 && elect_one()) {
       // ===== MMA issuer (leader CTA only): UMMA 256 x 256 x 16 over both CTAs' smem / TMEM =====
-      constexpr uint32_t idesc = make_idesc(256, T2_BN, AMN, BMN);
+      constexpr uint32_t idesc_full = make_idesc(256, T2_BN, AMN, BMN);
       constexpr int KSTEP_A = (AMN ? 2048 : 32) >> 4, KSTEP_B = (BMN ? 2048 : 32) >> 4;   // descriptor step per UMMA_K slice
       const uint64_t da0 = operand_desc<AMN>(smem_base, 0), db0 = operand_desc<BMN>(smem_base + T2_A_BYTES, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int item = cid; item < items; item += ncl) {
+        const T2Item it = t2_decode(item, num_mp, num_n, N);
+        const uint32_t idesc = it.ntile == T2_BN ? idesc_full : make_idesc(256, it.ntile, AMN, BMN);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * T2_BN);
@@ -160,13 +178,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int et = threadIdx.x - 64;
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = cid; item < items; item += ncl) {
-      const int m0 = (item / num_n) * 256 + crank * 128, n0 = (item % num_n) * T2_BN;
+      const T2Item it = t2_decode(item, num_mp, num_n, N);
+      const int m0 = it.mp * 256 + crank * 128, n0 = it.nb * T2_BN;
       float* bias_s = bias_smem + acc * T2_BN;
       for (int i = et; i < T2_BN; i += 32 * EW) bias_s[i] = (ep.bias && n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
       named_bar_sync(1, 32 * EW);
       if (ep.vec_ok && item + ncl < items) {
-        const int nit = item + ncl;
-        const int nm = (nit / num_n) * 256 + crank * 128 + quarter * 32 + lane, nn0 = (nit % num_n) * T2_BN;
+        const T2Item nit = t2_decode(item + ncl, num_mp, num_n, N);
+        const int nm = nit.mp * 256 + crank * 128 + quarter * 32 + lane, nn0 = nit.nb * T2_BN;
         for (int c = sub; c < T2_BN / 32; c += EW / 4) epi_prefetch(ep, nm, nn0 + c * 32);
       }
       const int m = m0 + quarter * 32 + lane;
