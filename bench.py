@@ -353,7 +353,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
-                "launch_mode": "whole-step CUDA graph replay" if (gstep is not None and gstep.graph is not None) else "eager", "clocks": clocks,
+                "launch_mode": "whole-step CUDA graph replay" if (gstep is not None and gstep.graph is not None) else
+                ("eager" if gstep is None or gstep.failed is None else "eager (graph capture failed: %s)" % gstep.failed[:200]), "clocks": clocks,
                 "model_flops_per_sample": tr_flops if train else fw_flops,
                 "model_tflops_per_gpu": (tr_flops if train else fw_flops) * B / (per_step / 1e3) / 1e12,
                 "model_frac_of_bf16_peak": (tr_flops if train else fw_flops) * B / (per_step / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],

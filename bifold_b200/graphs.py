@@ -38,6 +38,7 @@ class GraphedTrainStep:
         self.static_in: Optional[Dict[str, torch.Tensor]] = None
         self.static_loss: Optional[torch.Tensor] = None
         self.launches_per_replay = 0
+        self.failed: Optional[str] = None
         optimizer.enable_device_schedule()
 
     def _eager(self, sample):
@@ -67,14 +68,32 @@ class GraphedTrainStep:
             loss = self._eager(s)
             eng.k.seed_dev.add_(1)
             return loss
+        if self.failed is not None:                # capture was refused once: stay on the eager path (still correct)
+            loss = self._eager(self._stage(sample))
+            eng.k.seed_dev.add_(1)
+            return loss
         if self.graph is None:
             s = self._stage(sample)
             torch.cuda.synchronize()
             l0, o0 = eng.k.launches, self.optimizer.launches
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.static_loss = self._eager(s)
-                eng.k.seed_dev.add_(1)           # the next replay draws new dropout masks
+            graph = torch.cuda.CUDAGraph()
+            steps_before = {gi: st["step"] for gi, st in self.optimizer._flat.items()}
+            try:
+                with torch.cuda.graph(graph):
+                    self.static_loss = self._eager(s)
+                    eng.k.seed_dev.add_(1)       # the next replay draws new dropout masks
+            except Exception as e:               # e.g. an allocator / driver that refuses the capture
+                self.failed = f"{type(e).__name__}: {e}"
+                torch.cuda.synchronize()
+                for gi, st in self.optimizer._flat.items():      # the recorded step never ran: restore the host counters
+                    back = st["step"] - steps_before.get(gi, st["step"])
+                    st["step"] -= back
+                    for p in st["ps"]:
+                        self.optimizer.state[p]["step"] -= back
+                loss = self._eager(s)            # stay on the eager path from here on (still correct)
+                eng.k.seed_dev.add_(1)
+                return loss
+            self.graph = graph
             self.launches_per_replay = (eng.k.launches - l0) + (self.optimizer.launches - o0)
             # capture does not execute: run the step that was just recorded
             self.graph.replay()
