@@ -237,18 +237,19 @@ def main():
         action = model.get_action(sample)      # D2H of the (heads,B,2) pixel table happens inside
         return action
 
-    # Single-process training replays ONE captured CUDA graph per step (bifold_b200.graphs): the ~750 launches of the
-    # eager step cost ~14 ms of host time against ~23 ms of GPU work, so any host contention makes it launch-bound.
-    # Multi-GPU (the gradient all-reduce is not captured) and inference use the eager path.
+    # Training replays ONE captured CUDA graph per step (bifold_b200.graphs): the ~750 launches of the eager step cost
+    # 14-19 ms of host time against ~22 ms of GPU work, so any host contention makes it launch-bound.  With N > 1 the
+    # bucketed NCCL all-reduces of BatchShardedDDP are captured in the same graph (every rank captures and replays in
+    # lock-step; tools/ddp_graph_check.py: bit-identical to the eager DDP step).  Inference uses the eager path.
     try:    # the extra instrumented eager step after the capture keeps old AccumulateGrad nodes alive: a benign warning
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
     except Exception:
         pass
-    use_graph = train and world == 1 and not args.no_graph
+    use_graph = train and not args.no_graph
     gstep = None
     if use_graph:
         from bifold_b200.graphs import GraphedTrainStep
-        gstep = GraphedTrainStep(model, loss_fn, optim, warmup=2)
+        gstep = GraphedTrainStep(model, loss_fn, optim, warmup=2, allow_distributed=world > 1)
 
     def step(sample, read_back):
         if gstep is not None:
@@ -361,7 +362,20 @@ def main():
                 "roofline": roofline, "roofline_tail": tail, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear-down order matters: NCCL must not destroy a communicator that a live CUDA graph still references.
+        # A watchdog ends the process if the tear-down itself stalls (the result line is already printed).
+        import gc
+        import threading
+        sys.stdout.flush()
+        threading.Thread(target=lambda: (time.sleep(30), os._exit(0)), daemon=True).start()
+        if gstep is not None:
+            gstep.graph = None
+            gstep.static_loss = None
+            gstep.static_in = None
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

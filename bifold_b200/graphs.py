@@ -28,9 +28,11 @@ class GraphedTrainStep:
     ``loss_fn(out, sample)`` must return ``(loss, aux)`` like ``bifold.losses`` does.
     """
 
-    def __init__(self, model, loss_fn: Callable, optimizer, warmup: int = 3):
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            raise RuntimeError("GraphedTrainStep captures single-process steps only (the gradient all-reduce is not captured)")
+    def __init__(self, model, loss_fn: Callable, optimizer, warmup: int = 3, allow_distributed: bool = False):
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1 \
+                and not allow_distributed:
+            raise RuntimeError("GraphedTrainStep: pass allow_distributed=True to capture the NCCL all-reduces of "
+                               "BatchShardedDDP inside the graph (every rank must capture and replay in lock-step)")
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
         self.warmup = max(2, int(warmup))
         self.calls = 0
