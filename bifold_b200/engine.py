@@ -412,15 +412,15 @@ class Engine:
     # Weight / bias gradients are leaves of the backward dependency chain: they run on a second stream (in a captured
     # step: a parallel graph branch) and fill the SM time the chain's kernels leave idle (tails, short LayerNorm passes).
     def _off_chain(self, fn, *inputs):
-        # (multi-process runs keep the gradients on the chain: the all-reduce hooks order themselves behind ONE stream, and
-        #  the eager DDP step measured slower with a third compute stream competing with the NCCL kernels)
-        if not self.overlap_wgrad or self.grad_ready_hook is not None:
-            fn()
-            return
         cur = torch.cuda.current_stream()
         ws = self._wgrad_streams.get(cur.cuda_stream)
         if ws is None:
             ws = self._wgrad_streams[cur.cuda_stream] = torch.cuda.Stream(device=cur.device)
+        # Eager multi-process runs keep the gradients on the chain (measured: a third compute stream plus record_stream
+        # churn made the eager DDP step slower); inside a captured graph the branch is free again.
+        if not self.overlap_wgrad or (self.grad_ready_hook is not None and not torch.cuda.is_current_stream_capturing()):
+            fn()
+            return
         ws.wait_stream(cur)                       # everything the gradient reads has been enqueued on `cur`
         with torch.cuda.stream(ws):
             fn()
@@ -661,11 +661,11 @@ class Engine:
         ca = K.DecoderCollapseArgs(heads, D, Wt.data_ptr(), bt.data_ptr(), w_eff.data_ptr(), b_eff.data_ptr(), chain.data_ptr(),
                                    None, None, None, None)
         ev = None
-        if off_chain and self.overlap_wgrad and self.grad_ready_hook is None:
-            cur = torch.cuda.current_stream()
-            ws = self._wgrad_streams.get(cur.cuda_stream)
-            if ws is None:
-                ws = self._wgrad_streams[cur.cuda_stream] = torch.cuda.Stream(device=cur.device)
+        cur = torch.cuda.current_stream()
+        ws = self._wgrad_streams.get(cur.cuda_stream)
+        if ws is None:
+            ws = self._wgrad_streams[cur.cuda_stream] = torch.cuda.Stream(device=cur.device)
+        if off_chain and self.overlap_wgrad and (self.grad_ready_hook is None or torch.cuda.is_current_stream_capturing()):
             ws.wait_stream(cur)
             with torch.cuda.stream(ws):
                 K.check(k.lib.bfk_decoder_collapse_fwd(C.byref(ca), _stream()), "bfk_decoder_collapse_fwd")
@@ -777,7 +777,7 @@ class Engine:
         self._off_chain(collapse_bwd, d_w_eff, d_b_eff, chain_t)
         k.launches += 7
         if self.grad_ready_hook:
-            self.grad_ready_hook("decoders")
+            self._hook_after_off_chain("decoders")
 
         # ---- fusion transformer ----
         dx, dx_T = dX, (dX_T if dX_T is not None else dX)
