@@ -76,6 +76,7 @@ class GraphedTrainStep:
             return loss
         if self.graph is None:
             s = self._stage(sample)
+            self.optimizer.sync_lr()             # a pending learning-rate change must not be recorded as a graph node
             torch.cuda.synchronize()
             l0, o0 = eng.k.launches, self.optimizer.launches
             graph = torch.cuda.CUDAGraph()
