@@ -239,10 +239,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           uint32_t sreg[32];
           tc_ld32(tS + lane_off + c, sreg);
           tc_wait_ld();
-          const int lim = min(32, nvalid - c);
+          const int lim = nvalid - c;
+          if (lim >= 32) {                       // full chunk (all but the sequence tail): no per-element predicate
 #pragma unroll
-          for (int t = 0; t < 32; ++t)
-            if (t < lim) mx = fmaxf(mx, __uint_as_float(sreg[t]));
+            for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(sreg[t]));
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+              if (t < lim) mx = fmaxf(mx, __uint_as_float(sreg[t]));
+          }
         }
         exchange_max();
 #pragma unroll 1
