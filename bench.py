@@ -245,7 +245,7 @@ def main():
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
     except Exception:
         pass
-    use_graph = train and not args.no_graph
+    use_graph = train and not args.no_graph and args.precision == "bf16"     # fp32 = SIMT parity mode, eager only
     gstep = None
     if use_graph:
         from bifold_b200.graphs import GraphedTrainStep

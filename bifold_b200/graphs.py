@@ -33,6 +33,10 @@ class GraphedTrainStep:
                 and not allow_distributed:
             raise RuntimeError("GraphedTrainStep: pass allow_distributed=True to capture the NCCL all-reduces of "
                                "BatchShardedDDP inside the graph (every rank must capture and replay in lock-step)")
+        eng = model._ensure_engine()
+        if eng.precision != "bf16" and eng.cfg.lora and eng.cfg.lora_dropout > 0:
+            # the fp32 parity kernels (bfk_lora_down & co) take their dropout seed by value: a replay would reuse the mask
+            raise RuntimeError("GraphedTrainStep needs precision='bf16' when LoRA dropout is active")
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
         self.warmup = max(2, int(warmup))
         self.calls = 0
