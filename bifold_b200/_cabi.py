@@ -161,6 +161,8 @@ _PROTOS = {
     "bfk_argmax2d": (i32, [vp, i32, i32, vp, vp]),
     "bfk_action": (i32, [C.POINTER(ActionArgs), vp]),
     "bfk_adamw": (i32, [C.POINTER(AdamWArgs), vp]),
+    "bfk_gauss_targets": (i32, [vp, i32, i32, i32, i32, f32, vp, vp]),
+    "bfk_normalize_u8": (i32, [vp, i64, i32, i32, f32, f32, vp, vp]),
     "bfk_cast_bf16": (i32, [vp, vp, i64, vp]),
     "bfk_cast_f32_to": (i32, [vp, vp, i32, i64, i64, i64, i64, vp]),
 }

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(bfk_layernorm_fwd
   TY* y = reinterpret_cast<TY*>(a.y) + (long long)row * a.ldy;
   TY* y2 = a.y2 ? reinterpret_cast<TY*>(a.y2) + (long long)row * a.ldy2 : nullptr;
   const float keep2 = a.y2_dropout_p > 0.f ? 1.f / (1.f - a.y2_dropout_p) : 1.f;
-  const uint64_t seed2 = a.y2_seed + (a.seed_ptr ? *a.seed_ptr : 0ull);
+  const uint64_t seed2 = a.y2_seed + (a.seed_ptr ? (uint64_t)*a.seed_ptr * 4096ull : 0ull);   // replay counter: same stride as the host step counter
   float lacc[LORA ? 16 : 1];
   if constexpr (LORA) {
 #pragma unroll
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PARAM_GRADS || LN_MAXC > 6) ? 
   const int r_begin = blockIdx.x * rows_per_block;
   const int r_end = min(a.M, r_begin + rows_per_block);
   const float keep2 = a.dy2_dropout_p > 0.f ? 1.f / (1.f - a.dy2_dropout_p) : 1.f;
-  const uint64_t seed2 = a.dy2_seed + (a.seed_ptr ? *a.seed_ptr : 0ull);
+  const uint64_t seed2 = a.dy2_seed + (a.seed_ptr ? (uint64_t)*a.seed_ptr * 4096ull : 0ull);
   for (int row = r_begin + warp; row < r_end; row += LN_WARPS) {
     const float4* x4 = reinterpret_cast<const float4*>(a.x + (long long)row * a.ldx);
     const RawDY* dy = reinterpret_cast<const RawDY*>(reinterpret_cast<const TDY*>(a.dy) + (long long)row * a.ld_dy);

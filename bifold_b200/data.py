@@ -111,3 +111,42 @@ class ScalarReader:
                 self.values.append(float(self.buf[slot]))
                 self.events[slot] = None
         return self.values
+
+
+class InputStage:
+    """GPU-side input stage: raw batch -> the sample dict the reference's model and loss read.
+
+    The reference builds every training sample on the host (``bifold/data/processor.py``): frames go through the SigLIP image
+    processor (``_process_rgb``, :143-148) and every pick/place pixel becomes an H x W fp32 Gaussian map (``_make_gaussmap``,
+    :405-439).  Shipped over PCIe that is ~103 MB per 64-sample bimanual batch, half of it Gaussian maps that 8 integers per
+    sample describe.  Here the host sends the raw form and two kernels rebuild the reference's tensors on the device:
+
+        raw["rgb_u8"]            uint8 [B, H, W, 3]      frame at model resolution          -> sample["rgb"]  fp32 [B, 3, H, W]
+        raw["rgb_context_u8"]    uint8 [B, T, H, W, 3]   (sequential models)                -> sample["rgb_context"]
+        raw["centers"]           int32 [heads, B, 2]     rounded [x, y] per head, x = NO_ACTION for a missing arm
+                                 or    [heads, B, P, 2]  several candidate pixels ("gmm")   -> sample["<head>_heatmap"] fp32 [B, H, W]
+        raw["mask_u8"]           uint8 [B, H, W]         cloth mask (get_action only)       -> sample["mask"] fp32 [B, 1, H, W]
+        everything else (instruction ids, context_attention_mask, ...) passes through.
+
+    Capturable: no allocation-dependent host logic, so ``GraphedTrainStep(..., input_stage=stage)`` records it in the step graph.
+    """
+
+    def __init__(self, heads_out, image_size: int, sigma: float = 5.0, mean: float = 0.5, std: float = 0.5):
+        from . import ops  # noqa: F401  (registers torch.ops.bfk.*)
+        self.heads_out, self.image_size = list(heads_out), int(image_size)
+        self.sigma, self.mean, self.std = float(sigma), float(mean), float(std)
+
+    def __call__(self, raw: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        H = self.image_size
+        s = {k: v for k, v in raw.items() if k not in ("rgb_u8", "rgb_context_u8", "centers", "mask_u8")}
+        s["rgb"] = torch.ops.bfk.normalize_u8(raw["rgb_u8"], self.mean, self.std)
+        if "rgb_context_u8" in raw:
+            s["rgb_context"] = torch.ops.bfk.normalize_u8(raw["rgb_context_u8"], self.mean, self.std)
+        if "centers" in raw:
+            c = raw["centers"]
+            maps = torch.ops.bfk.gauss_targets(c, H, H, self.sigma, c.dim() == 4)
+            for i, h in enumerate(self.heads_out):
+                s[f"{h}_heatmap"] = maps[i]
+        if "mask_u8" in raw:
+            s["mask"] = raw["mask_u8"].unsqueeze(1).to(torch.float32)
+        return s

@@ -98,19 +98,31 @@ class BatchShardedDDP:
         # identical weights on every rank
         for p in model.parameters():
             dist.broadcast(p.data, src=0, group=process_group)
-        orig_backward = eng.backward
-
-        def backward(ctx, dheat, dloss):
-            # the arena is allocated at the start of Engine.backward; bind lazily through the hook
-            return orig_backward(ctx, dheat, dloss)
+        self.engine = eng
 
         def hook(group):
-            self.reducer.bind(eng.last_arena)
+            if group == "decoders":                         # first announcement of every backward
+                optimizer.grad_scale = 1.0 / self.world     # (finish_reduce() of the previous step may have reset it)
+            self.reducer.bind(eng.last_arena)               # the arena is allocated at the start of Engine.backward
             self.reducer.on_ready(group)
 
         eng.grad_ready_hook = hook
         optimizer.grad_scale = 1.0 / self.world
         optimizer.pre_step_hook = self.reducer.wait
+
+    def finish_reduce(self):
+        """Wait for the outstanding all-reduces and turn the summed gradients into the global-batch MEAN in place.
+
+        Between ``loss.backward()`` and ``optimizer.step()`` the ``.grad`` tensors are otherwise in flight on the
+        communication stream and hold un-averaged sums (the 1/world factor normally rides inside the Adam kernel).
+        Call this before anything that reads gradients there — the reference Trainer's optional
+        ``clip_grad_norm_`` (bifold/__main__.py:148-149), gradient logging, a debugger.  ``optimizer.step()`` afterwards
+        applies the gradients as they are (scale 1)."""
+        self.reducer.wait()
+        arena = getattr(self.engine, "last_arena", None)
+        if arena is not None and self.world > 1 and self.optimizer.grad_scale != 1.0:
+            arena.mul_(1.0 / self.world)
+            self.optimizer.grad_scale = 1.0
 
     def shard(self, global_batch: int, rank: int = None):
         rank = dist.get_rank() if rank is None else rank

@@ -46,6 +46,8 @@ class Kernels:
     def __init__(self):
         self.lib = K.load()
         self.launches = 0          # C-ABI calls issued (each is >= 1 kernel launch); bench.py reports it
+        # algorithmic work issued so far, by roofline class (bench.py divides it by the measured per-class device time)
+        self.work = {"gemm_flops": 0.0, "attn_flops": 0.0, "ln_bytes": 0.0, "tail_bytes": 0.0}
         self.backend = K.BACKEND_AUTO
         self._ws = None
         self.seed_dev = None   # device int64 counter added to every dropout seed (advanced inside captured CUDA graphs)
@@ -79,6 +81,7 @@ class Kernels:
         assert _dt(A) == _dt(B)
         K.check(self.lib.bfk_gemm(C.byref(a), _stream()), "bfk_gemm")
         self.launches += 1
+        self.work["gemm_flops"] += 2.0 * M * N * Kd
 
     def colsum(self, X, M, N, ld, out):
         ws = torch.empty(self.lib.bfk_colsum_workspace_floats(M, N), device=X.device, dtype=torch.float32)
@@ -93,6 +96,7 @@ class Kernels:
                                K.ptr(self.seed_dev) if y2_p > 0.0 else None)
         K.check(self.lib.bfk_layernorm_fwd(C.byref(a), _stream()), "bfk_layernorm_fwd")
         self.launches += 1
+        self.work["ln_bytes"] += M * D * (4.0 + y.element_size() + (y2.element_size() if y2 is not None else 0))
 
     def layernorm_bwd(self, dy, ld_dy, x, M, D, mean, rstd, gamma, dres, dx, dx2=None, dgamma=None, dbeta=None,
                       dy2=None, ld_dy2=0, dy2_p=0.0, dy2_seed=0):
@@ -105,6 +109,8 @@ class Kernels:
                                K.ptr(dy2), ld_dy2, dy2_p, dy2_seed, K.ptr(self.seed_dev) if dy2_p > 0.0 else None)
         K.check(self.lib.bfk_layernorm_bwd(C.byref(a), _stream()), "bfk_layernorm_bwd")
         self.launches += 2 if dgamma is not None else 1
+        self.work["ln_bytes"] += M * D * (dy.element_size() + 4.0 + (4.0 if dres is not None else 0) + 4.0 +
+                                          (dx2.element_size() if dx2 is not None else 0) + (dy2.element_size() if dy2 is not None else 0))
 
     # -- attention -----------------------------------------------------------------------------------
     def attention_fwd(self, qkv, out, lse, B, N, H, hd, scale, row_mask=None, mask_fill=-100000.0):
@@ -112,6 +118,7 @@ class Kernels:
                             scale, mask_fill, _dt(qkv), self.backend, None, 0, None, 0, None)
         K.check(self.lib.bfk_attention_fwd(C.byref(a), _stream()), "bfk_attention_fwd")
         self.launches += 1
+        self.work["attn_flops"] += 4.0 * B * H * N * N * hd            # S = QK^T and O = PV
 
     def attention_bwd(self, qkv, out, lse, dout, dqkv, B, N, H, hd, scale, row_mask=None, mask_fill=-100000.0):
         delta = torch.empty(B * H * N, device=qkv.device, dtype=torch.float32)
@@ -120,6 +127,7 @@ class Kernels:
                             delta.data_ptr())
         K.check(self.lib.bfk_attention_bwd(C.byref(a), _stream()), "bfk_attention_bwd")
         self.launches += 3
+        self.work["attn_flops"] += 8.0 * B * H * N * N * hd            # dP, dV, dK, dQ (recomputing S is not algorithmic work)
 
     # -- misc ------------------------------------------------------------------------------------------
     def cast(self, src, dst, rows, cols, ld_src, ld_dst):
@@ -564,6 +572,8 @@ class Engine:
         rgb = sample["rgb"]
         dev = rgb.device
         self.training = training
+        if training and need_grad and cfg.lora and cfg.lora_dropout > 0.0:
+            self.step_seed += 1     # every training forward draws fresh LoRA-dropout masks (a captured graph adds seed_dev on top)
         self.prepare(dev)
         pre = self._collapse_fwd(dev, off_chain=True)     # needs only the decoder weights: overlaps the towers
         B, Np, L = rgb.shape[0], cfg.num_patches, cfg.text_len
@@ -708,6 +718,8 @@ class Engine:
                               K.ptr(loss), K.ptr(key), K.ptr(part))
         K.check(lib.bfk_heatmap_fwd(C.byref(ha), st), "bfk_heatmap_fwd")
         k.launches += 3 + (1 if targets is not None else 0)
+        # tokens read once (fp32), heatmaps written, targets read when the BCE is fused
+        k.work["tail_bytes"] += 4.0 * (B * Np * D + heads * B * H * H * (2 if targets is not None else 1))
         return out
 
     # ------------------------------------------------------------------------------------------------
@@ -731,6 +743,16 @@ class Engine:
         for s in sizes:
             offs.append(tot); tot += (s + 7) // 8 * 8
         arena = torch.empty(tot, device=dev, dtype=torch.float32)
+        if os.environ.get("BFK_POISON_ARENA") == "1":       # tests: a trainable gradient that no kernel writes shows up as NaN
+            arena.fill_(float("nan"))
+        # the flat Adam launch and the DDP all-reduce read the pad slots (<= 7 floats behind a tensor): keep them zero
+        pad_key = (tuple(sizes), dev)
+        if getattr(self, "_pad_key", None) != pad_key:
+            idx = [o + s + j for o, s in zip(offs, sizes) for j in range((s + 7) // 8 * 8 - s)]
+            self._pad_idx = torch.tensor(idx, dtype=torch.int64, device=dev) if idx else None
+            self._pad_key = pad_key
+        if self._pad_idx is not None:
+            arena.index_fill_(0, self._pad_idx, 0.0)
         grads = {n: arena[o:o + s].view(self.params[n].shape) for n, o, s in zip(names, offs, sizes)}
         self.last_arena = arena
         tail = ctx["tail"]
@@ -776,6 +798,8 @@ class Engine:
             K.check(lib.bfk_decoder_collapse_bwd(C.byref(ca), _stream()), "bfk_decoder_collapse_bwd")
         self._off_chain(collapse_bwd, d_w_eff, d_b_eff, chain_t)
         k.launches += 7
+        # heatmaps + targets (or dheat) read, tokens read, dX written (fp32 + operand copy)
+        k.work["tail_bytes"] += 4.0 * (2 * heads * B * H * H + B * Np * D) + B * Nf * D * (4.0 + (dX_T.element_size() if dX_T is not None else 0))
         if self.grad_ready_hook:
             self._hook_after_off_chain("decoders")
 

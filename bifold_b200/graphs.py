@@ -10,8 +10,10 @@ launch.  What changes between replays lives in device memory:
 * Adam         - step count, bias corrections and learning rate come from device scalars (``FusedAdam`` device
                  schedule, ``bfk_adamw_advance``); the host pushes learning-rate changes before a replay.
 
-Two fork/join side streams (text tower, gradient all-reduce is NOT captured: single-process only) are captured as
-parallel branches of the graph.
+The fork/join side streams (text tower, off-chain weight gradients) become parallel branches of the graph; with
+``allow_distributed=True`` the bucketed NCCL all-reduces of ``BatchShardedDDP`` are captured on their own branch too (every rank
+captures and replays in lock-step).  An optional ``input_stage`` (``bifold_b200.data.InputStage``) is recorded in front of the
+forward, so the static inputs are the raw uint8 frames and integer target centres.
 """
 from __future__ import annotations
 
@@ -28,7 +30,8 @@ class GraphedTrainStep:
     ``loss_fn(out, sample)`` must return ``(loss, aux)`` like ``bifold.losses`` does.
     """
 
-    def __init__(self, model, loss_fn: Callable, optimizer, warmup: int = 3, allow_distributed: bool = False):
+    def __init__(self, model, loss_fn: Callable, optimizer, warmup: int = 3, allow_distributed: bool = False,
+                 input_stage: Optional[Callable] = None):
         if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1 \
                 and not allow_distributed:
             raise RuntimeError("GraphedTrainStep: pass allow_distributed=True to capture the NCCL all-reduces of "
@@ -38,16 +41,20 @@ class GraphedTrainStep:
             # the fp32 parity kernels (bfk_lora_down & co) take their dropout seed by value: a replay would reuse the mask
             raise RuntimeError("GraphedTrainStep needs precision='bf16' when LoRA dropout is active")
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
+        self.input_stage = input_stage      # e.g. bifold_b200.data.InputStage: raw uint8 frames / target centres -> sample, in-graph
         self.warmup = max(2, int(warmup))
         self.calls = 0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_in: Optional[Dict[str, torch.Tensor]] = None
         self.static_loss: Optional[torch.Tensor] = None
         self.launches_per_replay = 0
+        self.work_per_replay: Dict[str, float] = {}     # algorithmic work per replay by roofline class (Kernels.work deltas at capture)
         self.failed: Optional[str] = None
         optimizer.enable_device_schedule()
 
     def _eager(self, sample):
+        if self.input_stage is not None:
+            sample = self.input_stage(sample)
         out = self.model(sample)
         loss, _ = self.loss_fn(out, sample)
         self.optimizer.zero_grad()
@@ -82,7 +89,7 @@ class GraphedTrainStep:
             s = self._stage(sample)
             self.optimizer.sync_lr()             # a pending learning-rate change must not be recorded as a graph node
             torch.cuda.synchronize()
-            l0, o0 = eng.k.launches, self.optimizer.launches
+            l0, o0, w0 = eng.k.launches, self.optimizer.launches, dict(eng.k.work)
             graph = torch.cuda.CUDAGraph()
             steps_before = {gi: st["step"] for gi, st in self.optimizer._flat.items()}
             try:
@@ -102,6 +109,7 @@ class GraphedTrainStep:
                 return loss
             self.graph = graph
             self.launches_per_replay = (eng.k.launches - l0) + (self.optimizer.launches - o0)
+            self.work_per_replay = {k: eng.k.work[k] - w0[k] for k in w0}
             # capture does not execute: run the step that was just recorded
             self.graph.replay()
             # (the capture pass already advanced the optimizer's host-side counters for this step)
@@ -111,3 +119,63 @@ class GraphedTrainStep:
         self.graph.replay()
         self.optimizer.note_replayed_step()
         return self.static_loss
+
+
+class GraphedAction:
+    """``get_action`` for a fixed batch shape as ONE CUDA-graph launch (config 4: batched inference).
+
+    The eager ``model.get_action`` issues ~330 launches (≈8.7 ms of host time at B = 64 against ≈8.5 ms of GPU work, so the
+    host paces it).  Here forward + per-head argmax + mask snap + arm gate are captured once; a call copies the inputs into
+    static tensors, replays, and reads the (heads, B, 2) pixel table back — the only D2H traffic, as in
+    ``BaseModel.get_action`` (bifold/models/__init__.py:79-173 returns numpy pixel arrays).
+    """
+
+    def __init__(self, model, warmup: int = 2, input_stage: Optional[Callable] = None):
+        self.model, self.input_stage = model, input_stage
+        self.warmup = max(1, int(warmup))
+        self.calls = 0
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.static_in: Optional[Dict[str, torch.Tensor]] = None
+        self.static_xy = self.static_conf = None
+        self.launches_per_replay = 0
+        self.work_per_replay: Dict[str, float] = {}
+        self.failed: Optional[str] = None
+
+    _stage = GraphedTrainStep._stage
+
+    def _eager(self, sample):
+        if self.input_stage is not None:
+            sample = self.input_stage(sample)
+        xy, conf, _ = self.model.action_on_device(sample)
+        return xy, conf
+
+    def enqueue(self, sample):
+        """Stage the inputs and launch; returns the device pixel table (valid until the next call)."""
+        self.calls += 1
+        if self.model.training:
+            raise RuntimeError("GraphedAction captures the inference path: call model.eval() first")
+        s = self._stage(sample)
+        if self.calls <= self.warmup or self.failed is not None:
+            self.static_xy, self.static_conf = self._eager(s)
+            return self.static_xy
+        if self.graph is None:
+            eng = self.model._ensure_engine()
+            torch.cuda.synchronize()
+            l0, w0 = eng.k.launches, dict(eng.k.work)
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    self.static_xy, self.static_conf = self._eager(s)
+            except Exception as e:
+                self.failed = f"{type(e).__name__}: {e}"
+                torch.cuda.synchronize()
+                self.static_xy, self.static_conf = self._eager(s)
+                return self.static_xy
+            self.graph = graph
+            self.launches_per_replay = eng.k.launches - l0
+            self.work_per_replay = {k: eng.k.work[k] - w0[k] for k in w0}
+        self.graph.replay()
+        return self.static_xy
+
+    def __call__(self, sample):
+        return self.model.action_from_table(self.enqueue(sample))

@@ -6,7 +6,7 @@ heads, on our CUDA kernels:
 * fused path  – when the model already computed the per-head BCE inside its heatmap kernel against
   the very same target tensors (``PolicyOutput.fused_loss``), the loss is just read back and the
   gradient goes into the tail backward kernel as (p - t)/(B*H*W);
-* general path – ``bfk_bce_prob`` / ``bfk_bce_prob_bwd`` on the probabilities (any caller-supplied
+* general path – ``torch.ops.bfk.bce_prob`` (C ABI ``bfk_bce_prob`` / ``bfk_bce_prob_bwd``) on the probabilities (any caller-supplied
   heatmaps, or ``mask_pick_heatmap=True``).
 """
 from __future__ import annotations
@@ -14,6 +14,7 @@ from __future__ import annotations
 import torch
 
 from . import _cabi as K
+from . import ops  # noqa: F401  (registers torch.ops.bfk.*)
 
 
 class Losses:
@@ -52,36 +53,6 @@ class ComposedLoss:   # bifold/losses/__init__.py:30-51
         return loss, inter
 
 
-class _BCEProbFn(torch.autograd.Function):
-    """nn.BCELoss()(p, t [* mask]) on device via the C ABI."""
-
-    @staticmethod
-    def forward(ctx, p, t, t_mask):
-        lib = K.load()
-        p = p.contiguous()
-        t = t.to(torch.float32).contiguous()
-        tm = t_mask.to(torch.float32).contiguous() if t_mask is not None else None
-        loss = torch.empty(1, device=p.device, dtype=torch.float32)
-        part = torch.empty(1024, device=p.device, dtype=torch.float32)
-        st = torch.cuda.current_stream().cuda_stream
-        K.check(lib.bfk_bce_prob(p.data_ptr(), t.data_ptr(), K.ptr(tm), p.numel(), loss.data_ptr(), part.data_ptr(), st),
-                "bfk_bce_prob")
-        ctx.save_for_backward(p, t, tm if tm is not None else p.new_zeros(0))
-        return loss.reshape(())
-
-    @staticmethod
-    def backward(ctx, g):
-        p, t, tm = ctx.saved_tensors
-        tm = tm if tm.numel() else None
-        lib = K.load()
-        gs = (g.reshape(1).float() / p.numel()).contiguous()
-        dp = torch.empty_like(p)
-        st = torch.cuda.current_stream().cuda_stream
-        K.check(lib.bfk_bce_prob_bwd(p.data_ptr(), t.data_ptr(), K.ptr(tm), p.numel(), gs.data_ptr(), dp.data_ptr(), st),
-                "bfk_bce_prob_bwd")
-        return dp, None, None
-
-
 class BCEGaussMap:    # bifold/losses/__init__.py:54-109
     def __init__(self, is_bimanual, mask_pick_heatmap, **kwargs):
         self.is_bimanual = is_bimanual
@@ -107,7 +78,7 @@ class BCEGaussMap:    # bifold/losses/__init__.py:54-109
                 raise K.BfkError("bifold_b200 losses run on CUDA only (no CPU fallback)")
             t = sample[f"{h}_heatmap"].to(p.device)
             tm = sample["mask"].squeeze(1).to(p.device) if (self.mask_pick_heatmap and h.endswith("pick")) else None
-            cur = _BCEProbFn.apply(p, t, tm)
+            cur = torch.ops.bfk.bce_prob(p, t, tm)
             inter[h] = cur
             loss = cur if loss is None else loss + cur
         return loss, inter

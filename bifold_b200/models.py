@@ -21,20 +21,25 @@ import torch
 from torch import nn
 
 from . import _cabi as K
+from . import ops
 from .config import PolicyConfig, tower_shape_from_name
 from .engine import Engine
 
 DUMMY_PICK = -np.ones(2)
 
 
-class Action:
-    """Same container as bifold/env/__init__.py:1-22 (2 or 4 keyword arrays)."""
+try:                                   # drop-in: hand the caller the reference's own container (bifold/env/__init__.py:1-22)
+    from bifold.env import Action
+except Exception:                      # the reference package is not importable (GPU box, tests): same keyword contract
+    class Action:
+        """``Action(pick=, place=)`` or ``Action(left_pick=, right_pick=, left_place=, right_place=)``."""
+        _FIELDS = {2: ("pick", "place"), 4: ("left_pick", "right_pick", "left_place", "right_place")}
 
-    def __init__(self, **kwargs):
-        if len(kwargs) not in (2, 4):
-            raise ValueError(f"Cannot instantiate action with {kwargs}")
-        for k, v in kwargs.items():
-            setattr(self, k, v)
+        def __init__(self, **kwargs):
+            want = self._FIELDS.get(len(kwargs))
+            if want is None or set(kwargs) != set(want):
+                raise ValueError(f"Cannot instantiate action with {kwargs}")
+            self.__dict__.update(kwargs)
 
 
 class PolicyOutput(dict):
@@ -233,33 +238,9 @@ class Components:
 
 
 # ----------------------------------------------------------------------------------------------------
-class _PolicyFn(torch.autograd.Function):
-    """Whole-policy autograd node: forward = Engine.forward, backward = Engine.backward."""
-
-    @staticmethod
-    def forward(ctx, model, sample, targets, want_argmax, need_grad, *params):
-        # (grad mode is always off inside Function.forward, so the caller decides `need_grad`)
-        heat, loss, key, ectx = model.engine.forward(sample, need_grad, model.training, targets, want_argmax)
-        ctx.model, ctx.ectx = model, ectx
-        ctx.set_materialize_grads(False)
-        ctx.n_params = len(params)
-        model._last_key = key
-        if loss is None:
-            loss = heat.new_zeros(0)
-        ctx.mark_non_differentiable(*([] if targets is not None else [loss]))
-        return heat, loss
-
-    @staticmethod
-    def backward(ctx, dheat, dloss):
-        model = ctx.model
-        if ctx.ectx is None:
-            raise RuntimeError("backward through a forward that ran without grad")
-        grads = model.engine.backward(ctx.ectx, dheat, dloss if (dloss is not None and dloss.numel()) else None)
-        ctx.ectx = None
-        out = [grads.get(n) if p.requires_grad else None for n, p in zip(model._param_names, model._param_list)]
-        return (None, None, None, None, None, *out)
-
-
+# The whole policy is ONE torch custom op with a registered backward (bifold_b200/ops.py):
+#   torch.ops.bfk.policy_fwd -> Engine.forward,   torch.ops.bfk.policy_bwd -> Engine.backward
+# ----------------------------------------------------------------------------------------------------
 class BaseModel(nn.Module):
     def __init__(self, image_size, is_bimanual, device, threshold=0.01, requires_graph=False, constrain_pick_mask=True,
                  **kwargs):
@@ -285,13 +266,14 @@ class BaseModel(nn.Module):
             p.requires_grad = False
 
     # -- get_action: bifold/models/__init__.py:79-173 with argmax / mask snap / gate on device -------------
-    def get_action(self, sample, return_raw_output=False):
+    def action_on_device(self, sample):
+        """Device part of ``get_action``: forward + argmax keys + mask snap + arm gate, nothing leaves the GPU and nothing
+        synchronises (capturable: ``bifold_b200.graphs.GraphedAction``).  -> (xy int32 [heads,B,2], conf [heads,B], output)."""
         with torch.no_grad():
             output = self.forward(sample, _want_argmax=True)
-        cfg = self.cfg
+        names = self.cfg.heads_out
         heat = output.heat_all
         heads, B, H, W = heat.shape
-        names = cfg.heads_out
         if self.is_bimanual:
             pick = [names.index("left_pick"), names.index("right_pick")]
             place = [names.index("left_place"), names.index("right_place")]
@@ -302,30 +284,44 @@ class BaseModel(nn.Module):
             mask = sample.get("mask") if self.constrain_pick_mask else None
         if mask is not None:
             mask = mask.to(device=heat.device, dtype=torch.float32).reshape(B, H, W).contiguous()
-        xy = torch.empty(heads, B, 2, device=heat.device, dtype=torch.int32)
-        conf = torch.empty(heads, B, device=heat.device, dtype=torch.float32)
-        import ctypes as C
-        a = K.ActionArgs(B, heads, H, W, n_arms, heat.data_ptr(), self._last_key.data_ptr(), K.ptr(mask),
-                         (C.c_int32 * 2)(*pick), (C.c_int32 * 2)(*place), float(self.threshold), xy.data_ptr(), conf.data_ptr())
-        K.check(self.engine.k.lib.bfk_action(C.byref(a), torch.cuda.current_stream().cuda_stream), "bfk_action")
+        xy, conf = torch.ops.bfk.action(heat, self._last_key, mask, pick, place, n_arms, float(self.threshold))
         self.engine.k.launches += 1
-        xy = xy.cpu().numpy().astype(np.int64)
-        action = Action(**{n: xy[i] for i, n in enumerate(names)})
+        return xy, conf, output
+
+    def get_action(self, sample, return_raw_output=False):
+        xy, _, output = self.action_on_device(sample)
+        action = self.action_from_table(xy)
         if return_raw_output:
             return action, output
         return action
 
+    def action_from_table(self, xy):
+        """(heads,B,2) int32 pixel table (host or device) -> the reference's Action of int64 (B,2) arrays."""
+        xy = xy.cpu().numpy().astype(np.int64)
+        return Action(**{n: xy[i] for i, n in enumerate(self.cfg.heads_out)})
+
 
 class SigLip(BaseModel):
     def __init__(self, patch_size, dim, lora, r, lora_alpha, lora_dropout, automodel_name, target_modules,
-                 pick_place_model, precision="bf16", tower_config=None, **kwargs):
+                 pick_place_model, precision="bf16", tower_config=None, pretrained=True, **kwargs):
+        """``pretrained`` (not a reference key; default = the reference's behaviour): the towers are loaded with
+        ``AutoModel.from_pretrained(automodel_name)`` (HF cache, local directory or hub id) exactly like
+        bifold/models/siglip.py:26 and construction RAISES when that fails.  ``pretrained=False`` is the explicit
+        opt-in for randomly initialised towers of the shape ``automodel_name`` / ``tower_config`` describe
+        (benchmarks, tests, or when the weights arrive through ``load_state_dict`` of a BiFold checkpoint)."""
         super().__init__(**kwargs)
         self.patch_size = patch_size
         self.hidden_size = dim
         self.num_patches = (self.image_size // self.patch_size) ** 2
         if lora and sorted(target_modules) != ["q_proj", "v_proj"]:
             raise K.BfkError("LoRA target_modules other than [q_proj, v_proj] are not on the accelerated path")
-        tower = dict(tower_shape_from_name(automodel_name, dim))
+        hf_state = None
+        if pretrained:
+            hf_state, tower = self._load_pretrained(automodel_name, dim)
+        else:
+            print(f"bifold_b200: pretrained=False -> SigLIP towers of '{automodel_name}' keep their RANDOM initialisation "
+                  "(load a BiFold checkpoint with load_state_dict, or pass pretrained=True)", flush=True)
+            tower = dict(tower_shape_from_name(automodel_name, dim))
         tower.update(tower_config or {})
         tower.pop("dim", None)
         fusion_kw = {k: kwargs[k] for k in ("depth", "heads", "mlp_ratio") if k in kwargs}
@@ -333,7 +329,8 @@ class SigLip(BaseModel):
                                 is_bimanual=self.is_bimanual, lora=bool(lora), r=r, lora_alpha=lora_alpha,
                                 lora_dropout=lora_dropout, **fusion_kw, **tower)
         siglip = _SiglipShell(self.cfg, bool(lora), "siglip_adapter")
-        self._maybe_load_pretrained(siglip, automodel_name)
+        if hf_state is not None:
+            self._install_pretrained(siglip, hf_state, bool(lora), automodel_name)
         if lora:
             self.siglip_model = _LoraModelShell(siglip)
         else:
@@ -347,18 +344,43 @@ class SigLip(BaseModel):
         self.engine = None
         self._last_key = None
 
-    @staticmethod
-    def _maybe_load_pretrained(shell, automodel_name):
-        """Load a locally cached HF checkpoint when one exists (offline); otherwise keep the random init."""
+    def _load_pretrained(self, automodel_name, dim):
+        """AutoModel.from_pretrained like bifold/models/siglip.py:26-29: returns (state_dict, tower shape); raises on failure."""
+        from transformers import AutoModel
         try:
-            import os
-            if not automodel_name or not os.path.isdir(str(automodel_name)):
-                return
-            from transformers import AutoModel
-            hf = AutoModel.from_pretrained(automodel_name, local_files_only=True)
-            shell.load_state_dict(hf.state_dict(), strict=False)
-        except Exception:
-            pass
+            hf = AutoModel.from_pretrained(automodel_name)
+        except Exception as e:
+            raise RuntimeError(f"cannot load the SigLIP towers '{automodel_name}' (AutoModel.from_pretrained failed: {type(e).__name__}: "
+                               f"{e}); pass pretrained=False to build randomly initialised towers on purpose") from e
+        tc, vc = hf.config.text_config, hf.config.vision_config
+        assert dim == vc.hidden_size and dim == tc.hidden_size            # bifold/models/siglip.py:28-29
+        if vc.image_size != self.image_size or vc.patch_size != self.patch_size:
+            raise ValueError(f"'{automodel_name}' is a {vc.image_size}px / patch {vc.patch_size} checkpoint, the model config says "
+                             f"{self.image_size}px / patch {self.patch_size}")
+        same = ("num_hidden_layers", "num_attention_heads", "intermediate_size", "layer_norm_eps")
+        if any(getattr(tc, k) != getattr(vc, k) for k in same):
+            raise K.BfkError("text and vision towers of different depth/width are not on the accelerated path")
+        if getattr(vc, "hidden_act", "gelu_pytorch_tanh") != "gelu_pytorch_tanh":
+            raise K.BfkError(f"tower activation {vc.hidden_act} is not on the accelerated path")
+        tower = dict(tower_layers=vc.num_hidden_layers, tower_heads=vc.num_attention_heads, tower_mlp=vc.intermediate_size,
+                     vocab_size=tc.vocab_size, text_len=tc.max_position_embeddings, tower_ln_eps=float(vc.layer_norm_eps))
+        return {k: v.detach().clone() for k, v in hf.state_dict().items()}, tower
+
+    @staticmethod
+    def _install_pretrained(shell, hf_state, lora, automodel_name):
+        """Strict load of the HF SiglipModel weights into the parameter tree (peft renames wrapped linears to *.base_layer.*)."""
+        sd = {}
+        for k, v in hf_state.items():
+            if lora:
+                for proj in (".q_proj.", ".v_proj."):
+                    if proj in k and ".encoder.layers." in k:
+                        k = k.replace(proj, proj + "base_layer.")
+            sd[k] = v
+        res = shell.load_state_dict(sd, strict=False)
+        missing = [k for k in res.missing_keys if ".lora_A." not in k and ".lora_B." not in k]
+        if missing or res.unexpected_keys:
+            raise RuntimeError(f"'{automodel_name}' does not match the SigLIP tower layout: missing {missing[:5]}, "
+                               f"unexpected {list(res.unexpected_keys)[:5]}")
 
     # ------------------------------------------------------------------------------------------------
     def _ensure_engine(self):
@@ -366,6 +388,8 @@ class SigLip(BaseModel):
             self._param_names = [n for n, _ in self.named_parameters()]
             self._param_list = [p for _, p in self.named_parameters()]
             self.engine = Engine(self.cfg, dict(zip(self._param_names, self._param_list)), self.precision)
+            if getattr(self, "_handle", None) is None:
+                self._handle = ops.register_model(self)
         return self.engine
 
     def _apply(self, fn, *a, **k):
@@ -387,7 +411,10 @@ class SigLip(BaseModel):
                    and tuple(t.shape) == (rgb.shape[0], cfg.image_size, cfg.image_size) for t in ts):
                 targets = ts
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list)
-        heat, loss = _PolicyFn.apply(self, x, targets, _want_argmax, need_grad, *self._param_list)
+        heat, loss, key = torch.ops.bfk.policy_fwd(self._handle, rgb, x["instruction"], x.get("rgb_context") if cfg.sequential else None,
+                                                   x.get("context_attention_mask") if cfg.sequential else None,
+                                                   targets or [], self._param_list, self.training, need_grad, _want_argmax)
+        self._last_key = key if _want_argmax else None
         out = PolicyOutput(attn_weights=None)
         for i, h in enumerate(cfg.heads_out):
             out[f"{h}_heatmap"] = heat[i]

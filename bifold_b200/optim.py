@@ -1,6 +1,9 @@
 """Host-side mirror of ``bifold.optim`` (bifold/optim/__init__.py:4-92): Adam / AdamW with torch
-semantics executed by one fused CUDA kernel over flat buffers (bfk_adamw), plus the LinearWarmup
-scheduler (host Python, unchanged semantics)."""
+semantics executed by one fused CUDA kernel over flat buffers (bfk_adamw).
+
+The reference's learning-rate scheduler (``bifold.optim.Schedulers`` / ``LinearWarmup``, bifold/optim/__init__.py:17-92) is host
+Python that only rewrites ``optimizer.param_groups[i]["lr"]``; it is NOT re-implemented here — the reference's own class drives
+``FusedAdam`` unchanged, eagerly and under CUDA-graph replay (``sync_lr`` pushes the new value to the device)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -98,6 +101,9 @@ class FusedAdam(torch.optim.Optimizer):
             st["step"] += 1
             for p in st["ps"]:
                 self.state[p]["step"] += 1
+            # the replayed kernels wrote the parameters through raw pointers: an eager forward after a replay must
+            # re-derive its operand copies (Engine.prepare compares version counters)
+            torch._C._increment_version(st["ps"])
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -155,48 +161,3 @@ class Optimizers:
             del cfg.name
             return FusedAdam(params, decoupled=True, **cfg)
         raise ValueError(f"Optimizer {cfg.name} not recognized")
-
-
-class Schedulers:
-    @staticmethod
-    def get_by_name(cfg, *args, **kwargs):
-        if cfg.name is None:
-            return None
-        if cfg.name == "linear_warmup":
-            return LinearWarmup(cfg, *args, **kwargs)
-        raise ValueError(f"Scheduler {cfg.name} not recognized")
-
-
-class LinearWarmup:   # bifold/optim/__init__.py:28-92 (host-side; mutates param_groups[i]["lr"])
-    def __init__(self, cfg, optimizer, max_iters):
-        self.warmup_steps = int(cfg.warmup_portion * max_iters)
-        self.optimizer = optimizer
-        self.base_lrs = [g["lr"] for g in optimizer.param_groups]
-        self.last_step = -1
-        if isinstance(cfg.warmup_start_lr, (list, tuple)):
-            assert len(cfg.warmup_start_lr) == len(self.base_lrs)
-            self.warmup_start_lrs = cfg.warmup_start_lr
-        else:
-            self.warmup_start_lrs = [cfg.warmup_start_lr] * len(self.base_lrs)
-        self.lr_scheduler = (torch.optim.lr_scheduler.CosineAnnealingLR(optimizer=optimizer, T_max=max_iters - self.warmup_steps)
-                             if cfg.use_cosine_decay else None)
-        self.step()
-
-    def get_last_lr(self):
-        return self._last_lr
-
-    def state_dict(self):
-        return {k: v for k, v in self.__dict__.items() if k not in ("optimizer", "lr_scheduler")}
-
-    def load_state_dict(self, state_dict):
-        self.__dict__.update(state_dict)
-
-    def step(self, epoch=None):
-        if self.last_step <= self.warmup_steps:
-            values = [w + (b - w) * (self.last_step / self.warmup_steps) for w, b in zip(self.warmup_start_lrs, self.base_lrs)]
-            for g, lr in zip(self.optimizer.param_groups, values):
-                g["lr"] = lr
-            self.last_step += 1
-        elif self.lr_scheduler is not None:
-            self.lr_scheduler.step()
-        self._last_lr = [g["lr"] for g in self.optimizer.param_groups]

@@ -368,6 +368,21 @@ BFK_API int32_t bfk_cast_bf16(const float* src, void* dst, int64_t n, bfk_stream
 BFK_API int32_t bfk_cast_f32_to(const float* src, void* dst, int32_t dst_dtype, int64_t rows, int64_t cols,
                         int64_t ld_src, int64_t ld_dst, bfk_stream_t s);
 
+/* ------------------------------------------------------------------------------------------------
+ * GPU-side input stage (the per-sample host loops of bifold/data/processor.py that dominate host->device bytes).
+ * bfk_gauss_targets: Processor._make_gaussmap (bifold/data/processor.py:405-425), evaluated in fp64 and rounded to fp32:
+ *   centers int32 [n_maps, n_points, 2] = [cx, cy] (already rounded like round()/np.round); a point with cx == INT32_MIN is
+ *   padding.  One valid point: strategy "first", out = exp(-((x-cx)^2 + (y-cy)^2) / (2 sigma^2)).  Several: strategy "gmm",
+ *   sum of Gaussians / (2 pi sigma^2) divided by the map maximum.  No valid point ("no action for this arm",
+ *   processor.py:296): all zeros.  out fp32 [n_maps, H, W].
+ * bfk_normalize_u8: Processor._process_rgb through the SigLIP image processor (bifold/data/processor.py:143-148) for frames
+ *   already at model resolution: uint8 [n, H, W, 3] -> fp32 [n, 3, H, W] = (x / 255 - mean) / std.
+ * ---------------------------------------------------------------------------------------------- */
+BFK_API int32_t bfk_gauss_targets(const int32_t* centers, int32_t n_maps, int32_t n_points, int32_t H, int32_t W, float sigma,
+                          float* out, bfk_stream_t s);
+BFK_API int32_t bfk_normalize_u8(const uint8_t* frames, int64_t n_frames, int32_t H, int32_t W, float mean, float std_, float* out,
+                         bfk_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,7 +63,7 @@ def test_oracle_matches_reference_tiny(name):
     _check_case(name)
 
 
-@pytest.mark.parametrize("name", ["base224_bi_lora"])
+@pytest.mark.parametrize("name", ["base224_bi_lora", "base224_bi_seq_lora"])
 def test_oracle_matches_reference_base(name):
     if not os.path.exists(os.path.join(GOLDEN, f"{name}.npz")):
         pytest.skip("fixture not generated")

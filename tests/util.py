@@ -14,7 +14,7 @@ def model_cfg(spec: PolicySpec, precision="fp32") -> Cfg:
               r=spec.r, lora_alpha=spec.lora_alpha, lora_dropout=spec.lora_dropout, target_modules=["q_proj", "v_proj"],
               threshold=0.5, text_encoder=None, pick_place_model="pick_place_convdecoder",
               fusion_model="concat_transformer", depth=spec.depth, heads=spec.heads, mlp_ratio=spec.mlp_ratio, dropout=0.0,
-              precision=precision,
+              precision=precision, pretrained=False,
               tower_config=dict(tower_layers=spec.tower_layers, tower_heads=spec.tower_heads, tower_mlp=spec.tower_mlp,
                                 vocab_size=spec.vocab_size, text_len=spec.text_len))
     if spec.name == "siglip_sequential":
