@@ -14,6 +14,7 @@ kernels; there is no eager fallback, so ``forward`` raises on a non-CUDA device.
 from __future__ import annotations
 
 import math
+import sys
 from typing import Dict
 
 import numpy as np
@@ -320,7 +321,7 @@ class SigLip(BaseModel):
             hf_state, tower = self._load_pretrained(automodel_name, dim)
         else:
             print(f"bifold_b200: pretrained=False -> SigLIP towers of '{automodel_name}' keep their RANDOM initialisation "
-                  "(load a BiFold checkpoint with load_state_dict, or pass pretrained=True)", flush=True)
+                  "(load a BiFold checkpoint with load_state_dict, or pass pretrained=True)", file=sys.stderr, flush=True)
             tower = dict(tower_shape_from_name(automodel_name, dim))
         tower.update(tower_config or {})
         tower.pop("dim", None)

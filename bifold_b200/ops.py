@@ -106,21 +106,34 @@ def _(handle, rgb, instruction, rgb_context, context_attention_mask, targets, pa
 
 
 @torch.library.custom_op("bfk::policy_bwd", mutates_args=(), device_types="cuda")
-def policy_bwd(handle: int, ticket: int, dheat: Optional[Tensor], dloss: Optional[Tensor]) -> List[Tensor]:
-    """Explicit backward of the policy: one fp32 gradient per trainable parameter (views of ONE flat arena, in
-    ``engine.trainable_names()`` order).  ``ticket`` names the saved forward context."""
+def policy_bwd(handle: int, ticket: int, dheat: Optional[Tensor], dloss: Optional[Tensor]) -> Tensor:
+    """Explicit backward of the policy -> ONE flat fp32 gradient arena; the gradient of the i-th trainable parameter
+    (``engine.trainable_names()`` order) is the view ``arena[off_i : off_i + numel_i]`` with every tensor padded to 8 floats
+    (``arena_views`` slices it).  ``ticket`` names the saved forward context."""
     model = _model(handle)
     ectx = _BWD_SLOT.pop((handle, ticket), None)
     if ectx is None:
         raise RuntimeError("backward through a policy forward that ran without grad (or was already consumed)")
-    grads = model.engine.backward(ectx, dheat, dloss)
-    return [grads[n] for n in model.engine.trainable_names()]
+    model.engine.backward(ectx, dheat, dloss)
+    return model.engine.last_arena
 
 
 @policy_bwd.register_fake
 def _(handle, ticket, dheat, dloss):
-    model = _model(handle)
-    return [torch.empty_like(model.engine.params[n], dtype=torch.float32) for n in model.engine.trainable_names()]
+    eng = _model(handle).engine
+    tot = sum((eng.params[n].numel() + 7) // 8 * 8 for n in eng.trainable_names())
+    ref = dheat if dheat is not None else dloss
+    return ref.new_empty((tot,), dtype=torch.float32)
+
+
+def arena_views(engine, arena: Tensor):
+    """{trainable parameter name: gradient view of the flat arena} (same layout as Engine.backward / FusedAdam / the DDP buckets)."""
+    out, off = {}, 0
+    for n in engine.trainable_names():
+        p = engine.params[n]
+        out[n] = arena[off:off + p.numel()].view(p.shape)
+        off += (p.numel() + 7) // 8 * 8
+    return out
 
 
 def _policy_setup(ctx, inputs, output):
@@ -142,12 +155,12 @@ def _policy_backward(ctx, dheat, dloss, dkey):
     ticket = _TICKET[0]
     _BWD_SLOT[(ctx.handle, ticket)], ctx.ectx = ctx.ectx, None     # ops take no Python objects: hand the context over by ticket
     try:
-        gl = torch.ops.bfk.policy_bwd(ctx.handle, ticket, dheat, dl)
+        arena = torch.ops.bfk.policy_bwd(ctx.handle, ticket, dheat, dl)
     finally:
         _BWD_SLOT.pop((ctx.handle, ticket), None)
     gparams: List[Optional[Tensor]] = [None] * ctx.n_params
     model = _model(ctx.handle)
-    by_name = dict(zip(model.engine.trainable_names(), gl))
+    by_name = arena_views(model.engine, arena)
     for i in ctx.trainable:
         gparams[i] = by_name.get(model._param_names[i])
     return None, None, None, None, None, [None] * ctx.n_targets, gparams, None, None, None

@@ -391,10 +391,10 @@ def test_argmax2d_first_max_and_action_gate(kern):
 
 
 def test_bce_prob_clamp_matches_torch(kern):
-    from bifold_b200.losses import _BCEProbFn
+    from bifold_b200 import ops  # noqa: F401
     p = torch.tensor([0.0, 1.0, 0.5, 1e-30, 1 - 1e-7, 0.3], device="cuda").repeat(100).requires_grad_(True)
     t = torch.tensor([1.0, 0.0, 0.5, 1.0, 0.2, 0.0], device="cuda").repeat(100)
-    loss = _BCEProbFn.apply(p, t, None)
+    loss = torch.ops.bfk.bce_prob(p, t, None)
     ref_p = p.detach().clone().requires_grad_(True)
     ref = F.binary_cross_entropy(ref_p, t)
     assert abs(loss.item() - ref.item()) <= 1e-5 * ref.item()
