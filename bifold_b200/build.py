@@ -73,11 +73,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 os.remove(os.path.join(OBJ, f))
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(_compile, sources()))
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-cudart", "static",
+    tmp = LIB + f".tmp{os.getpid()}"      # link next to the target, then rename: readers never see a half-written library
+    cmd = [_nvcc(), "-shared", "-o", tmp, *objs, "-cudart", "static",
            "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     if verbose:
         print(f"built {LIB}")
     return LIB

@@ -67,13 +67,18 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return 0.5f * (1.f + erff(x * 0.7071067811865476f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
-// Counter-based keep-mask for LoRA dropout: hash of (seed, row, col) -> uniform in [0,1).
-__device__ __forceinline__ float hash_uniform(uint64_t seed, uint32_t row, uint32_t col) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (((uint64_t)row << 32) | col);
+// Counter-based keep-mask for LoRA dropout: hash of (seed, row, col / 4) -> four 16-bit uniforms in [0,1), one per column of
+// the aligned group of four (kernels that walk rows four columns at a time evaluate the 64-bit mix once per group: the
+// compiler merges the identical sub-expressions).  Drop probability resolution: 2^-16.
+__device__ __forceinline__ uint64_t hash_mix(uint64_t seed, uint32_t row, uint32_t col4) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (((uint64_t)row << 32) | col4);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint32_t row, uint32_t col) {
+  const uint64_t z = hash_mix(seed, row, col >> 2);
+  return (float)((uint32_t)(z >> (16 * (col & 3))) & 0xFFFFu) * (1.0f / 65536.0f);
 }
 
 }  // namespace bfk

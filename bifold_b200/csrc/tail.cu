@@ -20,6 +20,11 @@ __device__ __forceinline__ unsigned long long pack_key(float v, uint32_t idx) {
   return ((unsigned long long)f2ord(v) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
 }
 
+__device__ __forceinline__ float exp2f_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {   // read-once data: do not keep it in L1
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -257,22 +262,70 @@ __global__ void __launch_bounds__(256) head_project_bwd_db_kernel(bfk_head_proje
 }
 
 // ---- heatmap forward: x16 upsample + sigmoid (+ BCE partials, + argmax) ---------------------------
-constexpr int HM_ROWS = 32;  // output rows per CTA
+constexpr int HM_ROWS = 32;  // backward: output rows per CTA
 constexpr int HM_THREADS = 256;
-constexpr int HM_MAXIN = HM_ROWS / 16 + 4;  // input rows feeding a band
+constexpr int HM_MAXIN = HM_ROWS / 16 + 4;  // input rows feeding a backward band
+constexpr int HF_ROWS = 16;  // forward: output rows per CTA (more, smaller CTAs: 3584 at B = 64 keep every SM streaming)
+constexpr int HF_MAXIN = HF_ROWS / 16 + 4;
+constexpr int HF_BATCH = 4;  // rows of one thread whose target loads are in flight together
 
+// One pixel: p = sigmoid(z) and (LOSS) its nn.BCELoss term in units of ln 2, both from e = 2^(-|z| log2 e):
+//   p = z >= 0 ? 1/(1+e) : e/(1+e);   -[t log p + (1-t) log(1-p)] = max(z,0) - t z + log(1 + e)          (3 MUFU: ex2, rcp, lg2)
+// The closed form is what torch computes from its ROUNDED p up to the rounding of 1 - p, i.e. to <= 6e-8 / (1 - p) absolute:
+// below 3e-5 for z <= BCE_ZFAST.  Above it (and where exp(-z) overflows: p == 0, log p == -inf) torch's result is dominated
+// by that rounding and by its -100 clamp, so those pixels take the literal path: logs of the rounded p, clamped.
+constexpr float BCE_ZFAST = 6.f;
+template <bool LOSS>
+__device__ __forceinline__ float sigmoid_bce(float z, float t, float& loss_l2) {
+  const float e = exp2f_fast(-fabsf(z) * 1.4426950408889634f);
+  const float r = __fdividef(1.f, 1.f + e);
+  const float p = z >= 0.f ? r : e * r;
+  if (LOSS) {
+    if (z <= BCE_ZFAST && z >= -80.f) {
+      loss_l2 += fmaf(fmaxf(z, 0.f) - t * z, 1.4426950408889634f, __log2f(1.f + e));
+    } else {
+      const float cl = -144.26950408889634f;   // -100 / ln 2
+      loss_l2 -= t * fmaxf(__log2f(p), cl) + (1.f - t) * fmaxf(__log2f(1.f - p), cl);
+    }
+  }
+  return p;
+}
 
-// grid: (bands, heads, B).  smem: taps (start + 3 weights per output index), grid g*g, tmp HM_MAXIN*W floats
+// grid: (bands, heads, B).  smem: tmp HF_MAXIN*W floats, taps (3 weights + start per output index), grid g*g
 template <bool STREAM>
-__global__ void __launch_bounds__(HM_THREADS) heatmap_fwd_kernel(bfk_heatmap_fwd_args a) {
+__global__ void __launch_bounds__(HM_THREADS, 5) heatmap_fwd_kernel(bfk_heatmap_fwd_args a) {
   extern __shared__ __align__(16) float sm[];
   __shared__ float red_f[HM_THREADS / 32];
   __shared__ unsigned long long red_k[HM_THREADS / 32];
   const int g = a.g, W = 16 * g, H = W;
   const int band = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int y0 = band * HM_ROWS, y1 = min(H, y0 + HM_ROWS);
-  float* tmp_s = sm;                                   // [HM_MAXIN][W], 16-byte aligned
-  float* tapw_s = tmp_s + HM_MAXIN * W;                // [W][3]
+  const int y0 = band * HF_ROWS, y1 = min(H, y0 + HF_ROWS);
+  // thread -> fixed float4 column, rows y0+grp, y0+grp+groups, ...
+  const int W4 = W / 4;
+  const int groups = blockDim.x / W4;
+  const int grp = threadIdx.x / W4, x = (threadIdx.x % W4) * 4;
+  const bool has_t = a.target != nullptr;
+  const float* tgt = has_t ? a.target[h] + (long long)b * H * W : nullptr;
+  const float* tmask = (has_t && a.target_mask && ((a.mask_heads >> h) & 1u)) ? a.target_mask + (long long)b * H * W : nullptr;
+  auto load_t = [&](int y) -> float4 {
+    float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_t && grp < groups && y < y1) {
+      const long long off = (long long)y * W + x;
+      tv = STREAM ? ldg_stream4(tgt + off) : __ldg(reinterpret_cast<const float4*>(tgt + off));
+      if (tmask) {
+        const float4 mv = __ldg(reinterpret_cast<const float4*>(tmask + off));
+        tv.x *= mv.x; tv.y *= mv.y; tv.z *= mv.z; tv.w *= mv.w;
+      }
+    }
+    return tv;
+  };
+  // the targets do not depend on anything this CTA computes: their loads go out FIRST and fly during the set-up below
+  float4 tv[HF_BATCH];
+#pragma unroll
+  for (int u = 0; u < HF_BATCH; ++u) tv[u] = load_t(y0 + grp + u * groups);
+
+  float* tmp_s = sm;                                   // [HF_MAXIN][W], 16-byte aligned
+  float* tapw_s = tmp_s + HF_MAXIN * W;                // [W][3]
   int* taps_s = reinterpret_cast<int*>(tapw_s + 3 * W);   // [W]
   float* grid_s = reinterpret_cast<float*>(taps_s + W);   // [g][g]
   const float* gsrc = a.grid + ((long long)b * a.heads + h) * g * g;
@@ -284,71 +337,61 @@ __global__ void __launch_bounds__(HM_THREADS) heatmap_fwd_kernel(bfk_heatmap_fwd
   const int i_hi = min(g, taps_s[y1 - 1] + 3);  // exclusive
   // horizontal pass for the needed input rows
   for (int t = threadIdx.x; t < (i_hi - i_lo) * W; t += blockDim.x) {
-    int ii = t / W, x = t % W;
-    int js = taps_s[x];
-    const float* w = tapw_s + 3 * x;
+    int ii = t / W, xx = t % W;
+    int js = taps_s[xx];
+    const float* w = tapw_s + 3 * xx;
     const float* row = grid_s + (i_lo + ii) * g;
     float v = w[0] * row[js];
     if (js + 1 < g) v = fmaf(w[1], row[js + 1], v);
     if (js + 2 < g) v = fmaf(w[2], row[js + 2], v);
-    tmp_s[ii * W + x] = v;
+    tmp_s[ii * W + xx] = v;
   }
   __syncthreads();
-  const bool has_t = a.target != nullptr;
-  const float* tgt = has_t ? a.target[h] + (long long)b * H * W : nullptr;
-  const float* tmask = (has_t && a.target_mask && ((a.mask_heads >> h) & 1u)) ? a.target_mask + (long long)b * H * W : nullptr;
   float* heat = a.heat + ((long long)h * a.B + b) * H * W;
-  float loss = 0.f;
+  float loss = 0.f;            // in units of ln 2
   float best = -INFINITY;
   uint32_t best_idx = 0xFFFFFFFFu;
-  // thread -> fixed float4 column, rows y0+grp, y0+grp+groups, ... (no integer division in the loop)
-  const int W4 = W / 4;
-  const int groups = HM_THREADS / W4;
-  const int grp = threadIdx.x / W4, x = (threadIdx.x % W4) * 4;
   const int nin = i_hi - i_lo;
   if (grp < groups) {
-    for (int y = y0 + grp; y < y1; y += groups) {
-      const long long off = (long long)y * W + x;
-      float4 tv;
-      if (has_t) {
-        tv = STREAM ? ldg_stream4(tgt + off) : __ldg(reinterpret_cast<const float4*>(tgt + off));
-        if (tmask) {
-          const float4 mv = __ldg(reinterpret_cast<const float4*>(tmask + off));
-          tv.x *= mv.x; tv.y *= mv.y; tv.z *= mv.z; tv.w *= mv.w;
+    for (int yb = y0 + grp; yb < y1; yb += HF_BATCH * groups) {
+      if (yb != y0 + grp) {                                  // later batches (only for g >= 24: more than HF_BATCH rows per thread)
+#pragma unroll
+        for (int u = 0; u < HF_BATCH; ++u) tv[u] = load_t(yb + u * groups);
+      }
+#pragma unroll
+      for (int u = 0; u < HF_BATCH; ++u) {
+        const int y = yb + u * groups;
+        if (y < y1) {
+          const long long off = (long long)y * W + x;
+          const int is = taps_s[y] - i_lo;
+          const float* wy = tapw_s + 3 * y;
+          float4 r0 = *reinterpret_cast<const float4*>(tmp_s + is * W + x);
+          float4 z = make_float4(wy[0] * r0.x, wy[0] * r0.y, wy[0] * r0.z, wy[0] * r0.w);
+          if (is + 1 < nin) {
+            float4 r1 = *reinterpret_cast<const float4*>(tmp_s + (is + 1) * W + x);
+            z.x = fmaf(wy[1], r1.x, z.x); z.y = fmaf(wy[1], r1.y, z.y); z.z = fmaf(wy[1], r1.z, z.z); z.w = fmaf(wy[1], r1.w, z.w);
+          }
+          if (is + 2 < nin) {
+            float4 r2 = *reinterpret_cast<const float4*>(tmp_s + (is + 2) * W + x);
+            z.x = fmaf(wy[2], r2.x, z.x); z.y = fmaf(wy[2], r2.y, z.y); z.z = fmaf(wy[2], r2.z, z.z); z.w = fmaf(wy[2], r2.w, z.w);
+          }
+          float4 p;
+          if (has_t) {
+            p.x = sigmoid_bce<true>(z.x, tv[u].x, loss); p.y = sigmoid_bce<true>(z.y, tv[u].y, loss);
+            p.z = sigmoid_bce<true>(z.z, tv[u].z, loss); p.w = sigmoid_bce<true>(z.w, tv[u].w, loss);
+          } else {
+            p.x = sigmoid_bce<false>(z.x, 0.f, loss); p.y = sigmoid_bce<false>(z.y, 0.f, loss);
+            p.z = sigmoid_bce<false>(z.z, 0.f, loss); p.w = sigmoid_bce<false>(z.w, 0.f, loss);
+          }
+          if (STREAM) stg_stream4(heat + off, p); else *reinterpret_cast<float4*>(heat + off) = p;
+          if (a.argmax_key) {
+            const uint32_t idx = (uint32_t)off;
+            if (p.x > best) { best = p.x; best_idx = idx; }
+            if (p.y > best) { best = p.y; best_idx = idx + 1; }
+            if (p.z > best) { best = p.z; best_idx = idx + 2; }
+            if (p.w > best) { best = p.w; best_idx = idx + 3; }
+          }
         }
-      }
-      const int is = taps_s[y] - i_lo;
-      const float* wy = tapw_s + 3 * y;
-      float4 r0 = *reinterpret_cast<const float4*>(tmp_s + is * W + x);
-      float4 z = make_float4(wy[0] * r0.x, wy[0] * r0.y, wy[0] * r0.z, wy[0] * r0.w);
-      if (is + 1 < nin) {
-        float4 r1 = *reinterpret_cast<const float4*>(tmp_s + (is + 1) * W + x);
-        z.x = fmaf(wy[1], r1.x, z.x); z.y = fmaf(wy[1], r1.y, z.y); z.z = fmaf(wy[1], r1.z, z.z); z.w = fmaf(wy[1], r1.w, z.w);
-      }
-      if (is + 2 < nin) {
-        float4 r2 = *reinterpret_cast<const float4*>(tmp_s + (is + 2) * W + x);
-        z.x = fmaf(wy[2], r2.x, z.x); z.y = fmaf(wy[2], r2.y, z.y); z.z = fmaf(wy[2], r2.z, z.z); z.w = fmaf(wy[2], r2.w, z.w);
-      }
-      // sigmoid with ex2/rcp (rel. error ~3e-7); the BCE below is evaluated from this rounded p, like torch does
-      float4 p = make_float4(__fdividef(1.f, 1.f + __expf(-z.x)), __fdividef(1.f, 1.f + __expf(-z.y)),
-                             __fdividef(1.f, 1.f + __expf(-z.z)), __fdividef(1.f, 1.f + __expf(-z.w)));
-      if (STREAM) stg_stream4(heat + off, p); else *reinterpret_cast<float4*>(heat + off) = p;
-      if (has_t) {
-        // log2 domain (one MUFU each); ln2 and the -100 clamp are applied as -100/ln2 here and *ln2 at the end.
-        // 1 - p is exact near p = 1 (Sterbenz) and rounds to 1 for tiny p (|error| <= 6e-8); log(0) = -inf hits the
-        // clamp exactly like torch's max(log, -100)
-        const float cl = -144.26950408889634f;   // -100 / ln 2
-        loss -= tv.x * fmaxf(__log2f(p.x), cl) + (1.f - tv.x) * fmaxf(__log2f(1.f - p.x), cl);
-        loss -= tv.y * fmaxf(__log2f(p.y), cl) + (1.f - tv.y) * fmaxf(__log2f(1.f - p.y), cl);
-        loss -= tv.z * fmaxf(__log2f(p.z), cl) + (1.f - tv.z) * fmaxf(__log2f(1.f - p.z), cl);
-        loss -= tv.w * fmaxf(__log2f(p.w), cl) + (1.f - tv.w) * fmaxf(__log2f(1.f - p.w), cl);
-      }
-      if (a.argmax_key) {
-        const uint32_t idx = (uint32_t)off;
-        if (p.x > best) { best = p.x; best_idx = idx; }
-        if (p.y > best) { best = p.y; best_idx = idx + 1; }
-        if (p.z > best) { best = p.z; best_idx = idx + 2; }
-        if (p.w > best) { best = p.w; best_idx = idx + 3; }
       }
     }
   }
@@ -738,7 +781,8 @@ extern "C" int32_t bfk_upsample16_taps(int32_t g, int32_t* tap_start, float* tap
   return BFK_OK;
 }
 
-extern "C" int32_t bfk_heatmap_bands(int32_t g) { return (16 * g + HM_ROWS - 1) / HM_ROWS; }
+extern "C" int32_t bfk_heatmap_bands(int32_t g) { return (16 * g + HF_ROWS - 1) / HF_ROWS; }     // forward bands (loss partials)
+static int heatmap_bwd_bands(int g) { return (16 * g + HM_ROWS - 1) / HM_ROWS; }
 
 extern "C" int32_t bfk_heatmap_fwd(const bfk_heatmap_fwd_args* a, bfk_stream_t s_) {
   BFK_CHECK_ARG(a && a->grid && a->tap_start && a->tap_w && a->heat && a->B > 0 && a->heads > 0 && a->g > 0, "bfk_heatmap_fwd: bad arguments");
@@ -746,7 +790,7 @@ extern "C" int32_t bfk_heatmap_fwd(const bfk_heatmap_fwd_args* a, bfk_stream_t s
   cudaStream_t s = to_stream(s_);
   const int W = 16 * a->g, bands = bfk_heatmap_bands(a->g);
   if (a->argmax_key) cudaMemsetAsync(a->argmax_key, 0, sizeof(unsigned long long) * a->heads * a->B, s);
-  size_t smem = ((size_t)HM_MAXIN * W + 3 * (size_t)W + (size_t)W + (size_t)a->g * a->g) * sizeof(float);
+  size_t smem = ((size_t)HF_MAXIN * W + 3 * (size_t)W + (size_t)W + (size_t)a->g * a->g) * sizeof(float);
   bfk_heatmap_fwd_args k = *a;
   static int variant = -1;
   if (variant < 0) { const char* e = getenv("BFK_HM_VARIANT"); variant = e ? atoi(e) : 0; }
@@ -763,14 +807,14 @@ extern "C" int32_t bfk_heatmap_fwd(const bfk_heatmap_fwd_args* a, bfk_stream_t s
 }
 
 extern "C" size_t bfk_heatmap_bwd_workspace_floats(int32_t B, int32_t heads, int32_t g) {
-  return (size_t)B * heads * bfk_heatmap_bands(g) * HM_MAXIN * g;
+  return (size_t)B * heads * heatmap_bwd_bands(g) * HM_MAXIN * g;
 }
 
 extern "C" int32_t bfk_heatmap_bwd(const bfk_heatmap_bwd_args* a, bfk_stream_t s_) {
   BFK_CHECK_ARG(a && a->heat && a->tap_start && a->tap_w && a->dgrid && a->partials && a->g > 0 && 16 * a->g <= 448,
                 "bfk_heatmap_bwd: bad arguments (W <= 448, partials required)");
   BFK_CHECK_ARG(a->mode == 0 ? (a->target && a->gscale) : (a->dheat != nullptr), "bfk_heatmap_bwd: mode inputs missing");
-  const int W = 16 * a->g, bands = bfk_heatmap_bands(a->g);
+  const int W = 16 * a->g, bands = heatmap_bwd_bands(a->g);
   const int groups = HB_THREADS / (W / 4);
   size_t smem = (size_t)groups * HM_MAXIN * W * sizeof(float);
   if (int rc = opt_in_smem(heatmap_bwd_stage1, smem, "heatmap_bwd")) return rc;
