@@ -602,7 +602,7 @@ def main():
         plans = [("C3_context_T3_train", W(w, mode="train", batch=16, context=3, image_size=224, tower="base")),
                  ("C4_infer_b64", W(w, mode="infer", batch=64, context=0, image_size=224, tower="base")),
                  ("C2_384_train", W(w, mode="train", batch=32, context=0, image_size=384, tower="base")),
-                 ("C5_so400m_384_train", W(w, mode="train", batch=8, context=0, image_size=384, tower="so400m"))]
+                 ("C5_so400m_384_train", W(w, mode="train", batch=16, context=0, image_size=384, tower="so400m"))]
         if world == 1:
             plans.insert(2, ("C4_infer_b512", W(w, mode="infer", batch=512, context=0, image_size=224, tower="base")))
         for name, pw in plans:

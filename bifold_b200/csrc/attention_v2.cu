@@ -6,21 +6,27 @@
 // Both kernels here are PERSISTENT (one CTA per SM loops over (sample, head) items) and keep the whole K and V of an item
 // resident in shared memory, so every operand is fetched once per item and the set-up cost is paid once per SM.
 //
-//   attn_fwd_v2 : 10 warps.  Warps 0-3 / 4-7 are two softmax GROUPS; each group owns one 128-row query tile of the item at a
-//                 time (one thread = one query row = one TMEM lane) and ping-pongs with the other group: while one group
-//                 exponentiates its S tile the tensor pipe computes the other group's S = Q K^T / O += P V.  Warp 8 issues every
-//                 tcgen05.mma from one elected thread, warp 9 issues every TMA load; they run ahead through mbarriers, so the
-//                 next item's Q and K land while the current softmax runs (K is released as soon as the last S of the item
-//                 is done, V after the last P V).  The key range is cut into `nblk` blocks of `bw` <= 256 columns chosen so that
-//                 two S tiles (+ two O tiles when nblk > 1) fit the 512 TMEM columns: N = 196 / 64 run with ONE block (plain
-//                 softmax over the whole row, O aliases the S columns), N = 262 with two (online softmax).
+//   attn_fwd_v2 : 10 warps: 8 row warps (two per TMEM lane quarter, each owning half of the key columns of its 32 query rows),
+//                 warp 8 issues every tcgen05.mma from one elected thread, warp 9 every TMA load.  The work of an item is a
+//                 sequence of STEPS (query tile, key block); S of step s+1 is computed into the second TMEM slot while the row
+//                 warps work on step s, P V(s) runs while they work on step s+1, and the output epilogue of a tile runs one step
+//                 late — in the steady state no warp waits for the tensor pipe (round-2 profile of the first version: 47 % of the
+//                 row warps' samples were mbarrier waits).  A row warp reads its half row block from TMEM ONCE into registers
+//                 (maximum and exponentials both come from registers), exchanges the row maximum with its sibling warp through
+//                 shared memory and writes bf16 P into the swizzled tile the P V product reads.  The key range is cut into `nblk`
+//                 blocks of `bw` <= 256 columns so that two S slots (+ two O tiles when nblk > 1) fit the 512 TMEM columns:
+//                 N = 196 / 64 run with ONE block (plain softmax over the whole row, O reuses the S columns), N = 262 with two
+//                 (online softmax, O rescaled in TMEM).  K is released as soon as the last S of the item is done, V after the last
+//                 P V, so the next item's operands land while the current softmax runs.
 //   attn_bwd_v2 : ONE merged kernel for dQ, dK and dV (and the row statistic delta = rowsum(dO * O), which used to be a launch
 //                 of its own).  Q, K, V, dO of the item stay in shared memory; per (128 query rows x 128 keys) block the tensor
 //                 pipe computes S and dP = dO V^T once, all 8 row warps turn them into P and dS (bf16, swizzled shared memory)
 //                 and the three gradient products dQ_i += dS K_j, dV_j += P^T dO_i, dK_j += dS^T Q_i read those tiles as
 //                 K-major / MN-major UMMA operands.  Accumulators: S, dP (128 columns each), dV_j, dK_j and one dQ per query
-//                 tile — 512 TMEM columns at N = 196 / head_dim 64.  S / dP of block b+1 are issued before the gradient
-//                 products of block b, so the exponentials of the next block overlap the tensor work of the current one.
+//                 tile — 512 TMEM columns at N = 196 / head_dim 64.  The row warps pull S / dP into registers, release the TMEM
+//                 columns at once (S / dP of block b+1 are computed while block b is exponentiated), keep P / dS packed in
+//                 registers and store them only when the gradient products of block b-1 have released the shared tiles; the
+//                 statistics of the CTA's next item are fetched while the last products of the current one run.
 //
 // Query-row mask (bifold/models/transformer.py:33-35): a masked row has p == 1/N for every key and dS == 0.
 #include "attention_common.cuh"
@@ -51,23 +57,42 @@ __device__ __forceinline__ int round16(int x) { return (x + 15) & ~15; }
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
-template <int NA>
+// TMEM -> register loads of one warp's share of an S block: NC8 groups of 8 columns, group g predicated on g < n8 (warp-uniform)
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// MAXC: upper bound (multiple of 8) of the S columns one warp holds in registers = bw / 2.
+// A "step" is one (query tile, key block) pair of an item; steps run back to back through the 8 row warps:
+//   S(step)   lives in TMEM slot step & 1  (two slots: the tensor pipe computes S(step + 1) while the warps work on S(step)),
+//   P(step)   in shared-memory slot step & 1,
+//   O(tile)   in TMEM behind / on top of the S slot of parity tile & 1.
+// Each warp reads its half of the S row block from TMEM ONCE into registers (the TMEM read port, 16 fp32 per clock and SM, is
+// as scarce as the MUFU), takes the row maximum there, exchanges it with the sibling warp of its lane quarter through shared
+// memory, exponentiates in place and writes bf16 P.  The epilogue of a tile runs one step late, so its P V product has long
+// finished; nothing in the steady state waits for the tensor pipe.
+template <int NA, int MAXC>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, AttnV2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
-  constexpr uint32_t QT = NA * AT_ATOM;                       // one group's Q tile (128 rows)
+  constexpr uint32_t QT = NA * AT_ATOM;                       // one Q tile (128 rows)
   const uint32_t KATOM = (uint32_t)p.krows * 128u, KT = NA * KATOM;
-  const uint32_t PT = (uint32_t)p.patoms * AT_ATOM;           // one group's P tile (128 rows x bw keys, bf16)
-  const uint32_t sQ = base, sK = sQ + 2 * QT, sV = sK + KT, sP = sV + KT, bars = sP + 2 * PT;
+  const uint32_t PT = (uint32_t)p.patoms * AT_ATOM;           // one P tile (128 rows x bw keys, bf16)
+  const uint32_t sQ = base, sK = sQ + 2 * QT, sV = sK + KT, sP = sV + KT, xch_off = sP + 2 * PT, bars = xch_off + 3 * 1024;
   enum { B_Q = 0, B_QFREE = 2, B_K = 4, B_KFREE = 5, B_V = 6, B_VFREE = 7, B_S = 8, B_P = 10, B_O = 12, B_OF = 14, NBAR = 16 };
   auto BAR = [&](int i) { return bars + 8u * (uint32_t)i; };
   const uint32_t tmem_slot = bars + 8u * NBAR;
+  float* xch = reinterpret_cast<float*>(smem_raw + (xch_off - base));   // [2 parities][2 halves][128] row maxima, then [2][128] row sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ns = p.ntq * p.nblk;                              // steps per item
 
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
-    for (int i = 0; i < NBAR; ++i) mbar_init(BAR(i), (i == B_P || i == B_P + 1 || i == B_OF || i == B_OF + 1) ? 128u : 1u);
+    for (int i = 0; i < NBAR; ++i) mbar_init(BAR(i), (i == B_P || i == B_P + 1 || i == B_OF || i == B_OF + 1) ? 256u : 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -79,13 +104,13 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
-  // group g: S at column g*256; O behind it, or on top of it when the whole row is one block (S is dead once P is in smem)
-  const uint32_t o_off = p.nblk == 1 ? 0u : (uint32_t)p.bw;
+  const uint32_t o_off = p.nblk == 1 ? 0u : (uint32_t)p.bw;   // one block per row: O reuses the columns of its (dead) S tile
 
   if (warp == 9) {
     // ---------------------------------------------- TMA loader ----------------------------------------------
     if (elect_one()) {
       uint32_t qcnt[2] = {0, 0};
+      uint32_t gt = 0;                                         // global tile counter: Q buffer = gt & 1
       int n = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
         const int b = item / p.H, h = item % p.H;
@@ -96,11 +121,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
               tma_load_4d(dst + a * KATOM + (uint32_t)(bx * p.box_rows) * 128u, &map_kv, BAR(bar), 64 * a, slot, bx * p.box_rows, b);
         };
         auto load_q = [&](int i) {
-          const int g = i & 1;
-          if (qcnt[g] > 0) mbar_wait(BAR(B_QFREE + g), (qcnt[g] - 1) & 1);   // the tile's last S product has read the buffer
-          mbar_expect_tx(BAR(B_Q + g), QT);
-          load_tile<NA>(sQ + g * QT, &map_q, BAR(B_Q + g), h, i * 128, b);
-          ++qcnt[g];
+          const int qb = (gt + i) & 1;
+          if (qcnt[qb] > 0) mbar_wait(BAR(B_QFREE + qb), (qcnt[qb] - 1) & 1);   // the last S product of the buffer's previous tile is done
+          mbar_expect_tx(BAR(B_Q + qb), QT);
+          load_tile<NA>(sQ + qb * QT, &map_q, BAR(B_Q + qb), h, i * 128, b);
+          ++qcnt[qb];
         };
         if (n > 0) mbar_wait(BAR(B_KFREE), (n - 1) & 1);
         load_kv(sK, B_K, p.H + h);
@@ -109,6 +134,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (n > 0) mbar_wait(BAR(B_VFREE), (n - 1) & 1);
         load_kv(sV, B_V, 2 * p.H + h);
         for (int i = 2; i < p.ntq; ++i) load_q(i);
+        gt += p.ntq;
       }
     }
   } else if (warp == 8) {
@@ -116,149 +142,164 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     if (elect_one()) {
       const uint32_t idesc_o = make_idesc(128, p.n_o, false, true);
       auto blk_cols = [&](int j) { return round16(min(p.bw, p.N - j * p.bw)); };
-      auto issue_s = [&](int g, int j) {
+      uint32_t qwait[2] = {0, 0};      // tiles whose Q buffer this thread has waited for, per buffer
+      uint32_t pwait[2] = {0, 0};      // bar_p phases consumed, per S slot
+      uint32_t ofwait[2] = {0, 0};     // bar_of phases consumed, per tile parity
+      uint32_t tiles_on[2] = {0, 0};   // tiles started on each tile parity (an O buffer is busy until its epilogue has read it)
+      uint32_t gs = 0, gt = 0;         // global step / tile counters of this CTA
+      int n = 0;
+      // S(step s of the current item) into TMEM slot (gs0 + s) & 1
+      auto issue_s = [&](int s, uint32_t gs0, uint32_t gt0, bool last_of_item) {
+        const int i = s / p.nblk, j = s % p.nblk;
+        const uint32_t slot = (gs0 + s) & 1u, tp = (gt0 + i) & 1u;
+        if (j == 0) {                                            // first block of a tile: its Q tile must have landed
+          mbar_wait(BAR(B_Q + tp), qwait[tp] & 1);
+          ++qwait[tp];
+        }
+        if (p.nblk == 1 && tiles_on[tp] > ofwait[tp]) {          // O of the tile that last used this slot has not been released yet
+          mbar_wait(BAR(B_OF + tp), ofwait[tp] & 1);
+          ++ofwait[tp];
+        }
+        tc_fence_after();
         const uint32_t idesc = make_idesc(128, blk_cols(j), false, false);
-        uint64_t da = kmajor_desc(sQ + g * QT, 0), db = kmajor_desc(sK + (uint32_t)(j * p.bw) * 128u, 0, KATOM);
+        uint64_t da = kmajor_desc(sQ + tp * QT, 0), db = kmajor_desc(sK + (uint32_t)(j * p.bw) * 128u, 0, KATOM);
         for (int k = 0; k < p.ksteps; ++k) {
-          tc_mma_bf16(tmem + g * 256, da, db, idesc, k > 0);
+          tc_mma_bf16(tmem + slot * 256, da, db, idesc, k > 0);
           da += 2; db += 2;
           if ((k & 3) == 3) { da += (AT_ATOM >> 4) - 8; db += (KATOM >> 4) - 8; }
         }
+        tc_commit(BAR(B_S + slot));
+        if (j == p.nblk - 1) tc_commit(BAR(B_QFREE + tp));
+        if (last_of_item) tc_commit(BAR(B_KFREE));
+        if (j == 0) ++tiles_on[tp];
       };
-      auto issue_pv = [&](int g, int j) {
-        const int nk = blk_cols(j) >> 4;
-        uint64_t da = kmajor_desc(sP + g * PT, 0), db = mnmajor_desc(sV + (uint32_t)(j * p.bw) * 128u, 0, KATOM);
-        for (int k = 0; k < nk; ++k) {
-          tc_mma_bf16(tmem + g * 256 + o_off, da, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-          da += 2; db += 2048 >> 4;
-          if ((k & 3) == 3) da += (AT_ATOM >> 4) - 8;
-        }
-      };
-      uint32_t tcnt[2] = {0, 0}, pcnt[2] = {0, 0};
-      int n = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
         mbar_wait(BAR(B_K), n & 1);
-        bool v_ready = false;
-        for (int r0 = 0; r0 < p.ntq; r0 += 2) {
-          const int ng = min(2, p.ntq - r0);
-          const bool last_round = r0 + 2 >= p.ntq;
-          for (int g = 0; g < ng; ++g) {
-            mbar_wait(BAR(B_Q + g), tcnt[g] & 1);
-            if (tcnt[g] > 0) mbar_wait(BAR(B_OF + g), (tcnt[g] - 1) & 1);   // the group has read its previous O tile out of TMEM
-            tc_fence_after();
-            issue_s(g, 0);
-            tc_commit(BAR(B_S + g));
-            if (p.nblk == 1) {
-              tc_commit(BAR(B_QFREE + g));
-              if (last_round && g == ng - 1) tc_commit(BAR(B_KFREE));
-            }
+        issue_s(0, gs, gt, ns == 1);
+        if (ns > 1) issue_s(1, gs, gt, ns == 2);
+        for (int s = 0; s < ns; ++s) {
+          const int i = s / p.nblk, j = s % p.nblk;
+          const uint32_t slot = (gs + s) & 1u, tp = (gt + i) & 1u;
+          mbar_wait(BAR(B_P + slot), pwait[slot] & 1);           // P(s) is in shared memory and S(s) has been read
+          ++pwait[slot];
+          if (s == 0) mbar_wait(BAR(B_V), n & 1);
+          if (p.nblk > 1 && j == 0 && tiles_on[tp] - 1 > ofwait[tp]) {   // separate O buffer: previous tile of this parity read out?
+            mbar_wait(BAR(B_OF + tp), ofwait[tp] & 1);
+            ++ofwait[tp];
           }
-          for (int j = 0; j < p.nblk; ++j) {
-            for (int g = 0; g < ng; ++g) {
-              mbar_wait(BAR(B_P + g), pcnt[g] & 1);     // P(j) is in shared memory and S(j) has been read
-              ++pcnt[g];
-              if (!v_ready) { mbar_wait(BAR(B_V), n & 1); v_ready = true; }
-              tc_fence_after();
-              issue_pv(g, j);
-              if (j + 1 < p.nblk) {
-                issue_s(g, j + 1);                       // in-order completion: bar_s(j+1) also says P V(j) is done
-                tc_commit(BAR(B_S + g));
-                if (j + 2 == p.nblk) {
-                  tc_commit(BAR(B_QFREE + g));
-                  if (last_round && g == ng - 1) tc_commit(BAR(B_KFREE));
-                }
-              } else {
-                tc_commit(BAR(B_O + g));
-                if (last_round && g == ng - 1) tc_commit(BAR(B_VFREE));
-              }
-            }
+          tc_fence_after();
+          const int nk = blk_cols(j) >> 4;
+          uint64_t da = kmajor_desc(sP + slot * PT, 0), db = mnmajor_desc(sV + (uint32_t)(j * p.bw) * 128u, 0, KATOM);
+          for (int k = 0; k < nk; ++k) {
+            tc_mma_bf16(tmem + tp * 256 + o_off, da, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            da += 2; db += 2048 >> 4;
+            if ((k & 3) == 3) da += (AT_ATOM >> 4) - 8;
           }
-          for (int g = 0; g < ng; ++g) ++tcnt[g];
+          tc_commit(BAR(B_O + tp));                              // one phase per P V product (rescale of the next block / epilogue wait for it)
+          if (s == ns - 1) tc_commit(BAR(B_VFREE));
+          if (s + 2 < ns) issue_s(s + 2, gs, gt, s + 3 == ns);
         }
+        gs += ns; gt += p.ntq;
       }
     }
   } else {
-    // ---------------------------------------------- softmax groups ----------------------------------------------
-    const int g = warp >> 2, quarter = warp & 3;
+    // ---------------------------------------------- row warps ----------------------------------------------
+    const int quarter = warp & 3, half = warp >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tS = tmem + g * 256 + lane_off, tO = tS + o_off;
-    const uint32_t myP = sP + g * PT;
-    uint32_t scnt = 0, ocnt = 0;
+    const int cw = p.bw >> 1;                                   // columns of an S block held by this warp: [half * cw, half * cw + cw)
+    uint32_t swait[2] = {0, 0}, owait[2] = {0, 0};
+    uint32_t gs = 0, gt = 0;
+    float* xsum = xch + 512;                                    // [2][128]
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int b = item / p.H, h = item % p.H;
-      for (int i = g; i < p.ntq; i += 2) {
+      float m_run = -INFINITY, l_run = 0.f;
+      // epilogue of tile i (global parity tp): O / rowsum -> global, lse; releases the O buffer
+      auto epilogue = [&](int i, uint32_t tp, float m_fin, float l_part) {
         const int q = i * 128 + r;
-        const bool quarter_live = i * 128 + quarter * 32 < p.N;       // warp-uniform: any real query row in this quarter?
+        const bool quarter_live = i * 128 + quarter * 32 < p.N;
+        mbar_wait(BAR(B_O + tp), owait[tp] & 1);
+        ++owait[tp];
+        tc_fence_after();
+        if (quarter_live) {
+          // total row sum = the two halves' partial sums (same rescaling history)
+          xsum[half * 128 + r] = l_part;
+          named_bar_sync(1 + quarter, 64);
+          const float l_tot = l_part + xsum[(half ^ 1) * 128 + r];
+          named_bar_sync(1 + quarter, 64);
+          const float inv = 1.f / l_tot;
+          __nv_bfloat16* orow = p.out + ((long long)b * p.N + q) * p.ld_out + h * p.hd;
+          const uint32_t tO = tmem + tp * 256 + o_off + lane_off;
+          for (int c = half; c < p.n_o / 16; c += 2) {
+            uint32_t o[16];
+            tc_ld16(tO + c * 16, o);
+            tc_wait_ld();
+            if (q < p.N) store_row16(orow, c * 16, p.hd, o, inv);
+          }
+          if (half == 0 && q < p.N && p.lse) p.lse[((long long)b * p.H + h) * p.N + q] = m_fin * LN2 + logf(l_tot);
+        }
+        tc_fence_before();
+        mbar_arrive(BAR(B_OF + tp));
+      };
+      float m_prev = 0.f, l_prev = 0.f;                         // finished tile waiting for its (deferred) epilogue
+      int pend_tile = -1;
+      for (int s = 0; s < ns; ++s) {
+        const int i = s / p.nblk, j = s % p.nblk;
+        const uint32_t slot = (gs + s) & 1u, tp = (gt + i) & 1u;
+        const int q = i * 128 + r;
+        const bool quarter_live = i * 128 + quarter * 32 < p.N;
         const bool masked = p.row_mask && q < p.N && p.row_mask[(long long)b * p.N + q] == 0.f;
-        const float sl2 = masked ? 0.f : p.scale * LOG2E;            // masked row: every score equal => p == 1 for every key
-        float m_run = -INFINITY, l_run = 0.f;
-        for (int j = 0; j < p.nblk; ++j) {
-          const int nvalid = min(p.bw, p.N - j * p.bw), nc = round16(nvalid);
-          mbar_wait(BAR(B_S + g), scnt & 1);
-          ++scnt;
-          tc_fence_after();
-          if (quarter_live) {
-            // pass 1: row maximum over the real keys
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < nc; c += 32) {
-              uint32_t sreg[32];
-              const int lim = nvalid - c;
-              if (nc - c >= 32) {
-                tc_ld32(tS + c, sreg);
-                tc_wait_ld();
-                if (lim >= 32) {
+        const float sl2 = masked ? 0.f : p.scale * LOG2E;       // masked row: every score equal => p == 1 for every key
+        if (j == 0) { m_run = -INFINITY; l_run = 0.f; }
+        const int nvalid_blk = min(p.bw, p.N - j * p.bw);       // real keys of the block
+        const int c0 = half * cw;                               // first column of this warp
+        const int nvalid = max(0, min(cw, nvalid_blk - c0));    // real keys among this warp's columns
+        const int n8 = (min(round16(nvalid_blk), c0 + cw) - c0 + 7) >> 3;   // 8-column groups the MMA computed for this warp (<= 0: none)
+        mbar_wait(BAR(B_S + slot), swait[slot] & 1);
+        ++swait[slot];
+        tc_fence_after();
+        if (quarter_live) {
+          uint32_t sv[MAXC];
+          const uint32_t tS = tmem + slot * 256 + lane_off + (uint32_t)c0;
 #pragma unroll
-                  for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(sreg[t]));
-                } else {
+          for (int g8 = 0; g8 < MAXC / 8; ++g8)
+            if (g8 < n8) tc_ld8(tS + g8 * 8, sv + g8 * 8);
+          tc_wait_ld();
+          float mx = -INFINITY;
 #pragma unroll
-                  for (int t = 0; t < 32; ++t) if (t < lim) mx = fmaxf(mx, __uint_as_float(sreg[t]));
-                }
-              } else {
-                uint32_t (&s16)[16] = *reinterpret_cast<uint32_t(*)[16]>(sreg);
-                tc_ld16(tS + c, s16);
-                tc_wait_ld();
+          for (int t = 0; t < MAXC; ++t)
+            if (t < nvalid) mx = fmaxf(mx, __uint_as_float(sv[t]));
+          // both halves of a row must subtract the same reference: exchange the maxima (buffers alternate by step parity)
+          float* xm = xch + (slot * 2) * 128;
+          xm[half * 128 + r] = mx;
+          named_bar_sync(1 + quarter, 64);
+          mx = fmaxf(mx, xm[(half ^ 1) * 128 + r]);
+          const float m_new = masked ? 0.f : fmaxf(m_run, mx * sl2);
+          const float alpha = ex2f(m_run - m_new);
+          float rowsum = 0.f;
+          const uint32_t myP = sP + slot * PT;
 #pragma unroll
-                for (int t = 0; t < 16; ++t) if (t < lim) mx = fmaxf(mx, __uint_as_float(s16[t]));
-              }
-            }
-            const float m_new = masked ? 0.f : fmaxf(m_run, mx * sl2);
-            const float alpha = ex2f(m_run - m_new);
-            // pass 2: p = 2^(s*scale*log2e - m) -> bf16 into the swizzled P tile, fp32 row sum
-            float rowsum = 0.f;
-            auto emit8 = [&](const uint32_t* s8, int col) {        // 8 consecutive keys starting at column `col`
+          for (int g8 = 0; g8 < MAXC / 8; ++g8) {
+            if (g8 < n8) {
               float v[8];
 #pragma unroll
-              for (int t = 0; t < 8; ++t) v[t] = ex2f(fmaf(__uint_as_float(s8[t]), sl2, -m_new));
-              if (col + 8 > nvalid) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) if (col + t >= nvalid) v[t] = 0.f;
+              for (int t = 0; t < 8; ++t) {
+                v[t] = ex2f(fmaf(__uint_as_float(sv[g8 * 8 + t]), sl2, -m_new));
+                if (g8 * 8 + t >= nvalid) v[t] = 0.f;           // keys beyond the sequence
+                rowsum += v[t];
               }
-#pragma unroll
-              for (int t = 0; t < 8; ++t) rowsum += v[t];
-              store_p_chunk(myP, r, col >> 3, v);
-            };
-#pragma unroll 1
-            for (int c = 0; c < nc; c += 32) {
-              uint32_t sreg[32];
-              if (nc - c >= 32) {
-                tc_ld32(tS + c, sreg);
-                tc_wait_ld();
-#pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) emit8(sreg + 8 * g8, c + 8 * g8);
-              } else {
-                uint32_t (&s16)[16] = *reinterpret_cast<uint32_t(*)[16]>(sreg);
-                tc_ld16(tS + c, s16);
-                tc_wait_ld();
-#pragma unroll
-                for (int g8 = 0; g8 < 2; ++g8) emit8(sreg + 8 * g8, c + 8 * g8);
-              }
+              store_p_chunk(myP, r, (c0 >> 3) + g8, v);
             }
-            l_run = l_run * alpha + rowsum;
-            m_run = m_new;
-            if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {     // bar_s(j) implies P V(j-1) is complete
-              for (int c = 0; c < p.n_o / 16; ++c) {
+          }
+          l_run = l_run * alpha + rowsum;
+          m_run = m_new;
+          if (j > 0) {                                          // O += needs the old O scaled: wait for P V(j-1), rescale in TMEM
+            mbar_wait(BAR(B_O + tp), owait[tp] & 1);
+            ++owait[tp];
+            tc_fence_after();
+            if (!__all_sync(0xffffffffu, alpha == 1.f)) {
+              const uint32_t tO = tmem + tp * 256 + o_off + lane_off;
+              for (int c = half; c < p.n_o / 16; c += 2) {
                 uint32_t o[16];
                 tc_ld16(tO + c * 16, o);
                 tc_wait_ld();
@@ -269,27 +310,19 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
               tc_wait_st();
             }
           }
-          fence_async_smem();
-          tc_fence_before();
-          mbar_arrive(BAR(B_P + g));
+        } else if (j > 0) {                                     // dead quarter: stay in step with the barrier phases
+          mbar_wait(BAR(B_O + tp), owait[tp] & 1);
+          ++owait[tp];
         }
-        mbar_wait(BAR(B_O + g), ocnt & 1);
-        ++ocnt;
-        tc_fence_after();
-        if (quarter_live) {
-          const float inv = 1.f / l_run;
-          __nv_bfloat16* orow = p.out + ((long long)b * p.N + q) * p.ld_out + h * p.hd;
-          for (int c = 0; c < p.n_o / 16; ++c) {
-            uint32_t o[16];
-            tc_ld16(tO + c * 16, o);
-            tc_wait_ld();
-            if (q < p.N) store_row16(orow, c * 16, p.hd, o, inv);
-          }
-          if (q < p.N && p.lse) p.lse[((long long)b * p.H + h) * p.N + q] = m_run * LN2 + logf(l_run);
-        }
+        fence_async_smem();
         tc_fence_before();
-        mbar_arrive(BAR(B_OF + g));
+        mbar_arrive(BAR(B_P + slot));
+        // deferred epilogue of the tile finished one step ago: its last P V product ran while this step was processed
+        if (pend_tile >= 0) { epilogue(pend_tile, (gt + pend_tile) & 1u, m_prev, l_prev); pend_tile = -1; }
+        if (j == p.nblk - 1) { pend_tile = i; m_prev = m_run; l_prev = l_run; }
       }
+      if (pend_tile >= 0) epilogue(pend_tile, (gt + pend_tile) & 1u, m_prev, l_prev);
+      gs += ns; gt += p.ntq;
     }
   }
   tc_fence_before();
@@ -311,20 +344,21 @@ attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   const uint32_t KATOM = (uint32_t)p.krows * 128u, KT = NA * KATOM;
   constexpr uint32_t BT = 2 * AT_ATOM;                        // P / dS block: 128 query rows x 128 keys (bf16)
   const uint32_t sQ = base, sdO = sQ + KT, sK = sdO + KT, sV = sK + KT, sP = sV + KT, sdS = sP + BT, stat = sdS + BT;
-  const uint32_t stat_bytes = (uint32_t)p.ntq * 128u * 12u;   // float2 {lse*log2e, delta} + int flag per query row
+  const uint32_t stat_rows = (uint32_t)p.ntq * 128u;
+  const uint32_t stat_bytes = 2u * stat_rows * 12u;           // two buffers of {float2 {lse*log2e, delta}, int flag} per query row
   const uint32_t bars = (stat + stat_bytes + 15u) & ~15u;
-  enum { B_LD0 = 0, B_LD1 = 1, B_FREE = 2, B_S = 3, B_P = 4, B_G = 5, NBAR = 6 };
+  enum { B_LD0 = 0, B_LD1 = 1, B_FREE = 2, B_S = 3, B_C = 4, B_P = 5, B_G = 6, NBAR = 7 };
   auto BAR = [&](int i) { return bars + 8u * (uint32_t)i; };
   const uint32_t tmem_slot = bars + 8u * NBAR;
-  float2* s_stat = reinterpret_cast<float2*>(smem_raw + (stat - base));
-  int* s_flag = reinterpret_cast<int*>(smem_raw + (stat - base) + (size_t)p.ntq * 128 * 8);
+  float2* s_stat_all = reinterpret_cast<float2*>(smem_raw + (stat - base));                         // [2][stat_rows]
+  int* s_flag_all = reinterpret_cast<int*>(smem_raw + (stat - base) + (size_t)2 * stat_rows * 8);   // [2][stat_rows]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.N + 127) / 128;              // 128-key blocks (the M tile of dV / dK)
   const int nb = nkb * p.ntq;                     // (query tile, key block) blocks per item, key block outermost
 
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
-    for (int i = 0; i < NBAR; ++i) mbar_init(BAR(i), i == B_P ? 256u : 1u);
+    for (int i = 0; i < NBAR; ++i) mbar_init(BAR(i), (i == B_P || i == B_C) ? 256u : 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -389,10 +423,12 @@ attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         issue_sdp(0);
         for (int bidx = 0; bidx < nb; ++bidx) {
           const int j = bidx / p.ntq, i = bidx % p.ntq;
-          mbar_wait(BAR(B_P), pc & 1);          // P / dS of this block are in shared memory, S / dP have been read
+          mbar_wait(BAR(B_C), pc & 1);          // S / dP of this block are in the row warps' registers: their TMEM columns are free
+          tc_fence_after();
+          if (bidx + 1 < nb) issue_sdp(bidx + 1);    // runs while the warps exponentiate block bidx
+          mbar_wait(BAR(B_P), pc & 1);          // P / dS of this block are in shared memory
           ++pc;
           tc_fence_after();
-          if (bidx + 1 < nb) issue_sdp(bidx + 1);    // first: the row warps wait for these; the gradient products below only feed accumulators
           const int nkk = key_cols(j) >> 4;                                   // K steps over the keys of the block (dQ)
           const int nkq = round16(min(128, p.N - i * 128)) >> 4;              // K steps over the live query rows (dV, dK)
           uint64_t da = kmajor_desc(sdS, 0), db = mnmajor_desc(sK + (uint32_t)j * AT_ATOM, 0, KATOM);
@@ -425,10 +461,13 @@ attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const float log2n = log2f((float)p.N);
     const long long HD = (long long)p.H * p.hd;
     uint32_t sc = 0, gc = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    // per-row statistics of one item into buffer `buf`: {lse * log2e, delta = rowsum(dO * O)};
+    // flag 1 = live, 2 = masked query row (p = 1/N, dS = 0), 0 = beyond N
+    auto compute_stats = [&](int item, int buf) {
       const int b = item / p.H, h = item % p.H;
-      // ---- per-row statistics: {lse * log2e, delta = rowsum(dO * O)}; flag 1 = live, 2 = masked query row (p = 1/N, dS = 0), 0 = beyond N ----
-      for (int row = tid; row < p.ntq * 128; row += 256) {
+      float2* s_stat = s_stat_all + (size_t)buf * stat_rows;
+      int* s_flag = s_flag_all + (size_t)buf * stat_rows;
+      for (int row = tid; row < (int)stat_rows; row += 256) {
         float2 st = make_float2(INFINITY, 0.f);
         int fl = 0;
         if (row < p.N) {
@@ -456,7 +495,14 @@ attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         s_stat[row] = st;
         s_flag[row] = fl;
       }
-      named_bar_sync(1, 256);
+    };
+    int n = 0;
+    if (blockIdx.x < p.items) compute_stats(blockIdx.x, 0);
+    named_bar_sync(1, 256);
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      const int b = item / p.H, h = item % p.H;
+      const float2* s_stat = s_stat_all + (size_t)(n & 1) * stat_rows;
+      const int* s_flag = s_flag_all + (size_t)(n & 1) * stat_rows;
 
       auto epilogue_dkv = [&](int j) {       // half 0 stores dV, half 1 stores dK of key block j
         const int kv = j * 128 + r;
@@ -475,42 +521,68 @@ attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       for (int bidx = 0; bidx < nb; ++bidx) {
         const int j = bidx / p.ntq, i = bidx % p.ntq;
         const int nc = round16(min(128, p.N - j * 128));
+        const bool quarter_live = i * 128 + quarter * 32 < p.N;
+        // this warp's two 32-column chunks of the block: columns half*32 + {0, 64}; results packed to bf16 in registers
+        uint32_t pk[2][16], dk[2][16];
+        int wch[2] = {0, 0};
         mbar_wait(BAR(B_S), sc & 1);
         ++sc;
-        if (bidx > 0) {                       // gradient products of the previous block are done: P / dS may be overwritten,
-          mbar_wait(BAR(B_G), gc & 1);        // and dV / dK of a finished key block are final
-          ++gc;
-        }
         tc_fence_after();
-        if (bidx > 0 && i == 0) epilogue_dkv(j - 1);
-        if (i * 128 + quarter * 32 < p.N) {
+        if (quarter_live) {
           const float2 st = s_stat[i * 128 + r];
           const int fl = s_flag[i * 128 + r];
           const float sl2_eff = fl == 1 ? sl2 : 0.f;
-#pragma unroll 1
-          for (int c = half * 32; c < nc; c += 64) {
-            uint32_t sreg[32], dreg[32];
-            const int w = min(32, nc - c);
-            if (w == 32) {
-              tc_ld32(tS + lane_off + c, sreg);
-              tc_ld32(tdP + lane_off + c, dreg);
-            } else {
-              tc_ld16(tS + lane_off + c, *reinterpret_cast<uint32_t(*)[16]>(sreg));
-              tc_ld16(tdP + lane_off + c, *reinterpret_cast<uint32_t(*)[16]>(dreg));
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int c = half * 32 + u * 64;
+            const int w = max(0, min(32, nc - c));            // 0, 16 or 32 computed columns in this chunk (warp-uniform)
+            wch[u] = w;
+            if (w > 0) {
+              uint32_t sreg[32], dreg[32];
+              if (w == 32) {
+                tc_ld32(tS + lane_off + c, sreg);
+                tc_ld32(tdP + lane_off + c, dreg);
+              } else {
+                tc_ld16(tS + lane_off + c, *reinterpret_cast<uint32_t(*)[16]>(sreg));
+                tc_ld16(tdP + lane_off + c, *reinterpret_cast<uint32_t(*)[16]>(dreg));
+              }
+              tc_wait_ld();
+#pragma unroll
+              for (int t = 0; t < 16; ++t) {
+                if (2 * t < w) {
+                  const float p0 = fl == 0 ? 0.f : ex2f(fmaf(__uint_as_float(sreg[2 * t]), sl2_eff, -st.x));
+                  const float p1 = fl == 0 ? 0.f : ex2f(fmaf(__uint_as_float(sreg[2 * t + 1]), sl2_eff, -st.x));
+                  const float d0 = fl == 1 ? p0 * (__uint_as_float(dreg[2 * t]) - st.y) : 0.f;
+                  const float d1 = fl == 1 ? p1 * (__uint_as_float(dreg[2 * t + 1]) - st.y) : 0.f;
+                  __nv_bfloat162 hp = __floats2bfloat162_rn(p0, p1), hd2 = __floats2bfloat162_rn(d0, d1);
+                  pk[u][t] = *reinterpret_cast<uint32_t*>(&hp);
+                  dk[u][t] = *reinterpret_cast<uint32_t*>(&hd2);
+                }
+              }
             }
-            tc_wait_ld();
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(BAR(B_C));                  // S / dP are in registers: the tensor pipe may overwrite them with the next block
+        if (bidx > 0) {                         // gradient products of the previous block are done: P / dS may be overwritten,
+          mbar_wait(BAR(B_G), gc & 1);          // and dV / dK of a finished key block are final
+          ++gc;
+          tc_fence_after();
+          if (i == 0) epilogue_dkv(j - 1);
+        }
+        if (quarter_live) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int c = half * 32 + u * 64;
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
-              if (g8 * 8 < w) {
-                float pv[8], dv[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                  const float pr = fl == 0 ? 0.f : ex2f(fmaf(__uint_as_float(sreg[g8 * 8 + t]), sl2_eff, -st.x));
-                  pv[t] = pr;
-                  dv[t] = fl == 1 ? pr * (__uint_as_float(dreg[g8 * 8 + t]) - st.y) : 0.f;
-                }
-                store_p_chunk(sP, r, (c >> 3) + g8, pv);
-                store_p_chunk(sdS, r, (c >> 3) + g8, dv);
+              if (g8 * 8 < wch[u]) {
+                const int c16 = (c >> 3) + g8;
+                const uint32_t off = (uint32_t)(c16 >> 3) * AT_ATOM + (uint32_t)r * 128u + (uint32_t)(((c16 & 7) ^ (r & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "r"(pk[u][4 * g8]), "r"(pk[u][4 * g8 + 1]),
+                             "r"(pk[u][4 * g8 + 2]), "r"(pk[u][4 * g8 + 3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS + off), "r"(dk[u][4 * g8]), "r"(dk[u][4 * g8 + 1]),
+                             "r"(dk[u][4 * g8 + 2]), "r"(dk[u][4 * g8 + 3]) : "memory");
               }
             }
           }
@@ -519,6 +591,9 @@ attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         tc_fence_before();
         mbar_arrive(BAR(B_P));
       }
+      // the statistics of the CTA's next item are fetched while the last gradient products run
+      const int next_item = item + gridDim.x;
+      if (next_item < p.items) compute_stats(next_item, (n + 1) & 1);
       mbar_wait(BAR(B_G), gc & 1);
       ++gc;
       tc_fence_after();
@@ -536,7 +611,7 @@ attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         }
       }
       tc_fence_before();
-      named_bar_sync(1, 256);       // the statistics of this item have been read by everybody before the next item overwrites them
+      named_bar_sync(1, 256);       // next item's statistics are complete and visible to every row warp
     }
   }
   tc_fence_before();
@@ -589,7 +664,7 @@ static bool plan_fwd(const bfk_attention_args* a, AttnV2Params& p, size_t& smem)
   }
   if (!ok) return false;
   p.patoms = (p.bw + 63) / 64;
-  smem = (size_t)2 * NA * AT_ATOM + (size_t)2 * NA * p.krows * 128 + (size_t)2 * p.patoms * AT_ATOM + 8 * 16 + 16;
+  smem = (size_t)2 * NA * AT_ATOM + (size_t)2 * NA * p.krows * 128 + (size_t)2 * p.patoms * AT_ATOM + 3 * 1024 + 8 * 16 + 16;
   return smem <= A2_SMEM_MAX;
 }
 
@@ -598,7 +673,7 @@ static bool plan_bwd(const bfk_attention_args* a, AttnV2Params& p, size_t& smem)
   plan_common(a, p);
   const int NA = a->hd <= 64 ? 1 : 2;
   if (256 + (2 + p.ntq) * p.n_o > 512) return false;                   // S, dP, dV, dK and one dQ per query tile in TMEM
-  smem = (size_t)4 * NA * p.krows * 128 + (size_t)4 * AT_ATOM + (size_t)p.ntq * 128 * 12 + 16 + 8 * 6 + 16;
+  smem = (size_t)4 * NA * p.krows * 128 + (size_t)4 * AT_ATOM + (size_t)2 * p.ntq * 128 * 12 + 16 + 8 * 7 + 16;
   return smem <= A2_SMEM_MAX;
 }
 
@@ -618,13 +693,18 @@ int attention_fwd_v2(const bfk_attention_args* a, cudaStream_t s) {
   if (!make_map4(&mq, a->qkv, a->hd, 3 * a->H, a->N, a->B, a->ld_qkv, 128)) return BFK_E_CUDA;
   if (!make_map4(&mkv, a->qkv, a->hd, 3 * a->H, a->N, a->B, a->ld_qkv, p.box_rows)) return BFK_E_CUDA;
   const int grid = p.items < sm_count() ? p.items : sm_count();
+  const int cw = p.bw / 2;
+#define A2_FWD(NA_, MAXC_)                                                                        \
+  do {                                                                                            \
+    if (int rc = set_smem(attn_fwd_v2_kernel<NA_, MAXC_>, smem, "attn_fwd_v2")) return rc;        \
+    attn_fwd_v2_kernel<NA_, MAXC_><<<grid, A2_THREADS, smem, s>>>(mq, mkv, p);                    \
+  } while (0)
   if (a->hd <= 64) {
-    if (int rc = set_smem(attn_fwd_v2_kernel<1>, smem, "attn_fwd_v2")) return rc;
-    attn_fwd_v2_kernel<1><<<grid, A2_THREADS, smem, s>>>(mq, mkv, p);
+    if (cw <= 32) A2_FWD(1, 32); else if (cw <= 72) A2_FWD(1, 72); else if (cw <= 104) A2_FWD(1, 104); else A2_FWD(1, 128);
   } else {
-    if (int rc = set_smem(attn_fwd_v2_kernel<2>, smem, "attn_fwd_v2")) return rc;
-    attn_fwd_v2_kernel<2><<<grid, A2_THREADS, smem, s>>>(mq, mkv, p);
+    if (cw <= 32) A2_FWD(2, 32); else if (cw <= 72) A2_FWD(2, 72); else if (cw <= 104) A2_FWD(2, 104); else A2_FWD(2, 128);
   }
+#undef A2_FWD
   BFK_CHECK_LAUNCH("attention_fwd_v2");
   return BFK_OK;
 }

@@ -290,6 +290,24 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, l
     *d = accumulate ? (*d + alpha * s) : alpha * s;
   }
 }
+// same, four columns per thread (N, ldd, split_stride multiples of 4, 16-byte aligned pointers): the partials are read once as
+// float4 streams and the row / column of an element comes from one division per four elements
+__global__ void __launch_bounds__(256) splitk_reduce4_kernel(const float4* __restrict__ ws, int splits, long long split_stride4, int M,
+                                                             int N4, float alpha, float* __restrict__ D, long long ldd, int accumulate) {
+  const long long total = (long long)M * N4;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    float4 s = __ldcs(ws + i);
+    for (int k = 1; k < splits; ++k) {
+      const float4 v = __ldcs(ws + k * split_stride4 + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const int m = (int)(i / N4), n4 = (int)(i - (long long)m * N4);
+    float4* d = reinterpret_cast<float4*>(D + (long long)m * ldd) + n4;
+    float4 o = make_float4(alpha * s.x, alpha * s.y, alpha * s.z, alpha * s.w);
+    if (accumulate) { const float4 c = *d; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+    *d = o;
+  }
+}
 
 // K splits for short-and-wide problems (wgrad: few output tiles, very long K) so every SM gets work.
 static int choose_splits(const bfk_gemm_args* a, int BN) {
@@ -390,9 +408,17 @@ static int launch_tc_cl(const bfk_gemm_args* a, cudaStream_t s, int splits, bool
   if (rc) return rc;
   if (splits > 1 && !partial_only) {
     const long long total = (long long)a->M * a->N;
-    const int rg = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
-    splitk_reduce_kernel<<<rg, 256, 0, s>>>((const float*)a->workspace, splits, split_stride, a->M, a->N, a->alpha, (float*)a->D, a->ldd,
-                                            a->accumulate);
+    const bool v4 = a->N % 4 == 0 && a->ldd % 4 == 0 && split_stride % 4 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(a->workspace) | reinterpret_cast<uintptr_t>(a->D)) & 15u) == 0;
+    if (v4) {
+      const int rg = (int)std::min<long long>((total / 4 + 255) / 256, (long long)sm_count() * 8);
+      splitk_reduce4_kernel<<<rg, 256, 0, s>>>((const float4*)a->workspace, splits, split_stride / 4, a->M, a->N / 4, a->alpha, (float*)a->D,
+                                               a->ldd, a->accumulate);
+    } else {
+      const int rg = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
+      splitk_reduce_kernel<<<rg, 256, 0, s>>>((const float*)a->workspace, splits, split_stride, a->M, a->N, a->alpha, (float*)a->D, a->ldd,
+                                              a->accumulate);
+    }
   }
   BFK_CHECK_LAUNCH("gemm_tc");
   return BFK_OK;
