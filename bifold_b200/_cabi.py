@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libbifold_b200.so")
 
 F32, BF16 = 0, 1
-BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
+BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05, BACKEND_TCGEN05_PERSISTENT = 0, 1, 2, 3
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_DGELU_TANH, ACT_DGELU_ERF = 0, 1, 2, 3, 4
 ACT_GELU_TANH_GRAD, ACT_GELU_ERF_GRAD, ACT_MUL_AUX = 5, 6, 7
 

@@ -79,7 +79,7 @@ extern "C" int32_t bfk_attention_fwd(const bfk_attention_args* a, bfk_stream_t s
   cudaStream_t s = to_stream(s_);
   const char* why = "";
   if (a->backend != BFK_BACKEND_SIMT && a->dtype == BFK_BF16 && attention_tc_supported(a, false, &why)) return attention_fwd_tc(a, s);
-  if (a->backend == BFK_BACKEND_TCGEN05) { set_error("bfk_attention_fwd: tensor-core backend unsupported: %s", why); return BFK_E_UNSUPPORTED; }
+  if (a->backend >= BFK_BACKEND_TCGEN05) { set_error("bfk_attention_fwd: tensor-core backend unsupported: %s", why); return BFK_E_UNSUPPORTED; }
   return attention_fwd_simt(a, s);
 }
 
@@ -88,6 +88,6 @@ extern "C" int32_t bfk_attention_bwd(const bfk_attention_args* a, bfk_stream_t s
   cudaStream_t s = to_stream(s_);
   const char* why = "";
   if (a->backend != BFK_BACKEND_SIMT && a->dtype == BFK_BF16 && attention_tc_supported(a, true, &why)) return attention_bwd_tc(a, s);
-  if (a->backend == BFK_BACKEND_TCGEN05) { set_error("bfk_attention_bwd: tensor-core backend unsupported: %s", why); return BFK_E_UNSUPPORTED; }
+  if (a->backend >= BFK_BACKEND_TCGEN05) { set_error("bfk_attention_bwd: tensor-core backend unsupported: %s", why); return BFK_E_UNSUPPORTED; }
   return attention_bwd_simt(a, s);
 }

@@ -32,7 +32,8 @@ typedef void* bfk_stream_t; /* cudaStream_t */
 
 enum { BFK_F32 = 0, BFK_BF16 = 1 };
 enum { BFK_OK = 0, BFK_E_INVALID = -1, BFK_E_UNSUPPORTED = -2, BFK_E_CUDA = -3 };
-enum { BFK_BACKEND_AUTO = 0, BFK_BACKEND_SIMT = 1, BFK_BACKEND_TCGEN05 = 2 };
+enum { BFK_BACKEND_AUTO = 0, BFK_BACKEND_SIMT = 1, BFK_BACKEND_TCGEN05 = 2,
+       BFK_BACKEND_TCGEN05_PERSISTENT = 3 /* attention only: force the persistent forward kernel (attention_v2.cu) */ };
 enum {
   BFK_ACT_NONE = 0,
   BFK_ACT_GELU_TANH = 1,   /* HF:323-327 (gelu_pytorch_tanh)            */
