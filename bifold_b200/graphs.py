@@ -25,6 +25,10 @@ import torch
 class GraphedTrainStep:
     """``step(sample) -> loss`` (a device scalar, valid until the next call).
 
+    Drop references to losses of earlier EAGER steps before the capturing call: a live autograd graph keeps its AccumulateGrad
+    nodes bound to the stream they were created on, and autograd then synchronises the capture stream with it (capture fails;
+    the step object falls back to the eager path and records the reason in ``failed``).
+
     The first ``warmup`` calls run eagerly (they also build every cache the capture must not touch: tensor maps,
     pointer tables, split-K workspaces, optimizer flat buffers); the next call captures; later calls replay.
     ``loss_fn(out, sample)`` must return ``(loss, aux)`` like ``bifold.losses`` does.
