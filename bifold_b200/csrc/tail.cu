@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) head_project_bwd_db_kernel(bfk_head_proje
 constexpr int HM_ROWS = 32;  // backward: output rows per CTA
 constexpr int HM_THREADS = 256;
 constexpr int HM_MAXIN = HM_ROWS / 16 + 4;  // input rows feeding a backward band
-constexpr int HF_ROWS = 16;  // forward: output rows per CTA (more, smaller CTAs: 3584 at B = 64 keep every SM streaming)
+constexpr int HF_ROWS = 32;  // forward: output rows per CTA
 constexpr int HF_MAXIN = HF_ROWS / 16 + 4;
 constexpr int HF_BATCH = 4;  // rows of one thread whose target loads are in flight together
 
@@ -275,17 +275,28 @@ constexpr int HF_BATCH = 4;  // rows of one thread whose target loads are in fli
 // below 3e-5 for z <= BCE_ZFAST.  Above it (and where exp(-z) overflows: p == 0, log p == -inf) torch's result is dominated
 // by that rounding and by its -100 clamp, so those pixels take the literal path: logs of the rounded p, clamped.
 constexpr float BCE_ZFAST = 6.f;
-template <bool LOSS>
-__device__ __forceinline__ float sigmoid_bce(float z, float t, float& loss_l2) {
-  const float e = exp2f_fast(-fabsf(z) * 1.4426950408889634f);
+__device__ __forceinline__ float sigmoid_e(float z, float& e) {      // p = sigmoid(z), e = 2^(-|z| log2 e)
+  e = exp2f_fast(-fabsf(z) * 1.4426950408889634f);
   const float r = __fdividef(1.f, 1.f + e);
-  const float p = z >= 0.f ? r : e * r;
+  return z >= 0.f ? r : e * r;
+}
+// four pixels: probabilities and (LOSS) the sum of their BCE terms in units of ln 2; ONE (almost never divergent) branch per four
+template <bool LOSS>
+__device__ __forceinline__ float4 sigmoid_bce4(const float4& z, const float4& t, float& loss_l2) {
+  float4 e, p;
+  p.x = sigmoid_e(z.x, e.x); p.y = sigmoid_e(z.y, e.y); p.z = sigmoid_e(z.z, e.z); p.w = sigmoid_e(z.w, e.w);
   if (LOSS) {
-    if (z <= BCE_ZFAST && z >= -80.f) {
-      loss_l2 += fmaf(fmaxf(z, 0.f) - t * z, 1.4426950408889634f, __log2f(1.f + e));
+    const float zmax = fmaxf(fmaxf(z.x, z.y), fmaxf(z.z, z.w)), zmin = fminf(fminf(z.x, z.y), fminf(z.z, z.w));
+    if (zmax <= BCE_ZFAST && zmin >= -80.f) {
+      const float lin = (fmaxf(z.x, 0.f) - t.x * z.x) + (fmaxf(z.y, 0.f) - t.y * z.y) + (fmaxf(z.z, 0.f) - t.z * z.z) + (fmaxf(z.w, 0.f) - t.w * z.w);
+      // log(1+ex) + log(1+ey) + ... = log2 of the product: two MUFU instead of four (each factor is in (1, 2])
+      loss_l2 += fmaf(lin, 1.4426950408889634f, __log2f((1.f + e.x) * (1.f + e.y)) + __log2f((1.f + e.z) * (1.f + e.w)));
     } else {
       const float cl = -144.26950408889634f;   // -100 / ln 2
-      loss_l2 -= t * fmaxf(__log2f(p), cl) + (1.f - t) * fmaxf(__log2f(1.f - p), cl);
+      loss_l2 -= t.x * fmaxf(__log2f(p.x), cl) + (1.f - t.x) * fmaxf(__log2f(1.f - p.x), cl);
+      loss_l2 -= t.y * fmaxf(__log2f(p.y), cl) + (1.f - t.y) * fmaxf(__log2f(1.f - p.y), cl);
+      loss_l2 -= t.z * fmaxf(__log2f(p.z), cl) + (1.f - t.z) * fmaxf(__log2f(1.f - p.z), cl);
+      loss_l2 -= t.w * fmaxf(__log2f(p.w), cl) + (1.f - t.w) * fmaxf(__log2f(1.f - p.w), cl);
     }
   }
   return p;
@@ -293,7 +304,7 @@ __device__ __forceinline__ float sigmoid_bce(float z, float t, float& loss_l2) {
 
 // grid: (bands, heads, B).  smem: tmp HF_MAXIN*W floats, taps (3 weights + start per output index), grid g*g
 template <bool STREAM>
-__global__ void __launch_bounds__(HM_THREADS, 5) heatmap_fwd_kernel(bfk_heatmap_fwd_args a) {
+__global__ void __launch_bounds__(HM_THREADS, 4) heatmap_fwd_kernel(bfk_heatmap_fwd_args a) {
   extern __shared__ __align__(16) float sm[];
   __shared__ float red_f[HM_THREADS / 32];
   __shared__ unsigned long long red_k[HM_THREADS / 32];
@@ -312,12 +323,8 @@ __global__ void __launch_bounds__(HM_THREADS, 5) heatmap_fwd_kernel(bfk_heatmap_
     if (has_t && grp < groups && y < y1) {
       const long long off = (long long)y * W + x;
       tv = STREAM ? ldg_stream4(tgt + off) : __ldg(reinterpret_cast<const float4*>(tgt + off));
-      if (tmask) {
-        const float4 mv = __ldg(reinterpret_cast<const float4*>(tmask + off));
-        tv.x *= mv.x; tv.y *= mv.y; tv.z *= mv.z; tv.w *= mv.w;
-      }
     }
-    return tv;
+    return tv;      // raw target: nothing may depend on it before the set-up below is done (the optional mask is applied at the use)
   };
   // the targets do not depend on anything this CTA computes: their loads go out FIRST and fly during the set-up below
   float4 tv[HF_BATCH];
@@ -354,10 +361,9 @@ __global__ void __launch_bounds__(HM_THREADS, 5) heatmap_fwd_kernel(bfk_heatmap_
   const int nin = i_hi - i_lo;
   if (grp < groups) {
     for (int yb = y0 + grp; yb < y1; yb += HF_BATCH * groups) {
-      if (yb != y0 + grp) {                                  // later batches (only for g >= 24: more than HF_BATCH rows per thread)
+      float4 tn[HF_BATCH];                                   // the next batch's targets fly while this batch is computed
 #pragma unroll
-        for (int u = 0; u < HF_BATCH; ++u) tv[u] = load_t(yb + u * groups);
-      }
+      for (int u = 0; u < HF_BATCH; ++u) tn[u] = load_t(yb + (HF_BATCH + u) * groups);
 #pragma unroll
       for (int u = 0; u < HF_BATCH; ++u) {
         const int y = yb + u * groups;
@@ -377,11 +383,14 @@ __global__ void __launch_bounds__(HM_THREADS, 5) heatmap_fwd_kernel(bfk_heatmap_
           }
           float4 p;
           if (has_t) {
-            p.x = sigmoid_bce<true>(z.x, tv[u].x, loss); p.y = sigmoid_bce<true>(z.y, tv[u].y, loss);
-            p.z = sigmoid_bce<true>(z.z, tv[u].z, loss); p.w = sigmoid_bce<true>(z.w, tv[u].w, loss);
+            float4 t = tv[u];
+            if (tmask) {
+              const float4 mv = __ldg(reinterpret_cast<const float4*>(tmask + off));
+              t.x *= mv.x; t.y *= mv.y; t.z *= mv.z; t.w *= mv.w;
+            }
+            p = sigmoid_bce4<true>(z, t, loss);
           } else {
-            p.x = sigmoid_bce<false>(z.x, 0.f, loss); p.y = sigmoid_bce<false>(z.y, 0.f, loss);
-            p.z = sigmoid_bce<false>(z.z, 0.f, loss); p.w = sigmoid_bce<false>(z.w, 0.f, loss);
+            p = sigmoid_bce4<false>(z, z, loss);
           }
           if (STREAM) stg_stream4(heat + off, p); else *reinterpret_cast<float4*>(heat + off) = p;
           if (a.argmax_key) {
@@ -393,6 +402,8 @@ __global__ void __launch_bounds__(HM_THREADS, 5) heatmap_fwd_kernel(bfk_heatmap_
           }
         }
       }
+#pragma unroll
+      for (int u = 0; u < HF_BATCH; ++u) tv[u] = tn[u];
     }
   }
   loss *= 0.6931471805599453f;   // back to natural log

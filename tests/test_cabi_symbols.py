@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_cabi._PROTOS) == _declared()
     assert lib.bfk_version() >= 100
-    assert lib.bfk_heatmap_bands(14) == 14
+    assert lib.bfk_heatmap_bands(14) == 7
 
 
 def test_missing_library_fails_loudly(monkeypatch):
