@@ -545,22 +545,40 @@ def tail_roofline(B, g, dev):
     targets = [torch.rand(B, H, H, device=dev) for _ in range(heads)]
     tptr = torch.tensor([t.data_ptr() for t in targets], dtype=torch.int64).to(dev)
     loss = torch.empty(heads + 1, device=dev); key = torch.empty(heads * B, device=dev, dtype=torch.int64)
-    part = torch.empty(heads * B * lib.bfk_heatmap_bands(g), device=dev)
+    part = torch.empty(lib.bfk_heatmap_fwd_workspace_floats(B, heads, g), device=dev)
+    counters = torch.zeros(1 + heads * B, device=dev, dtype=torch.int32)
     fa = K.HeatmapFwdArgs(B, heads, g, grid.data_ptr(), ts.data_ptr(), tw.data_ptr(), heat.data_ptr(), tptr.data_ptr(), None, 0,
-                          loss.data_ptr(), key.data_ptr(), part.data_ptr())
+                          loss.data_ptr(), key.data_ptr(), part.data_ptr(), counters.data_ptr())
+    gscale = torch.ones(heads + 1, device=dev); dgrid = torch.empty(B, heads, g * g, device=dev)
+    ws = torch.empty(lib.bfk_heatmap_bwd_workspace_floats(B, heads, g), device=dev)
+    ba = K.HeatmapBwdArgs(B, heads, g, 0, heat.data_ptr(), tptr.data_ptr(), None, 0, gscale.data_ptr(), 1.0 / (B * H * H), 1, None,
+                          ts.data_ptr(), tw.data_ptr(), dgrid.data_ptr(), ws.data_ptr(), counters.data_ptr())
+    D, Np, Nf = 768, g * g, 65 + g * g + 1
+    X = torch.randn(B * Nf, D, device=dev); w_eff = torch.randn(heads, D, device=dev); b_eff = torch.randn(heads, device=dev)
+    pa = K.HeadProjectArgs(B, heads, Np, D, X.data_ptr(), Nf * D, Nf - Np, w_eff.data_ptr(), b_eff.data_ptr(), grid.data_ptr(),
+                           None, Nf, None, None, 0, None, None, None)
     flush = torch.empty(192 * 1024 * 1024, device=dev, dtype=torch.uint8)
     st = torch.cuda.current_stream().cuda_stream
-    ts_ms = []
-    for it in range(8):
-        flush.sum()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); K.check(lib.bfk_heatmap_fwd(C.byref(fa), st)); e1.record(); torch.cuda.synchronize()
-        if it >= 3:
-            ts_ms.append(e0.elapsed_time(e1))
-    ms = sorted(ts_ms)[len(ts_ms) // 2]
+
+    def med(call):
+        ts_ms = []
+        for it in range(8):
+            flush.sum()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); call(); e1.record(); torch.cuda.synchronize()
+            if it >= 3:
+                ts_ms.append(e0.elapsed_time(e1))
+        return sorted(ts_ms)[len(ts_ms) // 2]
+    ms = med(lambda: K.check(lib.bfk_heatmap_fwd(C.byref(fa), st)))
     by = heads * B * H * H * 4 * 2 + grid.numel() * 4
     peaks = load_peaks()
     ach = by / ms / 1e6
+    others = {}
+    for nm, call, nbytes in (("heatmap_bwd (BCE gradient -> dgrid)", lambda: K.check(lib.bfk_heatmap_bwd(C.byref(ba), st)), heads * B * H * H * 4 * 2),
+                             ("head_project_fwd (fp32 tokens -> 4 x g x g grids)", lambda: K.check(lib.bfk_head_project_fwd(C.byref(pa), st)), B * Np * D * 4)):
+        t_ms = med(call)
+        others[nm] = {"us_per_launch": t_ms * 1e3, "bytes_per_launch": nbytes, "achieved": nbytes / t_ms / 1e6,
+                      "frac": nbytes / t_ms / 1e6 / peaks["hbm_gbs"]}
     t, n = _profile_json("r02_tail_traffic.json")
     traffic = None
     if t is not None:
@@ -568,7 +586,8 @@ def tail_roofline(B, g, dev):
                    "kernel": t.get("kernel"), "shape": t.get("shape"), "source": f"profiles/{n} (ncu --set full)"}
     return {"bound": "hbm", "kernel": "heatmap_fwd_kernel (x16 upsample + sigmoid + BCE + argmax)", "achieved": ach,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "bytes_per_launch": by,
-            "us_per_launch": ms * 1e3, "peak_source": peaks["source"], "how": "isolated launches, L2 flushed between them, CUDA events, median of 5"}
+            "us_per_launch": ms * 1e3, "peak_source": peaks["source"], "other_tail_kernels": others,
+            "how": "isolated launches, L2 flushed between them, CUDA events, median of 5"}
 
 
 # ---------------------------------------------------------------------------------------------------

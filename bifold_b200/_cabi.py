@@ -85,14 +85,14 @@ class HeatmapFwdArgs(C.Structure):
     _fields_ = [("B", i32), ("heads", i32), ("g", i32),
                 ("grid", vp), ("tap_start", vp), ("tap_w", vp), ("heat", vp),
                 ("target", vp), ("target_mask", vp), ("mask_heads", u32),
-                ("loss", vp), ("argmax_key", vp), ("partials", vp)]
+                ("loss", vp), ("argmax_key", vp), ("partials", vp), ("counters", vp)]
 
 
 class HeatmapBwdArgs(C.Structure):
     _fields_ = [("B", i32), ("heads", i32), ("g", i32), ("mode", i32),
                 ("heat", vp), ("target", vp), ("target_mask", vp), ("mask_heads", u32),
                 ("gscale", vp), ("gscale_mul", f32), ("gscale_has_total", i32),
-                ("dheat", vp), ("tap_start", vp), ("tap_w", vp), ("dgrid", vp), ("partials", vp)]
+                ("dheat", vp), ("tap_start", vp), ("tap_w", vp), ("dgrid", vp), ("partials", vp), ("counters", vp)]
 
 
 class ActionArgs(C.Structure):
@@ -153,6 +153,7 @@ _PROTOS = {
     "bfk_head_project_bwd": (i32, [C.POINTER(HeadProjectArgs), vp]),
     "bfk_upsample16_taps": (i32, [i32, vp, vp]),
     "bfk_heatmap_bands": (i32, [i32]),
+    "bfk_heatmap_fwd_workspace_floats": (C.c_size_t, [i32, i32, i32]),
     "bfk_heatmap_fwd": (i32, [C.POINTER(HeatmapFwdArgs), vp]),
     "bfk_heatmap_bwd_workspace_floats": (C.c_size_t, [i32, i32, i32]),
     "bfk_heatmap_bwd": (i32, [C.POINTER(HeatmapBwdArgs), vp]),

@@ -2,6 +2,9 @@
 // x16 bilinear upsample, sigmoid, nn.BCELoss, first-max argmax and the get_action gate.
 // All HBM-bound: the forward heatmap kernel writes heads*H*W*4 B per sample (+ reads as much target).
 #include <math.h>
+#include <algorithm>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -23,6 +26,11 @@ __device__ __forceinline__ unsigned long long pack_key(float v, uint32_t idx) {
 __device__ __forceinline__ float exp2f_fast(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2f_fast(float x) {     // normal positive inputs only (no denormal rescue code)
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {   // read-once data: do not keep it in L1
@@ -182,6 +190,65 @@ __global__ void __launch_bounds__(256) head_project_fwd_kernel(bfk_head_project_
   }
 }
 
+// Fast path (D = 128 NV, heads <= 4): persistent warps, w_eff held in REGISTERS (4 heads x NV float4 per lane), the next
+// token's row prefetched while the current one is reduced: NV (x2) 16-byte loads in flight per lane.
+template <int NV, bool PREFETCH>
+__global__ void __launch_bounds__(128, PREFETCH ? 3 : 2) head_project_fwd_v2_kernel(bfk_head_project_args a) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = (long long)blockIdx.x * 4 + (threadIdx.x >> 5), nw = (long long)gridDim.x * 4;
+  const long long toks = (long long)a.B * a.Np;
+  float4 w[4][NV];
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      w[h][v] = h < a.heads ? __ldg(reinterpret_cast<const float4*>(a.w_eff + (long long)h * a.D) + v * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float be[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) be[h] = h < a.heads ? a.b_eff[h] : 0.f;
+  auto row_of = [&](long long tok) {
+    const int b = (int)(tok / a.Np), n = (int)(tok % a.Np);
+    return a.X + (long long)b * a.x_batch_stride + (long long)(a.row0 + n) * a.D + lane * 4;
+  };
+  float4 x[NV], xn[NV];
+  long long tok = gw;
+  if (tok < toks) {
+    const float* r = row_of(tok);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) x[v] = ldg_stream4(r + v * 128);
+  }
+  for (; tok < toks; tok += nw) {
+    const long long nxt = tok + nw;
+    if (PREFETCH && nxt < toks) {
+      const float* r = row_of(nxt);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) xn[v] = ldg_stream4(r + v * 128);
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+        acc[h] = fmaf(x[v].x, w[h][v].x, fmaf(x[v].y, w[h][v].y, fmaf(x[v].z, w[h][v].z, fmaf(x[v].w, w[h][v].w, acc[h]))));
+#pragma unroll
+    for (int h = 0; h < 4; ++h) acc[h] = warp_sum(acc[h]);
+    const int b = (int)(tok / a.Np), n = (int)(tok % a.Np);
+    if (lane < a.heads) {
+      const float s = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+      const float bb = lane == 0 ? be[0] : lane == 1 ? be[1] : lane == 2 ? be[2] : be[3];
+      a.grid[((long long)b * a.heads + lane) * a.Np + n] = s + bb;
+    }
+    if (PREFETCH) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) x[v] = xn[v];
+    } else if (nxt < toks) {
+      const float* r = row_of(nxt);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) x[v] = ldg_stream4(r + v * 128);
+    }
+  }
+}
+
 // dX rows: grid (Nf, B)
 template <typename T2>
 __global__ void head_project_bwd_dx_kernel(bfk_head_project_args a) {
@@ -261,36 +328,33 @@ __global__ void __launch_bounds__(256) head_project_bwd_db_kernel(bfk_head_proje
   }
 }
 
-// ---- heatmap forward: x16 upsample + sigmoid (+ BCE partials, + argmax) ---------------------------
-constexpr int HM_ROWS = 32;  // backward: output rows per CTA
+// ---- heatmap forward: x16 upsample + sigmoid (+ BCE, + argmax) --------------------------------------------
+// A map (H = W = 16 g) is cut into bands of 16 g / bands rows (default 2 bands: measured best of 1/2/4/8 at B = 64 and 512); one CTA per (band, head, sample).  Threads own a
+// fixed float4 column and walk down the rows of the band, so the set-up (taps, grid, horizontal pass) is paid
+// once per 4 g rows.  The last CTA to finish (device counter, self-resetting) reduces the per-band BCE partial
+// sums and argmax keys in a FIXED order: one launch, deterministic results.
+constexpr int HM_BANDS_DEFAULT = 2;   // forward bands per map (BFK_HM_BANDS overrides; must divide 16)
 constexpr int HM_THREADS = 256;
-constexpr int HM_MAXIN = HM_ROWS / 16 + 4;  // input rows feeding a backward band
-constexpr int HF_ROWS = 32;  // forward: output rows per CTA
-constexpr int HF_MAXIN = HF_ROWS / 16 + 4;
-constexpr int HF_BATCH = 4;  // rows of one thread whose target loads are in flight together
+constexpr int HF_BATCH = 4;   // rows of one thread whose target loads are in flight together
+constexpr int HM_RED = 128;   // logical width of the final loss reduction (independent of the block size)
 
-// One pixel: p = sigmoid(z) and (LOSS) its nn.BCELoss term in units of ln 2, both from e = 2^(-|z| log2 e):
-//   p = z >= 0 ? 1/(1+e) : e/(1+e);   -[t log p + (1-t) log(1-p)] = max(z,0) - t z + log(1 + e)          (3 MUFU: ex2, rcp, lg2)
-// The closed form is what torch computes from its ROUNDED p up to the rounding of 1 - p, i.e. to <= 6e-8 / (1 - p) absolute:
-// below 3e-5 for z <= BCE_ZFAST.  Above it (and where exp(-z) overflows: p == 0, log p == -inf) torch's result is dominated
-// by that rounding and by its -100 clamp, so those pixels take the literal path: logs of the rounded p, clamped.
-constexpr float BCE_ZFAST = 6.f;
-__device__ __forceinline__ float sigmoid_e(float z, float& e) {      // p = sigmoid(z), e = 2^(-|z| log2 e)
-  e = exp2f_fast(-fabsf(z) * 1.4426950408889634f);
-  const float r = __fdividef(1.f, 1.f + e);
-  return z >= 0.f ? r : e * r;
-}
-// four pixels: probabilities and (LOSS) the sum of their BCE terms in units of ln 2; ONE (almost never divergent) branch per four
+// nn.BCELoss computes -[t log p + (1-t) log(1-p)] from the ROUNDED p with both logs clamped at -100.  The closed (softplus) form
+// below equals it up to the rounding of 1 - p, i.e. to <= 6e-8 / (1 - p) absolute: below 3e-5 for z <= BCE_ZFAST.  Above that (and
+// for very negative z) torch's result is dominated by that rounding and by its clamp, so those pixels take the literal path.
+constexpr float BCE_ZFAST = 6.f, BCE_ZLOW = -40.f;
+// four pixels: probabilities and (LOSS) the sum of their BCE terms in units of ln 2; ONE (almost never divergent) branch per four.
+//   e = 2^(-z log2 e) = exp(-z);  p = 1 / (1 + e)  (e = inf for z < -88: p = 0);  BCE = (1 - t) z + log(1 + e)    [softplus form]
+// For z in [BCE_ZLOW, BCE_ZFAST] the four 1 + e are <= 2.4e17, so two products of two stay finite: two lg2 for four pixels.
 template <bool LOSS>
 __device__ __forceinline__ float4 sigmoid_bce4(const float4& z, const float4& t, float& loss_l2) {
-  float4 e, p;
-  p.x = sigmoid_e(z.x, e.x); p.y = sigmoid_e(z.y, e.y); p.z = sigmoid_e(z.z, e.z); p.w = sigmoid_e(z.w, e.w);
+  const float kl = 1.4426950408889634f;
+  const float dx = 1.f + exp2f_fast(-z.x * kl), dy = 1.f + exp2f_fast(-z.y * kl), dz = 1.f + exp2f_fast(-z.z * kl), dw = 1.f + exp2f_fast(-z.w * kl);
+  const float4 p = make_float4(__fdividef(1.f, dx), __fdividef(1.f, dy), __fdividef(1.f, dz), __fdividef(1.f, dw));
   if (LOSS) {
     const float zmax = fmaxf(fmaxf(z.x, z.y), fmaxf(z.z, z.w)), zmin = fminf(fminf(z.x, z.y), fminf(z.z, z.w));
-    if (zmax <= BCE_ZFAST && zmin >= -80.f) {
-      const float lin = (fmaxf(z.x, 0.f) - t.x * z.x) + (fmaxf(z.y, 0.f) - t.y * z.y) + (fmaxf(z.z, 0.f) - t.z * z.z) + (fmaxf(z.w, 0.f) - t.w * z.w);
-      // log(1+ex) + log(1+ey) + ... = log2 of the product: two MUFU instead of four (each factor is in (1, 2])
-      loss_l2 += fmaf(lin, 1.4426950408889634f, __log2f((1.f + e.x) * (1.f + e.y)) + __log2f((1.f + e.z) * (1.f + e.w)));
+    if (zmax <= BCE_ZFAST && zmin >= BCE_ZLOW) {
+      const float lin = fmaf(1.f - t.x, z.x, fmaf(1.f - t.y, z.y, fmaf(1.f - t.z, z.z, (1.f - t.w) * z.w)));
+      loss_l2 += fmaf(lin, kl, lg2f_fast(dx * dy) + lg2f_fast(dz * dw));
     } else {
       const float cl = -144.26950408889634f;   // -100 / ln 2
       loss_l2 -= t.x * fmaxf(__log2f(p.x), cl) + (1.f - t.x) * fmaxf(__log2f(1.f - p.x), cl);
@@ -302,287 +366,392 @@ __device__ __forceinline__ float4 sigmoid_bce4(const float4& z, const float4& t,
   return p;
 }
 
-// grid: (bands, heads, B).  smem: tmp HF_MAXIN*W floats, taps (3 weights + start per output index), grid g*g
-template <bool STREAM>
-__global__ void __launch_bounds__(HM_THREADS, 4) heatmap_fwd_kernel(bfk_heatmap_fwd_args a) {
+// taps of output index i as one 16-byte smem word: {w0, w1, w2, bits(first input index)}
+__device__ __forceinline__ void stage_taps(float4* tap_s, const int32_t* __restrict__ tap_start, const float* __restrict__ tap_w, int W) {
+  for (int i = threadIdx.x; i < W; i += blockDim.x)
+    tap_s[i] = make_float4(tap_w[3 * i], tap_w[3 * i + 1], tap_w[3 * i + 2], __int_as_float(tap_start[i]));
+}
+// whole-block sum of one value per logical lane < HM_RED (fixed tree: identical for every block size >= HM_RED)
+__device__ __forceinline__ float red128(float s, float* red_s) {
+  s = warp_sum(s);
+  __syncthreads();
+  if (threadIdx.x < HM_RED && (threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5] = s;
+  __syncthreads();
+  return (red_s[0] + red_s[1]) + (red_s[2] + red_s[3]);
+}
+__device__ __forceinline__ unsigned long long* hm_key_partials(float* partials, int n_maps, int bands) {
+  return reinterpret_cast<unsigned long long*>(partials + (((long long)n_maps * bands + 1) & ~1ll));
+}
+
+// Final reduction over the bands (all threads of ONE block): loss[h] = sum(partials[h]) / count, loss[heads] = their sum in
+// head order (bifold/losses/__init__.py:84-88); argmax_key[m] = max over the bands of the per-band keys.
+__device__ void hm_finalize(const bfk_heatmap_fwd_args& a, int bands, bool loss, bool keys, float* red_s) {
+  const int n_maps = a.heads * a.B;
+  if (loss) {
+    const int n = a.B * bands;
+    const float W = 16.f * (float)a.g, inv = 1.f / ((float)a.B * W * W);
+    float total = 0.f;
+    for (int h = 0; h < a.heads; ++h) {
+      float s = 0.f;
+      if (threadIdx.x < HM_RED)
+        for (int i = threadIdx.x; i < n; i += HM_RED) s += __ldcg(a.partials + (long long)h * n + i);
+      const float t = red128(s, red_s) * inv;
+      if (threadIdx.x == 0) a.loss[h] = t;
+      total = h == 0 ? t : total + t;
+    }
+    if (threadIdx.x == 0) a.loss[a.heads] = total;
+  }
+  if (keys) {
+    const unsigned long long* kp = hm_key_partials(a.partials, n_maps, bands);
+    for (int m = threadIdx.x; m < n_maps; m += blockDim.x) {
+      unsigned long long k = 0ull;
+      for (int q = 0; q < bands; ++q) { const unsigned long long o = __ldcg(kp + (long long)m * bands + q); k = o > k ? o : k; }
+      a.argmax_key[m] = k;
+    }
+  }
+}
+__global__ void __launch_bounds__(HM_RED) heatmap_finalize_kernel(bfk_heatmap_fwd_args a, int bands, int loss, int keys) {
+  __shared__ float red_s[4];
+  hm_finalize(a, bands, loss != 0, keys != 0, red_s);
+}
+
+// grid: (bands, heads, B).  smem: taps [W] float4, tmp [(nin_max + 2)][W], grid [g*g]
+template <bool LOSS, bool MASK, bool ARGMAX, int MINB>
+__global__ void __launch_bounds__(HM_THREADS, MINB) heatmap_fwd_kernel(bfk_heatmap_fwd_args a, int nin_max) {
   extern __shared__ __align__(16) float sm[];
   __shared__ float red_f[HM_THREADS / 32];
   __shared__ unsigned long long red_k[HM_THREADS / 32];
-  const int g = a.g, W = 16 * g, H = W;
+  __shared__ int last_s;
+  const int g = a.g, W = 16 * g, bands = gridDim.x, R = W / bands;
   const int band = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int y0 = band * HF_ROWS, y1 = min(H, y0 + HF_ROWS);
-  // thread -> fixed float4 column, rows y0+grp, y0+grp+groups, ...
+  const int y0 = band * R, y1 = y0 + R;
   const int W4 = W / 4;
-  const int groups = blockDim.x / W4;
+  const int groups = blockDim.x / W4;                 // rows worked on in parallel; thread -> fixed float4 column
   const int grp = threadIdx.x / W4, x = (threadIdx.x % W4) * 4;
-  const bool has_t = a.target != nullptr;
-  const float* tgt = has_t ? a.target[h] + (long long)b * H * W : nullptr;
-  const float* tmask = (has_t && a.target_mask && ((a.mask_heads >> h) & 1u)) ? a.target_mask + (long long)b * H * W : nullptr;
-  auto load_t = [&](int y) -> float4 {
-    float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_t && grp < groups && y < y1) {
-      const long long off = (long long)y * W + x;
-      tv = STREAM ? ldg_stream4(tgt + off) : __ldg(reinterpret_cast<const float4*>(tgt + off));
-    }
-    return tv;      // raw target: nothing may depend on it before the set-up below is done (the optional mask is applied at the use)
-  };
+  const bool active = grp < groups;
+  const long long map_off = (long long)b * W * W;
+  const float* tgt = LOSS ? a.target[h] + map_off : nullptr;
+  const bool masked = MASK && ((a.mask_heads >> h) & 1u);
+  const float* tmask = a.target_mask + map_off;        // dereferenced only if `masked`
+  // thread-relative addressing: 32-bit element offsets from per-thread base pointers (row r of this thread = r * stride)
+  const int nrows = active ? (R - grp + groups - 1) / groups : 0;
+  const int stride = groups * W, off0 = (y0 + grp) * W + x;
+  const float* tg = tgt + off0;
   // the targets do not depend on anything this CTA computes: their loads go out FIRST and fly during the set-up below
   float4 tv[HF_BATCH];
+  if (LOSS) {
 #pragma unroll
-  for (int u = 0; u < HF_BATCH; ++u) tv[u] = load_t(y0 + grp + u * groups);
-
-  float* tmp_s = sm;                                   // [HF_MAXIN][W], 16-byte aligned
-  float* tapw_s = tmp_s + HF_MAXIN * W;                // [W][3]
-  int* taps_s = reinterpret_cast<int*>(tapw_s + 3 * W);   // [W]
-  float* grid_s = reinterpret_cast<float*>(taps_s + W);   // [g][g]
+    for (int u = 0; u < HF_BATCH; ++u) tv[u] = u < nrows ? ldg_stream4(tg + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4* tap_s = reinterpret_cast<float4*>(sm);        // [W]
+  float* tmp_s = sm + 4 * W;                            // [(nin_max + 2)][W]
+  float* grid_s = tmp_s + (nin_max + 2) * W;            // [g][g]
   const float* gsrc = a.grid + ((long long)b * a.heads + h) * g * g;
   for (int i = threadIdx.x; i < g * g; i += blockDim.x) grid_s[i] = gsrc[i];
-  for (int i = threadIdx.x; i < W; i += blockDim.x) taps_s[i] = a.tap_start[i];
-  for (int i = threadIdx.x; i < 3 * W; i += blockDim.x) tapw_s[i] = a.tap_w[i];
+  stage_taps(tap_s, a.tap_start, a.tap_w, W);
   __syncthreads();
-  const int i_lo = taps_s[y0];
-  const int i_hi = min(g, taps_s[y1 - 1] + 3);  // exclusive
-  // horizontal pass for the needed input rows
-  for (int t = threadIdx.x; t < (i_hi - i_lo) * W; t += blockDim.x) {
-    int ii = t / W, xx = t % W;
-    int js = taps_s[xx];
-    const float* w = tapw_s + 3 * xx;
-    const float* row = grid_s + (i_lo + ii) * g;
-    float v = w[0] * row[js];
-    if (js + 1 < g) v = fmaf(w[1], row[js + 1], v);
-    if (js + 2 < g) v = fmaf(w[2], row[js + 2], v);
-    tmp_s[ii * W + xx] = v;
+  const int i_lo = __float_as_int(tap_s[y0].w);
+  const int nin = min(g, __float_as_int(tap_s[y1 - 1].w) + 3) - i_lo;     // <= nin_max (checked on the host)
+  // horizontal pass for the input rows this band needs (+ two zero rows: taps past the grid carry weight 0)
+  for (int xx = threadIdx.x; xx < W; xx += blockDim.x) {
+    const float4 tp = tap_s[xx];
+    const int js = __float_as_int(tp.w), j1 = min(js + 1, g - 1), j2 = min(js + 2, g - 1);
+    for (int ii = 0; ii < nin; ++ii) {
+      const float* row = grid_s + (i_lo + ii) * g;
+      tmp_s[ii * W + xx] = fmaf(tp.z, row[j2], fmaf(tp.y, row[j1], tp.x * row[js]));
+    }
+    tmp_s[nin * W + xx] = 0.f;
+    tmp_s[(nin + 1) * W + xx] = 0.f;
   }
   __syncthreads();
-  float* heat = a.heat + ((long long)h * a.B + b) * H * W;
+  float* hp = a.heat + ((long long)h * a.B + b) * W * W + off0;
+  const float4* tp = tap_s + y0 + grp;
+  const float* tmx = tmp_s + x - i_lo * W;       // + (first input row of an output row) * W
+  const float* tmk = tmask + off0;
   float loss = 0.f;            // in units of ln 2
   float best = -INFINITY;
   uint32_t best_idx = 0xFFFFFFFFu;
-  const int nin = i_hi - i_lo;
-  if (grp < groups) {
-    for (int yb = y0 + grp; yb < y1; yb += HF_BATCH * groups) {
-      float4 tn[HF_BATCH];                                   // the next batch's targets fly while this batch is computed
+  float4 tn[HF_BATCH];
+  // one batch of HF_BATCH rows: the other buffer's targets (rows r + HF_BATCH ..) are requested first and fly during the maths
+  auto batch = [&](int r, const float4 (&tc)[HF_BATCH], float4 (&tnext)[HF_BATCH]) {
+    if (LOSS) {
 #pragma unroll
-      for (int u = 0; u < HF_BATCH; ++u) tn[u] = load_t(yb + (HF_BATCH + u) * groups);
+      for (int u = 0; u < HF_BATCH; ++u)
+        tnext[u] = r + HF_BATCH + u < nrows ? ldg_stream4(tg + (r + HF_BATCH + u) * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
-      for (int u = 0; u < HF_BATCH; ++u) {
-        const int y = yb + u * groups;
-        if (y < y1) {
-          const long long off = (long long)y * W + x;
-          const int is = taps_s[y] - i_lo;
-          const float* wy = tapw_s + 3 * y;
-          float4 r0 = *reinterpret_cast<const float4*>(tmp_s + is * W + x);
-          float4 z = make_float4(wy[0] * r0.x, wy[0] * r0.y, wy[0] * r0.z, wy[0] * r0.w);
-          if (is + 1 < nin) {
-            float4 r1 = *reinterpret_cast<const float4*>(tmp_s + (is + 1) * W + x);
-            z.x = fmaf(wy[1], r1.x, z.x); z.y = fmaf(wy[1], r1.y, z.y); z.z = fmaf(wy[1], r1.z, z.z); z.w = fmaf(wy[1], r1.w, z.w);
-          }
-          if (is + 2 < nin) {
-            float4 r2 = *reinterpret_cast<const float4*>(tmp_s + (is + 2) * W + x);
-            z.x = fmaf(wy[2], r2.x, z.x); z.y = fmaf(wy[2], r2.y, z.y); z.z = fmaf(wy[2], r2.z, z.z); z.w = fmaf(wy[2], r2.w, z.w);
-          }
-          float4 p;
-          if (has_t) {
-            float4 t = tv[u];
-            if (tmask) {
-              const float4 mv = __ldg(reinterpret_cast<const float4*>(tmask + off));
-              t.x *= mv.x; t.y *= mv.y; t.z *= mv.z; t.w *= mv.w;
-            }
-            p = sigmoid_bce4<true>(z, t, loss);
-          } else {
-            p = sigmoid_bce4<false>(z, z, loss);
-          }
-          if (STREAM) stg_stream4(heat + off, p); else *reinterpret_cast<float4*>(heat + off) = p;
-          if (a.argmax_key) {
-            const uint32_t idx = (uint32_t)off;
-            if (p.x > best) { best = p.x; best_idx = idx; }
-            if (p.y > best) { best = p.y; best_idx = idx + 1; }
-            if (p.z > best) { best = p.z; best_idx = idx + 2; }
-            if (p.w > best) { best = p.w; best_idx = idx + 3; }
+    for (int u = 0; u < HF_BATCH; ++u) {
+      if (r + u < nrows) {
+        const int o = (r + u) * stride;
+        const float4 wy = tp[(r + u) * groups];
+        const float* rp = tmx + __float_as_int(wy.w) * W;
+        const float4 r0 = *reinterpret_cast<const float4*>(rp);
+        const float4 r1 = *reinterpret_cast<const float4*>(rp + W);
+        const float4 r2 = *reinterpret_cast<const float4*>(rp + 2 * W);
+        float4 z;
+        z.x = fmaf(wy.z, r2.x, fmaf(wy.y, r1.x, wy.x * r0.x));
+        z.y = fmaf(wy.z, r2.y, fmaf(wy.y, r1.y, wy.x * r0.y));
+        z.z = fmaf(wy.z, r2.z, fmaf(wy.y, r1.z, wy.x * r0.z));
+        z.w = fmaf(wy.z, r2.w, fmaf(wy.y, r1.w, wy.x * r0.w));
+        float4 t = LOSS ? tc[u] : z;
+        if (masked) {
+          const float4 mv = __ldg(reinterpret_cast<const float4*>(tmk + o));
+          t.x *= mv.x; t.y *= mv.y; t.z *= mv.z; t.w *= mv.w;
+        }
+        const float4 p = sigmoid_bce4<LOSS>(z, t, loss);
+        *reinterpret_cast<float4*>(hp + o) = p;
+        if (ARGMAX) {
+          const float m = fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w));
+          if (m > best) {      // first maximum: strict, rows visited in increasing order
+            best = m;
+            best_idx = (uint32_t)(off0 + o) + (p.x == m ? 0u : p.y == m ? 1u : p.z == m ? 2u : 3u);
           }
         }
       }
-#pragma unroll
-      for (int u = 0; u < HF_BATCH; ++u) tv[u] = tn[u];
     }
+  };
+  for (int r = 0; r < nrows; r += 2 * HF_BATCH) {
+    batch(r, tv, tn);
+    if (r + HF_BATCH < nrows) batch(r + HF_BATCH, tn, tv);
   }
-  loss *= 0.6931471805599453f;   // back to natural log
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (has_t) {
-    loss = warp_sum(loss);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  if (LOSS) {
+    loss = warp_sum(loss * 0.6931471805599453f);   // back to natural log
     if (lane == 0) red_f[warp] = loss;
   }
-  if (a.argmax_key) {
+  if (ARGMAX) {
     unsigned long long k = best_idx == 0xFFFFFFFFu ? 0ull : pack_key(best, best_idx);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
       k = other > k ? other : k;
     }
     if (lane == 0) red_k[warp] = k;
   }
   __syncthreads();
+  const long long map = (long long)h * a.B + b;
   if (threadIdx.x == 0) {
-    if (has_t) {
+    if (LOSS) {
       float s = 0.f;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red_f[w];
-      a.partials[((long long)h * a.B + b) * gridDim.x + band] = s;
+      for (int w = 0; w < nwarp; ++w) s += red_f[w];
+      a.partials[map * bands + band] = s;
     }
-    if (a.argmax_key) {
+    if (ARGMAX) {
       unsigned long long k = 0ull;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) k = red_k[w] > k ? red_k[w] : k;
-      atomicMax(a.argmax_key + (long long)h * a.B + b, k);
+      for (int w = 0; w < nwarp; ++w) k = red_k[w] > k ? red_k[w] : k;
+      if (a.partials) hm_key_partials(a.partials, a.heads * a.B, bands)[map * bands + band] = k;
+      else atomicMax(a.argmax_key + map, k);             // no workspace: keys pre-zeroed by the launcher
+    }
+    last_s = 0;
+    if (a.counters) {
+      __threadfence();
+      const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+      last_s = atomicAdd(reinterpret_cast<unsigned*>(a.counters), 1u) == total - 1u;
     }
   }
-}
-
-// single block.  loss[h] = sum(partials[h]) / count for h < heads; optionally loss[heads] = sum_h loss[h]
-// (left-to-right, the order of bifold/losses/__init__.py:84-88).  Fixed assignment + fixed tree => deterministic.
-__global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ partials, int heads, int n_per_head,
-                                                            float inv_count, float* __restrict__ loss, int write_total) {
-  __shared__ float red[8];
-  float total = 0.f;
-  for (int h = 0; h < heads; ++h) {
-    float s = 0.f;
-    for (int i = threadIdx.x; i < n_per_head; i += 256) s += partials[(long long)h * n_per_head + i];
-    s = warp_sum(s);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float t = 0.f;
-      for (int w = 0; w < 8; ++w) t += red[w];
-      t *= inv_count;
-      loss[h] = t;
-      total = h == 0 ? t : total + t;
-    }
+  __syncthreads();
+  if (last_s) {        // every other CTA's partials are visible: reduce them here instead of in a second launch
+    __threadfence();
+    hm_finalize(a, bands, LOSS, ARGMAX && a.partials != nullptr, red_f);
+    if (threadIdx.x == 0) a.counters[0] = 0;
   }
-  if (threadIdx.x == 0 && write_total) loss[heads] = total;
 }
 
 // ---- heatmap backward: dlogit -> dgrid through the transposed composite upsample -----------------------
-// Stage 1, grid (bands, heads, B): a CTA streams HM_ROWS rows of (heat, target | dheat) once (float4, coalesced),
-// folds them vertically into the <= HM_MAXIN grid rows they touch (registers), then horizontally into grid
-// columns (shared memory) and writes one partial [HM_MAXIN][g] block.  Stage 2 sums the bands of a map in
-// fixed order (deterministic).  HBM-bound: reads heads*H*W*4 B (x2 with targets) per sample.
-constexpr int HB_THREADS = 256;
-__global__ void __launch_bounds__(HB_THREADS) heatmap_bwd_stage1(bfk_heatmap_bwd_args a, float* __restrict__ partials) {
-  extern __shared__ __align__(16) float sm[];
-  const int g = a.g, W = 16 * g, H = W, W4 = W / 4;
-  const int band = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int y0 = band * HM_ROWS, y1 = min(H, y0 + HM_ROWS);
-  const int i_lo = a.tap_start[y0];
-  const int groups = HB_THREADS / W4;                 // row groups working in parallel (>= 2 for W <= 448)
-  const int grp = threadIdx.x / W4, x4 = threadIdx.x % W4;
-  float* tmp = sm;                                     // [groups][HM_MAXIN][W]
-  const float* heat = a.heat + ((long long)h * a.B + b) * H * W;
-  const float* tgt = nullptr; const float* tmask = nullptr; const float* dheat = nullptr;
-  float gs = 0.f;
-  if (a.mode == 0) {
-    tgt = a.target[h] + (long long)b * H * W;
-    if (a.target_mask && ((a.mask_heads >> h) & 1u)) tmask = a.target_mask + (long long)b * H * W;
-    gs = (a.gscale[h] + (a.gscale_has_total ? a.gscale[a.heads] : 0.f)) * a.gscale_mul;
-  } else {
-    dheat = a.dheat[h] ? a.dheat[h] + (long long)b * H * W : nullptr;
-  }
-  float4 acc[HM_MAXIN];
-#pragma unroll
-  for (int ii = 0; ii < HM_MAXIN; ++ii) acc[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (grp < groups) {
-    constexpr int RB = 2;   // rows whose loads are issued together
-    for (int yb = y0 + grp; yb < y1; yb += groups * RB) {
-      float4 pv[RB], qv[RB];
-#pragma unroll
-      for (int k = 0; k < RB; ++k) {
-        const int y = yb + k * groups;
-        if (y < y1) {
-          const long long off = (long long)y * W + x4 * 4;
-          pv[k] = ldg_stream4(heat + off);
-          if (a.mode == 0) {
-            qv[k] = ldg_stream4(tgt + off);
-            if (tmask) {
-              const float4 m = ldg_stream4(tmask + off);
-              qv[k].x *= m.x; qv[k].y *= m.y; qv[k].z *= m.z; qv[k].w *= m.w;
-            }
-          } else if (dheat) {
-            qv[k] = ldg_stream4(dheat + off);
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < RB; ++k) {
-      const int y = yb + k * groups;
-      if (y >= y1) break;
-      const float4 p = pv[k];
-      float4 d;
-      if (a.mode == 0) {
-        const float4 t = qv[k];
-        d = make_float4(gs * (p.x - t.x), gs * (p.y - t.y), gs * (p.z - t.z), gs * (p.w - t.w));
-      } else if (dheat) {
-        const float4 u = qv[k];
-        d = make_float4(u.x * p.x * (1.f - p.x), u.y * p.y * (1.f - p.y), u.z * p.z * (1.f - p.z), u.w * p.w * (1.f - p.w));
-      } else {
-        d = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      const int is = a.tap_start[y] - i_lo;              // uniform across the CTA for a given y: no divergence
-      const float w0 = a.tap_w[3 * y], w1 = a.tap_w[3 * y + 1], w2 = a.tap_w[3 * y + 2];
-#define BFK_ACC3(I)                                                                                              \
-      acc[I].x = fmaf(w0, d.x, acc[I].x); acc[I].y = fmaf(w0, d.y, acc[I].y);                                    \
-      acc[I].z = fmaf(w0, d.z, acc[I].z); acc[I].w = fmaf(w0, d.w, acc[I].w);                                    \
-      acc[I + 1].x = fmaf(w1, d.x, acc[I + 1].x); acc[I + 1].y = fmaf(w1, d.y, acc[I + 1].y);                    \
-      acc[I + 1].z = fmaf(w1, d.z, acc[I + 1].z); acc[I + 1].w = fmaf(w1, d.w, acc[I + 1].w);                    \
-      acc[I + 2].x = fmaf(w2, d.x, acc[I + 2].x); acc[I + 2].y = fmaf(w2, d.y, acc[I + 2].y);                    \
-      acc[I + 2].z = fmaf(w2, d.z, acc[I + 2].z); acc[I + 2].w = fmaf(w2, d.w, acc[I + 2].w);
-      switch (is) {   // taps beyond the grid carry weight 0 and land in accumulator rows that stage 2 never reads
-        case 0: BFK_ACC3(0) break;
-        case 1: BFK_ACC3(1) break;
-        case 2: BFK_ACC3(2) break;
-        default: BFK_ACC3(3) break;
-      }
-#undef BFK_ACC3
-      }
-    }
-#pragma unroll
-    for (int ii = 0; ii < HM_MAXIN; ++ii)
-      *reinterpret_cast<float4*>(tmp + ((long long)(grp * HM_MAXIN + ii)) * W + x4 * 4) = acc[ii];
-  }
-  __syncthreads();
-  // combine the row groups (fixed order) into group 0
-  for (int t = threadIdx.x; t < HM_MAXIN * W; t += HB_THREADS) {
-    float v = tmp[t];
-    for (int gq = 1; gq < groups; ++gq) v += tmp[(long long)gq * HM_MAXIN * W + t];
-    tmp[t] = v;
-  }
-  __syncthreads();
-  // horizontal fold: out[ii][j] = sum_x Cx[x][j] * tmp[ii][x];  x in the support of j
-  float* out = partials + ((((long long)b * a.heads + h) * gridDim.x + band) * HM_MAXIN) * g;
-  for (int t = threadIdx.x; t < HM_MAXIN * g; t += HB_THREADS) {
-    const int ii = t / g, j = t % g;
-    const int xlo = max(0, 16 * j - 32), xhi = min(W, 16 * j + 48);
-    float sacc = 0.f;
-    for (int x = xlo; x < xhi; ++x) {
-      const int k = j - a.tap_start[x];
-      if (k >= 0 && k < 3) sacc = fmaf(a.tap_w[3 * x + k], tmp[ii * W + x], sacc);
-    }
-    out[t] = sacc;
-  }
-}
-// grid (heads, B): dgrid[b,h,i,j] = sum over bands of the partial rows that map to grid row i
-__global__ void heatmap_bwd_stage2(bfk_heatmap_bwd_args a, const float* __restrict__ partials, int bands) {
-  const int g = a.g, H = 16 * g;
-  const int h = blockIdx.x, b = blockIdx.y;
+// grid (bands, heads, B): a CTA streams 16 g / bands rows of (heat, target | dheat) once (float4, coalesced), folds them
+// vertically into the grid rows they touch (a sliding window of three accumulator rows in registers, flushed to
+// shared memory as the window moves), combines the row groups, folds horizontally through a transposed tap table
+// and writes one partial [nin][g] block.  The last CTA of a map (per-map device counter, self-resetting) sums the
+// bands in fixed order (deterministic).  HBM-bound: reads heads*H*W*4 B (x2 with targets) per sample.
+constexpr int HB_BANDS_DEFAULT = 1;  // backward bands per map (BFK_HB_BANDS overrides; measured best of 1/2/4): the folds after the streaming loop are paid once per band
+constexpr int HB_SPAN = 80;   // output indices that can touch one grid column: [16 j - 32, 16 j + 48)
+
+__device__ void hb_sum_bands(const bfk_heatmap_bwd_args& a, const float* __restrict__ partials, int nin_max, int bands, int b, int h,
+                             const float4* tap_s) {
+  const int g = a.g, R = 16 * g / bands;
   float* out = a.dgrid + ((long long)b * a.heads + h) * g * g;
   for (int t = threadIdx.x; t < g * g; t += blockDim.x) {
     const int i = t / g, j = t % g;
     float s = 0.f;
     for (int band = 0; band < bands; ++band) {
-      const int i_lo = a.tap_start[band * HM_ROWS];
+      const int i_lo = __float_as_int(tap_s[band * R].w);
+      const int nin = min(g, __float_as_int(tap_s[band * R + R - 1].w) + 3) - i_lo;
       const int ii = i - i_lo;
-      if (ii >= 0 && ii < HM_MAXIN) s += partials[((((long long)b * a.heads + h) * bands + band) * HM_MAXIN + ii) * g + j];
+      if (ii >= 0 && ii < nin)
+        s += __ldcg(partials + ((((long long)b * a.heads + h) * bands + band) * nin_max + ii) * g + j);
     }
     out[t] = s;
   }
-  (void)H;
+}
+__global__ void heatmap_bwd_stage2(bfk_heatmap_bwd_args a, int nin_max, int bands) {
+  extern __shared__ __align__(16) float sm[];
+  float4* tap_s = reinterpret_cast<float4*>(sm);
+  stage_taps(tap_s, a.tap_start, a.tap_w, 16 * a.g);
+  __syncthreads();
+  hb_sum_bands(a, a.partials, nin_max, bands, blockIdx.y, blockIdx.x, tap_s);
+}
+
+// smem: taps [W] float4, wT [g][HB_SPAN], tmp [groups][nin_max][W]
+template <int MODE, bool MASK>
+__global__ void __launch_bounds__(HM_THREADS, 3) heatmap_bwd_stage1(bfk_heatmap_bwd_args a, int nin_max) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ int last_s;
+  const int g = a.g, W = 16 * g, bands = gridDim.x, R = W / bands, W4 = W / 4;
+  const int band = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int y0 = band * R, y1 = y0 + R;
+  const int groups = blockDim.x / W4;
+  const int grp = threadIdx.x / W4, x = (threadIdx.x % W4) * 4;
+  const bool active = grp < groups;
+  float4* tap_s = reinterpret_cast<float4*>(sm);        // [W]
+  float* wT = sm + 4 * W;                               // [g][HB_SPAN]
+  float* tmp = wT + g * HB_SPAN;                        // [groups][nin_max][W]
+  const long long map_off = (long long)b * W * W;
+  const float* heat = a.heat + ((long long)h * a.B + b) * W * W;
+  const float* src = nullptr;                           // target (MODE 0) or upstream gradient (MODE 1)
+  float gs = 0.f;
+  if (MODE == 0) {
+    src = a.target[h] + map_off;
+    gs = (a.gscale[h] + (a.gscale_has_total ? a.gscale[a.heads] : 0.f)) * a.gscale_mul;
+  } else {
+    src = a.dheat[h] ? a.dheat[h] + map_off : nullptr;
+  }
+  const bool masked = MASK && MODE == 0 && ((a.mask_heads >> h) & 1u);
+  const float* tmask = a.target_mask + map_off;
+  // thread-relative addressing: 32-bit element offsets from per-thread base pointers (row r of this thread = r * stride)
+  const int nrows = (active && src != nullptr) ? (R - grp + groups - 1) / groups : 0;
+  const int stride = groups * W, off0 = (y0 + grp) * W + x;
+  const float* hp = heat + off0;
+  const float* sp = src + off0;
+  const float* tmk = tmask + off0;
+  constexpr int RB = 2;   // rows whose loads are in flight together (x2: the next batch is requested before this one is used)
+  float4 pv[RB], qv[RB];
+#pragma unroll
+  for (int k = 0; k < RB; ++k) {                         // in flight during the set-up
+    if (k < nrows) { pv[k] = ldg_stream4(hp + k * stride); qv[k] = ldg_stream4(sp + k * stride); }
+    else { pv[k] = make_float4(0.f, 0.f, 0.f, 0.f); qv[k] = pv[k]; }
+  }
+  stage_taps(tap_s, a.tap_start, a.tap_w, W);
+  __syncthreads();
+  // transposed taps: wT[j][q] = weight of output index x = 16 j - 32 + q on grid column j (0 outside its support):
+  // zero the table, then every output index scatters its (at most three) weights
+  for (int t = threadIdx.x; t < g * HB_SPAN; t += blockDim.x) wT[t] = 0.f;
+  __syncthreads();
+  for (int xx = threadIdx.x; xx < W; xx += blockDim.x) {
+    const float4 tp = tap_s[xx];
+    const int js = __float_as_int(tp.w);
+    const int q = xx + 32 - 16 * js;                       // position of xx in the span of column js
+    if (q >= 0 && q < HB_SPAN) wT[js * HB_SPAN + q] = tp.x;
+    if (js + 1 < g && q - 16 >= 0 && q - 16 < HB_SPAN) wT[(js + 1) * HB_SPAN + q - 16] = tp.y;
+    if (js + 2 < g && q - 32 >= 0 && q - 32 < HB_SPAN) wT[(js + 2) * HB_SPAN + q - 32] = tp.z;
+  }
+  const int i_lo = __float_as_int(tap_s[y0].w);
+  const int nin = min(g, __float_as_int(tap_s[y1 - 1].w) + 3) - i_lo;
+  if (active) {
+    float* mine = tmp + grp * nin_max * W + x;
+    const float4* tp = tap_s + y0 + grp;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+    int cur = 0;                                         // window = accumulator rows cur, cur+1, cur+2
+    for (int r = 0; r < nrows; r += RB) {
+      float4 pn[RB], qn[RB];
+#pragma unroll
+      for (int k = 0; k < RB; ++k) {
+        if (r + RB + k < nrows) { pn[k] = ldg_stream4(hp + (r + RB + k) * stride); qn[k] = ldg_stream4(sp + (r + RB + k) * stride); }
+        else { pn[k] = make_float4(0.f, 0.f, 0.f, 0.f); qn[k] = pn[k]; }
+      }
+#pragma unroll
+      for (int k = 0; k < RB; ++k) {
+        if (r + k < nrows) {
+          const float4 p = pv[k];
+          float4 q = qv[k];
+          float4 d;
+          if (MODE == 0) {
+            if (masked) {
+              const float4 m = __ldg(reinterpret_cast<const float4*>(tmk + (r + k) * stride));
+              q.x *= m.x; q.y *= m.y; q.z *= m.z; q.w *= m.w;
+            }
+            d = make_float4(gs * (p.x - q.x), gs * (p.y - q.y), gs * (p.z - q.z), gs * (p.w - q.w));
+            // torch: dL/dp = (p - t) / max(p (1 - p), 1e-12) times dp/dz = p (1 - p): equal to (p - t) unless p (1 - p) < 1e-12
+            // (p rounded to 1, or below 1e-12), where the product collapses towards 0 — reproduced on this rare path
+            if (fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w)) == 1.f || fminf(fminf(p.x, p.y), fminf(p.z, p.w)) < 1.0001e-12f) {
+              d.x *= fminf(p.x * (1.f - p.x) * 1e12f, 1.f); d.y *= fminf(p.y * (1.f - p.y) * 1e12f, 1.f);
+              d.z *= fminf(p.z * (1.f - p.z) * 1e12f, 1.f); d.w *= fminf(p.w * (1.f - p.w) * 1e12f, 1.f);
+            }
+          } else {
+            d = make_float4(q.x * p.x * (1.f - p.x), q.y * p.y * (1.f - p.y), q.z * p.z * (1.f - p.z), q.w * p.w * (1.f - p.w));
+          }
+          const float4 wy = tp[(r + k) * groups];
+          const int is = __float_as_int(wy.w) - i_lo;
+          while (cur < is) {                             // the window moves down: retire its first row
+            if (cur < nin) *reinterpret_cast<float4*>(mine + cur * W) = a0;
+            a0 = a1; a1 = a2; a2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            ++cur;
+          }
+          a0.x = fmaf(wy.x, d.x, a0.x); a0.y = fmaf(wy.x, d.y, a0.y); a0.z = fmaf(wy.x, d.z, a0.z); a0.w = fmaf(wy.x, d.w, a0.w);
+          a1.x = fmaf(wy.y, d.x, a1.x); a1.y = fmaf(wy.y, d.y, a1.y); a1.z = fmaf(wy.y, d.z, a1.z); a1.w = fmaf(wy.y, d.w, a1.w);
+          a2.x = fmaf(wy.z, d.x, a2.x); a2.y = fmaf(wy.z, d.y, a2.y); a2.z = fmaf(wy.z, d.z, a2.z); a2.w = fmaf(wy.z, d.w, a2.w);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < RB; ++k) { pv[k] = pn[k]; qv[k] = qn[k]; }
+    }
+    // retire the window and zero-fill the rows this thread never reached
+    if (cur < nin) *reinterpret_cast<float4*>(mine + cur * W) = a0;
+    if (cur + 1 < nin) *reinterpret_cast<float4*>(mine + (cur + 1) * W) = a1;
+    if (cur + 2 < nin) *reinterpret_cast<float4*>(mine + (cur + 2) * W) = a2;
+    for (int r = cur + 3; r < nin; ++r) *reinterpret_cast<float4*>(mine + r * W) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  // combine the row groups (fixed order) into group 0
+  for (int t = threadIdx.x; t < nin * W; t += blockDim.x) {
+    float v = tmp[t];
+    for (int gq = 1; gq < groups; ++gq) v += tmp[(long long)gq * nin_max * W + t];
+    tmp[t] = v;
+  }
+  __syncthreads();
+  // horizontal fold: out[ii][j] = sum_q wT[j][q] * tmp[ii][16 j - 32 + q]; two lanes per output (even / odd q)
+  float* out = a.partials + ((((long long)b * a.heads + h) * bands + band) * nin_max) * g;
+  const int n_out = nin * g;
+  for (int t0 = 0; t0 < 2 * n_out; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    const bool valid = t < 2 * n_out;
+    const int o = valid ? t >> 1 : 0, half = t & 1;
+    const int ii = o / g, j = o % g;
+    const int qlo = max(0, 32 - 16 * j), qhi = min(HB_SPAN, W + 32 - 16 * j);
+    const float* trow = tmp + ii * W + 16 * j - 32;
+    const float* wrow = wT + j * HB_SPAN;
+    float s = 0.f;
+    for (int q = qlo + half; q < qhi; q += 2) s = fmaf(wrow[q], trow[q], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (valid && half == 0) out[o] = s;
+  }
+  if (a.counters) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      last_s = atomicAdd(reinterpret_cast<unsigned*>(a.counters) + 1 + b * a.heads + h, 1u) == (unsigned)(bands - 1);
+    }
+    __syncthreads();
+    if (last_s) {
+      __threadfence();
+      hb_sum_bands(a, a.partials, nin_max, bands, b, h, tap_s);
+      if (threadIdx.x == 0) a.counters[1 + b * a.heads + h] = 0;
+    }
+  }
+}
+
+// single block: loss[0] = sum(partials) / count.  Fixed assignment + fixed tree => deterministic.
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ partials, int n, float inv_count, float* __restrict__ loss) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    loss[0] = t * inv_count;
+  }
 }
 
 // ---- standalone BCE on probabilities ---------------------------------------------------------------------
@@ -736,10 +905,20 @@ extern "C" int32_t bfk_decoder_collapse_bwd(const bfk_decoder_collapse_args* a, 
 
 extern "C" int32_t bfk_head_project_fwd(const bfk_head_project_args* a, bfk_stream_t s_) {
   BFK_CHECK_ARG(a && a->X && a->w_eff && a->b_eff && a->grid && a->heads > 0 && a->heads <= 8 && a->D % 4 == 0, "bfk_head_project_fwd: bad arguments");
-  size_t smem = (size_t)a->heads * a->D * sizeof(float);
-  if (int rc = opt_in_smem(head_project_fwd_kernel, smem, "head_project_fwd")) return rc;
-  long long toks = (long long)a->B * a->Np;
-  head_project_fwd_kernel<<<(unsigned)((toks + 8 * HP_TOK_PER_WARP - 1) / (8 * HP_TOK_PER_WARP)), 256, smem, to_stream(s_)>>>(*a);
+  const long long toks = (long long)a->B * a->Np;
+  cudaStream_t s = to_stream(s_);
+  static int v2 = -1;
+  if (v2 < 0) { const char* e = getenv("BFK_HEAD_PROJECT_V2"); v2 = e ? atoi(e) : 1; }
+  if (v2 && a->heads <= 4 && (a->D == 768 || a->D == 1152) && (reinterpret_cast<uintptr_t>(a->X) & 15) == 0 && a->x_batch_stride % 4 == 0) {
+    // persistent warps, ~8 tokens each when there are enough tokens
+    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * (a->D == 768 ? 3 : 2), (toks + 3) / 4));
+    if (a->D == 768) head_project_fwd_v2_kernel<6, true><<<grid, 128, 0, s>>>(*a);
+    else head_project_fwd_v2_kernel<9, false><<<grid, 128, 0, s>>>(*a);
+  } else {
+    size_t smem = (size_t)a->heads * a->D * sizeof(float);
+    if (int rc = opt_in_smem(head_project_fwd_kernel, smem, "head_project_fwd")) return rc;
+    head_project_fwd_kernel<<<(unsigned)((toks + 8 * HP_TOK_PER_WARP - 1) / (8 * HP_TOK_PER_WARP)), 256, smem, s>>>(*a);
+  }
   BFK_CHECK_LAUNCH("bfk_head_project_fwd");
   return BFK_OK;
 }
@@ -792,46 +971,108 @@ extern "C" int32_t bfk_upsample16_taps(int32_t g, int32_t* tap_start, float* tap
   return BFK_OK;
 }
 
-extern "C" int32_t bfk_heatmap_bands(int32_t g) { return (16 * g + HF_ROWS - 1) / HF_ROWS; }     // forward bands (loss partials)
-static int heatmap_bwd_bands(int g) { return (16 * g + HM_ROWS - 1) / HM_ROWS; }
+static int env_bands(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : dflt;
+  return (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) ? v : dflt;
+}
+static int hm_bands() { static int v = env_bands("BFK_HM_BANDS", HM_BANDS_DEFAULT); return v; }
+static int hb_bands() { static int v = env_bands("BFK_HB_BANDS", HB_BANDS_DEFAULT); return v; }
+extern "C" int32_t bfk_heatmap_bands(int32_t g) { (void)g; return hm_bands(); }
+
+// largest number of grid rows one band of 4 g output rows touches (from the host taps; cached per g)
+static int band_nin_max(int g, int bands) {
+  static std::mutex mu;
+  static std::map<int, int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(g * 64 + bands);
+  if (it != cache.end()) return it->second;
+  std::vector<int32_t> ts(16 * g);
+  std::vector<float> tw(48 * g);
+  if (bfk_upsample16_taps(g, ts.data(), tw.data()) != BFK_OK) return -1;
+  const int R = 16 * g / bands;
+  int m = 0;
+  for (int band = 0; band < bands; ++band)
+    m = std::max(m, std::min(g, ts[band * R + R - 1] + 3) - ts[band * R]);
+  cache[g * 64 + bands] = m;
+  return m;
+}
+static int hm_threads(int W) {     // whole rows of float4 columns (+ idle lanes up to a full warp)
+  const int W4 = W / 4;
+  return ((HM_THREADS / W4) * W4 + 31) / 32 * 32;
+}
+
+extern "C" size_t bfk_heatmap_fwd_workspace_floats(int32_t B, int32_t heads, int32_t g) {
+  (void)g;
+  const size_t n = (size_t)B * heads * hm_bands();
+  return ((n + 1) & ~(size_t)1) + 2 * n;      // BCE partial sums, then the per-band argmax keys (u64)
+}
+
+template <bool LOSS, bool MASK, bool ARGMAX>
+static void launch_heatmap_fwd(const bfk_heatmap_fwd_args& k, int nin_max, dim3 grid, int threads, size_t smem, cudaStream_t s) {
+  static int minb = -1;
+  if (minb < 0) { const char* e = getenv("BFK_HM_MINB"); minb = e ? atoi(e) : 4; }
+  if (minb == 3) heatmap_fwd_kernel<LOSS, MASK, ARGMAX, 3><<<grid, threads, smem, s>>>(k, nin_max);
+  else heatmap_fwd_kernel<LOSS, MASK, ARGMAX, 4><<<grid, threads, smem, s>>>(k, nin_max);
+}
 
 extern "C" int32_t bfk_heatmap_fwd(const bfk_heatmap_fwd_args* a, bfk_stream_t s_) {
-  BFK_CHECK_ARG(a && a->grid && a->tap_start && a->tap_w && a->heat && a->B > 0 && a->heads > 0 && a->g > 0, "bfk_heatmap_fwd: bad arguments");
+  BFK_CHECK_ARG(a && a->grid && a->tap_start && a->tap_w && a->heat && a->B > 0 && a->heads > 0 && a->g > 0 && a->g <= 32,
+                "bfk_heatmap_fwd: bad arguments (g <= 32)");
   BFK_CHECK_ARG(!a->target || (a->loss && a->partials), "bfk_heatmap_fwd: target needs loss and partials");
   cudaStream_t s = to_stream(s_);
-  const int W = 16 * a->g, bands = bfk_heatmap_bands(a->g);
-  if (a->argmax_key) cudaMemsetAsync(a->argmax_key, 0, sizeof(unsigned long long) * a->heads * a->B, s);
-  size_t smem = ((size_t)HF_MAXIN * W + 3 * (size_t)W + (size_t)W + (size_t)a->g * a->g) * sizeof(float);
-  bfk_heatmap_fwd_args k = *a;
-  static int variant = -1;
-  if (variant < 0) { const char* e = getenv("BFK_HM_VARIANT"); variant = e ? atoi(e) : 0; }
-  dim3 grid(bands, a->heads, a->B);
-  const int threads = ((HM_THREADS / (W / 4)) * (W / 4) + 31) / 32 * 32;   // whole rows of float4 columns (+ idle lanes to a full warp)
-  if (variant == 1) heatmap_fwd_kernel<true><<<grid, threads, smem, s>>>(k);    // streaming (L1 no-allocate) accesses
-  else heatmap_fwd_kernel<false><<<grid, threads, smem, s>>>(k);
-  if (a->target) {
-    float inv = 1.f / ((float)a->B * (float)W * (float)W);
-    loss_finalize_kernel<<<1, 256, 0, s>>>(a->partials, a->heads, a->B * bands, inv, a->loss, 1);
+  const int W = 16 * a->g;
+  const int bands = hm_bands();
+  const int nin_max = band_nin_max(a->g, bands);
+  BFK_CHECK_ARG(nin_max > 0, "bfk_heatmap_fwd: no 3-tap composite for g = %d", a->g);
+  const bool loss = a->target != nullptr, amax = a->argmax_key != nullptr;
+  const bool mask = loss && a->target_mask && a->mask_heads;
+  if (amax && !a->partials) cudaMemsetAsync(a->argmax_key, 0, sizeof(unsigned long long) * a->heads * a->B, s);
+  const size_t smem = ((size_t)4 * W + (size_t)(nin_max + 2) * W + (size_t)a->g * a->g) * sizeof(float);
+  const dim3 grid(bands, a->heads, a->B);
+  const int threads = hm_threads(W);
+  if (loss) {
+    if (mask) { if (amax) launch_heatmap_fwd<true, true, true>(*a, nin_max, grid, threads, smem, s); else launch_heatmap_fwd<true, true, false>(*a, nin_max, grid, threads, smem, s); }
+    else      { if (amax) launch_heatmap_fwd<true, false, true>(*a, nin_max, grid, threads, smem, s); else launch_heatmap_fwd<true, false, false>(*a, nin_max, grid, threads, smem, s); }
+  } else {
+    if (amax) launch_heatmap_fwd<false, false, true>(*a, nin_max, grid, threads, smem, s); else launch_heatmap_fwd<false, false, false>(*a, nin_max, grid, threads, smem, s);
   }
+  const bool keys = amax && a->partials;
+  if (!a->counters && (loss || keys)) heatmap_finalize_kernel<<<1, HM_RED, 0, s>>>(*a, bands, loss, keys);
   BFK_CHECK_LAUNCH("bfk_heatmap_fwd");
   return BFK_OK;
 }
 
 extern "C" size_t bfk_heatmap_bwd_workspace_floats(int32_t B, int32_t heads, int32_t g) {
-  return (size_t)B * heads * heatmap_bwd_bands(g) * HM_MAXIN * g;
+  const int nin_max = std::max(band_nin_max(g, hb_bands()), 1);
+  return (size_t)B * heads * hb_bands() * nin_max * g;
+}
+
+template <int MODE, bool MASK>
+static int launch_heatmap_bwd(const bfk_heatmap_bwd_args& k, int nin_max, dim3 grid, int threads, size_t smem, cudaStream_t s) {
+  if (int rc = opt_in_smem(heatmap_bwd_stage1<MODE, MASK>, smem, "heatmap_bwd")) return rc;
+  heatmap_bwd_stage1<MODE, MASK><<<grid, threads, smem, s>>>(k, nin_max);
+  return BFK_OK;
 }
 
 extern "C" int32_t bfk_heatmap_bwd(const bfk_heatmap_bwd_args* a, bfk_stream_t s_) {
-  BFK_CHECK_ARG(a && a->heat && a->tap_start && a->tap_w && a->dgrid && a->partials && a->g > 0 && 16 * a->g <= 448,
-                "bfk_heatmap_bwd: bad arguments (W <= 448, partials required)");
+  BFK_CHECK_ARG(a && a->heat && a->tap_start && a->tap_w && a->dgrid && a->partials && a->g > 0 && a->g <= 32,
+                "bfk_heatmap_bwd: bad arguments (g <= 32, partials required)");
   BFK_CHECK_ARG(a->mode == 0 ? (a->target && a->gscale) : (a->dheat != nullptr), "bfk_heatmap_bwd: mode inputs missing");
-  const int W = 16 * a->g, bands = heatmap_bwd_bands(a->g);
-  const int groups = HB_THREADS / (W / 4);
-  size_t smem = (size_t)groups * HM_MAXIN * W * sizeof(float);
-  if (int rc = opt_in_smem(heatmap_bwd_stage1, smem, "heatmap_bwd")) return rc;
+  const int W = 16 * a->g;
+  const int bands = hb_bands();
+  const int nin_max = band_nin_max(a->g, bands);
+  BFK_CHECK_ARG(nin_max > 0, "bfk_heatmap_bwd: no 3-tap composite for g = %d", a->g);
+  const int threads = hm_threads(W), groups = HM_THREADS / (W / 4);
+  const size_t smem = ((size_t)4 * W + (size_t)a->g * HB_SPAN + (size_t)groups * nin_max * W) * sizeof(float);
   cudaStream_t s = to_stream(s_);
-  heatmap_bwd_stage1<<<dim3(bands, a->heads, a->B), HB_THREADS, smem, s>>>(*a, a->partials);
-  heatmap_bwd_stage2<<<dim3(a->heads, a->B), 256, 0, s>>>(*a, a->partials, bands);
+  const dim3 grid(bands, a->heads, a->B);
+  int rc;
+  if (a->mode != 0) rc = launch_heatmap_bwd<1, false>(*a, nin_max, grid, threads, smem, s);
+  else if (a->target_mask && a->mask_heads) rc = launch_heatmap_bwd<0, true>(*a, nin_max, grid, threads, smem, s);
+  else rc = launch_heatmap_bwd<0, false>(*a, nin_max, grid, threads, smem, s);
+  if (rc) return rc;
+  if (!a->counters) heatmap_bwd_stage2<<<dim3(a->heads, a->B), 256, (size_t)4 * W * sizeof(float), s>>>(*a, nin_max, bands);
   BFK_CHECK_LAUNCH("bfk_heatmap_bwd");
   return BFK_OK;
 }
@@ -842,7 +1083,7 @@ extern "C" int32_t bfk_bce_prob(const float* p, const float* t, const float* t_m
   cudaStream_t s = to_stream(s_);
   int blocks = (int)std::min<long long>(1024, (n + 255) / 256);
   bce_prob_stage1<<<blocks, 256, 0, s>>>(p, t, t_mask, n, partials);
-  loss_finalize_kernel<<<1, 256, 0, s>>>(partials, 1, blocks, 1.f / (float)n, loss, 0);
+  loss_finalize_kernel<<<1, 256, 0, s>>>(partials, blocks, 1.f / (float)n, loss);
   BFK_CHECK_LAUNCH("bfk_bce_prob");
   return BFK_OK;
 }

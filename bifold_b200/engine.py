@@ -687,6 +687,13 @@ class Engine:
             K.check(k.lib.bfk_decoder_collapse_fwd(C.byref(ca), _stream()), "bfk_decoder_collapse_fwd")
         return dict(w_eff=w_eff, b_eff=b_eff, chain=chain, tables=(Wt, bt), ev=ev)
 
+    def _tail_counters(self, n_maps, dev):
+        """Zeroed int32 counters the heatmap kernels use to elect the CTA that finishes a reduction (they reset them)."""
+        c = getattr(self, "_counters", None)
+        if c is None or c.numel() < 1 + n_maps or c.device != dev:
+            c = self._counters = torch.zeros(1 + max(n_maps, 4096), device=dev, dtype=torch.int32)
+        return c
+
     def _tail_fwd(self, x, B, Nf, targets, want_argmax, need_grad, pre=None):
         cfg, k, D, dev = self.cfg, self.k, self.cfg.dim, x.device
         heads, Np, g = len(cfg.heads_out), cfg.num_patches, cfg.grid
@@ -709,15 +716,16 @@ class Engine:
         if targets is not None:
             tptr = self._ptr_table([t.data_ptr() for t in targets])
             loss = torch.empty(heads + 1, device=dev, dtype=torch.float32)
-            part = torch.empty(heads * B * lib.bfk_heatmap_bands(g), device=dev, dtype=torch.float32)
             out.update(loss=loss, tptr=tptr)
         if want_argmax:
             key = torch.empty(heads * B, device=dev, dtype=torch.int64)
             out["key"] = key
+        if targets is not None or want_argmax:
+            part = torch.empty(lib.bfk_heatmap_fwd_workspace_floats(B, heads, g), device=dev, dtype=torch.float32)
         ha = K.HeatmapFwdArgs(B, heads, g, grid.data_ptr(), ts.data_ptr(), tw.data_ptr(), heat.data_ptr(), K.ptr(tptr), None, 0,
-                              K.ptr(loss), K.ptr(key), K.ptr(part))
+                              K.ptr(loss), K.ptr(key), K.ptr(part), self._tail_counters(B * heads, dev).data_ptr())
         K.check(lib.bfk_heatmap_fwd(C.byref(ha), st), "bfk_heatmap_fwd")
-        k.launches += 3 + (1 if targets is not None else 0)
+        k.launches += 3
         # tokens read once (fp32), heatmaps written, targets read when the BCE is fused
         k.work["tail_bytes"] += 4.0 * (B * Np * D + heads * B * H * H * (2 if targets is not None else 1))
         return out
@@ -765,7 +773,8 @@ class Engine:
         if dloss is not None:
             gscale = dloss.contiguous()     # [heads + 1]: per-head grads then the grad of their sum
             ba = K.HeatmapBwdArgs(B, heads, g, 0, tail["heat"].data_ptr(), tail["tptr"].data_ptr(), None, 0, gscale.data_ptr(),
-                                  1.0 / float(B * H * H), 1, None, ts.data_ptr(), tw.data_ptr(), dgrid.data_ptr(), hws.data_ptr())
+                                  1.0 / float(B * H * H), 1, None, ts.data_ptr(), tw.data_ptr(), dgrid.data_ptr(), hws.data_ptr(),
+                                  self._tail_counters(B * heads, dev).data_ptr())
             K.check(lib.bfk_heatmap_bwd(C.byref(ba), st), "bfk_heatmap_bwd")
             first = False
         if dheat is not None:
@@ -773,7 +782,8 @@ class Engine:
             dptr = self._ptr_table([dheat[h].data_ptr() for h in range(heads)])
             tgt = dgrid if first else torch.empty_like(dgrid)
             ba = K.HeatmapBwdArgs(B, heads, g, 1, tail["heat"].data_ptr(), None, None, 0, None, 1.0, 0, dptr.data_ptr(),
-                                  ts.data_ptr(), tw.data_ptr(), tgt.data_ptr(), hws.data_ptr())
+                                  ts.data_ptr(), tw.data_ptr(), tgt.data_ptr(), hws.data_ptr(),
+                                  self._tail_counters(B * heads, dev).data_ptr())
             K.check(lib.bfk_heatmap_bwd(C.byref(ba), st), "bfk_heatmap_bwd")
             if not first:
                 dgrid.add_(tgt)   # both a fused-loss and a heatmap gradient (rare): tiny [B,heads,Np] add
@@ -797,7 +807,7 @@ class Engine:
         def collapse_bwd(ca=ca):      # weight gradients of the decoder chain: a leaf of the backward, off the chain
             K.check(lib.bfk_decoder_collapse_bwd(C.byref(ca), _stream()), "bfk_decoder_collapse_bwd")
         self._off_chain(collapse_bwd, d_w_eff, d_b_eff, chain_t)
-        k.launches += 7
+        k.launches += 6
         # heatmaps + targets (or dheat) read, tokens read, dX written (fp32 + operand copy)
         k.work["tail_bytes"] += 4.0 * (2 * heads * B * H * H + B * Np * D) + B * Nf * D * (4.0 + (dX_T.element_size() if dX_T is not None else 0))
         if self.grad_ready_hook:

@@ -287,9 +287,14 @@ typedef struct {
   uint32_t mask_heads;               /* bit h set: target_h *= target_mask */
   float* loss;                       /* [heads+1]: mean BCE per head, then their sum (if target) */
   unsigned long long* argmax_key;    /* [heads, B] workspace+result: (float bits << 32) | ~index, or NULL */
-  float* partials;                   /* [heads*B*bfk_heatmap_bands(g)] workspace (if target) */
+  float* partials;                   /* bfk_heatmap_fwd_workspace_floats(B, heads, g) floats, 8-byte aligned (required with target;
+                                      * with argmax_key only: optional, NULL = atomic keys) */
+  int32_t* counters;                 /* optional DEVICE int32 [>= 1], zero before the FIRST call and left zero by every call: the
+                                      * last CTA then also reduces the per-band partials (one launch instead of three).  Must not
+                                      * be shared by calls that can run concurrently.  NULL = separate finalize launch. */
 } bfk_heatmap_fwd_args;
-BFK_API int32_t bfk_heatmap_bands(int32_t g);
+BFK_API int32_t bfk_heatmap_bands(int32_t g);   /* bands per map (loss partials per map) */
+BFK_API size_t bfk_heatmap_fwd_workspace_floats(int32_t B, int32_t heads, int32_t g);
 BFK_API int32_t bfk_heatmap_fwd(const bfk_heatmap_fwd_args* a, bfk_stream_t s);
 
 /* dgrid from either the fused BCE gradient  dlogit = g_h*(p - t)         (mode 0)
@@ -304,6 +309,9 @@ typedef struct {
   const int32_t* tap_start; const float* tap_w;
   float* dgrid;                      /* [B, heads, g*g] */
   float* partials;                   /* bfk_heatmap_bwd_workspace_floats(B, heads, g) floats */
+  int32_t* counters;                 /* optional DEVICE int32 [>= 1 + B*heads], zero before the first call and left zero by every
+                                      * call (same buffer as bfk_heatmap_fwd_args.counters): the last band of a map sums the
+                                      * bands.  NULL = separate second-stage launch. */
 } bfk_heatmap_bwd_args;
 BFK_API size_t bfk_heatmap_bwd_workspace_floats(int32_t B, int32_t heads, int32_t g);
 BFK_API int32_t bfk_heatmap_bwd(const bfk_heatmap_bwd_args* a, bfk_stream_t s);

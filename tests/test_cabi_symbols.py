@@ -30,7 +30,9 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_cabi._PROTOS) == _declared()
     assert lib.bfk_version() >= 100
-    assert lib.bfk_heatmap_bands(14) == 7
+    nb = lib.bfk_heatmap_bands(14)
+    assert nb in (1, 2, 4, 8, 16)
+    assert lib.bfk_heatmap_fwd_workspace_floats(2, 4, 14) == 3 * 2 * 4 * nb
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -405,3 +405,94 @@ def test_bce_prob_clamp_matches_torch(kern):
     assert abs(loss.item() - ref.item()) <= 1e-5 * ref.item()
     loss.backward(); ref.backward()
     assert torch.allclose(p.grad, ref_p.grad, rtol=1e-4, atol=1e-6)
+
+
+def _up16(grid):
+    x = grid
+    for _ in range(4):
+        x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    return x
+
+
+@pytest.mark.parametrize("g,B,heads", [(2, 3, 2), (3, 2, 4), (14, 5, 4), (24, 2, 2), (27, 2, 4)])
+@pytest.mark.parametrize("use_counters", [True, False])
+def test_heatmap_fwd_bwd_vs_torch(kern, g, B, heads, use_counters):
+    """bfk_heatmap_fwd / bfk_heatmap_bwd (all band / group geometries, fused and two-launch reductions, target mask, generic
+    upstream gradient) against four torch x2 bilinear stages + sigmoid + BCELoss (bifold/models/modules.py:57-74,
+    bifold/losses/__init__.py:76-83) and autograd."""
+    from bifold_b200 import _cabi as K
+    lib, dev = kern.lib, "cuda"
+    H = 16 * g
+    gen = torch.Generator().manual_seed(g * 100 + B)
+    grid = (torch.randn(B, heads, g, g, generator=gen) * 3).to(dev)
+    grid[0, 0, 0, 0] = 30.0          # saturated pixels: the literal (clamped) BCE path
+    targets = [torch.rand(B, H, H, generator=gen).to(dev) for _ in range(heads)]
+    tmask = (torch.rand(B, H, H, generator=gen) > 0.5).float().to(dev)
+    ts_h = torch.empty(H, dtype=torch.int32); tw_h = torch.empty(H, 3)
+    K.check(lib.bfk_upsample16_taps(g, ts_h.data_ptr(), tw_h.data_ptr()))
+    ts, tw = ts_h.to(dev), tw_h.to(dev)
+    tptr = torch.tensor([t.data_ptr() for t in targets], dtype=torch.int64).to(dev)
+    counters = torch.zeros(1 + heads * B, device=dev, dtype=torch.int32)
+    cptr = counters.data_ptr() if use_counters else None
+    st = torch.cuda.current_stream().cuda_stream
+    for mask_heads in (0, 0b01):
+        heat = torch.empty(heads, B, H, H, device=dev)
+        loss = torch.empty(heads + 1, device=dev); key = torch.empty(heads * B, device=dev, dtype=torch.int64)
+        part = torch.empty(lib.bfk_heatmap_fwd_workspace_floats(B, heads, g), device=dev)
+        fa = K.HeatmapFwdArgs(B, heads, g, grid.data_ptr(), ts.data_ptr(), tw.data_ptr(), heat.data_ptr(), tptr.data_ptr(),
+                              tmask.data_ptr() if mask_heads else None, mask_heads, loss.data_ptr(), key.data_ptr(), part.data_ptr(), cptr)
+        for _ in range(2):     # twice: the counters must come back to zero
+            K.check(lib.bfk_heatmap_fwd(C.byref(fa), st))
+        gref = grid.clone().requires_grad_(True)
+        p_ref = _up16(gref).sigmoid()                              # [B, heads, H, H]
+        assert (heat.permute(1, 0, 2, 3) - p_ref).abs().max().item() < 2e-6
+        tt = [t * tmask if (mask_heads >> h) & 1 else t for h, t in enumerate(targets)]
+        losses = [F.binary_cross_entropy(p_ref[:, h], tt[h]) for h in range(heads)]
+        for h in range(heads):
+            assert abs(loss[h].item() - losses[h].item()) <= 2e-5 * abs(losses[h].item()) + 1e-7, (h, loss[h].item(), losses[h].item())
+        assert abs(loss[heads].item() - sum(l.item() for l in losses)) <= 1e-4 * sum(l.item() for l in losses)
+        idx = 0xFFFFFFFF - (key.cpu().numpy().astype(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        np.testing.assert_array_equal(idx, heat.view(heads * B, -1).cpu().numpy().argmax(1))
+        # argmax-only call without a workspace (atomic keys)
+        key2 = torch.empty_like(key)
+        fa2 = K.HeatmapFwdArgs(B, heads, g, grid.data_ptr(), ts.data_ptr(), tw.data_ptr(), heat.data_ptr(), None, None, 0, None,
+                               key2.data_ptr(), None, None)
+        K.check(lib.bfk_heatmap_fwd(C.byref(fa2), st))
+        assert torch.equal(key, key2)
+        # backward, mode 0: d(sum_h w_h loss_h + w_tot total)/dgrid
+        gscale = torch.tensor([0.5 + h for h in range(heads)] + [2.0], device=dev)
+        (sum((gscale[h] + gscale[heads]) * losses[h] for h in range(heads))).backward()
+        dgrid = torch.empty(B, heads, g * g, device=dev)
+        ws = torch.empty(lib.bfk_heatmap_bwd_workspace_floats(B, heads, g), device=dev)
+        ba = K.HeatmapBwdArgs(B, heads, g, 0, heat.data_ptr(), tptr.data_ptr(), tmask.data_ptr() if mask_heads else None, mask_heads,
+                              gscale.data_ptr(), 1.0 / (B * H * H), 1, None, ts.data_ptr(), tw.data_ptr(), dgrid.data_ptr(), ws.data_ptr(), cptr)
+        for _ in range(2):
+            K.check(lib.bfk_heatmap_bwd(C.byref(ba), st))
+        ref = gref.grad.view(B, heads, g * g)
+        assert (dgrid - ref).abs().max().item() <= 2e-4 * ref.abs().max().item() + 1e-9
+    # backward, mode 1: arbitrary upstream gradient w.r.t. the heatmaps (one head without gradient)
+    dheat = [torch.randn(B, H, H, generator=gen).to(dev) for _ in range(heads)]
+    dptr = torch.tensor([0 if h == 1 else d.data_ptr() for h, d in enumerate(dheat)], dtype=torch.int64).to(dev)
+    gref = grid.clone().requires_grad_(True)
+    p_ref = _up16(gref).sigmoid()
+    sum((p_ref[:, h] * dheat[h]).sum() for h in range(heads) if h != 1).backward()
+    ba = K.HeatmapBwdArgs(B, heads, g, 1, heat.data_ptr(), None, None, 0, None, 1.0, 0, dptr.data_ptr(), ts.data_ptr(), tw.data_ptr(),
+                          dgrid.data_ptr(), ws.data_ptr(), cptr)
+    K.check(lib.bfk_heatmap_bwd(C.byref(ba), st))
+    ref = gref.grad.view(B, heads, g * g)
+    assert (dgrid - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    assert int(counters.abs().sum().item()) == 0
+
+
+@pytest.mark.parametrize("D,heads,B,Np,Nf", [(768, 4, 3, 196, 262), (768, 2, 2, 9, 30), (1152, 4, 2, 50, 120), (64, 4, 3, 16, 40)])
+def test_head_project_fwd_vs_torch(kern, D, heads, B, Np, Nf):
+    from bifold_b200 import _cabi as K
+    gen = torch.Generator().manual_seed(D + Np)
+    X = torch.randn(B * Nf, D, generator=gen).cuda()
+    w = torch.randn(heads, D, generator=gen).cuda(); b = torch.randn(heads, generator=gen).cuda()
+    grid = torch.empty(B, heads, Np, device="cuda")
+    pa = K.HeadProjectArgs(B, heads, Np, D, X.data_ptr(), Nf * D, Nf - Np, w.data_ptr(), b.data_ptr(), grid.data_ptr(),
+                           None, Nf, None, None, 0, None, None, None)
+    K.check(kern.lib.bfk_head_project_fwd(C.byref(pa), torch.cuda.current_stream().cuda_stream))
+    ref = torch.einsum("bnd,hd->bhn", X.view(B, Nf, D)[:, Nf - Np:], w) + b[None, :, None]
+    assert (grid - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()

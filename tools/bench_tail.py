@@ -36,20 +36,21 @@ for B in (64, 512):
     targets = [torch.rand(B, H, H, device="cuda") for _ in range(heads)]
     tptr = torch.tensor([t.data_ptr() for t in targets], dtype=torch.int64).cuda()
     loss = torch.empty(heads + 1, device="cuda"); key = torch.empty(heads * B, device="cuda", dtype=torch.int64)
-    part = torch.empty(heads * B * lib.bfk_heatmap_bands(g), device="cuda")
+    part = torch.empty(lib.bfk_heatmap_fwd_workspace_floats(B, heads, g), device="cuda")
+    counters = torch.zeros(1 + heads * B, device="cuda", dtype=torch.int32)
     fa = K.HeatmapFwdArgs(B, heads, g, grid.data_ptr(), ts.data_ptr(), tw.data_ptr(), heat.data_ptr(), tptr.data_ptr(), None, 0,
-                          loss.data_ptr(), key.data_ptr(), part.data_ptr())
+                          loss.data_ptr(), key.data_ptr(), part.data_ptr(), counters.data_ptr())
     ms = timeit(lambda: K.check(lib.bfk_heatmap_fwd(C.byref(fa), st())))
     by = heads * B * H * H * 4 * 2 + grid.numel() * 4
     out[f"heatmap_fwd_loss_argmax_B{B}"] = dict(us=ms * 1e3, GBps=by / ms / 1e6, frac=by / ms / 1e6 / peak, bytes=by)
-    fa2 = K.HeatmapFwdArgs(B, heads, g, grid.data_ptr(), ts.data_ptr(), tw.data_ptr(), heat.data_ptr(), None, None, 0, None, key.data_ptr(), None)
+    fa2 = K.HeatmapFwdArgs(B, heads, g, grid.data_ptr(), ts.data_ptr(), tw.data_ptr(), heat.data_ptr(), None, None, 0, None, key.data_ptr(), part.data_ptr(), counters.data_ptr())
     ms = timeit(lambda: K.check(lib.bfk_heatmap_fwd(C.byref(fa2), st())))
     by = heads * B * H * H * 4 + grid.numel() * 4
     out[f"heatmap_fwd_infer_argmax_B{B}"] = dict(us=ms * 1e3, GBps=by / ms / 1e6, frac=by / ms / 1e6 / peak, bytes=by)
     gscale = torch.ones(heads + 1, device="cuda"); dgrid = torch.empty(B, heads, g * g, device="cuda")
     ws = torch.empty(lib.bfk_heatmap_bwd_workspace_floats(B, heads, g), device="cuda")
     ba = K.HeatmapBwdArgs(B, heads, g, 0, heat.data_ptr(), tptr.data_ptr(), None, 0, gscale.data_ptr(), 1.0 / (B * H * H), 1, None,
-                          ts.data_ptr(), tw.data_ptr(), dgrid.data_ptr(), ws.data_ptr())
+                          ts.data_ptr(), tw.data_ptr(), dgrid.data_ptr(), ws.data_ptr(), counters.data_ptr())
     ms = timeit(lambda: K.check(lib.bfk_heatmap_bwd(C.byref(ba), st())))
     by = heads * B * H * H * 4 * 2
     out[f"heatmap_bwd_bce_B{B}"] = dict(us=ms * 1e3, GBps=by / ms / 1e6, frac=by / ms / 1e6 / peak, bytes=by)
