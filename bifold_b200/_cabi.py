@@ -102,6 +102,16 @@ class ActionArgs(C.Structure):
                 ("out_xy", vp), ("out_conf", vp)]
 
 
+class MaskGateArgs(C.Structure):
+    _fields_ = [("B", i32), ("heads", i32), ("H", i32), ("W", i32), ("pick_heads", u32),
+                ("heat_raw", vp), ("mask_p", vp), ("heat_out", vp)]
+
+
+class MaskGateBwdArgs(C.Structure):
+    _fields_ = [("B", i32), ("heads", i32), ("H", i32), ("W", i32), ("pick_heads", u32), ("detach_mask", i32),
+                ("dheat_out", vp), ("has_dmask", i32), ("heat_raw", vp), ("mask_p", vp), ("dheat_raw", vp), ("dmask", vp)]
+
+
 class LoraGradsArgs(C.Structure):
     _fields_ = [("M", i32), ("D", i32), ("r", i32),
                 ("dqkv", vp), ("ld_dqkv", i64), ("u", vp), ("ld_u", i64), ("du", vp), ("ld_du", i64), ("x", vp), ("ld_x", i64),
@@ -164,6 +174,14 @@ _PROTOS = {
     "bfk_adamw": (i32, [C.POINTER(AdamWArgs), vp]),
     "bfk_gauss_targets": (i32, [vp, i32, i32, i32, i32, f32, vp, vp]),
     "bfk_normalize_u8": (i32, [vp, i64, i32, i32, f32, f32, vp, vp]),
+    "bfk_mask_gate_fwd": (i32, [C.POINTER(MaskGateArgs), vp]),
+    "bfk_mask_gate_bwd": (i32, [C.POINTER(MaskGateBwdArgs), vp]),
+    "bfk_add_inplace": (i32, [vp, vp, i64, vp]),
+    "bfk_dice_loss_workspace_floats": (C.c_size_t, [i32]),
+    "bfk_dice_loss_fwd": (i32, [vp, vp, i32, i64, vp, vp, vp, vp]),
+    "bfk_dice_loss_bwd": (i32, [vp, i32, i64, vp, vp, vp, vp]),
+    "bfk_focal_loss_fwd": (i32, [vp, vp, i64, f32, f32, f32, vp, vp, vp]),
+    "bfk_focal_loss_bwd": (i32, [vp, vp, i64, f32, f32, f32, vp, vp, vp]),
     "bfk_cast_bf16": (i32, [vp, vp, i64, vp]),
     "bfk_cast_f32_to": (i32, [vp, vp, i32, i64, i64, i64, i64, vp]),
 }

@@ -43,6 +43,8 @@ class PolicyConfig:
     vocab_size: int = 32000
     text_len: int = 64
     tower_ln_eps: float = 1e-6
+    compute_mask: bool = False           # PickPlaceConvDecoder(compute_mask=True): mask head + gated pick heatmaps
+    detach_mask: bool = False
 
     @property
     def grid(self) -> int:
@@ -62,6 +64,15 @@ class PolicyConfig:
         if self.is_bimanual:
             return ["left_pick", "left_place", "right_pick", "right_place"]
         return ["pick", "place"]
+
+    @property
+    def decoder_prefixes(self):
+        """Parameter prefixes of the ConvDecoders, policy heads first (bifold/models/pickplace.py:27-47)."""
+        return [f"pick_place.{h}_decoder" for h in self.heads_out] + (["pick_place.mask_head"] if self.compute_mask else [])
+
+    @property
+    def pick_head_bits(self) -> int:
+        return sum(1 << i for i, h in enumerate(self.heads_out) if h.endswith("pick"))
 
     def fusion_len(self, t: int) -> int:
         return (self.text_len + 1) + (t + 1) * (self.num_patches + 1)

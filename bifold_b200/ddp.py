@@ -25,7 +25,7 @@ def plan_groups(names: List[str], sizes: List[int]) -> Dict[str, List[Tuple[int,
     off = 0
     for n, s in zip(names, sizes):
         padded = (s + 7) // 8 * 8
-        if "_decoder." in n:
+        if "_decoder." in n or ".mask_head." in n:
             g = "decoders"
         elif ".transformer_encoder.layers." in n:
             g = "fusion." + n.split(".transformer_encoder.layers.")[1].split(".")[0]

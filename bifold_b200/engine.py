@@ -572,6 +572,8 @@ class Engine:
         rgb = sample["rgb"]
         dev = rgb.device
         self.training = training
+        if cfg.compute_mask:
+            targets = None          # the pick outputs are sigmoid * mask: the BCE cannot be fused into the sigmoid kernel
         if training and need_grad and cfg.lora and cfg.lora_dropout > 0.0:
             self.step_seed += 1     # every training forward draws fresh LoRA-dropout masks (a captured graph adds seed_dev on top)
         self.prepare(dev)
@@ -626,18 +628,18 @@ class Engine:
 
         # ---- heatmap tail ----
         heads = len(cfg.heads_out)
-        tail = self._tail_fwd(x, B, Nf, targets, want_argmax, need_grad, pre=pre)
+        tail = self._tail_fwd(x, B, Nf, targets, want_argmax, need_grad, pre=pre, X_in=X)
         if need_grad:
             ctx.update(vsave=vsave, tsave=tsave, fsave=fsave, mask=mask, xf=x, Nf=Nf, tail=tail, targets=targets,
-                       heads=heads)
+                       heads=heads, X_in=X if cfg.compute_mask else None)
         return tail["heat"], tail.get("loss"), tail.get("key"), ctx
 
     def _decoder_ptr_tables(self, grads=None):
         cfg = self.cfg
         ws, bs, dws, dbs = [], [], [], []
-        for h in cfg.heads_out:
+        for pre in cfg.decoder_prefixes:          # policy heads, then the mask head (compute_mask)
             for j in range(5):
-                wn, bn = f"pick_place.{h}_decoder.decoder_net.{2 * j}.weight", f"pick_place.{h}_decoder.decoder_net.{2 * j}.bias"
+                wn, bn = f"{pre}.decoder_net.{2 * j}.weight", f"{pre}.decoder_net.{2 * j}.bias"
                 ws.append(self._p(wn).data_ptr()); bs.append(self._p(bn).data_ptr())
                 if grads is not None:
                     dws.append(grads[wn].data_ptr()); dbs.append(grads[bn].data_ptr())
@@ -663,7 +665,7 @@ class Engine:
         """w_eff / b_eff of the linear decoders.  Depends on the decoder weights only, so with `off_chain` it runs on the
         second stream at the START of the forward (four latency-bound CTAs, ~180 us) instead of on the critical path."""
         cfg, k, D = self.cfg, self.k, self.cfg.dim
-        heads = len(cfg.heads_out)
+        heads = len(cfg.decoder_prefixes)
         Wt, bt = self._decoder_ptr_tables()
         w_eff = torch.empty(heads, D, device=dev, dtype=torch.float32)
         b_eff = torch.empty(heads, device=dev, dtype=torch.float32)
@@ -694,7 +696,7 @@ class Engine:
             c = self._counters = torch.zeros(1 + max(n_maps, 4096), device=dev, dtype=torch.int32)
         return c
 
-    def _tail_fwd(self, x, B, Nf, targets, want_argmax, need_grad, pre=None):
+    def _tail_fwd(self, x, B, Nf, targets, want_argmax, need_grad, pre=None, X_in=None):
         cfg, k, D, dev = self.cfg, self.k, self.cfg.dim, x.device
         heads, Np, g = len(cfg.heads_out), cfg.num_patches, cfg.grid
         H = 16 * g
@@ -710,6 +712,9 @@ class Engine:
                                None, Nf, None, None, 0, None, None, None)
         K.check(lib.bfk_head_project_fwd(C.byref(pa), st), "bfk_head_project_fwd")
         ts, tw = self.taps(g)
+        counters = self._tail_counters(B * (heads + 1), dev).data_ptr()
+        if cfg.compute_mask:
+            return self._tail_fwd_masked(X_in, B, Nf, want_argmax, pre, grid, counters)
         heat = torch.empty(heads, B, H, H, device=dev, dtype=torch.float32)
         out = dict(heat=heat, w_eff=w_eff, b_eff=b_eff, chain=chain, grid=grid, tables=(Wt, bt))
         tptr = loss = part = key = None
@@ -723,11 +728,42 @@ class Engine:
         if targets is not None or want_argmax:
             part = torch.empty(lib.bfk_heatmap_fwd_workspace_floats(B, heads, g), device=dev, dtype=torch.float32)
         ha = K.HeatmapFwdArgs(B, heads, g, grid.data_ptr(), ts.data_ptr(), tw.data_ptr(), heat.data_ptr(), K.ptr(tptr), None, 0,
-                              K.ptr(loss), K.ptr(key), K.ptr(part), self._tail_counters(B * heads, dev).data_ptr())
+                              K.ptr(loss), K.ptr(key), K.ptr(part), counters)
         K.check(lib.bfk_heatmap_fwd(C.byref(ha), st), "bfk_heatmap_fwd")
         k.launches += 3
         # tokens read once (fp32), heatmaps written, targets read when the BCE is fused
         k.work["tail_bytes"] += 4.0 * (B * Np * D + heads * B * H * H * (2 if targets is not None else 1))
+        return out
+
+    def _tail_fwd_masked(self, X_in, B, Nf, want_argmax, pre, grid, counters):
+        """compute_mask=True (bifold/models/pickplace.py:66-69,78-101): the mask head is a fifth ConvDecoder applied to the
+        image rows of the fusion INPUT (image tokens + type embedding: ConcatTransformer adds it in place, fusion.py:52), the pick
+        heatmaps are sigmoid(pick) * mask_heatmap.  -> heat [heads + 1, B, H, W], the last map is mask_heatmap."""
+        cfg, k, D, dev = self.cfg, self.k, self.cfg.dim, X_in.device
+        heads, Np, g = len(cfg.heads_out), cfg.num_patches, cfg.grid
+        H = 16 * g
+        lib, st = k.lib, _stream()
+        w_eff, b_eff = pre["w_eff"], pre["b_eff"]
+        ts, tw = self.taps(g)
+        grid_m = torch.empty(B, 1, Np, device=dev, dtype=torch.float32)
+        pa = K.HeadProjectArgs(B, 1, Np, D, X_in.data_ptr(), Nf * D, Nf - Np, w_eff.data_ptr() + heads * D * 4,
+                               b_eff.data_ptr() + heads * 4, grid_m.data_ptr(), None, Nf, None, None, 0, None, None, None)
+        K.check(lib.bfk_head_project_fwd(C.byref(pa), st), "bfk_head_project_fwd")
+        heat_raw = torch.empty(heads, B, H, H, device=dev, dtype=torch.float32)
+        heat = torch.empty(heads + 1, B, H, H, device=dev, dtype=torch.float32)
+        for gr, nh, dst in ((grid, heads, heat_raw), (grid_m, 1, heat[heads])):
+            ha = K.HeatmapFwdArgs(B, nh, g, gr.data_ptr(), ts.data_ptr(), tw.data_ptr(), dst.data_ptr(), None, None, 0, None, None, None,
+                                  counters)
+            K.check(lib.bfk_heatmap_fwd(C.byref(ha), st), "bfk_heatmap_fwd")
+        ga = K.MaskGateArgs(B, heads, H, H, cfg.pick_head_bits, heat_raw.data_ptr(), heat[heads].data_ptr(), heat.data_ptr())
+        K.check(lib.bfk_mask_gate_fwd(C.byref(ga), st), "bfk_mask_gate_fwd")
+        out = dict(heat=heat, heat_raw=heat_raw, w_eff=w_eff, b_eff=b_eff, chain=pre["chain"], grid=grid, tables=pre["tables"])
+        if want_argmax:
+            key = torch.empty(heads * B, device=dev, dtype=torch.int64)
+            K.check(lib.bfk_argmax2d(heat.data_ptr(), heads * B, H * H, key.data_ptr(), st), "bfk_argmax2d")
+            out["key"] = key
+        k.launches += 7
+        k.work["tail_bytes"] += 4.0 * (2 * B * Np * D + (3 * heads + 2) * B * H * H)
         return out
 
     # ------------------------------------------------------------------------------------------------
@@ -769,21 +805,41 @@ class Engine:
         # ---- tail backward: dlogit -> dgrid -> (dX, d w_eff) -> decoder weights ----
         dgrid = torch.empty(B, heads, Np, device=dev, dtype=torch.float32)
         hws = torch.empty(lib.bfk_heatmap_bwd_workspace_floats(B, heads, g), device=dev, dtype=torch.float32)
+        counters = self._tail_counters(B * (heads + 1), dev).data_ptr()
         first = True
+        heat_p = tail["heat"]              # probabilities the sigmoid backward is taken at
+        dgrid_m = None
+        if cfg.compute_mask:
+            heat_p = tail["heat_raw"]
+            if dheat is not None:
+                # product rule of pick = sigmoid(pick) * mask (and the mask head's own upstream gradient)
+                dheat = dheat.contiguous()
+                dheat_raw = torch.empty(heads, B, H, H, device=dev, dtype=torch.float32)
+                dmask = torch.empty(B, H, H, device=dev, dtype=torch.float32)
+                gb = K.MaskGateBwdArgs(B, heads, H, H, cfg.pick_head_bits, int(cfg.detach_mask), dheat.data_ptr(), 1, heat_p.data_ptr(),
+                                       tail["heat"][heads].data_ptr(), dheat_raw.data_ptr(), dmask.data_ptr())
+                K.check(lib.bfk_mask_gate_bwd(C.byref(gb), st), "bfk_mask_gate_bwd")
+                dgrid_m = torch.empty(B, 1, Np, device=dev, dtype=torch.float32)
+                mws = torch.empty(lib.bfk_heatmap_bwd_workspace_floats(B, 1, g), device=dev, dtype=torch.float32)
+                mptr = self._ptr_table([dmask.data_ptr()])
+                ba = K.HeatmapBwdArgs(B, 1, g, 1, tail["heat"][heads].data_ptr(), None, None, 0, None, 1.0, 0, mptr.data_ptr(),
+                                      ts.data_ptr(), tw.data_ptr(), dgrid_m.data_ptr(), mws.data_ptr(), counters)
+                K.check(lib.bfk_heatmap_bwd(C.byref(ba), st), "bfk_heatmap_bwd")
+                dheat = dheat_raw
+                k.launches += 2
         if dloss is not None:
             gscale = dloss.contiguous()     # [heads + 1]: per-head grads then the grad of their sum
-            ba = K.HeatmapBwdArgs(B, heads, g, 0, tail["heat"].data_ptr(), tail["tptr"].data_ptr(), None, 0, gscale.data_ptr(),
+            ba = K.HeatmapBwdArgs(B, heads, g, 0, heat_p.data_ptr(), tail["tptr"].data_ptr(), None, 0, gscale.data_ptr(),
                                   1.0 / float(B * H * H), 1, None, ts.data_ptr(), tw.data_ptr(), dgrid.data_ptr(), hws.data_ptr(),
-                                  self._tail_counters(B * heads, dev).data_ptr())
+                                  counters)
             K.check(lib.bfk_heatmap_bwd(C.byref(ba), st), "bfk_heatmap_bwd")
             first = False
         if dheat is not None:
             dheat = dheat.contiguous()
             dptr = self._ptr_table([dheat[h].data_ptr() for h in range(heads)])
             tgt = dgrid if first else torch.empty_like(dgrid)
-            ba = K.HeatmapBwdArgs(B, heads, g, 1, tail["heat"].data_ptr(), None, None, 0, None, 1.0, 0, dptr.data_ptr(),
-                                  ts.data_ptr(), tw.data_ptr(), tgt.data_ptr(), hws.data_ptr(),
-                                  self._tail_counters(B * heads, dev).data_ptr())
+            ba = K.HeatmapBwdArgs(B, heads, g, 1, heat_p.data_ptr(), None, None, 0, None, 1.0, 0, dptr.data_ptr(),
+                                  ts.data_ptr(), tw.data_ptr(), tgt.data_ptr(), hws.data_ptr(), counters)
             K.check(lib.bfk_heatmap_bwd(C.byref(ba), st), "bfk_heatmap_bwd")
             if not first:
                 dgrid.add_(tgt)   # both a fused-loss and a heatmap gradient (rare): tiny [B,heads,Np] add
@@ -792,15 +848,29 @@ class Engine:
             dgrid.zero_()
         dX = torch.empty(B * Nf, D, device=dev, dtype=torch.float32)
         dX_T = torch.empty(B * Nf, D, device=dev, dtype=T) if T != torch.float32 else None
-        d_w_eff = torch.empty(heads, D, device=dev, dtype=torch.float32)
-        d_b_eff = torch.empty(heads, device=dev, dtype=torch.float32)
+        nd = len(cfg.decoder_prefixes)
+        d_w_eff = torch.empty(nd, D, device=dev, dtype=torch.float32)
+        d_b_eff = torch.empty(nd, device=dev, dtype=torch.float32)
         ws = torch.empty(lib.bfk_head_project_bwd_workspace_floats(B, heads, Np, D), device=dev, dtype=torch.float32)
         pa = K.HeadProjectArgs(B, heads, Np, D, ctx["xf"].data_ptr(), Nf * D, Nf - Np, tail["w_eff"].data_ptr(),
                                tail["b_eff"].data_ptr(), None, dgrid.data_ptr(), Nf, dX.data_ptr(), K.ptr(dX_T),
                                _dt(dX_T) if dX_T is not None else 0, d_w_eff.data_ptr(), d_b_eff.data_ptr(), ws.data_ptr())
         K.check(lib.bfk_head_project_bwd(C.byref(pa), st), "bfk_head_project_bwd")
+        dX_mask = None
+        if cfg.compute_mask:
+            if dgrid_m is None:
+                d_w_eff[heads:].zero_(); d_b_eff[heads:].zero_()
+            else:
+                # the mask head reads the fusion INPUT: its token gradient joins the fusion backward's at the assembly
+                dX_mask = torch.empty(B * Nf, D, device=dev, dtype=torch.float32)
+                ws_m = torch.empty(lib.bfk_head_project_bwd_workspace_floats(B, 1, Np, D), device=dev, dtype=torch.float32)
+                pm = K.HeadProjectArgs(B, 1, Np, D, ctx["X_in"].data_ptr(), Nf * D, Nf - Np, tail["w_eff"].data_ptr() + heads * D * 4,
+                                       tail["b_eff"].data_ptr() + heads * 4, None, dgrid_m.data_ptr(), Nf, dX_mask.data_ptr(), None, 0,
+                                       d_w_eff.data_ptr() + heads * D * 4, d_b_eff.data_ptr() + heads * 4, ws_m.data_ptr())
+                K.check(lib.bfk_head_project_bwd(C.byref(pm), st), "bfk_head_project_bwd")
+                k.launches += 4
         Wt, bt, dWt, dbt = self._decoder_ptr_tables(grads)
-        ca = K.DecoderCollapseArgs(heads, D, Wt.data_ptr(), bt.data_ptr(), None, None, tail["chain"].data_ptr(),
+        ca = K.DecoderCollapseArgs(nd, D, Wt.data_ptr(), bt.data_ptr(), None, None, tail["chain"].data_ptr(),
                                    d_w_eff.data_ptr(), d_b_eff.data_ptr(), dWt.data_ptr(), dbt.data_ptr())
         chain_t = tail["chain"]
 
@@ -823,6 +893,9 @@ class Engine:
             if self.grad_ready_hook:
                 self._hook_after_off_chain(f"fusion.{l}")
         self._join_off_chain()
+        if dX_mask is not None:
+            K.check(lib.bfk_add_inplace(dx.data_ptr(), dX_mask.data_ptr(), dx.numel(), st), "bfk_add_inplace")
+            k.launches += 1
 
         # ---- assembly ----
         need_tower = cfg.lora

@@ -1,4 +1,4 @@
-"""Host-side mirror of ``bifold.losses`` for the hot path (bifold/losses/__init__.py:5-109).
+"""Host-side mirror of ``bifold.losses`` for the hot path (bifold/losses/__init__.py:5-155).
 
 ``BCEGaussMap`` computes nn.BCELoss per head (mean over B*H*W, log clamped at -100) summed over
 heads, on our CUDA kernels:
@@ -26,8 +26,12 @@ class Losses:
             Loss = BCEGaussMap
         elif name == "composed":
             Loss = ComposedLoss
-        elif name in ("bce_mask", "dice", "focal"):
-            raise ValueError(f"Loss {name} needs mask_heatmap (compute_mask=True), which is outside the accelerated hot path")
+        elif name == "bce_mask":
+            Loss = BCEMask
+        elif name == "dice":
+            Loss = DiceLoss
+        elif name == "focal":
+            Loss = FocalLoss
         else:
             raise ValueError(f"Loss {name} not recognized")
         if cfg is not None:
@@ -82,3 +86,38 @@ class BCEGaussMap:    # bifold/losses/__init__.py:54-109
             inter[h] = cur
             loss = cur if loss is None else loss + cur
         return loss, inter
+
+
+def _mask_inputs(output, sample):
+    p = output["mask_heatmap"]            # needs a compute_mask=True model, like the reference (KeyError otherwise)
+    if not p.is_cuda:
+        raise K.BfkError("bifold_b200 losses run on CUDA only (no CPU fallback)")
+    return p, sample["mask"].to(p.device)
+
+
+class BCEMask:        # bifold/losses/__init__.py:112-117
+    def __init__(self, **kwargs):
+        pass
+
+    def __call__(self, output, sample):
+        p, m = _mask_inputs(output, sample)
+        return torch.ops.bfk.bce_prob(p, m.squeeze(1), None), {}
+
+
+class DiceLoss:       # bifold/losses/__init__.py:126-136
+    def __init__(self, *args, **kwargs):
+        pass
+
+    def __call__(self, output, sample):
+        p, m = _mask_inputs(output, sample)
+        return torch.ops.bfk.dice_loss(p.flatten(1), m.flatten(1))[0], {}
+
+
+class FocalLoss:      # bifold/losses/__init__.py:139-155
+    def __init__(self, alpha=0.25, gamma=2, **kwargs):
+        self.alpha = alpha
+        self.gamma = gamma
+
+    def __call__(self, output, sample):
+        p, m = _mask_inputs(output, sample)
+        return torch.ops.bfk.focal_loss(p, m.squeeze(1), float(self.alpha), float(self.gamma)), {}

@@ -198,12 +198,14 @@ class PickPlaceConvDecoder(_Holder):   # bifold/models/pickplace.py:10-47
     def __init__(self, dim, is_bimanual, fusion_model, num_patches, patch_size, compute_mask=False, detach_mask=False,
                  **kwargs):
         super().__init__()
-        if compute_mask:
-            raise K.BfkError("pick_place_convdecoder: compute_mask=True is not on the accelerated path (no shipped config sets it)")
         self.is_bimanual = is_bimanual
         self.fusion = Components.get_by_name(fusion_model, dim=dim, **kwargs)
         self.num_patches_sqrt = int(math.sqrt(num_patches))
-        self.mask_head = None
+        if compute_mask:                 # bifold/models/pickplace.py:27-32
+            self.detach_mask = detach_mask
+            self.mask_head = ConvDecoder(dim)
+        else:
+            self.mask_head = None
         if is_bimanual:
             self.left_pick_decoder, self.right_pick_decoder = ConvDecoder(dim), ConvDecoder(dim)
             self.left_place_decoder, self.right_place_decoder = ConvDecoder(dim), ConvDecoder(dim)
@@ -328,7 +330,8 @@ class SigLip(BaseModel):
         fusion_kw = {k: kwargs[k] for k in ("depth", "heads", "mlp_ratio") if k in kwargs}
         self.cfg = PolicyConfig(name="siglip", image_size=self.image_size, patch_size=patch_size, dim=dim,
                                 is_bimanual=self.is_bimanual, lora=bool(lora), r=r, lora_alpha=lora_alpha,
-                                lora_dropout=lora_dropout, **fusion_kw, **tower)
+                                lora_dropout=lora_dropout, compute_mask=bool(kwargs.get("compute_mask", False)),
+                                detach_mask=bool(kwargs.get("detach_mask", False)), **fusion_kw, **tower)
         siglip = _SiglipShell(self.cfg, bool(lora), "siglip_adapter")
         if hf_state is not None:
             self._install_pretrained(siglip, hf_state, bool(lora), automodel_name)
@@ -406,7 +409,7 @@ class SigLip(BaseModel):
         cfg = self.cfg
         # fused BCE when the targets travel with the sample (training loop: bifold/__main__.py:135-137)
         targets = None
-        if self.training and torch.is_grad_enabled():
+        if self.training and torch.is_grad_enabled() and not cfg.compute_mask:
             ts = [x.get(f"{h}_heatmap") for h in cfg.heads_out]
             if all(t is not None and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
                    and tuple(t.shape) == (rgb.shape[0], cfg.image_size, cfg.image_size) for t in ts):
@@ -417,9 +420,11 @@ class SigLip(BaseModel):
                                                    targets or [], self._param_list, self.training, need_grad, _want_argmax)
         self._last_key = key if _want_argmax else None
         out = PolicyOutput(attn_weights=None)
+        if cfg.compute_mask:              # key order of the reference's return_dict (bifold/models/pickplace.py:64-69)
+            out["mask_heatmap"] = heat[len(cfg.heads_out)]
         for i, h in enumerate(cfg.heads_out):
             out[f"{h}_heatmap"] = heat[i]
-        out.heat_all = heat
+        out.heat_all = heat[:len(cfg.heads_out)]
         if targets is not None:
             out.fused_loss = loss
             out.fused_targets = tuple(t.data_ptr() for t in targets)

@@ -13,7 +13,8 @@ Single ops (usable from the reference's own nn.Modules):
     bfk::linear       nn.Linear (+GELU tanh/erf)         HF:285-287,309,324-326; bifold/models/transformer.py:19-24
     bfk::layernorm    nn.LayerNorm                        HF:334-336; bifold/models/modules.py:11
     bfk::attention    softmax(QK^T s [query-row mask])V   HF:293-306; bifold/models/transformer.py:31-41
-    bfk::bce_prob     nn.BCELoss()(p, t [* mask])         bifold/losses/__init__.py:80-83
+    bfk::bce_prob     nn.BCELoss()(p, t [* mask])         bifold/losses/__init__.py:80-83,112-117
+    bfk::dice_loss / bfk::focal_loss  mask losses         bifold/losses/__init__.py:126-155
     bfk::argmax2d     first-max index per map             bifold/models/utils.py:66-73
     bfk::action       argmax + mask snap + arm gate       bifold/models/__init__.py:108-141, utils.py:80-83
     bfk::gauss_targets / bfk::normalize_u8                bifold/data/processor.py:405-439 / :143-148 (GPU input stage)
@@ -80,7 +81,7 @@ def _model(handle: int):
 def policy_fwd(handle: int, rgb: Tensor, instruction: Tensor, rgb_context: Optional[Tensor],
                context_attention_mask: Optional[Tensor], targets: Sequence[Tensor], params: Sequence[Tensor],
                training: bool, need_grad: bool, want_argmax: bool) -> Tuple[Tensor, Tensor, Tensor]:
-    """-> (heat [heads,B,H,W] fp32 post-sigmoid, loss [heads+1] (per-head BCE, then their sum; empty without targets),
+    """-> (heat [heads,B,H,W] fp32 post-sigmoid (compute_mask: [heads+1,...], pick maps gated, last map = mask_heatmap), loss [heads+1] (per-head BCE, then their sum; empty without targets),
     argmax keys [heads*B] int64 (empty unless want_argmax)).  ``params`` only carries the autograd edges; the engine reads
     the parameters it was built on."""
     model = _model(handle)
@@ -100,7 +101,7 @@ def policy_fwd(handle: int, rgb: Tensor, instruction: Tensor, rgb_context: Optio
 def _(handle, rgb, instruction, rgb_context, context_attention_mask, targets, params, training, need_grad, want_argmax):
     cfg = _model(handle).cfg
     B, heads, H = rgb.shape[0], len(cfg.heads_out), cfg.image_size
-    return (rgb.new_empty((heads, B, H, H), dtype=torch.float32),
+    return (rgb.new_empty((heads + int(cfg.compute_mask), B, H, H), dtype=torch.float32),
             rgb.new_empty((heads + 1 if len(targets) else 0,), dtype=torch.float32),
             rgb.new_empty((heads * B if want_argmax else 0,), dtype=torch.int64))
 
@@ -409,6 +410,104 @@ def _bce_backward(ctx, g):
 
 
 bce_prob.register_autograd(_bce_backward, setup_context=_bce_setup)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# mask losses on mask_heatmap (compute_mask=True): bifold/losses/__init__.py:126-155
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("bfk::dice_loss", mutates_args=(), device_types="cuda")
+def dice_loss(p: Tensor, t: Tensor) -> Tuple[Tensor, Tensor]:
+    """DiceLoss: p, t [B, ...] -> (sum_b 1 - (2 sum(p t) + 1) / (sum p + sum t + 1), per-sample sums [B,3] for the backward)."""
+    _need_cuda(p, t)
+    B = p.shape[0]
+    p2, t2 = p.reshape(B, -1).float().contiguous(), t.reshape(B, -1).to(torch.float32).contiguous()
+    lib = K.load()
+    sums = torch.empty(B, 3, device=p.device, dtype=torch.float32)
+    loss = torch.empty(1, device=p.device, dtype=torch.float32)
+    part = torch.empty(lib.bfk_dice_loss_workspace_floats(B), device=p.device, dtype=torch.float32)
+    K.check(lib.bfk_dice_loss_fwd(p2.data_ptr(), t2.data_ptr(), B, p2.shape[1], sums.data_ptr(), loss.data_ptr(), part.data_ptr(), _stream()),
+            "bfk_dice_loss_fwd")
+    return loss.reshape(()), sums
+
+
+@dice_loss.register_fake
+def _(p, t):
+    return p.new_empty((), dtype=torch.float32), p.new_empty((p.shape[0], 3), dtype=torch.float32)
+
+
+@torch.library.custom_op("bfk::dice_loss_bwd", mutates_args=(), device_types="cuda")
+def dice_loss_bwd(g: Tensor, t: Tensor, sums: Tensor) -> Tensor:
+    B = t.shape[0]
+    t2 = t.reshape(B, -1).to(torch.float32).contiguous()
+    dp = torch.empty_like(t2)
+    K.check(K.load().bfk_dice_loss_bwd(t2.data_ptr(), B, t2.shape[1], sums.data_ptr(), g.reshape(1).float().contiguous().data_ptr(),
+                                       dp.data_ptr(), _stream()), "bfk_dice_loss_bwd")
+    return dp
+
+
+@dice_loss_bwd.register_fake
+def _(g, t, sums):
+    return t.new_empty((t.shape[0], t[0].numel()), dtype=torch.float32)
+
+
+def _dice_setup(ctx, inputs, output):
+    p, t = inputs
+    ctx.save_for_backward(t, output[1])
+    ctx.p_shape = p.shape
+    ctx.mark_non_differentiable(output[1])
+
+
+def _dice_backward(ctx, g, gsums):
+    t, sums = ctx.saved_tensors
+    return torch.ops.bfk.dice_loss_bwd(g, t, sums).reshape(ctx.p_shape), None
+
+
+dice_loss.register_autograd(_dice_backward, setup_context=_dice_setup)
+
+
+@torch.library.custom_op("bfk::focal_loss", mutates_args=(), device_types="cuda")
+def focal_loss(p: Tensor, t: Tensor, alpha: float, gamma: float) -> Tensor:
+    """FocalLoss: alpha_t * BCE(p, t) * (1 - p_t)^gamma, ``.mean(1).sum()`` over p [B, H, W] (= sum / H)."""
+    _need_cuda(p, t)
+    p2, t2 = p.float().contiguous(), t.to(torch.float32).contiguous()
+    loss = torch.empty(1, device=p.device, dtype=torch.float32)
+    part = torch.empty(1024, device=p.device, dtype=torch.float32)
+    K.check(K.load().bfk_focal_loss_fwd(p2.data_ptr(), t2.data_ptr(), p2.numel(), float(alpha), float(gamma), 1.0 / p.shape[1],
+                                        loss.data_ptr(), part.data_ptr(), _stream()), "bfk_focal_loss_fwd")
+    return loss.reshape(())
+
+
+@focal_loss.register_fake
+def _(p, t, alpha, gamma):
+    return p.new_empty((), dtype=torch.float32)
+
+
+@torch.library.custom_op("bfk::focal_loss_bwd", mutates_args=(), device_types="cuda")
+def focal_loss_bwd(g: Tensor, p: Tensor, t: Tensor, alpha: float, gamma: float) -> Tensor:
+    p2, t2 = p.float().contiguous(), t.to(torch.float32).contiguous()
+    dp = torch.empty_like(p2)
+    K.check(K.load().bfk_focal_loss_bwd(p2.data_ptr(), t2.data_ptr(), p2.numel(), float(alpha), float(gamma), 1.0 / p.shape[1],
+                                        g.reshape(1).float().contiguous().data_ptr(), dp.data_ptr(), _stream()), "bfk_focal_loss_bwd")
+    return dp
+
+
+@focal_loss_bwd.register_fake
+def _(g, p, t, alpha, gamma):
+    return torch.empty_like(p, dtype=torch.float32)
+
+
+def _focal_setup(ctx, inputs, output):
+    p, t, alpha, gamma = inputs
+    ctx.save_for_backward(p, t)
+    ctx.ag = (alpha, gamma)
+
+
+def _focal_backward(ctx, g):
+    p, t = ctx.saved_tensors
+    return torch.ops.bfk.focal_loss_bwd(g, p, t, ctx.ag[0], ctx.ag[1]), None, None, None
+
+
+focal_loss.register_autograd(_focal_backward, setup_context=_focal_setup)
 
 
 @torch.library.custom_op("bfk::argmax2d", mutates_args=(), device_types="cuda")

@@ -392,6 +392,47 @@ BFK_API int32_t bfk_gauss_targets(const int32_t* centers, int32_t n_maps, int32_
 BFK_API int32_t bfk_normalize_u8(const uint8_t* frames, int64_t n_frames, int32_t H, int32_t W, float mean, float std_, float* out,
                          bfk_stream_t s);
 
+/* ------------------------------------------------------------------------------------------------
+ * Mask branch of PickPlaceConvDecoder (compute_mask=True) and the mask losses.
+ * bfk_mask_gate_fwd: pick heatmaps = sigmoid(pick) * mask_heatmap (bifold/models/pickplace.py:78-101,111-122);
+ *   heads whose bit is clear in `pick_heads` are copied.  bfk_mask_gate_bwd: the product rule, with the mask side of it
+ *   dropped when detach_mask is set (pickplace.py:80-89).  B*H*W must be a multiple of 4.
+ * bfk_dice_loss_*:  DiceLoss  (bifold/losses/__init__.py:126-136): sum_b 1 - (2 sum(p t) + 1) / (sum p + sum t + 1).
+ * bfk_focal_loss_*: FocalLoss (bifold/losses/__init__.py:139-155): scale * sum alpha_t * bce(p, t) * (1 - p_t)^gamma with
+ *   nn.BCELoss's -100 log clamp; the reference's `loss.mean(1).sum()` is scale = 1 / H.  alpha < 0 disables alpha_t.
+ * bfk_add_inplace: dst += src (the mask head's gradient w.r.t. the fusion INPUT joins the fusion backward's).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, heads, H, W;
+  uint32_t pick_heads;               /* bit h set: head h is gated by the mask */
+  const float* heat_raw;             /* [heads, B, H, W] sigmoid outputs */
+  const float* mask_p;               /* [B, H, W] mask heatmap */
+  float* heat_out;                   /* [heads, B, H, W] */
+} bfk_mask_gate_args;
+BFK_API int32_t bfk_mask_gate_fwd(const bfk_mask_gate_args* a, bfk_stream_t s);
+typedef struct {
+  int32_t B, heads, H, W;
+  uint32_t pick_heads; int32_t detach_mask;
+  const float* dheat_out;            /* [heads (+1), B, H, W] upstream gradient; map `heads` = d mask_heatmap if has_dmask */
+  int32_t has_dmask;
+  const float* heat_raw; const float* mask_p;
+  float* dheat_raw;                  /* [heads, B, H, W] gradient w.r.t. the sigmoid outputs */
+  float* dmask;                      /* [B, H, W] total gradient w.r.t. the mask heatmap */
+} bfk_mask_gate_bwd_args;
+BFK_API int32_t bfk_mask_gate_bwd(const bfk_mask_gate_bwd_args* a, bfk_stream_t s);
+BFK_API int32_t bfk_add_inplace(float* dst, const float* src, int64_t n, bfk_stream_t s);
+/* p, t: [B, n] fp32.  sums [B, 3] = {sum p t, sum p, sum t} (saved for the backward), loss [1]. */
+BFK_API size_t bfk_dice_loss_workspace_floats(int32_t B);
+BFK_API int32_t bfk_dice_loss_fwd(const float* p, const float* t, int32_t B, int64_t n, float* sums, float* loss, float* partials,
+                          bfk_stream_t s);
+BFK_API int32_t bfk_dice_loss_bwd(const float* t, int32_t B, int64_t n, const float* sums, const float* g /* DEVICE [1] */, float* dp,
+                          bfk_stream_t s);
+/* p, t: n fp32 elements; partials: >= 1024 floats; g: DEVICE [1] upstream gradient. */
+BFK_API int32_t bfk_focal_loss_fwd(const float* p, const float* t, int64_t n, float alpha, float gamma, float scale, float* loss,
+                           float* partials, bfk_stream_t s);
+BFK_API int32_t bfk_focal_loss_bwd(const float* p, const float* t, int64_t n, float alpha, float gamma, float scale, const float* g,
+                           float* dp, bfk_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,14 @@ CASES = {
     "base224_bi_lora": (base224_spec(name="siglip", is_bimanual=True, lora=True), 2, False),
     "base224_bi_seq_lora": (base224_spec(name="siglip_sequential", is_bimanual=True, lora=True, context_length=3), 2, False),
 }
+# compute_mask=True cases (mask head + gated pick maps + the mask losses of bifold/conf/loss/composed*.yaml):
+# name: (spec, batch, composed loss names, weights)
+MASK_CASES = {
+    "tiny_bi_seq_lora_mask": (tiny_spec(name="siglip_sequential", is_bimanual=True, lora=True, context_length=2, compute_mask=True),
+                              4, ["bce_gaussmap", "focal", "dice"], [40, 20, 1]),
+    "tiny_uni_mask_detach": (tiny_spec(name="siglip", is_bimanual=False, lora=False, compute_mask=True, detach_mask=True),
+                             3, ["bce_gaussmap", "bce_mask"], [2, 1]),
+}
 PROBE = 97  # prime stride for probes of big tensors
 
 
@@ -96,12 +104,56 @@ def run_case(name: str, spec: PolicySpec, batch: int, full: bool):
     print(f"{name}: loss={float(loss):.6f} loss_after={float(loss2):.6f} -> {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def run_mask_case(name: str, spec: PolicySpec, batch: int, loss_names, weights):
+    """compute_mask=True model + ComposedLoss through the reference's own factories (bifold/losses/__init__.py:30-51,112-155)."""
+    _, Losses, Optimizers = ref_shims.import_reference()
+    sd = make_state_dict(spec, seed=3407)
+    sample = make_sample(spec, batch, seed=0)
+    model = ref_shims.build_reference_model(spec, sd)
+    model.train()
+    assert sorted(k for k, p in model.named_parameters() if p.requires_grad) == sorted(trainable_keys(spec, sd))
+    loss_fn = Losses.get_by_name(cfg=ref_shims.Cfg(name="composed", loss_names=list(loss_names), weights=list(weights),
+                                                   is_bimanual=spec.is_bimanual, mask_pick_heatmap=True))
+    optim = Optimizers.get_by_name(cfg=ref_shims.Cfg(name="adam", lr=1e-3, betas=[0.9, 0.999], eps=1e-8, weight_decay=0),
+                                   params=filter(lambda p: p.requires_grad, model.parameters()))
+    out = model(dict(sample))
+    loss, inter = loss_fn(out, sample)
+    optim.zero_grad()
+    loss.backward()
+    g = {"loss": loss.detach().numpy()}
+    for k, v in inter.items():
+        g[f"loss/{k}"] = v.detach().numpy()
+    for k, v in out.items():
+        if v is not None:
+            g[f"heatmap/{k}"] = v.detach().numpy()
+    for k, p in model.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None, k
+            g[f"grad/{k}"] = p.grad.detach().numpy()
+            g[f"gradnorm/{k}"] = p.grad.double().norm().numpy()
+    optim.step()
+    for k, p in model.named_parameters():
+        if p.requires_grad:
+            g[f"param1/{k}"] = p.detach().numpy()
+    model.eval()
+    action, out2 = model.get_action(dict(sample), return_raw_output=True)
+    g["loss_after_step"] = loss_fn(out2, sample)[0].detach().numpy()
+    for k, v in vars(action).items():
+        g[f"action/{k}"] = np.asarray(v).astype(np.int64)
+    path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+    np.savez_compressed(path, **g)
+    print(f"{name}: loss={float(loss):.6f} -> {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 def main(argv):
-    names = argv or list(CASES)
+    names = argv or (list(CASES) + list(MASK_CASES))
     torch.set_num_threads(os.cpu_count() or 1)
     for n in names:
-        spec, batch, full = CASES[n]
-        run_case(n, spec, batch, full)
+        if n in MASK_CASES:
+            run_mask_case(n, *MASK_CASES[n])
+        else:
+            spec, batch, full = CASES[n]
+            run_case(n, spec, batch, full)
 
 
 if __name__ == "__main__":

@@ -161,6 +161,8 @@ def build_reference_model(spec, state_dict):
               depth=spec.depth, heads=spec.heads, mlp_ratio=spec.mlp_ratio, dropout=0.0)
     if spec.name == "siglip_sequential":
         cfg["context_length"] = spec.context_length
+    if getattr(spec, "compute_mask", False):
+        cfg["compute_mask"], cfg["detach_mask"] = True, spec.detach_mask
     torch.manual_seed(3407)
     model = Models.get_by_name(cfg, device=torch.device("cpu"))
     missing, unexpected = model.load_state_dict(state_dict, strict=True)

@@ -40,6 +40,8 @@ class PolicySpec:
     vocab_size: int = 32000
     text_len: int = 64
     tower_ln_eps: float = 1e-6
+    compute_mask: bool = False      # PickPlaceConvDecoder(compute_mask=..., detach_mask=...) (bifold/models/pickplace.py:18-32)
+    detach_mask: bool = False
 
     @property
     def grid(self) -> int:
@@ -58,7 +60,7 @@ class PolicySpec:
 
     @property
     def decoder_names(self):
-        return [f"{h}_decoder" for h in self.heads_out]
+        return [f"{h}_decoder" for h in self.heads_out] + (["mask_head"] if self.compute_mask else [])
 
     def fusion_len(self) -> int:
         t = self.context_length if self.name == "siglip_sequential" else 0

@@ -68,3 +68,33 @@ def test_oracle_matches_reference_base(name):
     if not os.path.exists(os.path.join(GOLDEN, f"{name}.npz")):
         pytest.skip("fixture not generated")
     _check_case(name)
+
+
+@pytest.mark.parametrize("name", ["tiny_bi_seq_lora_mask", "tiny_uni_mask_detach"])
+def test_oracle_matches_reference_mask_branch(name):
+    """compute_mask=True (mask head on the fusion input, gated pick maps, detach_mask) and the composed mask losses
+    (bce_mask / focal / dice) against fixtures from the real reference."""
+    from oracle.make_golden import MASK_CASES
+    spec, batch, loss_names, weights = MASK_CASES[name]
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    sd = make_state_dict(spec, seed=3407)
+    sample = make_sample(spec, batch, seed=0)
+    keys = trainable_keys(spec, sd)
+    assert any(".mask_head." in k for k in keys)
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in keys}
+    work = dict(sd)
+    work.update(leaves)
+    out = po.policy_forward(work, sample, spec, training=True)
+    loss, inter = po.composed_loss(out, sample, spec, loss_names, weights)
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=3e-5)
+    for n in loss_names:
+        np.testing.assert_allclose(inter[n].item(), g[f"loss/{n}"], rtol=3e-5)
+    for k, v in out.items():
+        if v is not None:
+            np.testing.assert_allclose(v.detach().numpy(), g[f"heatmap/{k}"], atol=1e-5, rtol=0)
+    grads = dict(zip(keys, torch.autograd.grad(loss, [leaves[k] for k in keys])))
+    for k in keys:
+        gn = float(g[f"gradnorm/{k}"])
+        np.testing.assert_allclose(grads[k].double().norm().item(), gn, rtol=2e-3, atol=1e-9, err_msg=k)
+        np.testing.assert_allclose(grads[k].numpy(), g[f"grad/{k}"], atol=3e-4 * gn / max(1.0, np.sqrt(grads[k].numel() / 64)) + 1e-9,
+                                   rtol=2e-3, err_msg=k)

@@ -19,6 +19,8 @@ def model_cfg(spec: PolicySpec, precision="fp32") -> Cfg:
                                 vocab_size=spec.vocab_size, text_len=spec.text_len))
     if spec.name == "siglip_sequential":
         cfg["context_length"] = spec.context_length
+    if spec.compute_mask:
+        cfg["compute_mask"], cfg["detach_mask"] = True, spec.detach_mask
     return cfg
 
 
