@@ -1,6 +1,7 @@
 // LayerNorm forward / backward: one warp per row, fp32 statistics, float4 accesses.
 // HBM-bound: forward reads 4D bytes and writes 2D (bf16) or 4D per row; backward reads dy, x (+dres)
 // and writes dx (+ a bf16 copy).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace bfk {
@@ -123,6 +124,61 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(bfk_layernorm_fwd
       if (lane == j) mine = t;
     }
     if (lane < 16) reinterpret_cast<__nv_bfloat16*>(a.lora_u)[(long long)row * a.ld_u + lane] = __float2bfloat16_rn(mine);
+  }
+}
+
+// LoRA down-projection u[m, 0..16) = sum_k h[m, k] * A[j, k] over the bf16 rows the LayerNorm pass has just written (still in
+// L2): warp-level tensor-core MMA (m16n8k16), 16 rows per CTA, the K range split over the 4 warps.  Every thread loads 16
+// contiguous bytes of "its" row per 32-wide K block (whole 32-byte sectors per row); the k order inside an MMA is a free
+// permutation as long as both operands use the same one, so the same 16-byte pattern is used for A's rows.
+// Replaces 16 per-row dot products inside ln_fwd_kernel (96 L1 loads + ~600 FMA/convert instructions per lane and row).
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <int NB>   // NB = 32-wide K blocks per warp (D = 128 * NB)
+__global__ void __launch_bounds__(128) lora_down_mma_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int M,
+                                                            const __nv_bfloat16* __restrict__ A, int D,
+                                                            __nv_bfloat16* __restrict__ u, long long ldu) {
+  __shared__ float red[4][16][17];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int row0 = blockIdx.x * 16;
+  const int r0 = min(row0 + g, M - 1), r1 = min(row0 + g + 8, M - 1);      // clamped loads, predicated stores
+  const uint4* h0 = reinterpret_cast<const uint4*>(h + (long long)r0 * ldh) + t;
+  const uint4* h1 = reinterpret_cast<const uint4*>(h + (long long)r1 * ldh) + t;
+  const uint4* A0 = reinterpret_cast<const uint4*>(A + (long long)g * D) + t;
+  const uint4* A1 = reinterpret_cast<const uint4*>(A + (long long)(g + 8) * D) + t;
+  uint4 ra[NB], rb[NB], b0[NB], b1[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {           // K block (warp + 4 i): uint4 index 4 * block + t
+    const int o = 4 * (warp + 4 * i);
+    ra[i] = __ldg(h0 + o); rb[i] = __ldg(h1 + o);
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const int o = 4 * (warp + 4 * i);
+    b0[i] = __ldg(A0 + o); b1[i] = __ldg(A1 + o);
+  }
+  float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    mma16816(c0, ra[i].x, rb[i].x, ra[i].y, rb[i].y, b0[i].x, b0[i].y);
+    mma16816(c1, ra[i].x, rb[i].x, ra[i].y, rb[i].y, b1[i].x, b1[i].y);
+    mma16816(c0, ra[i].z, rb[i].z, ra[i].w, rb[i].w, b0[i].z, b0[i].w);
+    mma16816(c1, ra[i].z, rb[i].z, ra[i].w, rb[i].w, b1[i].z, b1[i].w);
+  }
+  red[warp][g][2 * t] = c0[0]; red[warp][g][2 * t + 1] = c0[1];
+  red[warp][g + 8][2 * t] = c0[2]; red[warp][g + 8][2 * t + 1] = c0[3];
+  red[warp][g][8 + 2 * t] = c1[0]; red[warp][g][8 + 2 * t + 1] = c1[1];
+  red[warp][g + 8][8 + 2 * t] = c1[2]; red[warp][g + 8][8 + 2 * t + 1] = c1[3];
+  __syncthreads();
+  // 128 threads: row = tid / 8, column pair = tid % 8; fixed summation order over the 4 K slices
+  const int r = threadIdx.x >> 3, cp = (threadIdx.x & 7) * 2;
+  if (row0 + r < M) {
+    const float s0 = (red[0][r][cp] + red[1][r][cp]) + (red[2][r][cp] + red[3][r][cp]);
+    const float s1 = (red[0][r][cp + 1] + red[1][r][cp + 1]) + (red[2][r][cp + 1] + red[3][r][cp + 1]);
+    *reinterpret_cast<__nv_bfloat162*>(u + (long long)(row0 + r) * ldu + cp) = __floats2bfloat162_rn(s0, s1);
   }
 }
 
@@ -279,6 +335,13 @@ static int ln_bwd_blocks(int M, int& rows_per_block, bool param_grads = true) {
 
 }  // namespace bfk
 
+namespace bfk {
+static bool lora_down_fused_forced() {          // BFK_LORA_DOWN_FUSED=1: measurement / test knob, keeps the in-LayerNorm dot products
+  static const bool v = [] { const char* e = getenv("BFK_LORA_DOWN_FUSED"); return e && e[0] == '1'; }();
+  return v;
+}
+}  // namespace bfk
+
 extern "C" int32_t bfk_layernorm_fwd(const bfk_layernorm_fwd_args* a, bfk_stream_t s_) {
   using namespace bfk;
   BFK_CHECK_ARG(a && a->x && a->y && a->gamma && a->beta, "bfk_layernorm_fwd: null pointer");
@@ -289,14 +352,29 @@ extern "C" int32_t bfk_layernorm_fwd(const bfk_layernorm_fwd_args* a, bfk_stream
                 "bfk_layernorm_fwd: need D%%4==0, D<=%d, ld%%4==0 (D=%d)", 128 * LN_MAXC, a->D);
   cudaStream_t s = to_stream(s_);
   int grid = (a->M + LN_WARPS - 1) / LN_WARPS;
+  // LoRA down-projection: a second, tensor-core launch over the rows just written (D = 768 / 1152, 16-byte aligned rows);
+  // other shapes keep the per-row dot products inside the LayerNorm kernel
+  const void* lsrc = a->y2 ? a->y2 : a->y;
+  const long long lld = a->y2 ? a->ldy2 : a->ldy;
+  const bool lora_mma = a->lora_a && a->y_dtype == BFK_BF16 && (a->D == 768 || a->D == 1152) && lld % 8 == 0 && a->ld_u % 2 == 0 &&
+                        ((reinterpret_cast<uintptr_t>(lsrc) | reinterpret_cast<uintptr_t>(a->lora_a)) & 15u) == 0 &&
+                        (reinterpret_cast<uintptr_t>(a->lora_u) & 3u) == 0 && !lora_down_fused_forced();
+  const bool lora_fused = a->lora_a && !lora_mma;
 #define LN_FWD(NC)                                                                          \
   do {                                                                                      \
-    if (a->y_dtype == BFK_BF16 && a->lora_a) ln_fwd_kernel<__nv_bfloat16, NC, true><<<grid, LN_WARPS * 32, 0, s>>>(*a); \
+    if (a->y_dtype == BFK_BF16 && lora_fused) ln_fwd_kernel<__nv_bfloat16, NC, true><<<grid, LN_WARPS * 32, 0, s>>>(*a); \
     else if (a->y_dtype == BFK_BF16) ln_fwd_kernel<__nv_bfloat16, NC><<<grid, LN_WARPS * 32, 0, s>>>(*a); \
     else ln_fwd_kernel<float, NC><<<grid, LN_WARPS * 32, 0, s>>>(*a);                         \
   } while (0)
   if (a->D <= 256) LN_FWD(2); else if (a->D <= 768) LN_FWD(6); else if (a->D <= 1152) LN_FWD(9); else LN_FWD(12);
 #undef LN_FWD
+  if (lora_mma) {
+    const int g16 = (a->M + 15) / 16;
+    if (a->D == 768)
+      lora_down_mma_kernel<6><<<g16, 128, 0, s>>>((const __nv_bfloat16*)lsrc, lld, a->M, (const __nv_bfloat16*)a->lora_a, a->D, (__nv_bfloat16*)a->lora_u, a->ld_u);
+    else
+      lora_down_mma_kernel<9><<<g16, 128, 0, s>>>((const __nv_bfloat16*)lsrc, lld, a->M, (const __nv_bfloat16*)a->lora_a, a->D, (__nv_bfloat16*)a->lora_u, a->ld_u);
+  }
   BFK_CHECK_LAUNCH("bfk_layernorm_fwd");
   return BFK_OK;
 }

@@ -95,7 +95,7 @@ class Kernels:
                                K.ptr(mean), K.ptr(rstd), K.ptr(y2), ldy2, y2_p, y2_seed, K.ptr(lora_a), K.ptr(lora_u), ld_u,
                                K.ptr(self.seed_dev) if y2_p > 0.0 else None)
         K.check(self.lib.bfk_layernorm_fwd(C.byref(a), _stream()), "bfk_layernorm_fwd")
-        self.launches += 1
+        self.launches += 2 if lora_a is not None else 1      # + the tensor-core LoRA down-projection over the rows just written
         self.work["ln_bytes"] += M * D * (4.0 + y.element_size() + (y2.element_size() if y2 is not None else 0))
 
     def layernorm_bwd(self, dy, ld_dy, x, M, D, mean, rstd, gamma, dres, dx, dx2=None, dgamma=None, dbeta=None,

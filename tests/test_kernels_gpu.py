@@ -204,10 +204,11 @@ def test_layernorm_fwd_bwd(kern, D, ydt):
     assert (dx_b - gx).abs().max().item() <= tol * gx.abs().max().item()
 
 
-def test_layernorm_fwd_fused_dropout_copy(kern):
+@pytest.mark.parametrize("D", [768, 1152, 512])   # 768 / 1152: tensor-core LoRA down-projection; 512: in-LayerNorm dot products
+def test_layernorm_fwd_fused_dropout_copy(kern, D):
     """The optional second LN output equals bfk_dropout_copy applied to the first (same element hash)."""
     from bifold_b200 import _cabi as K
-    M, D, p, seed = 333, 768, 0.1, 1234567
+    M, p, seed = 333, 0.1, 1234567
     x = torch.randn(M, D, device="cuda")
     gam = torch.randn(D, device="cuda"); bet = torch.randn(D, device="cuda")
     y = torch.zeros(M, D + 16, device="cuda", dtype=torch.bfloat16)
