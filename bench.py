@@ -235,7 +235,7 @@ def run_reference(args, w, rank, world):
 KERNEL_CLASSES = (
     ("attention", ("attn_",)),
     ("gemm", ("gemm_tc", "gemm_simt", "splitk_reduce", "lora_grads")),
-    ("layernorm", ("ln_fwd", "ln_bwd")),
+    ("layernorm", ("ln_fwd", "ln_bwd", "lora_down_mma")),   # lora_down_mma: second launch of bfk_layernorm_fwd (LoRA down-projection over its output)
     ("tail", ("heatmap_", "head_project", "collapse_", "argmax2d", "action_kernel", "loss_finalize", "bce_prob", "gauss_targets")),
 )
 

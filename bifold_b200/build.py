@@ -12,16 +12,18 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
+# A/B builds (measurement only): BFK_BUILD_TAG=x BFK_EXTRA_NVCC_FLAGS="-DFOO=1" -> build_x/, lib/libbifold_b200_x.so (load with BFK_LIB_PATH)
+_TAG = os.environ.get("BFK_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + (f"_{_TAG}" if _TAG else ""))
 LIB_DIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIB_DIR, "libbifold_b200.so")
+LIB = os.path.join(LIB_DIR, "libbifold_b200" + (f"_{_TAG}" if _TAG else "") + ".so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-Xptxas", "-v", "-I", INCLUDE,
-]
+] + os.environ.get("BFK_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

@@ -9,7 +9,11 @@ namespace bfk {
 constexpr int TC_EPI_WARPS = 8;   // generic epilogue: two warps per TMEM lane quarter, alternating 32-column chunks
 // Kernels compiled for one specialised EpiMode need far fewer registers and run four warps per lane quarter: the fused
 // epilogues are instruction-bound (GELU / dGELU cost 10-25 instructions per element), more warps = more issue slots used.
-__host__ __device__ constexpr int epi_warps(int mode) { return mode == EPI_GENERIC ? 8 : 16; }
+#ifndef BFK_RES_EW
+#define BFK_RES_EW 8       // epilogue warps of the bias + fp32-residual mode: its 2 x 32 operand registers (residual double buffer) spill at the
+                           // 112-register cap of 16 warps (104 B, measured 37.7 us on 12544x768x768); 8 warps: 166 registers, 35.6 us, +1.3 % on the step
+#endif
+__host__ __device__ constexpr int epi_warps(int mode) { return mode == EPI_GENERIC ? 8 : (mode == EPI_RES_F32 ? BFK_RES_EW : 16); }
 
 // ---- fast epilogue math for bf16 outputs (the fp32 parity mode uses the exact functions of epilogue.cuh) ----
 __device__ __forceinline__ float tanh_fast(float x) {

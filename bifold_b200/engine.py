@@ -97,6 +97,8 @@ class Kernels:
         K.check(self.lib.bfk_layernorm_fwd(C.byref(a), _stream()), "bfk_layernorm_fwd")
         self.launches += 2 if lora_a is not None else 1      # + the tensor-core LoRA down-projection over the rows just written
         self.work["ln_bytes"] += M * D * (4.0 + y.element_size() + (y2.element_size() if y2 is not None else 0))
+        if lora_a is not None:
+            self.work["ln_bytes"] += M * D * 2.0      # the down-projection reads the (dropped) bf16 rows again
 
     def layernorm_bwd(self, dy, ld_dy, x, M, D, mean, rstd, gamma, dres, dx, dx2=None, dgamma=None, dbeta=None,
                       dy2=None, ld_dy2=0, dy2_p=0.0, dy2_seed=0):
