@@ -163,7 +163,7 @@ inline bool epi_from_args(const bfk_gemm_args* a, EpiParams& p) {
   p.mode = EPI_GENERIC;
   if (ok && a->alpha == 1.f && !a->accumulate && a->act == BFK_ACT_NONE && !a->residual) {
     p.mode = a->out_dtype == BFK_BF16 ? EPI_STORE_BF16 : EPI_STORE_F32;   // plain stores also take a ragged last chunk
-  } else if (ok && a->alpha == 1.f && !a->accumulate && a->N % 32 == 0) {
+  } else if (ok && a->alpha == 1.f && !a->accumulate && a->N % 16 == 0) {   // N % 32 == 16: the tile epilogues guard the last half chunk
     const bool bf = a->out_dtype == BFK_BF16;
     if (false) {}
     else if (a->act == BFK_ACT_NONE && a->residual && !bf) p.mode = EPI_RES_F32;

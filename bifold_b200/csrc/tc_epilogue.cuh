@@ -244,11 +244,11 @@ __device__ __forceinline__ void epi_load_ops(const EpiParams& ep, int m, int nc,
   if constexpr (EpiOps<MODE>::RES) {
     const float* rrow = ep.residual + (long long)(ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m) * ep.ldr;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) op[i] = ldg256(rrow + nc + 8 * i);
+    for (int i = 0; i < 4; ++i) if (nc + 8 * i < ep.N) op[i] = ldg256(rrow + nc + 8 * i);       // N % 16 == 0: a vector is all in or all out
   } else if constexpr (EpiOps<MODE>::DG) {
     const __nv_bfloat16* hrow = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)m * ep.ld_aux;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) op[i] = ldg256(hrow + nc + 16 * i);
+    for (int i = 0; i < 2; ++i) if (nc + 16 * i < ep.N) op[i] = ldg256(hrow + nc + 16 * i);
   }
 }
 template <int MODE>
@@ -325,7 +325,7 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, int m, int n0, int
           V8 w;
 #pragma unroll
           for (int t = 0; t < 8; ++t) w.w[t] = pack_bf16(v[q * 16 + 2 * t], v[q * 16 + 2 * t + 1]);
-          stg256(ap + 16 * q, w);
+          if (nc + 16 * q < ep.N) stg256(ap + 16 * q, w);
         }
       }
 #pragma unroll
@@ -350,8 +350,10 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, int m, int n0, int
           wg.w[t] = pack_bf16(g0, g1);
           wd.w[t] = pack_bf16(d0, d1);
         }
-        stg256(dp + 16 * q, wg);
-        stg256(ap + 16 * q, wd);
+        if (nc + 16 * q < ep.N) {          // ragged last chunk (N % 32 == 16, e.g. the so400m MLP width 4304): first half only
+          stg256(dp + 16 * q, wg);
+          stg256(ap + 16 * q, wd);
+        }
       }
     } else if constexpr (OUT_BF16) {
       __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(ep.D) + (long long)m * ep.ldd + nc;
@@ -360,7 +362,7 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, int m, int n0, int
         V8 w;
 #pragma unroll
         for (int t = 0; t < 8; ++t) w.w[t] = pack_bf16(v[q * 16 + 2 * t], v[q * 16 + 2 * t + 1]);
-        stg256(dp + 16 * q, w);
+        if (nc + 16 * q < ep.N) stg256(dp + 16 * q, w);
       }
     } else {
       float* dp = reinterpret_cast<float*>(ep.D) + (long long)m * ep.ldd + nc;
@@ -369,7 +371,7 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, int m, int n0, int
         V8 w;
 #pragma unroll
         for (int t = 0; t < 8; ++t) w.w[t] = __float_as_uint(v[q * 8 + t]);
-        stg256(dp + 8 * q, w);
+        if (nc + 8 * q < ep.N) stg256(dp + 8 * q, w);
       }
     }
   };

@@ -106,11 +106,12 @@ SPECIAL_CASES = [
 
 
 @pytest.mark.parametrize("case", SPECIAL_CASES)
-@pytest.mark.parametrize("shape", [(1280, 2048, 320), (1304, 2048, 328), (2560, 784, 328), (2560, 1136, 320)])
+@pytest.mark.parametrize("shape", [(1280, 2048, 320), (1304, 2048, 328), (2560, 784, 328), (2560, 1136, 320), (1280, 4304, 328)])
 def test_gemm_specialised_epilogues(kern, case, shape):
-    """The compile-time specialised tcgen05 epilogues (alpha == 1, N % 32 == 0) against fp32 torch; M = 1304 leaves a
+    """The compile-time specialised tcgen05 epilogues (alpha == 1, N % 16 == 0) against fp32 torch; M = 1304 leaves a
     ragged last row block, K = 328 a ragged last K block; N = 784 / 1136 end in a thin last n-tile (16 / 112 live columns)
-    whose MMA runs with a reduced N (modes that need N % 32 == 0 fall back to the generic epilogue there)."""
+    whose MMA runs with a reduced N; N = 784 / 1136 / 4304 (the so400m MLP width) have N % 32 == 16: the last 32-column chunk
+    is half live (guarded vector loads / stores)."""
     ta, tb, use_bias, act, use_res, out_bf16 = case
     M, N, Kd = shape
     dev = "cuda"
