@@ -615,6 +615,26 @@ def main():
 
     res = run_workload(w, dev, rank, world, args.steps, max(args.warmup, 3), args, main=True)
 
+    # ---- multi-GPU: what the gap to N x the 1-GPU step is made of.  Every rank times the SAME step locally (no collective, no
+    #      barrier inside) while all the other GPUs of the box do the same, i.e. under the same power / thermal conditions as the
+    #      data-parallel run: the lock-step job can never beat the slowest GPU (straggler share); what is left is the exposed part
+    #      of the gradient all-reduces (+ their SM / HBM contention with the backward kernels). ----
+    if world > 1 and args.mode == "train":
+        import copy
+        la = copy.copy(args); la.skip_e2e = True; la.no_roofline = True
+        dist.barrier()
+        lr = run_workload(w, dev, rank, 1, args.steps, max(args.warmup, 3), la, main=False)
+        t = torch.tensor([lr["ms_per_step"]], device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        loc = [x.item() for x in allt]
+        ddp_ms = res["ms_per_step"]
+        res["scaling_diag"] = {"local_ms_per_rank": [round(x, 3) for x in loc], "local_mean_ms": sum(loc) / world, "local_max_ms": max(loc),
+                               "ddp_ms": ddp_ms, "straggler_share": (max(loc) - sum(loc) / world) / ddp_ms,
+                               "exposed_comm_share": (ddp_ms - max(loc)) / ddp_ms,
+                               "how": "each rank replays the same captured step WITHOUT the all-reduces, all GPUs busy at the same time; "
+                                      "straggler = (slowest - mean local step) / DDP step, exposed comm = (DDP step - slowest local step) / DDP step"}
+
     # ---- the other BASELINE configs, short runs in the same process (driver-visible numbers for every config) ----
     extra = {}
     if not args.no_extra:
@@ -671,7 +691,7 @@ def main():
             "dtype": args.precision, "data": "synthetic (random uint8 frames / ids / target centres; random-init weights of the named architecture)",
             "config": workload_config(w, world)}
     for k in ("e2e", "gpu_launches", "host_enqueue_ms_per_step", "launch_mode", "clocks", "model_flops_per_sample", "model_tflops_per_gpu",
-              "model_frac_of_bf16_peak", "roofline", "roofline_by_class", "roofline_error", "ddp_param_drift"):
+              "model_frac_of_bf16_peak", "roofline", "roofline_by_class", "roofline_error", "ddp_param_drift", "scaling_diag"):
         if k in res:
             line[k] = res[k]
     line.setdefault("roofline", None)

@@ -36,11 +36,13 @@ class GraphedTrainStep:
 
     def __init__(self, model, loss_fn: Callable, optimizer, warmup: int = 3, allow_distributed: bool = False,
                  input_stage: Optional[Callable] = None):
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1 \
-                and not allow_distributed:
+        eng = model._ensure_engine()
+        # a model wired to BatchShardedDDP (its engine announces gradient groups to the reducer) captures NCCL all-reduces: the
+        # caller must say so; a purely local model inside a multi-process job (bench.py's scaling diagnostic) is not affected
+        if getattr(eng, "grad_ready_hook", None) is not None and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1 and not allow_distributed:
             raise RuntimeError("GraphedTrainStep: pass allow_distributed=True to capture the NCCL all-reduces of "
                                "BatchShardedDDP inside the graph (every rank must capture and replay in lock-step)")
-        eng = model._ensure_engine()
         if eng.precision != "bf16" and eng.cfg.lora and eng.cfg.lora_dropout > 0:
             # the fp32 parity kernels (bfk_lora_down & co) take their dropout seed by value: a replay would reuse the mask
             raise RuntimeError("GraphedTrainStep needs precision='bf16' when LoRA dropout is active")
