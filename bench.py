@@ -530,64 +530,84 @@ def gemm_traffic():
 
 
 def tail_roofline(B, g, dev):
-    """HBM roofline of the fused heatmap tail kernel (x16 upsample + sigmoid + BCE + argmax) at the bench batch:
-    algorithmic bytes = heads*B*H*W*4 written + as much target read (+ the tiny grid), CUDA events, L2 flushed."""
+    """HBM roofline of the heatmap tail kernels at the bench batch (and at batch 512, BASELINE config 4): algorithmic bytes =
+    heads*B*H*W*4 written + as much target read (+ the tiny grid) for the fused forward (x16 upsample + sigmoid + BCE + argmax).
+    Durations are KERNEL durations from CUPTI (torch.profiler) of isolated launches with the L2 flushed before each one; the
+    CUDA-event bracket of the same launches (which adds ~5 us of launch / event overhead to a 20-30 us kernel) is reported beside."""
     import ctypes as C
     import torch
     from bifold_b200 import _cabi as K
     lib = K.load()
-    heads, H = 4, 16 * g
-    grid = torch.randn(B, heads, g * g, device=dev)
-    ts_h = torch.empty(H, dtype=torch.int32); tw_h = torch.empty(H, 3)
-    K.check(lib.bfk_upsample16_taps(g, ts_h.data_ptr(), tw_h.data_ptr()))
-    ts, tw = ts_h.to(dev), tw_h.to(dev)
-    heat = torch.empty(heads, B, H, H, device=dev)
-    targets = [torch.rand(B, H, H, device=dev) for _ in range(heads)]
-    tptr = torch.tensor([t.data_ptr() for t in targets], dtype=torch.int64).to(dev)
-    loss = torch.empty(heads + 1, device=dev); key = torch.empty(heads * B, device=dev, dtype=torch.int64)
-    part = torch.empty(lib.bfk_heatmap_fwd_workspace_floats(B, heads, g), device=dev)
-    counters = torch.zeros(1 + heads * B, device=dev, dtype=torch.int32)
-    fa = K.HeatmapFwdArgs(B, heads, g, grid.data_ptr(), ts.data_ptr(), tw.data_ptr(), heat.data_ptr(), tptr.data_ptr(), None, 0,
-                          loss.data_ptr(), key.data_ptr(), part.data_ptr(), counters.data_ptr())
-    gscale = torch.ones(heads + 1, device=dev); dgrid = torch.empty(B, heads, g * g, device=dev)
-    ws = torch.empty(lib.bfk_heatmap_bwd_workspace_floats(B, heads, g), device=dev)
-    ba = K.HeatmapBwdArgs(B, heads, g, 0, heat.data_ptr(), tptr.data_ptr(), None, 0, gscale.data_ptr(), 1.0 / (B * H * H), 1, None,
-                          ts.data_ptr(), tw.data_ptr(), dgrid.data_ptr(), ws.data_ptr(), counters.data_ptr())
-    D, Np, Nf = 768, g * g, 65 + g * g + 1
-    X = torch.randn(B * Nf, D, device=dev); w_eff = torch.randn(heads, D, device=dev); b_eff = torch.randn(heads, device=dev)
-    pa = K.HeadProjectArgs(B, heads, Np, D, X.data_ptr(), Nf * D, Nf - Np, w_eff.data_ptr(), b_eff.data_ptr(), grid.data_ptr(),
-                           None, Nf, None, None, 0, None, None, None)
-    flush = torch.empty(192 * 1024 * 1024, device=dev, dtype=torch.uint8)
-    st = torch.cuda.current_stream().cuda_stream
-
-    def med(call):
-        ts_ms = []
-        for it in range(8):
-            flush.sum()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); call(); e1.record(); torch.cuda.synchronize()
-            if it >= 3:
-                ts_ms.append(e0.elapsed_time(e1))
-        return sorted(ts_ms)[len(ts_ms) // 2]
-    ms = med(lambda: K.check(lib.bfk_heatmap_fwd(C.byref(fa), st)))
-    by = heads * B * H * H * 4 * 2 + grid.numel() * 4
     peaks = load_peaks()
-    ach = by / ms / 1e6
-    others = {}
-    for nm, call, nbytes in (("heatmap_bwd (BCE gradient -> dgrid)", lambda: K.check(lib.bfk_heatmap_bwd(C.byref(ba), st)), heads * B * H * H * 4 * 2),
-                             ("head_project_fwd (fp32 tokens -> 4 x g x g grids)", lambda: K.check(lib.bfk_head_project_fwd(C.byref(pa), st)), B * Np * D * 4)):
-        t_ms = med(call)
-        others[nm] = {"us_per_launch": t_ms * 1e3, "bytes_per_launch": nbytes, "achieved": nbytes / t_ms / 1e6,
-                      "frac": nbytes / t_ms / 1e6 / peaks["hbm_gbs"]}
+    st = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(192 * 1024 * 1024, device=dev, dtype=torch.uint8)
+
+    def measure(B):
+        heads, H = 4, 16 * g
+        grid = torch.randn(B, heads, g * g, device=dev)
+        ts_h = torch.empty(H, dtype=torch.int32); tw_h = torch.empty(H, 3)
+        K.check(lib.bfk_upsample16_taps(g, ts_h.data_ptr(), tw_h.data_ptr()))
+        ts, tw = ts_h.to(dev), tw_h.to(dev)
+        heat = torch.empty(heads, B, H, H, device=dev)
+        targets = [torch.rand(B, H, H, device=dev) for _ in range(heads)]
+        tptr = torch.tensor([t.data_ptr() for t in targets], dtype=torch.int64).to(dev)
+        loss = torch.empty(heads + 1, device=dev); key = torch.empty(heads * B, device=dev, dtype=torch.int64)
+        part = torch.empty(lib.bfk_heatmap_fwd_workspace_floats(B, heads, g), device=dev)
+        counters = torch.zeros(1 + heads * B, device=dev, dtype=torch.int32)
+        fa = K.HeatmapFwdArgs(B, heads, g, grid.data_ptr(), ts.data_ptr(), tw.data_ptr(), heat.data_ptr(), tptr.data_ptr(), None, 0,
+                              loss.data_ptr(), key.data_ptr(), part.data_ptr(), counters.data_ptr())
+        gscale = torch.ones(heads + 1, device=dev); dgrid = torch.empty(B, heads, g * g, device=dev)
+        ws = torch.empty(lib.bfk_heatmap_bwd_workspace_floats(B, heads, g), device=dev)
+        ba = K.HeatmapBwdArgs(B, heads, g, 0, heat.data_ptr(), tptr.data_ptr(), None, 0, gscale.data_ptr(), 1.0 / (B * H * H), 1, None,
+                              ts.data_ptr(), tw.data_ptr(), dgrid.data_ptr(), ws.data_ptr(), counters.data_ptr())
+        D, Np, Nf = 768, g * g, 65 + g * g + 1
+        X = torch.randn(B * Nf, D, device=dev); w_eff = torch.randn(heads, D, device=dev); b_eff = torch.randn(heads, device=dev)
+        pa = K.HeadProjectArgs(B, heads, Np, D, X.data_ptr(), Nf * D, Nf - Np, w_eff.data_ptr(), b_eff.data_ptr(), grid.data_ptr(),
+                               None, Nf, None, None, 0, None, None, None)
+        out = {}
+        for nm, pat, call, nbytes in (
+                ("heatmap_fwd", "heatmap_fwd_kernel", lambda: K.check(lib.bfk_heatmap_fwd(C.byref(fa), st)), heads * B * H * H * 4 * 2 + grid.numel() * 4),
+                ("heatmap_bwd (BCE gradient -> dgrid)", "heatmap_bwd_stage1", lambda: K.check(lib.bfk_heatmap_bwd(C.byref(ba), st)), heads * B * H * H * 4 * 2),
+                ("head_project_fwd (fp32 tokens -> 4 x g x g grids)", "head_project_fwd", lambda: K.check(lib.bfk_head_project_fwd(C.byref(pa), st)), B * Np * D * 4)):
+            ev = []
+            for it in range(8):
+                flush.sum()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); call(); e1.record(); torch.cuda.synchronize()
+                if it >= 3:
+                    ev.append(e0.elapsed_time(e1))
+            ev_ms = sorted(ev)[len(ev) // 2]
+            k_ms = None
+            try:
+                agg = profile_kernels(lambda: (flush.sum(), call()), 5)
+                hit = [(cnt, us) for name, (cnt, us) in agg.items() if pat in name]
+                if hit:
+                    k_ms = sum(us for _, us in hit) / max(sum(c for c, _ in hit), 1) / 1e3
+            except Exception:
+                k_ms = None
+            t_ms = k_ms if k_ms else ev_ms
+            out[nm] = {"us_per_launch": t_ms * 1e3, "us_per_launch_events": ev_ms * 1e3, "timer": "cupti" if k_ms else "events",
+                       "bytes_per_launch": nbytes, "achieved": nbytes / t_ms / 1e6, "frac": nbytes / t_ms / 1e6 / peaks["hbm_gbs"]}
+        return out
+
+    main_b = measure(B)
+    fwd = main_b.pop("heatmap_fwd")
+    big = None
+    if B != 512:
+        try:
+            big = {k: {kk: v[kk] for kk in ("us_per_launch", "achieved", "frac", "bytes_per_launch")} for k, v in measure(512).items()}
+        except Exception as e:      # e.g. not enough free memory next to a large workload
+            big = {"error": f"{type(e).__name__}: {e}"[:200]}
     t, n = _profile_json("r02_tail_traffic.json")
     traffic = None
     if t is not None:
         traffic = {"dram_bytes_per_launch": t["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": t.get("algorithmic_bytes_per_launch"),
                    "kernel": t.get("kernel"), "shape": t.get("shape"), "source": f"profiles/{n} (ncu --set full)"}
-    return {"bound": "hbm", "kernel": "heatmap_fwd_kernel (x16 upsample + sigmoid + BCE + argmax)", "achieved": ach,
-            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "bytes_per_launch": by,
-            "us_per_launch": ms * 1e3, "peak_source": peaks["source"], "other_tail_kernels": others,
-            "how": "isolated launches, L2 flushed between them, CUDA events, median of 5"}
+    return {"bound": "hbm", "kernel": "heatmap_fwd_kernel (x16 upsample + sigmoid + BCE + argmax)", "achieved": fwd["achieved"],
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": fwd["frac"], "traffic": traffic, "bytes_per_launch": fwd["bytes_per_launch"],
+            "us_per_launch": fwd["us_per_launch"], "us_per_launch_events": fwd["us_per_launch_events"], "timer": fwd["timer"],
+            "batch": B, "peak_source": peaks["source"], "other_tail_kernels": main_b, "batch_512": big,
+            "how": "isolated launches, L2 flushed before each; kernel durations from CUPTI (median-free mean of 5), event-bracket times beside"}
 
 
 # ---------------------------------------------------------------------------------------------------

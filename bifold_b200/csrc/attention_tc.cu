@@ -47,6 +47,7 @@ struct AttnSmem {
 template <int NA, int BW>
 __global__ void __launch_bounds__(AT_THREADS, (NA == 1 && BW == 64) ? 3 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv, AttnTcParams p) {
+  pdl_trigger();   // the GEMM behind this kernel may set itself up during its tail (common.cuh)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t TILE = NA * AT_ATOM;                    // Q: 128 rows
   constexpr uint32_t KATOM = BW * 128, KTILE = NA * KATOM;   // K, V blocks: BW rows
@@ -264,6 +265,7 @@ template <int NA, int BW, int NBUF>
 __global__ void __launch_bounds__(AT_THREADS, NA == 1 && BW == 64 ? 2 : 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                       const __grid_constant__ CUtensorMap map_do, AttnTcParams p) {
+  pdl_trigger();   // the GEMM behind this kernel may set itself up during its tail (common.cuh)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t TILE = NA * AT_ATOM;             // Q, dO: 128 rows
   constexpr uint32_t KATOM = BW * 128, KTILE = NA * KATOM;   // K, V blocks: BW rows
@@ -418,6 +420,7 @@ template <int NA, int BW, int NBUF>
 __global__ void __launch_bounds__(AT_THREADS, NA == 1 && BW == 64 ? 2 : 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
                        const __grid_constant__ CUtensorMap map_do, AttnTcParams p) {
+  pdl_trigger();   // the GEMM behind this kernel may set itself up during its tail (common.cuh)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t TILE = NA * AT_ATOM;             // K, V: 128 rows
   constexpr uint32_t QATOM = BW * 128, QTILE = NA * QATOM;   // Q, dO blocks: BW rows

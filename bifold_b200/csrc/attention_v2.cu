@@ -102,6 +102,7 @@ template <int W> __device__ __forceinline__ void st_o(uint32_t taddr, const uint
 template <int NA, int LDW, int HD16>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, AttnV2Params p) {
+  pdl_trigger();   // the GEMM behind this kernel may set itself up during its tail (common.cuh)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   constexpr uint32_t QT = NA * AT_ATOM;                       // one Q tile (128 rows)
@@ -446,6 +447,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 template <int NA, int HD16>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, AttnV2Params p) {
+  pdl_trigger();   // the GEMM behind this kernel may set itself up during its tail (common.cuh)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   const uint32_t KATOM = (uint32_t)p.krows * 128u, KT = NA * KATOM;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/bifold_b200.h"
 
@@ -38,6 +39,19 @@ template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
+// its predecessor in the stream still runs: it sets itself up (barriers, TMEM, tensor-map prefetch) and then blocks in pdl_wait()
+// until the predecessor has COMPLETED and its writes are visible; nothing the predecessor produces may be touched before.
+// pdl_trigger() in the predecessor lets the dependent's CTAs be scheduled as soon as every CTA of the predecessor has started
+// and SM resources free up (without it: when the predecessor's last CTA exits).  Both are no-ops in ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// BFK_PDL=1: the tcgen05 GEMM launches carry the attribute (host side)
+inline bool pdl_enabled() {
+  static const bool v = [] { const char* e = getenv("BFK_PDL"); return e && e[0] == '1'; }();
+  return v;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -79,6 +79,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if constexpr (CL == 2) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();     // see common.cuh: a dependent kernel may be scheduled from here on
+  pdl_wait();        // PDL launch: the set-up above overlapped the predecessor's tail; its results may be read from here on
 
   if (warp == 0) {
     if (elect_one()) {
@@ -363,10 +365,12 @@ static int launch_tc_mode(const bfk_gemm_args* a, cudaStream_t s, const CUtensor
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * epi_warps(MODE)); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AMN, BMN, CL, MODE>, ma, mb, a->M, a->N, a->K, ep, splits, split_stride, gemm_dbg());
   if (le != cudaSuccess) { set_error("gemm_tc: launch failed: %s", cudaGetErrorString(le)); return BFK_E_CUDA; }
   return BFK_OK;

@@ -111,6 +111,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();     // a dependent kernel may be scheduled from here on (it blocks in its own pdl_wait until this grid is done)
+  pdl_wait();        // PDL launch: everything above overlapped the predecessor's tail; its results may be read from here on
 
   if (warp == 0) {
     if (elect_one()) {
@@ -238,10 +240,12 @@ static int launch_tc2_mode(const bfk_gemm_args* a, cudaStream_t s, const CUtenso
   const int grid = 2 * std::min(items, sm_count() / 2);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * epi_warps(MODE)); cfg.dynamicSmemBytes = T2_SMEM_BYTES; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<AMN, BMN, MODE>, ma, mb, a->M, a->N, a->K, ep);
   if (le != cudaSuccess) { set_error("gemm_tc2: launch failed: %s", cudaGetErrorString(le)); return BFK_E_CUDA; }
   BFK_CHECK_LAUNCH("gemm_tc2");

@@ -33,6 +33,7 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
 
 template <typename TY, int LN_MAXC, bool LORA = false>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(bfk_layernorm_fwd_args a) {
+  pdl_trigger();   // the GEMM behind this pass may set itself up while the last rows are normalised (it waits for this grid to finish)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * LN_WARPS + warp;
   if (row >= a.M) return;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(128) lora_down_mma_kernel(const __nv_bfloat16*
                                                             const __nv_bfloat16* __restrict__ A, int D,
                                                             __nv_bfloat16* __restrict__ u, long long ldu) {
   __shared__ float red[4][16][17];
+  pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int row0 = blockIdx.x * 16;
   const int r0 = min(row0 + g, M - 1), r1 = min(row0 + g + 8, M - 1);      // clamped loads, predicated stores
@@ -198,6 +200,7 @@ template <typename TDY, typename TDX2, bool PARAM_GRADS, int LN_MAXC>
 __global__ void __launch_bounds__(LN_WARPS * 32, (PARAM_GRADS || LN_MAXC > 6) ? 1 : 2) ln_bwd_kernel(bfk_layernorm_bwd_args a, int rows_per_block) {
   using RawDY = typename Raw4<TDY>::type;
   __shared__ float red[PARAM_GRADS ? LN_WARPS : 1][PARAM_GRADS ? 132 : 1];
+  pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nc = a.D >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(a.gamma);

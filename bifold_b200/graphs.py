@@ -19,6 +19,8 @@ from __future__ import annotations
 
 from typing import Callable, Dict, Optional
 
+import os
+
 import torch
 
 
@@ -99,7 +101,10 @@ class GraphedTrainStep:
             graph = torch.cuda.CUDAGraph()
             steps_before = {gi: st["step"] for gi, st in self.optimizer._flat.items()}
             try:
-                with torch.cuda.graph(graph):
+                # BFK_GRAPH_PRIORITY=1 (A/B knob): capture the dependency chain on a high-priority stream, so its kernel nodes win
+                # the block scheduler against the off-chain branches (weight gradients, text tower) whenever both are ready
+                cap_stream = torch.cuda.Stream(priority=-1) if os.environ.get("BFK_GRAPH_PRIORITY") == "1" else None
+                with torch.cuda.graph(graph, stream=cap_stream):
                     self.static_loss = self._eager(s)
                     eng.k.seed_dev.add_(1)       # the next replay draws new dropout masks
             except Exception as e:               # e.g. an allocator / driver that refuses the capture
