@@ -20,6 +20,13 @@
 
 namespace bfk {
 
+#ifndef BFK_AT_SINGLE_READ
+#define BFK_AT_SINGLE_READ 0                    // A/B knob: 1 = keep the S chunk in registers between the maximum and the exponential pass (measured: the 32 live registers spill at the 72-register cap of three CTAs per SM: vision fwd 56 vs 46 us)
+#endif
+#ifndef BFK_AT_LAZY
+#define BFK_AT_LAZY 8.f                         // A/B knob: 0 = move the reference with every block maximum (round-1 behaviour)
+#endif
+constexpr float AT_LAZY = BFK_AT_LAZY;          // forward: log2 slack of the lazily updated softmax reference
 constexpr int AT_ROW_WARPS = 8;                 // two warps per TMEM lane quarter, alternating 32-column chunks
 constexpr int AT_THREADS = 32 * AT_ROW_WARPS + 32;  // + control warp (TMA, tcgen05.mma issue, TMEM alloc)
 
@@ -161,7 +168,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         xch16[half * 128 + r] = mb;
         named_bar_sync(1 + quarter, 64);
         mx = fmaxf(__bfloat162float(mb), __bfloat162float(xch16[(half ^ 1) * 128 + r]));
-        m_new = masked ? 0.f : fmaxf(m_run, mx * sl2);
+        // LAZY reference: the running reference only moves when the block maximum exceeds it by more than 2^AT_LAZY (softmax is
+        // invariant to the reference as long as P, the row sum and O use the same one; exp2 of at most AT_LAZY stays far inside
+        // bf16 / fp32 range).  After the first block almost no step changes it, so the TMEM round trip that rescales O goes away.
+        const float cand = mx * sl2;
+        m_new = masked ? 0.f : ((j == 0 || cand > m_run + AT_LAZY) ? fmaxf(m_run, cand) : m_run);
         alpha = ex2f(m_run - m_new);
       };
       auto pass2 = [&](const uint32_t (&sreg)[32], int c) {
@@ -182,7 +193,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           }
         }
       };
-      {
+      if constexpr (BW == 64 && BFK_AT_SINGLE_READ) {
+        // one 32-column chunk per warp and block: S is read from TMEM ONCE, the maximum and the exponentials both come from
+        // the same registers
+        const int c = half * 32;
+        uint32_t sreg[32];
+        if (c < nc) {
+          tc_ld32(tS + lane_off + c, sreg);
+          tc_wait_ld();
+          const int lim = nvalid - c;
+          if (lim >= 32) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(sreg[t]));
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+              if (t < lim) mx = fmaxf(mx, __uint_as_float(sreg[t]));
+          }
+        }
+        exchange_max();
+        if (c < nc) pass2(sreg, c);
+      } else {
         // pass 1: raw row max over the real keys of this warp's chunks
 #pragma unroll 1
         for (int c = half * 32; c < nc; c += 64) {
