@@ -159,6 +159,42 @@ def test_gemm_specialised_epilogues(kern, case, shape):
         assert math.isfinite(err2) and err2 <= tol * max(aux_ref.abs().max().item(), 1.0), f"{case} {shape}: aux err {err2:.3e}"
 
 
+@pytest.mark.parametrize("case", [(0, 0, True, 0, True, False), (0, 0, True, 6, False, True), (0, 1, False, 7, False, True), (0, 0, True, 0, False, True)])
+def test_gemm_ragged_half_chunk_stays_inside_the_row(kern, case):
+    """N % 32 == 16 (so400m MLP width): the fused epilogues store the live half of the last 32-column chunk only.  The outputs
+    live in wider buffers (ld = N + 48) pre-filled with a sentinel: nothing beyond column N may change."""
+    ta, tb, use_bias, act, use_res, out_bf16 = case
+    M, N, Kd, pad = 1280, 4304, 192, 48
+    dev, T = "cuda", torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(77 + act)
+    A = (torch.randn(M, Kd, generator=g) * 0.25).to(dev).to(T)
+    B = (torch.randn((Kd, N) if tb else (N, Kd), generator=g) * 0.25).to(dev).to(T)
+    bias = torch.randn(N, generator=g).to(dev) if use_bias else None
+    res = torch.randn(M, N + pad, generator=g).to(dev) if use_res else None
+    out_T = torch.bfloat16 if out_bf16 else torch.float32
+    D = torch.full((M, N + pad), 777.0, device=dev, dtype=out_T)
+    aux = None
+    if act == 7:
+        aux = torch.randn(M, N + pad, generator=g).to(dev).to(T)
+    elif act == 6:
+        aux = torch.full((M, N + pad), 777.0, device=dev, dtype=T)
+    kern.gemm(A, B, D, M, N, Kd, Kd, B.shape[1], N + pad, trans_b=bool(tb), bias=bias, act=act, aux=aux, ld_aux=N + pad,
+              residual=res, ldr=N + pad, backend=2)
+    torch.cuda.synchronize()
+    assert (D[:, N:] == 777.0).all(), "store beyond column N"
+    if act == 6:
+        assert (aux[:, N:] == 777.0).all(), "derivative store beyond column N"
+    pre = A.float() @ (B.float() if tb else B.float().t()) + (bias if bias is not None else 0)
+    if act == 0:
+        ref = pre + (res[:, :N] if res is not None else 0)
+    elif act == 6:
+        ref = F.gelu(pre)
+    else:
+        ref = pre * aux[:, :N].float()
+    err = (D[:, :N].float() - ref).abs().max().item()
+    assert err <= (2e-2 if out_bf16 else 2e-3) * ref.abs().max().item(), err
+
+
 def test_gemm_accumulate(kern):
     M, N, Kd = 130, 72, 40
     A = torch.randn(M, Kd, device="cuda"); B = torch.randn(N, Kd, device="cuda")
