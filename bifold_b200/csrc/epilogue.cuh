@@ -15,6 +15,7 @@ struct EpiParams {
   float alpha;
   int accumulate;
   int vec_ok;  // host-verified: D/aux/residual/bias pointers and leading dims allow 32-byte vector access
+  int tma_store;   // CTA-pair kernel, bf16-output specialised modes: outputs leave through shared memory + TMA bulk-tensor stores
   int mode;    // EpiMode: compile-time specialised tcgen05 epilogue for the hot combinations (tc_epilogue.cuh), 0 = generic
 };
 
@@ -160,6 +161,7 @@ inline bool epi_from_args(const bfk_gemm_args* a, EpiParams& p) {
   if (a->aux) ok = ok && al32(a->aux) && (a->ld_aux * as) % 32 == 0;
   if (a->residual) ok = ok && al32(a->residual) && (a->ldr * 4) % 32 == 0;
   p.vec_ok = ok ? 1 : 0;
+  p.tma_store = 0;
   p.mode = EPI_GENERIC;
   if (ok && a->alpha == 1.f && !a->accumulate && a->act == BFK_ACT_NONE && !a->residual) {
     p.mode = a->out_dtype == BFK_BF16 ? EPI_STORE_BF16 : EPI_STORE_F32;   // plain stores also take a ragged last chunk

@@ -230,6 +230,7 @@ PFN_encodeTiled get_encode_tiled() {
 }
 static PFN_encodeTiled get_encode() { return get_encode_tiled(); }
 
+bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int swizzle_bytes = 128);
 struct MapKey {
   const void* ptr; long long inner, outer, ld; int box_inner, box_outer;
   bool operator==(const MapKey& o) const {
@@ -246,10 +247,10 @@ struct MapKeyHash {
 };
 
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch ld elements; 128B swizzle.
-bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer) {
+bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int swizzle_bytes) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer + (swizzle_bytes << 16)};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -262,7 +263,9 @@ bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long oute
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld", (int)r, inner, outer, ld); return false; }
   std::lock_guard<std::mutex> lk(mu);

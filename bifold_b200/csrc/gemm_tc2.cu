@@ -14,13 +14,17 @@
 namespace bfk {
 
 int gemm_dbg();   // gemm_tc.cu: BFK_GEMM_DBG measurement knobs (4 = no stores, 8 = no TMEM read, 16 = no epilogue body)
-bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer);
+bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int swizzle_bytes = 128);
 
 constexpr int T2_STAGES = 6;
 constexpr int T2_A_BYTES = 128 * 64 * 2, T2_B_BYTES = 128 * 64 * 2;
 constexpr int T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
 constexpr int T2_BN = 256;
-constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 256 + 2 * T2_BN * 4;
+constexpr int T2_AUX_BYTES = 256 + 2 * T2_BN * 4;                 // barriers + TMEM slot | bias [2][256]
+constexpr int T2_MAX_EPI_WARPS = 16;
+// operand ring | barriers, bias | TMA-store staging (2 KB per epilogue warp); the dynamic shared memory is declared 1024-byte aligned
+constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + T2_AUX_BYTES + T2_MAX_EPI_WARPS * TS_STAGE_BYTES;
+static_assert(T2_SMEM_BYTES <= 232448, "CTA-pair GEMM: shared memory budget");
 
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta_rank) {
   uint32_t r;
@@ -74,10 +78,12 @@ __device__ __forceinline__ T2Item t2_decode(int item, int num_mp, int num_n, int
 // registers); a specialised MODE compiles only its own epilogue and runs 16 epilogue warps (launch bound 576 threads).
 template <bool AMN, bool BMN, int MODE>
 __global__ void __launch_bounds__(64 + 32 * epi_warps(MODE), 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K, EpiParams ep) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_d,
+                const __grid_constant__ CUtensorMap tma_x, int M, int N, int K, EpiParams ep) {
   constexpr int EW = epi_warps(MODE);
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
   const uint32_t bar_base = smem_base + T2_STAGES * T2_STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (T2_STAGES + s); };
@@ -97,6 +103,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    if (epi_mode_can_tma_store(MODE) && ep.tma_store) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_d)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_x)) : "memory");
+    }
     for (int s = 0; s < T2_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -198,7 +208,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         epi_tile_preload<MODE>(ep, m, n0, sub, ops);           // first chunk's operands: in flight during the wait
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        if (!skip) epi_tile<MODE, (T2_BN / 32) / (EW / 4), EW / 4>(ep, m, n0, sub, taddr, bias_s, ops);
+        if (!skip) {
+          if (epi_mode_can_tma_store(MODE) && ep.tma_store)
+            epi_tile_ts<MODE, (T2_BN / 32) / (EW / 4), EW / 4>(ep, m, m0 + quarter * 32, n0, sub, taddr, bias_s, ops,
+                                                              bar_base + T2_AUX_BYTES + (uint32_t)((warp - 2) * TS_STAGE_BYTES), &tma_d, &tma_x, lane);
+          else
+            epi_tile<MODE, (T2_BN / 32) / (EW / 4), EW / 4>(ep, m, n0, sub, taddr, bias_s, ops);
+        }
       } else {
         EpiOperands cur, nxt;
         if (n0 + half * 32 < N) epi_load(ep, m, n0 + half * 32, cur);
@@ -218,6 +234,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (epi_mode_can_tma_store(MODE) && ep.tma_store && lane == 0) bulk_wait_all();   // the staged rows have left shared memory
   }
   tc_fence_before();
   __syncthreads();
@@ -229,7 +246,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 }
 
 template <bool AMN, bool BMN, int MODE>
-static int launch_tc2_mode(const bfk_gemm_args* a, cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const EpiParams& ep) {
+static int launch_tc2_mode(const bfk_gemm_args* a, cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const EpiParams& ep_in) {
+  EpiParams ep = ep_in;
+  // TMA-store epilogue (bf16 outputs): 32 x 16 boxes, SWIZZLE_32B; needs 16-byte aligned rows.  BFK_GEMM_TMA_STORE=0 keeps the
+  // register stores (A/B knob).
+  CUtensorMap md = ma, mx = ma;
+  static const bool ts_on = [] { const char* e = getenv("BFK_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+  if (epi_mode_can_tma_store(MODE) && ts_on && ep.vec_ok && (a->ldd % 8) == 0 && (reinterpret_cast<uintptr_t>(a->D) & 15u) == 0) {
+    const bool needs_x = MODE == EPI_GELUG_TANH_BF16 || MODE == EPI_GELUG_ERF_BF16 ||
+                         ((MODE == EPI_GELU_TANH_BF16 || MODE == EPI_GELU_ERF_BF16) && a->aux != nullptr);
+    bool ok = make_map(&md, a->D, a->N, a->M, a->ldd, 16, 32, 32);
+    if (ok && needs_x) ok = (a->ld_aux % 8) == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15u) == 0 && make_map(&mx, a->aux, a->N, a->M, a->ld_aux, 16, 32, 32);
+    ep.tma_store = ok ? 1 : 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<AMN, BMN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
@@ -246,7 +275,7 @@ static int launch_tc2_mode(const bfk_gemm_args* a, cudaStream_t s, const CUtenso
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<AMN, BMN, MODE>, ma, mb, a->M, a->N, a->K, ep);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<AMN, BMN, MODE>, ma, mb, md, mx, a->M, a->N, a->K, ep);
   if (le != cudaSuccess) { set_error("gemm_tc2: launch failed: %s", cudaGetErrorString(le)); return BFK_E_CUDA; }
   BFK_CHECK_LAUNCH("gemm_tc2");
   return BFK_OK;

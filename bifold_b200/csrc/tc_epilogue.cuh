@@ -439,6 +439,107 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, int m, int n0, int
   }
 }
 
+// ---- TMA-store variant of the bf16-output tile epilogues ---------------------------------------------------------------------
+// A register store writes 32 bytes per thread and ROW: 32 sectors in 32 different lines per warp instruction, i.e. 32 LSU
+// wavefronts.  With two bf16 outputs (value + derivative) that is 4096 wavefronts = 2.2 us per 128 x 256 tile and SM, which no
+// longer hides behind the 3.2 us main loop of a K = 768 tile (ncu: tensor pipe 46 % busy against 79 % for the single-output
+// store).  Here a warp stages 32 rows x 16 columns per output in shared memory (32-byte rows, SWIZZLE_32B: conflict-free
+// 16-byte stores), one lane issues a TMA bulk-tensor store per box, and the copy engine writes the rows; rows / columns beyond
+// the matrix are clipped by the tensor map.  `stage` = this warp's 2 KB: two 1 KB regions (value | derivative for the
+// dual-output modes, ping-pong for the others).
+constexpr int TS_STAGE_BYTES = 2048;
+// Measured on 12544 x 3072 x 768 (profiles/r02_gemm_tma_store.txt): value + derivative 68 -> 58-63 us, GELU 52 -> 46 us, dGELU 77 -> 73 us;
+// the plain store (44 -> 46 us) and the aux multiply (56 us both ways) do not gain and keep their register stores.
+__host__ __device__ constexpr bool epi_mode_can_tma_store(int mode) {
+  return mode == EPI_GELU_TANH_BF16 || mode == EPI_GELU_ERF_BF16 || mode == EPI_DGELU_TANH_BF16 ||
+         mode == EPI_DGELU_ERF_BF16 || mode == EPI_GELUG_TANH_BF16 || mode == EPI_GELUG_ERF_BF16;
+}
+__device__ __forceinline__ void ts_stage_half(uint32_t region, int lane, const uint32_t (&w)[8]) {
+  const uint32_t row = region + (uint32_t)lane * 32u, sw = ((uint32_t)lane >> 2) & 1u;     // SWIZZLE_32B: 16-byte chunk ^= bit 7 of the offset
+  sts128(row + ((0u ^ sw) << 4), w[0], w[1], w[2], w[3]);
+  sts128(row + ((1u ^ sw) << 4), w[4], w[5], w[6], w[7]);
+}
+template <int MODE, int NCH, int CS>
+__device__ __forceinline__ void epi_tile_ts(const EpiParams& ep, int m, int mrow0, int n0, int sub, uint32_t taddr, const float* __restrict__ bias_s,
+                                            EpiOps<MODE>& ops, uint32_t stage, const CUtensorMap* map_d, const CUtensorMap* map_x, int lane) {
+  constexpr bool DG = EpiOps<MODE>::DG;
+  constexpr bool GE = MODE == EPI_GELU_TANH_BF16 || MODE == EPI_GELU_ERF_BF16;
+  constexpr bool GG = MODE == EPI_GELUG_TANH_BF16 || MODE == EPI_GELUG_ERF_BF16;
+  constexpr int NOP = EpiOps<MODE>::NOP;
+  const bool row_ok = m < ep.M;
+  int phase = 0;      // single-output modes: region of the next half chunk (ping-pong)
+  auto chunk = [&](int i, V8 (&op)[NOP], V8 (&nxt)[NOP]) {
+    const int c = sub + CS * i, nc = n0 + c * 32;
+    if (nc >= ep.N) return;                                  // warp-uniform
+    if (DG && i + 1 < NCH && row_ok && nc + CS * 32 < ep.N) epi_load_ops<MODE>(ep, m, nc + CS * 32, nxt);
+    uint32_t r[32];
+    tc_ld32(taddr + (uint32_t)(c * 32), r);
+    tc_wait_ld();
+    float v[32];
+    if constexpr (DG) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const uint32_t hw = op[t >> 3].w[t & 7];
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw));
+        if constexpr (MODE == EPI_MULAUX_BF16) {
+          v[2 * t] = __uint_as_float(r[2 * t]) * f.x;
+          v[2 * t + 1] = __uint_as_float(r[2 * t + 1]) * f.y;
+        } else if constexpr (MODE == EPI_DGELU_TANH_BF16) {
+          v[2 * t] = __uint_as_float(r[2 * t]) * dgelu_tanh_fast(f.x);
+          v[2 * t + 1] = __uint_as_float(r[2 * t + 1]) * dgelu_tanh_fast(f.y);
+        } else {
+          v[2 * t] = __uint_as_float(r[2 * t]) * dgelu_erf_fast(f.x);
+          v[2 * t + 1] = __uint_as_float(r[2 * t + 1]) * dgelu_erf_fast(f.y);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]) + bias_s[c * 32 + t];
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (nc + 16 * q >= ep.N) break;                        // N % 32 == 16: the second half of the last chunk does not exist
+      uint32_t wd[8], wx[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float a = v[q * 16 + 2 * t], b = v[q * 16 + 2 * t + 1];
+        if constexpr (GG) {
+          gelu_both_h2<MODE == EPI_GELUG_ERF_BF16>(a, b, wd[t], wx[t]);
+        } else if constexpr (GE) {
+          wx[t] = pack_bf16(a, b);                            // pre-activation (only stored when ep.aux is set)
+          wd[t] = MODE == EPI_GELU_TANH_BF16 ? pack_bf16(gelu_tanh_fast(a), gelu_tanh_fast(b)) : pack_bf16(gelu_erf_fast(a), gelu_erf_fast(b));
+        } else {
+          wd[t] = pack_bf16(a, b);
+        }
+      }
+      const bool two = GG || (GE && ep.aux != nullptr);      // warp-uniform
+      // the region(s) about to be overwritten were handed to the copy engine one (two regions: two) group(s) ago
+      if (lane == 0) { if (two) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
+      __syncwarp();
+      const uint32_t reg_d = stage + (two ? 0u : (uint32_t)(phase * 1024)), reg_x = stage + 1024u;
+      ts_stage_half(reg_d, lane, wd);
+      if (two) ts_stage_half(reg_x, lane, wx);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(map_d, reg_d, nc + 16 * q, mrow0);
+        if (two) tma_store_2d(map_x, reg_x, nc + 16 * q, mrow0);
+        bulk_commit();
+      }
+      phase ^= 1;
+    }
+  };
+  if constexpr (NCH == 1) {
+    chunk(0, ops.a, ops.b);
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < NCH; i += 2) {
+      chunk(i, ops.a, ops.b);
+      chunk(i + 1, ops.b, ops.a);
+    }
+  }
+}
+
 // L2 prefetch of the operands the epilogue of (row m, chunk nc) will read (next work item of this CTA)
 __device__ __forceinline__ void epi_prefetch(const EpiParams& ep, int m, int nc) {
   if (m >= ep.M || nc + 32 > ep.N) return;
