@@ -16,6 +16,7 @@ struct EpiParams {
   int accumulate;
   int vec_ok;  // host-verified: D/aux/residual/bias pointers and leading dims allow 32-byte vector access
   int tma_store;   // CTA-pair kernel, bf16-output specialised modes: outputs leave through shared memory + TMA bulk-tensor stores
+  int tma_load;    // CTA-pair kernel, residual / aux-multiply modes: the epilogue operand arrives through TMA + shared memory
   int mode;    // EpiMode: compile-time specialised tcgen05 epilogue for the hot combinations (tc_epilogue.cuh), 0 = generic
 };
 
@@ -162,6 +163,7 @@ inline bool epi_from_args(const bfk_gemm_args* a, EpiParams& p) {
   if (a->residual) ok = ok && al32(a->residual) && (a->ldr * 4) % 32 == 0;
   p.vec_ok = ok ? 1 : 0;
   p.tma_store = 0;
+  p.tma_load = 0;
   p.mode = EPI_GENERIC;
   if (ok && a->alpha == 1.f && !a->accumulate && a->act == BFK_ACT_NONE && !a->residual) {
     p.mode = a->out_dtype == BFK_BF16 ? EPI_STORE_BF16 : EPI_STORE_F32;   // plain stores also take a ragged last chunk

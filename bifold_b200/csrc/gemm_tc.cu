@@ -230,7 +230,8 @@ PFN_encodeTiled get_encode_tiled() {
 }
 static PFN_encodeTiled get_encode() { return get_encode_tiled(); }
 
-bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int swizzle_bytes = 128);
+bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int swizzle_bytes = 128,
+              int elem_bytes = 2);
 struct MapKey {
   const void* ptr; long long inner, outer, ld; int box_inner, box_outer;
   bool operator==(const MapKey& o) const {
@@ -247,10 +248,11 @@ struct MapKeyHash {
 };
 
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch ld elements; 128B swizzle.
-bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int swizzle_bytes) {
+bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int swizzle_bytes,
+              int elem_bytes) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, inner, outer, ld, box_inner, box_outer + (swizzle_bytes << 16)};
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer + (swizzle_bytes << 16) + (elem_bytes << 28)};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -259,10 +261,10 @@ bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long oute
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return false; }
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -401,7 +403,7 @@ static int launch_tc_cl(const bfk_gemm_args* a, cudaStream_t s, int splits, bool
     ep.mode = ep.vec_ok ? EPI_STORE_F32 : EPI_GENERIC;
   }
   if (gemm_dbg() & 32) ep.mode = EPI_GENERIC;     // measurement only: force the generic epilogue
-  if (ep.vec_ok) ep.vec_ok |= gemm_dbg() & 28;
+  if (ep.vec_ok) ep.vec_ok |= gemm_dbg() & 92;     // bit 6 (64): no L2 prefetch of the next tile's epilogue operands
   const int num_m = (a->M + TC_BM - 1) / TC_BM, num_n = (a->N + BN - 1) / BN;
   const int items = ((num_m + CL - 1) / CL) * num_n * splits;
   const int grid = CL * std::min(items, sm_count() / CL);

@@ -14,13 +14,15 @@
 namespace bfk {
 
 int gemm_dbg();   // gemm_tc.cu: BFK_GEMM_DBG measurement knobs (4 = no stores, 8 = no TMEM read, 16 = no epilogue body)
-bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int swizzle_bytes = 128);
+bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int swizzle_bytes = 128,
+              int elem_bytes = 2);
 
 constexpr int T2_STAGES = 6;
 constexpr int T2_A_BYTES = 128 * 64 * 2, T2_B_BYTES = 128 * 64 * 2;
 constexpr int T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
 constexpr int T2_BN = 256;
-constexpr int T2_AUX_BYTES = 256 + 2 * T2_BN * 4;                 // barriers + TMEM slot | bias [2][256]
+constexpr int T2_TLBAR_OFF = 256 + 2 * T2_BN * 4;                 // barriers + TMEM slot | bias [2][256] | per-warp operand barriers
+constexpr int T2_AUX_BYTES = 3072;                                // rounded up: the staging area behind it is 1024-byte aligned (SWIZZLE_128B boxes)
 constexpr int T2_MAX_EPI_WARPS = 16;
 // operand ring | barriers, bias | TMA-store staging (2 KB per epilogue warp); the dynamic shared memory is declared 1024-byte aligned
 constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + T2_AUX_BYTES + T2_MAX_EPI_WARPS * TS_STAGE_BYTES;
@@ -103,12 +105,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    if (epi_mode_can_tma_load(MODE) && ep.tma_load) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_x)) : "memory");
     if (epi_mode_can_tma_store(MODE) && ep.tma_store) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_d)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_x)) : "memory");
     }
     for (int s = 0; s < T2_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EW); }
+    if (epi_mode_can_tma_load(MODE))
+      for (int w = 0; w < EW; ++w) mbar_init(bar_base + T2_TLBAR_OFF + 8u * w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -189,27 +194,41 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int half = sub;   // generic path: two warps per quarter
     const int et = threadIdx.x - 64;
     int acc = 0; uint32_t acc_phase = 0;
+    TlState tl{0u, false};
+    const uint32_t tl_bar = bar_base + T2_TLBAR_OFF + 8u * (uint32_t)(warp - 2);
+    const uint32_t tl_stage = bar_base + T2_AUX_BYTES + (uint32_t)((warp - 2) * (MODE == EPI_RES_F32 ? 4096 : 2048));
     for (int item = cid; item < items; item += ncl) {
       const T2Item it = t2_decode(item, num_mp, num_n, N);
       const int m0 = it.mp * 256 + crank * 128, n0 = it.nb * T2_BN;
       float* bias_s = bias_smem + acc * T2_BN;
       for (int i = et; i < T2_BN; i += 32 * EW) bias_s[i] = (ep.bias && n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
       named_bar_sync(1, 32 * EW);
-      if (ep.vec_ok && item + ncl < items) {
-        const T2Item nit = t2_decode(item + ncl, num_mp, num_n, N);
-        const int nm = nit.mp * 256 + crank * 128 + quarter * 32 + lane, nn0 = nit.nb * T2_BN;
-        for (int c = sub; c < T2_BN / 32; c += EW / 4) epi_prefetch(ep, nm, nn0 + c * 32);
-      }
+      // (no L2 prefetch of the next tile's epilogue operands: one prefetch per thread and ROW costs 32 LSU wavefronts per warp
+      //  instruction like the loads themselves; measured 2 us per launch slower on every variant that reads operands)
       const int m = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * T2_BN);
       const bool skip = (ep.vec_ok & 16) != 0;   // measurement only
       if constexpr (MODE != EPI_GENERIC) {
         EpiOps<MODE> ops;
-        epi_tile_preload<MODE>(ep, m, n0, sub, ops);           // first chunk's operands: in flight during the wait
+        const bool use_tl = epi_mode_can_tma_load(MODE) && ep.tma_load;
+        if (use_tl) {
+          // this tile's first box must be under way before the wait for the accumulator (normally requested one tile ago)
+          if (n0 + sub * 32 < N && !tl.pending) {
+            if (lane == 0) tl_request<MODE>(tl_stage, tl_bar, &tma_x, n0 + sub * 32, m0 + quarter * 32);
+            tl.pending = true;
+          }
+        } else {
+          epi_tile_preload<MODE>(ep, m, n0, sub, ops);         // first chunk's operands: in flight during the wait
+        }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         if (!skip) {
-          if (epi_mode_can_tma_store(MODE) && ep.tma_store)
+          if (use_tl) {
+            const bool has_next = item + ncl < items;
+            const T2Item nit = t2_decode(has_next ? item + ncl : item, num_mp, num_n, N);
+            epi_tile_tl<MODE, (T2_BN / 32) / (EW / 4), EW / 4>(ep, m, m0 + quarter * 32, n0, sub, taddr, bias_s, tl_stage, tl_bar, tl, &tma_x, lane,
+                                                              has_next, nit.mp * 256 + crank * 128 + quarter * 32, nit.nb * T2_BN);
+          } else if (epi_mode_can_tma_store(MODE) && ep.tma_store)
             epi_tile_ts<MODE, (T2_BN / 32) / (EW / 4), EW / 4>(ep, m, m0 + quarter * 32, n0, sub, taddr, bias_s, ops,
                                                               bar_base + T2_AUX_BYTES + (uint32_t)((warp - 2) * TS_STAGE_BYTES), &tma_d, &tma_x, lane);
           else
@@ -259,6 +278,17 @@ static int launch_tc2_mode(const bfk_gemm_args* a, cudaStream_t s, const CUtenso
     if (ok && needs_x) ok = (a->ld_aux % 8) == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15u) == 0 && make_map(&mx, a->aux, a->N, a->M, a->ld_aux, 16, 32, 32);
     ep.tma_store = ok ? 1 : 0;
   }
+  // TMA-load of the epilogue operand (fp32 residual / bf16 aux factor): 32 x 32 boxes.  BFK_GEMM_TMA_LOAD=0 keeps the register loads.
+  static const bool tl_on = [] { const char* e = getenv("BFK_GEMM_TMA_LOAD"); return !(e && e[0] == '0'); }();
+  if (epi_mode_can_tma_load(MODE) && tl_on && ep.vec_ok && !(ep.vec_ok & 16)) {
+    bool ok;
+    if (MODE == EPI_RES_F32)
+      ok = a->residual && a->res_row_mod == 0 && (a->ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0 &&
+           make_map(&mx, a->residual, a->N, a->M, a->ldr, 32, 32, 128, 4);
+    else
+      ok = a->aux && (a->ld_aux % 8) == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15u) == 0 && make_map(&mx, a->aux, a->N, a->M, a->ld_aux, 32, 32, 64, 2);
+    ep.tma_load = ok ? 1 : 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<AMN, BMN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
@@ -298,7 +328,7 @@ static int launch_tc2(const bfk_gemm_args* a, cudaStream_t s) {
   EpiParams ep;
   epi_from_args(a, ep);
   if (gemm_dbg() & 32) ep.mode = EPI_GENERIC;     // measurement only: force the generic epilogue
-  if (ep.vec_ok) ep.vec_ok |= gemm_dbg() & 28;
+  if (ep.vec_ok) ep.vec_ok |= gemm_dbg() & 92;     // bit 6 (64): no L2 prefetch of the next tile's epilogue operands
 #define T2_CASE(MODE_) case MODE_: return launch_tc2_mode<AMN, BMN, MODE_>(a, s, ma, mb, ep)
   if constexpr (!AMN && !BMN) {
     switch (ep.mode) { T2_CASE(EPI_STORE_BF16); T2_CASE(EPI_RES_F32); T2_CASE(EPI_GELU_TANH_BF16); T2_CASE(EPI_GELU_ERF_BF16);

@@ -540,6 +540,92 @@ __device__ __forceinline__ void epi_tile_ts(const EpiParams& ep, int m, int mrow
   }
 }
 
+// ---- TMA-load variant: the epilogue OPERAND (fp32 residual / bf16 aux factor) of a 32 x 32 chunk arrives as one TMA box ----------
+// Same reasoning as for the stores: a per-thread 32-byte load touches one line per ROW, 32 LSU wavefronts per warp instruction
+// (128 per chunk for the fp32 residual).  Here one lane requests the box of the NEXT chunk right after the warp has pulled the
+// current one out of shared memory (swizzled, conflict-free 16-byte reads), so the copy engine does the row gather.  One
+// mbarrier and one staging buffer per warp (2 KB bf16 / 4 KB fp32); rows / columns beyond the matrix arrive as zeros.
+struct TlState { uint32_t parity; bool pending; };
+__host__ __device__ constexpr bool epi_mode_can_tma_load(int mode) { return mode == EPI_RES_F32 || mode == EPI_MULAUX_BF16; }
+template <int MODE> __host__ __device__ constexpr int tl_box_bytes() { return MODE == EPI_RES_F32 ? 4096 : 2048; }
+template <int MODE>
+__device__ __forceinline__ void tl_request(uint32_t stage, uint32_t bar, const CUtensorMap* map, int col, int row) {
+  mbar_expect_tx(bar, tl_box_bytes<MODE>());
+  tma_load_2d(stage, map, bar, col, row);
+}
+template <int MODE, int NCH, int CS>
+__device__ __forceinline__ void epi_tile_tl(const EpiParams& ep, int m, int mrow0, int n0, int sub, uint32_t taddr, const float* __restrict__ bias_s,
+                                            uint32_t stage, uint32_t bar, TlState& st, const CUtensorMap* map_op, int lane,
+                                            bool has_next, int next_mrow0, int next_n0) {
+  constexpr bool RES = MODE == EPI_RES_F32;
+  const bool row_ok = m < ep.M;
+  // this warp's first chunk of the tile: requested by the previous tile's epilogue (or the kernel prologue); rarely not
+  if (n0 + sub * 32 < ep.N && !st.pending) {
+    if (lane == 0) tl_request<MODE>(stage, bar, map_op, n0 + sub * 32, mrow0);
+    st.pending = true;
+  }
+#pragma unroll 1
+  for (int i = 0; i < NCH; ++i) {
+    const int c = sub + CS * i, nc = n0 + c * 32;
+    if (nc >= ep.N) break;                                   // warp-uniform
+    mbar_wait(bar, st.parity);
+    st.parity ^= 1u;
+    uint32_t op[RES ? 32 : 16];
+    if constexpr (RES) {
+      const uint32_t rowa = stage + (uint32_t)lane * 128u, sw = (uint32_t)lane & 7u;        // SWIZZLE_128B
+#pragma unroll
+      for (int q = 0; q < 8; ++q) lds128(rowa + (((uint32_t)q ^ sw) << 4), op[4 * q], op[4 * q + 1], op[4 * q + 2], op[4 * q + 3]);
+    } else {
+      const uint32_t rowa = stage + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;  // SWIZZLE_64B
+#pragma unroll
+      for (int q = 0; q < 4; ++q) lds128(rowa + (((uint32_t)q ^ sw) << 4), op[4 * q], op[4 * q + 1], op[4 * q + 2], op[4 * q + 3]);
+    }
+    __syncwarp();
+    // the buffer is free: request the next chunk of this tile, else this warp's first chunk of the CTA's next tile
+    st.pending = false;
+    {
+      int ncol = -1, nrow = 0;
+      if (i + 1 < NCH && nc + CS * 32 < ep.N) { ncol = nc + CS * 32; nrow = mrow0; }
+      else if (has_next && next_n0 + sub * 32 < ep.N) { ncol = next_n0 + sub * 32; nrow = next_mrow0; }
+      if (ncol >= 0) {
+        if (lane == 0) tl_request<MODE>(stage, bar, map_op, ncol, nrow);
+        st.pending = true;
+      }
+    }
+    uint32_t r[32];
+    tc_ld32(taddr + (uint32_t)(c * 32), r);
+    tc_wait_ld();
+    if (!row_ok) continue;
+    if constexpr (RES) {
+      float* dp = reinterpret_cast<float*>(ep.D) + (long long)m * ep.ldd + nc;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        V8 w;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w.w[t] = __float_as_uint(__uint_as_float(r[q * 8 + t]) + bias_s[c * 32 + q * 8 + t] + __uint_as_float(op[q * 8 + t]));
+        if (nc + 8 * q < ep.N) stg256(dp + 8 * q, w);
+      }
+    } else {
+      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(ep.D) + (long long)m * ep.ldd + nc;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        V8 w;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&op[q * 8 + t]));
+          w.w[t] = pack_bf16(__uint_as_float(r[q * 16 + 2 * t]) * f.x, __uint_as_float(r[q * 16 + 2 * t + 1]) * f.y);
+        }
+        if (nc + 16 * q < ep.N) stg256(dp + 16 * q, w);
+      }
+    }
+  }
+  // a tile in which this warp owns no chunk still has to line up the next tile's first box
+  if (!st.pending && has_next && next_n0 + sub * 32 < ep.N) {
+    if (lane == 0) tl_request<MODE>(stage, bar, map_op, next_n0 + sub * 32, next_mrow0);
+    st.pending = true;
+  }
+}
+
 // L2 prefetch of the operands the epilogue of (row m, chunk nc) will read (next work item of this CTA)
 __device__ __forceinline__ void epi_prefetch(const EpiParams& ep, int m, int nc) {
   if (m >= ep.M || nc + 32 > ep.N) return;
