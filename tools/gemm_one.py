@@ -16,5 +16,9 @@ for _ in range(4):
     elif var == "gg": k.gemm(A, B, D, M, N, Kd, Kd, Kd, N, bias=bias, act=K.ACT_GELU_TANH_GRAD, aux=aux, ld_aux=N)
     elif var == "ge_aux": k.gemm(A, B, D, M, N, Kd, Kd, Kd, N, bias=bias, act=K.ACT_GELU_TANH, aux=aux, ld_aux=N)
     elif var == "mulaux": k.gemm(A, Bt, D, M, N, Kd, Kd, N, N, trans_b=True, act=K.ACT_MUL_AUX, aux=aux, ld_aux=N)
+    elif var == "res":
+        if "R" not in globals():
+            B2 = torch.randn(768, Kd, device="cuda").bfloat16(); R = torch.randn(M, 768, device="cuda"); D32 = torch.empty(M, 768, device="cuda")
+        k.gemm(A, B2, D32, M, 768, Kd, Kd, Kd, 768, bias=bias[:768].contiguous(), residual=R, ldr=768)
 torch.cuda.synchronize()
 print("done", var)
