@@ -96,6 +96,55 @@ __global__ void colsum_stage1(const T* __restrict__ X, int M, int N, long long l
   for (; r < r1; ++r) s0 += to_f32<T>(X[(long long)r * ld + n]);
   partials[(long long)blockIdx.y * N + n] = (s0 + s1) + (s2 + s3);
 }
+// Vector variant: a thread owns 16 bytes of a row (4 fp32 / 8 bf16 columns); a block = 32 column groups x 8 row slices, every thread
+// keeps four rows (64 bytes) in flight; the slices are combined in shared memory in a fixed order (deterministic).  The scalar
+// kernel (8-16 bytes in flight per thread) reached 3.5-3.8 TB/s on the bias-gradient shapes.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_stage1_vec(const T* __restrict__ X, int M, int N, long long ld, float* __restrict__ partials) {
+  constexpr int V = 16 / sizeof(T);
+  __shared__ float red[8][32 * V + 4];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = (blockIdx.x * 32 + tx) * V;
+  const int r0 = blockIdx.y * CS_ROWS, r1 = min(M, r0 + CS_ROWS);
+  float s[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) s[v] = 0.f;
+  if (n < N) {
+    auto add = [&](const uint4& u) {
+      if constexpr (sizeof(T) == 4) {
+        s[0] += __uint_as_float(u.x); s[1] += __uint_as_float(u.y); s[2] += __uint_as_float(u.z); s[3] += __uint_as_float(u.w);
+      } else {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+          s[2 * j] += f.x; s[2 * j + 1] += f.y;
+        }
+      }
+    };
+    int r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {          // rows r, r+8, r+16, r+24 of this slice: four loads in flight
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(X + (long long)(r + 8 * k) * ld + n));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) add(u[k]);
+    }
+    for (; r < r1; r += 8) add(__ldg(reinterpret_cast<const uint4*>(X + (long long)r * ld + n)));
+  }
+#pragma unroll
+  for (int v = 0; v < V; ++v) red[ty][tx * V + v] = s[v];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * V; c += 256) {
+    const int col = blockIdx.x * 32 * V + c;
+    if (col < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][c];
+      partials[(long long)blockIdx.y * N + col] = t;
+    }
+  }
+}
 // 32 columns x 8 row-slices per block; fixed summation order (deterministic)
 __global__ void __launch_bounds__(256) colsum_stage2(const float* __restrict__ partials, int nb, int N, float* __restrict__ out) {
   __shared__ float red[8][33];
@@ -126,9 +175,16 @@ extern "C" int32_t bfk_colsum(const void* X, int32_t dtype, int32_t M, int32_t N
   BFK_CHECK_ARG(X && out && partials && M > 0 && N > 0, "bfk_colsum: bad arguments");
   cudaStream_t s = to_stream(s_);
   int nb = (M + CS_ROWS - 1) / CS_ROWS;
-  dim3 grid((N + 127) / 128, nb);
-  if (dtype == BFK_BF16) colsum_stage1<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16*)X, M, N, ld, partials);
-  else colsum_stage1<float><<<grid, 128, 0, s>>>((const float*)X, M, N, ld, partials);
+  const int V = dtype == BFK_BF16 ? 8 : 4;
+  if (N % V == 0 && ld % V == 0 && (reinterpret_cast<uintptr_t>(X) & 15u) == 0) {
+    dim3 grid((N / V + 31) / 32, nb);
+    if (dtype == BFK_BF16) colsum_stage1_vec<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)X, M, N, ld, partials);
+    else colsum_stage1_vec<float><<<grid, 256, 0, s>>>((const float*)X, M, N, ld, partials);
+  } else {
+    dim3 grid((N + 127) / 128, nb);
+    if (dtype == BFK_BF16) colsum_stage1<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16*)X, M, N, ld, partials);
+    else colsum_stage1<float><<<grid, 128, 0, s>>>((const float*)X, M, N, ld, partials);
+  }
   colsum_stage2<<<(N + 31) / 32, 256, 0, s>>>(partials, nb, N, out);
   BFK_CHECK_LAUNCH("bfk_colsum");
   return BFK_OK;

@@ -313,8 +313,19 @@ __global__ void __launch_bounds__(256) ln_bwd_reduce(const float* __restrict__ p
   const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + col;
   float s = 0.f;
-  if (n < 2 * D)
-    for (int b = slice; b < nb; b += 8) s += partials[(long long)b * 2 * D + n];
+  if (n < 2 * D) {
+    // four independent chains (fixed assignment b -> chain, fixed combination order): the loads of a slice are in flight together
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int b = slice;
+    for (; b + 24 < nb; b += 32) {
+      s0 += partials[(long long)b * 2 * D + n];
+      s1 += partials[(long long)(b + 8) * 2 * D + n];
+      s2 += partials[(long long)(b + 16) * 2 * D + n];
+      s3 += partials[(long long)(b + 24) * 2 * D + n];
+    }
+    for (; b < nb; b += 8) s0 += partials[(long long)b * 2 * D + n];
+    s = (s0 + s1) + (s2 + s3);
+  }
   red[slice][col] = s;
   __syncthreads();
   if (slice == 0 && n < 2 * D) {

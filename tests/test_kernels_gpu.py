@@ -205,10 +205,11 @@ def test_gemm_accumulate(kern):
 
 def test_colsum(kern):
     for T in (torch.float32, torch.bfloat16):
-        X = torch.randn(1000, 300, device="cuda").to(T)
-        out = torch.empty(300, device="cuda")
-        kern.colsum(X, 1000, 300, 300, out)
-        assert torch.allclose(out, X.float().sum(0), atol=2e-3, rtol=1e-4)
+        for M, N in ((1000, 300), (1001, 768), (515, 3072)):      # 300: scalar kernel; 768 / 3072: 16-byte vector kernel
+            X = torch.randn(M, N, device="cuda").to(T)
+            out = torch.empty(N, device="cuda")
+            kern.colsum(X, M, N, N, out)
+            assert torch.allclose(out, X.float().sum(0), atol=2e-3, rtol=1e-4), (T, M, N)
 
 
 @pytest.mark.parametrize("D,ydt", [(64, torch.float32), (768, torch.bfloat16), (1152, torch.float32), (768, torch.float32)])
