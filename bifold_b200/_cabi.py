@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("BFK_LIB_PATH") or os.path.join(_HERE, "lib", "libbifold_b200.so")   # BFK_LIB_PATH: A/B builds (tools/ab_build.sh)
+LIB_PATH = os.environ.get("BFK_LIB_PATH") or os.path.join(_HERE, "lib", "libbifold_b200.so")   # BFK_LIB_PATH: A/B builds (BFK_BUILD_TAG of bifold_b200/build.py, tools/gpu_ab.sh)
 
 F32, BF16 = 0, 1
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05, BACKEND_TCGEN05_PERSISTENT = 0, 1, 2, 3
