@@ -17,7 +17,14 @@ int gemm_dbg();   // gemm_tc.cu: BFK_GEMM_DBG measurement knobs (4 = no stores, 
 bool make_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int swizzle_bytes = 128,
               int elem_bytes = 2);
 
-constexpr int T2_STAGES = 6;
+#ifndef BFK_GG_DOUBLE_STAGE
+#define BFK_GG_DOUBLE_STAGE 1      // A/B knob: 0 = 6 operand stages and 2 KB of store staging per warp for the value + derivative modes too
+#endif
+// Operand ring depth / store staging per epilogue warp.  The dual-output (value + derivative) modes trade one of the six operand
+// stages for 4 KB of staging per warp, so a half chunk is staged while the copy engine still reads the previous one.
+__host__ __device__ constexpr bool t2_is_gg(int mode) { return BFK_GG_DOUBLE_STAGE && (mode == EPI_GELUG_TANH_BF16 || mode == EPI_GELUG_ERF_BF16); }
+__host__ __device__ constexpr int t2_stages(int mode) { return t2_is_gg(mode) ? 5 : 6; }
+__host__ __device__ constexpr int t2_stage_bytes_per_warp(int mode) { return t2_is_gg(mode) ? 4096 : 2048; }
 constexpr int T2_A_BYTES = 128 * 64 * 2, T2_B_BYTES = 128 * 64 * 2;
 constexpr int T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
 constexpr int T2_BN = 256;
@@ -25,8 +32,10 @@ constexpr int T2_TLBAR_OFF = 256 + 2 * T2_BN * 4;                 // barriers + 
 constexpr int T2_AUX_BYTES = 3072;                                // rounded up: the staging area behind it is 1024-byte aligned (SWIZZLE_128B boxes)
 constexpr int T2_MAX_EPI_WARPS = 16;
 // operand ring | barriers, bias | TMA-store staging (2 KB per epilogue warp); the dynamic shared memory is declared 1024-byte aligned
-constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + T2_AUX_BYTES + T2_MAX_EPI_WARPS * TS_STAGE_BYTES;
-static_assert(T2_SMEM_BYTES <= 232448, "CTA-pair GEMM: shared memory budget");
+__host__ __device__ constexpr int t2_smem_bytes(int mode) {
+  return t2_stages(mode) * T2_STAGE_BYTES + T2_AUX_BYTES + T2_MAX_EPI_WARPS * t2_stage_bytes_per_warp(mode);
+}
+static_assert(t2_smem_bytes(EPI_GENERIC) <= 232448 && t2_smem_bytes(EPI_GELUG_TANH_BF16) <= 232448, "CTA-pair GEMM: shared memory budget");
 
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta_rank) {
   uint32_t r;
@@ -83,6 +92,7 @@ __global__ void __launch_bounds__(64 + 32 * epi_warps(MODE), 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_d,
                 const __grid_constant__ CUtensorMap tma_x, int M, int N, int K, EpiParams ep) {
   constexpr int EW = epi_warps(MODE);
+  constexpr int T2_STAGES = t2_stages(MODE);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();
@@ -229,8 +239,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             epi_tile_tl<MODE, (T2_BN / 32) / (EW / 4), EW / 4>(ep, m, m0 + quarter * 32, n0, sub, taddr, bias_s, tl_stage, tl_bar, tl, &tma_x, lane,
                                                               has_next, nit.mp * 256 + crank * 128 + quarter * 32, nit.nb * T2_BN);
           } else if (epi_mode_can_tma_store(MODE) && ep.tma_store)
-            epi_tile_ts<MODE, (T2_BN / 32) / (EW / 4), EW / 4>(ep, m, m0 + quarter * 32, n0, sub, taddr, bias_s, ops,
-                                                              bar_base + T2_AUX_BYTES + (uint32_t)((warp - 2) * TS_STAGE_BYTES), &tma_d, &tma_x, lane);
+            epi_tile_ts<MODE, (T2_BN / 32) / (EW / 4), EW / 4, t2_is_gg(MODE)>(ep, m, m0 + quarter * 32, n0, sub, taddr, bias_s, ops,
+                                                              bar_base + T2_AUX_BYTES + (uint32_t)((warp - 2) * t2_stage_bytes_per_warp(MODE)), &tma_d, &tma_x, lane);
           else
             epi_tile<MODE, (T2_BN / 32) / (EW / 4), EW / 4>(ep, m, n0, sub, taddr, bias_s, ops);
         }
@@ -291,14 +301,14 @@ static int launch_tc2_mode(const bfk_gemm_args* a, cudaStream_t s, const CUtenso
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<AMN, BMN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("gemm_tc2: cannot set smem %d: %s", T2_SMEM_BYTES, cudaGetErrorString(e)); return BFK_E_CUDA; }
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<AMN, BMN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, t2_smem_bytes(MODE));
+    if (e != cudaSuccess) { set_error("gemm_tc2: cannot set smem %d: %s", t2_smem_bytes(MODE), cudaGetErrorString(e)); return BFK_E_CUDA; }
     attr_set = true;
   }
   const int items = ((a->M + 255) / 256) * ((a->N + T2_BN - 1) / T2_BN);
   const int grid = 2 * std::min(items, sm_count() / 2);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * epi_warps(MODE)); cfg.dynamicSmemBytes = T2_SMEM_BYTES; cfg.stream = s;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * epi_warps(MODE)); cfg.dynamicSmemBytes = t2_smem_bytes(MODE); cfg.stream = s;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

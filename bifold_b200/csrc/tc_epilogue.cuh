@@ -459,7 +459,8 @@ __device__ __forceinline__ void ts_stage_half(uint32_t region, int lane, const u
   sts128(row + ((0u ^ sw) << 4), w[0], w[1], w[2], w[3]);
   sts128(row + ((1u ^ sw) << 4), w[4], w[5], w[6], w[7]);
 }
-template <int MODE, int NCH, int CS>
+// DBL: 4 KB of staging per warp (value + derivative modes of the CTA-pair kernel): both outputs ping-pong between two regions each
+template <int MODE, int NCH, int CS, bool DBL = false>
 __device__ __forceinline__ void epi_tile_ts(const EpiParams& ep, int m, int mrow0, int n0, int sub, uint32_t taddr, const float* __restrict__ bias_s,
                                             EpiOps<MODE>& ops, uint32_t stage, const CUtensorMap* map_d, const CUtensorMap* map_x, int lane) {
   constexpr bool DG = EpiOps<MODE>::DG;
@@ -514,9 +515,9 @@ __device__ __forceinline__ void epi_tile_ts(const EpiParams& ep, int m, int mrow
       }
       const bool two = GG || (GE && ep.aux != nullptr);      // warp-uniform
       // the region(s) about to be overwritten were handed to the copy engine one (two regions: two) group(s) ago
-      if (lane == 0) { if (two) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
+      if (lane == 0) { if (two && !DBL) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
       __syncwarp();
-      const uint32_t reg_d = stage + (two ? 0u : (uint32_t)(phase * 1024)), reg_x = stage + 1024u;
+      const uint32_t reg_d = stage + ((two && !DBL) ? 0u : (uint32_t)(phase * 1024)), reg_x = stage + (DBL ? 2048u + (uint32_t)(phase * 1024) : 1024u);
       ts_stage_half(reg_d, lane, wd);
       if (two) ts_stage_half(reg_x, lane, wx);
       fence_async_smem();
