@@ -29,6 +29,10 @@ CASES = {
     "tiny_uni": (tiny_spec(name="siglip", is_bimanual=False, lora=False), 3, True),
     "tiny_bi_lora": (tiny_spec(name="siglip", is_bimanual=True, lora=True), 4, True),
     "tiny_bi_seq_lora": (tiny_spec(name="siglip_sequential", is_bimanual=True, lora=True, context_length=3), 5, True),
+    # CrossAttention fusion (bifold/models/fusion.py:67-125): single frame, and with context frames (float attn_mask quirk)
+    "tiny_bi_lora_xattn": (tiny_spec(name="siglip", is_bimanual=True, lora=True, fusion_model="crossattention"), 4, True),
+    "tiny_uni_seq_xattn": (tiny_spec(name="siglip_sequential", is_bimanual=False, lora=False, context_length=2,
+                                     fusion_model="crossattention"), 5, True),
     "base224_bi_lora": (base224_spec(name="siglip", is_bimanual=True, lora=True), 2, False),
     "base224_bi_seq_lora": (base224_spec(name="siglip_sequential", is_bimanual=True, lora=True, context_length=3), 2, False),
 }

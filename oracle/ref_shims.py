@@ -157,7 +157,7 @@ def build_reference_model(spec, state_dict):
               patch_size=spec.patch_size, automodel_name="synthetic", dim=spec.dim, emb_dropout=0.0,
               lora=spec.lora, r=spec.r, lora_alpha=spec.lora_alpha, lora_dropout=spec.lora_dropout,
               target_modules=["q_proj", "v_proj"], threshold=0.5, text_encoder=None,
-              pick_place_model="pick_place_convdecoder", fusion_model="concat_transformer",
+              pick_place_model="pick_place_convdecoder", fusion_model=getattr(spec, "fusion_model", "concat_transformer"),
               depth=spec.depth, heads=spec.heads, mlp_ratio=spec.mlp_ratio, dropout=0.0)
     if spec.name == "siglip_sequential":
         cfg["context_length"] = spec.context_length

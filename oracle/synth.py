@@ -42,6 +42,7 @@ class PolicySpec:
     tower_ln_eps: float = 1e-6
     compute_mask: bool = False      # PickPlaceConvDecoder(compute_mask=..., detach_mask=...) (bifold/models/pickplace.py:18-32)
     detach_mask: bool = False
+    fusion_model: str = "concat_transformer"    # or "crossattention" (bifold/models/__init__.py:38-41, fusion.py:67-125)
 
     @property
     def grid(self) -> int:
@@ -164,7 +165,12 @@ def make_state_dict(spec: PolicySpec, seed: int = 3407) -> Dict[str, torch.Tenso
     # fusion transformer (bifold/models/fusion.py:8-34, transformer.py:8-58, modules.py:8-30)
     fp = "pick_place.fusion"
     sd[fp + ".token_type_embeddings.weight"] = normal((2, D), 0.5)
-    for l in range(spec.depth):
+    if spec.fusion_model == "crossattention":
+        # torch.nn.MultiheadAttention(embed_dim=D, num_heads=heads, batch_first=True) parameters (fusion.py:75-77)
+        sd[fp + ".cross_attention.in_proj_weight"] = normal((3 * D, D), 1.0 / np.sqrt(D))
+        sd[fp + ".cross_attention.in_proj_bias"] = normal((3 * D,), 0.05)
+        linear(fp + ".cross_attention.out_proj", D, D)
+    for l in range(spec.depth if spec.fusion_model == "concat_transformer" else 0):
         lp = f"{fp}.transformer_encoder.layers.{l}"
         layernorm(lp + ".0.norm", D)
         linear(lp + ".0.fn.to_qkv", 3 * D, D, bias=False)

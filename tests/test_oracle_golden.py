@@ -46,7 +46,13 @@ def _check_case(name):
         params = {k: sd[k] for k in keys}
         po.adam_step(params, grads, {}, lr=1e-3)
     for k in keys:
-        np.testing.assert_allclose(_probe(sd[k], full), g[f"param1/{k}"], atol=2e-5, rtol=1e-5, err_msg=k)
+        a, b = _probe(sd[k], full), g[f"param1/{k}"]
+        if k.endswith("cross_attention.in_proj_bias"):
+            # the key bias shifts every score of a query row by the same amount: its exact gradient is ZERO, what autograd
+            # returns is rounding noise (|g| ~ 1e-10) that Adam normalises to +-lr -> not comparable, in any implementation
+            d = a.shape[0] // 3
+            a, b = np.concatenate([a[:d], a[2 * d:]]), np.concatenate([b[:d], b[2 * d:]])
+        np.testing.assert_allclose(a, b, atol=2e-5, rtol=1e-5, err_msg=k)
     with torch.no_grad():
         out2 = po.policy_forward(sd, sample, spec)
         loss2, _ = po.bce_gaussmap(out2, sample, spec)
@@ -60,6 +66,14 @@ def _check_case(name):
 
 @pytest.mark.parametrize("name", ["tiny_uni", "tiny_bi_lora", "tiny_bi_seq_lora"])
 def test_oracle_matches_reference_tiny(name):
+    _check_case(name)
+
+
+@pytest.mark.parametrize("name", ["tiny_bi_lora_xattn", "tiny_uni_seq_xattn"])
+def test_oracle_matches_reference_cross_attention(name):
+    """fusion_model=crossattention (bifold/models/fusion.py:67-125): one MultiheadAttention layer, image tokens query the text
+    (+ context) tokens; with context frames the float attn_mask is ADDED to the scores with its batch axis tiled (the quirk the
+    restatement reproduces)."""
     _check_case(name)
 
 
