@@ -55,6 +55,13 @@ class AttentionArgs(C.Structure):
                 ("dout", vp), ("ld_dout", i64), ("dqkv", vp), ("ld_dqkv", i64), ("delta", vp)]
 
 
+class CrossAttentionArgs(C.Structure):
+    _fields_ = [("B", i32), ("Nf", i32), ("H", i32), ("hd", i32), ("q0", i32), ("nq", i32), ("k0", i32), ("nk", i32),
+                ("dtype", i32), ("qkv", vp), ("ld_qkv", i64), ("scale", f32), ("key_bias", vp),
+                ("out", vp), ("ld_out", i64), ("lse", vp), ("dout", vp), ("ld_dout", i64), ("dqkv", vp), ("ld_dqkv", i64),
+                ("delta", vp)]
+
+
 class AssembleArgs(C.Structure):
     _fields_ = [("B", i32), ("L", i32), ("Np", i32), ("T", i32), ("D", i32),
                 ("txt", vp), ("img", vp), ("ctx", vp), ("text_token", vp), ("image_token", vp),
@@ -143,6 +150,8 @@ _PROTOS = {
     "bfk_layernorm_bwd": (i32, [C.POINTER(LayerNormBwdArgs), vp]),
     "bfk_attention_fwd": (i32, [C.POINTER(AttentionArgs), vp]),
     "bfk_attention_bwd": (i32, [C.POINTER(AttentionArgs), vp]),
+    "bfk_cross_attention_fwd": (i32, [C.POINTER(CrossAttentionArgs), vp]),
+    "bfk_cross_attention_bwd": (i32, [C.POINTER(CrossAttentionArgs), vp]),
     "bfk_im2col": (i32, [vp, i32, i32, i32, i32, i32, vp, i64, i32, vp]),
     "bfk_text_embed": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "bfk_lora_down": (i32, [vp, i64, i32, i32, i32, vp, f32, u64, vp]),

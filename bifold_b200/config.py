@@ -45,6 +45,7 @@ class PolicyConfig:
     tower_ln_eps: float = 1e-6
     compute_mask: bool = False           # PickPlaceConvDecoder(compute_mask=True): mask head + gated pick heatmaps
     detach_mask: bool = False
+    fusion_model: str = "concat_transformer"   # or "crossattention" (bifold/models/fusion.py:67-125)
 
     @property
     def grid(self) -> int:

@@ -131,6 +131,21 @@ class Kernels:
         self.launches += 3
         self.work["attn_flops"] += 8.0 * B * H * N * N * hd            # dP, dV, dK, dQ (recomputing S is not algorithmic work)
 
+    def cross_attention(self, qkv, out, lse, B, Nf, H, hd, q0, nq, k0, nk, scale, key_bias=None, dout=None, dqkv=None):
+        """Alternate fusion module (fusion.py:67-125): rows [q0, q0+nq) of every sample attend to rows [k0, k0+nk) of the packed
+        projection.  Forward when ``dout`` is None, else backward into ``dqkv``."""
+        delta = torch.empty(B * H * nq, device=qkv.device, dtype=torch.float32) if dout is not None else None
+        a = K.CrossAttentionArgs(B, Nf, H, hd, q0, nq, k0, nk, _dt(qkv), qkv.data_ptr(), 3 * H * hd, scale, K.ptr(key_bias),
+                                 out.data_ptr(), H * hd, lse.data_ptr(), K.ptr(dout), H * hd, K.ptr(dqkv), 3 * H * hd, K.ptr(delta))
+        if dout is None:
+            K.check(self.lib.bfk_cross_attention_fwd(C.byref(a), _stream()), "bfk_cross_attention_fwd")
+            self.launches += 1
+            self.work["attn_flops"] += 4.0 * B * H * nq * nk * hd
+        else:
+            K.check(self.lib.bfk_cross_attention_bwd(C.byref(a), _stream()), "bfk_cross_attention_bwd")
+            self.launches += 3
+            self.work["attn_flops"] += 8.0 * B * H * nq * nk * hd
+
     # -- misc ------------------------------------------------------------------------------------------
     def cast(self, src, dst, rows, cols, ld_src, ld_dst):
         K.check(self.lib.bfk_cast_f32_to(src.data_ptr(), dst.data_ptr(), _dt(dst), rows, cols, ld_src, ld_dst, _stream()),
@@ -257,6 +272,18 @@ class Engine:
                 self._lora_segments(lw, segs)
         for lw in self.fusion_layers:
             self._fusion_segments(lw, segs)
+        if self.cfg.fusion_model == "crossattention":
+            xp = "pick_place.fusion.cross_attention."
+            for attr, name in (("xa_Wi", xp + "in_proj_weight"), ("xa_Wo", xp + "out_proj.weight")):
+                w = self._p(name)
+                if self.T == torch.float32:
+                    setattr(self, attr, w)
+                else:
+                    cur = getattr(self, attr, None)
+                    if cur is None or cur.shape != w.shape or cur.device != w.device:
+                        cur = torch.empty_like(w, dtype=self.T)
+                        setattr(self, attr, cur)
+                    segs.append((w, cur.data_ptr(), w.shape[0], w.shape[1], w.shape[1], 1.0, self.T))
         if not segs:
             return
         key = tuple((w.data_ptr(), dst) for (w, dst, *_rest) in segs)
@@ -290,7 +317,8 @@ class Engine:
             kpe = 3 * cfg.patch_size * cfg.patch_size
             self.kpe_ld = (kpe + 7) // 8 * 8
             self.W_pe = self._shadow(self._p(vp + ".embeddings.patch_embedding.weight"), self.kpe_ld - kpe)
-            self.fusion_layers = [self._fusion_layer_weights(l) for l in range(cfg.depth)]
+            self.fusion_layers = [self._fusion_layer_weights(l) for l in range(cfg.depth if cfg.fusion_model == "concat_transformer" else 0)]
+            self.xa_Wi = self.xa_Wo = None
             for lw in self.fusion_layers:
                 for k in ("Wqkv", "Wo", "W1", "W2"):
                     setattr(lw, k, None)
@@ -418,6 +446,63 @@ class Engine:
                         grads[n["ln1_w"]] if trainable else None, grads[n["ln1_b"]] if trainable else None,
                         dy2=dy2, ld_dy2=D, dy2_p=sv["p_drop"] if dy2 is not None else 0.0, dy2_seed=sv["seed"])
         return dx, (dx_T if dx_T is not None else dx)
+
+    # ------------------------------------------------------------------------------------------------
+    # alternate fusion module: CrossAttention (bifold/models/fusion.py:67-125)
+    # ------------------------------------------------------------------------------------------------
+    def _xattn_fwd(self, X, B, Nf, mask, save):
+        """X: fp32 [B*Nf, D] = per sample [text token + text | context frames | image token + patches], type embeddings added by
+        the assembly kernel.  ONE packed projection of all rows with MultiheadAttention's in_proj (q of the condition rows and
+        k / v of the image rows are computed and ignored: 3 x the minimum, at no extra launch), the image rows attend to the
+        condition rows, out_proj.  Returns fp32 [B*Nf, D]; only the image rows (the last Np + 1 of a sample) are meaningful -
+        the heatmap tail reads exactly those.  `mask` ([B*Nf] fp32, SiglipSequential): its first Nc entries per sample are
+        the additive key bias (float attn_mask, fusion.py:107-113)."""
+        cfg, k, D, T, dev = self.cfg, self.k, self.cfg.dim, self.T, X.device
+        M, H = B * Nf, cfg.heads
+        hd, nq = D // H, cfg.num_patches + 1
+        nc = Nf - nq
+        xp = "pick_place.fusion.cross_attention."
+        X_T = X
+        if T != torch.float32:
+            X_T = torch.empty(M, D, device=dev, dtype=T)
+            k.cast(X, X_T, M, D, D, D)
+        qkv = torch.empty(M, 3 * D, device=dev, dtype=T)
+        k.gemm(X_T, self.xa_Wi, qkv, M, 3 * D, D, D, D, 3 * D, bias=self._p(xp + "in_proj_bias"))
+        bias = None
+        if mask is not None:
+            bias = mask.view(B, Nf)[:, :nc].contiguous()
+        att = torch.zeros(M, D, device=dev, dtype=T)          # condition rows stay zero: they meet zero gradients in the wgrad
+        lse = torch.empty(B * H * nq, device=dev, dtype=torch.float32)
+        k.cross_attention(qkv, att, lse, B, Nf, H, hd, nc, nq, 0, nc, hd ** -0.5, key_bias=bias)
+        out = torch.empty(M, D, device=dev, dtype=torch.float32)
+        k.gemm(att, self.xa_Wo, out, M, D, D, D, D, D, bias=self._p(xp + "out_proj.bias"))
+        if save is not None:
+            save.append(dict(X_T=X_T, qkv=qkv, att=att, lse=lse, bias=bias, nc=nc, nq=nq))
+        return out
+
+    def _xattn_bwd(self, dx, dx_T, sv, B, Nf, mask, grads):
+        """dx: fp32 [B*Nf, D] gradient w.r.t. the module output (zero outside the image rows).  Returns dX fp32 [B*Nf, D]."""
+        cfg, k, D, T, dev = self.cfg, self.k, self.cfg.dim, self.T, dx.device
+        M, H = B * Nf, cfg.heads
+        hd = D // H
+        xp = "pick_place.fusion.cross_attention."
+        if dx_T is None or dx_T is dx and T != torch.float32:
+            dx_T = torch.empty(M, D, device=dev, dtype=T)
+            k.cast(dx, dx_T, M, D, D, D)
+        # out_proj: out = att Wo^T + bo
+        k.colsum(dx, M, D, D, grads[xp + "out_proj.bias"])
+        k.gemm(dx_T, sv["att"], grads[xp + "out_proj.weight"], D, D, M, D, D, D, trans_a=True, trans_b=True)
+        datt = torch.empty(M, D, device=dev, dtype=T)
+        k.gemm(dx_T, self.xa_Wo, datt, M, D, D, D, D, D, trans_b=True)
+        dqkv = torch.zeros(M, 3 * D, device=dev, dtype=T)
+        k.cross_attention(sv["qkv"], sv["att"], sv["lse"], B, Nf, H, hd, sv["nc"], sv["nq"], 0, sv["nc"], hd ** -0.5,
+                          key_bias=sv["bias"], dout=datt, dqkv=dqkv)
+        # in_proj: qkv = X Wi^T + bi
+        k.colsum(dqkv, M, 3 * D, 3 * D, grads[xp + "in_proj_bias"])
+        k.gemm(dqkv, sv["X_T"], grads[xp + "in_proj_weight"], 3 * D, D, M, 3 * D, D, D, trans_a=True, trans_b=True)
+        dX = torch.empty(M, D, device=dev, dtype=torch.float32)
+        k.gemm(dqkv, self.xa_Wi, dX, M, D, 3 * D, 3 * D, D, D, trans_b=True)
+        return dX
 
     # Weight / bias gradients are leaves of the backward dependency chain: they run on a second stream (in a captured
     # step: a parallel graph branch) and fill the SM time the chain's kernels leave idle (tails, short LayerNorm passes).
@@ -625,6 +710,8 @@ class Engine:
         del vis, txt
 
         x = X
+        if cfg.fusion_model == "crossattention":
+            x = self._xattn_fwd(X, B, Nf, mask, fsave)
         for lw in self.fusion_layers:
             x = self._layer_fwd(x, B, Nf, lw, cfg.heads, 1e-5, K.ACT_GELU_ERF, mask, fsave)
 
@@ -888,7 +975,10 @@ class Engine:
         # ---- fusion transformer ----
         dx, dx_T = dX, (dX_T if dX_T is not None else dX)
         fsave = ctx["fsave"]
-        for l in range(cfg.depth - 1, -1, -1):
+        if cfg.fusion_model == "crossattention":
+            dx = self._xattn_bwd(dx, dx_T, fsave[0], B, Nf, ctx["mask"], grads)
+            dx_T = None
+        for l in range(len(self.fusion_layers) - 1, -1, -1):
             dx, dx_T = self._layer_bwd(dx, dx_T, fsave[l], B, Nf, self.fusion_layers[l], cfg.heads, 1e-5, K.ACT_GELU_ERF,
                                        ctx["mask"], grads, trainable=True)
             fsave[l] = None

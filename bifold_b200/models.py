@@ -181,6 +181,22 @@ class ConcatTransformer(_Holder):   # bifold/models/fusion.py:8-34
         self.registers = None
 
 
+class CrossAttention(_Holder):      # bifold/models/fusion.py:67-78
+    """Alternate fusion module: the image tokens (+ type embedding) query the text (+ context) tokens through ONE
+    torch.nn.MultiheadAttention layer.  The torch module is only the parameter container (same names and initialisation as the
+    reference: in_proj_weight / in_proj_bias / out_proj.*); the math runs in Engine._xattn_fwd / _xattn_bwd."""
+
+    def __init__(self, dim, heads, depth=None, dropout=0.0, num_modalities=2, **kwargs):
+        super().__init__()
+        if dropout != 0.0:
+            raise K.BfkError("crossattention: attention dropout is not on the accelerated path")
+        self.num_modalities = num_modalities
+        self.token_type_embeddings = nn.Embedding(num_modalities, dim)
+        self.token_type_embeddings.weight.data.normal_(mean=0.0, std=0.02)   # bifold/models/utils.py:86-89
+        self.num_heads = heads
+        self.cross_attention = nn.MultiheadAttention(embed_dim=dim, num_heads=heads, dropout=dropout, batch_first=True)
+
+
 class ConvDecoder(_Holder):         # bifold/models/modules.py:33-74
     def __init__(self, input_dim, output_dim=1):
         super().__init__()
@@ -235,8 +251,11 @@ class Components:
             return PickPlaceConvDecoder(*args, **kwargs)
         if name == "concat_transformer":
             return ConcatTransformer(*args, **kwargs)
-        if name in ("pick_place_transdecoder", "crossattention"):
-            raise ValueError(f"Model {name} is not on the accelerated hot path (no shipped config selects it)")
+        if name == "crossattention":
+            return CrossAttention(*args, **kwargs)
+        if name == "pick_place_transdecoder":
+            raise ValueError(f"Model {name} is not on the accelerated hot path (no shipped config selects it; its TransformerDecoder "
+                             "needs timm)")
         raise ValueError(f"Model {name} not recognized")
 
 
@@ -327,7 +346,9 @@ class SigLip(BaseModel):
             tower = dict(tower_shape_from_name(automodel_name, dim))
         tower.update(tower_config or {})
         tower.pop("dim", None)
-        fusion_kw = {k: kwargs[k] for k in ("depth", "heads", "mlp_ratio") if k in kwargs}
+        fusion_kw = {k: kwargs[k] for k in ("depth", "heads", "mlp_ratio", "fusion_model") if k in kwargs}
+        if fusion_kw.get("fusion_model", "concat_transformer") == "crossattention" and kwargs.get("compute_mask", False):
+            raise K.BfkError("crossattention with compute_mask=True is not on the accelerated path")
         self.cfg = PolicyConfig(name="siglip", image_size=self.image_size, patch_size=patch_size, dim=dim,
                                 is_bimanual=self.is_bimanual, lora=bool(lora), r=r, lora_alpha=lora_alpha,
                                 lora_dropout=lora_dropout, compute_mask=bool(kwargs.get("compute_mask", False)),

@@ -153,6 +153,28 @@ typedef struct {
 BFK_API int32_t bfk_attention_fwd(const bfk_attention_args* a, bfk_stream_t s);
 BFK_API int32_t bfk_attention_bwd(const bfk_attention_args* a, bfk_stream_t s);
 
+/* Cross attention of the alternate fusion module `crossattention` (replaces the torch.nn.MultiheadAttention call of
+ * bifold/models/fusion.py:117-124): on the packed projection [B*Nf, 3*H*hd] = [q | k | v] of all fusion tokens, the rows
+ * [q0, q0+nq) of every sample attend to the rows [k0, k0+nk).  out / dq are written for the query rows, dk / dv for the key
+ * rows (their k and v slots); everything else in out / dqkv is left untouched (the caller zero-fills).
+ * key_bias (optional, fp32 [B, nk]) is ADDED to the scaled scores; problem (b, h) reads row (b*H + h) % B - the reference's
+ * float attn_mask with its tiled batch axis (fusion.py:107-113). */
+typedef struct {
+  int32_t B, Nf, H, hd;
+  int32_t q0, nq, k0, nk;
+  int32_t dtype;                     /* BFK_F32 | BFK_BF16 (qkv, out, dout, dqkv) */
+  const void* qkv; int64_t ld_qkv;
+  float scale;                       /* head_dim^-0.5 */
+  const float* key_bias;             /* or NULL */
+  void* out; int64_t ld_out;         /* [B*Nf, H*hd] */
+  float* lse;                        /* [B, H, nq] */
+  const void* dout; int64_t ld_dout; /* backward */
+  void* dqkv; int64_t ld_dqkv;
+  float* delta;                      /* [B, H, nq] workspace */
+} bfk_cross_attention_args;
+BFK_API int32_t bfk_cross_attention_fwd(const bfk_cross_attention_args* a, bfk_stream_t s);
+BFK_API int32_t bfk_cross_attention_bwd(const bfk_cross_attention_args* a, bfk_stream_t s);
+
 /* ------------------------------------------------------------------------------------------------
  * Embeddings and token assembly.
  * ---------------------------------------------------------------------------------------------- */

@@ -535,3 +535,42 @@ def test_head_project_fwd_vs_torch(kern, D, heads, B, Np, Nf):
     K.check(kern.lib.bfk_head_project_fwd(C.byref(pa), torch.cuda.current_stream().cuda_stream))
     ref = torch.einsum("bnd,hd->bhn", X.view(B, Nf, D)[:, Nf - Np:], w) + b[None, :, None]
     assert (grid - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_cross_attention_fwd_bwd(kern, dtype, with_bias):
+    """bfk_cross_attention_fwd/bwd against torch on the packed projection: queries = rows [q0, q0+nq) of each sample, keys /
+    values = rows [k0, k0+nk); the additive key bias is read at row (b*H + h) % B (the reference's tiled float attn_mask,
+    bifold/models/fusion.py:107-113)."""
+    B, Nf, H, hd, q0, nq, k0, nk = 3, 22, 4, 16, 9, 13, 0, 9
+    D = H * hd
+    T = torch.float32 if dtype == "fp32" else torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(5)
+    qkv = (torch.randn(B * Nf, 3 * D, generator=g) * 0.7).cuda().to(T)
+    dout = torch.randn(B * Nf, D, generator=g).cuda().to(T)
+    bias = (torch.rand(B, nk, generator=g) > 0.4).float().cuda() if with_bias else None
+    out = torch.zeros(B * Nf, D, device="cuda", dtype=T)
+    lse = torch.empty(B * H * nq, device="cuda")
+    sc = hd ** -0.5
+    kern.cross_attention(qkv, out, lse, B, Nf, H, hd, q0, nq, k0, nk, sc, key_bias=bias)
+    dqkv = torch.zeros_like(qkv)
+    kern.cross_attention(qkv, out, lse, B, Nf, H, hd, q0, nq, k0, nk, sc, key_bias=bias, dout=dout, dqkv=dqkv)
+    torch.cuda.synchronize()
+    x = qkv.float().view(B, Nf, 3, H, hd).requires_grad_(True)
+    q = x[:, q0:q0 + nq, 0].transpose(1, 2)
+    k = x[:, k0:k0 + nk, 1].transpose(1, 2)
+    v = x[:, k0:k0 + nk, 2].transpose(1, 2)
+    dots = q @ k.transpose(-1, -2) * sc
+    if bias is not None:
+        rows = (torch.arange(B)[:, None] * H + torch.arange(H)[None]) % B
+        dots = dots + bias[rows.cuda()][:, :, None, :]
+    ref = (dots.softmax(-1) @ v).transpose(1, 2).reshape(B, nq, D)
+    go = dout.float().view(B, Nf, D)[:, q0:q0 + nq]
+    (gx,) = torch.autograd.grad(ref, x, go)
+    tol = 2e-5 if dtype == "fp32" else 2e-2
+    got = out.float().view(B, Nf, D)
+    assert (got[:, q0:q0 + nq] - ref).abs().max().item() <= tol * ref.abs().max().item()
+    assert (got[:, :q0] == 0).all()                                        # rows outside the query range stay untouched
+    gref = gx.reshape(B * Nf, 3 * D)
+    assert (dqkv.float() - gref).abs().max().item() <= tol * gref.abs().max().item()

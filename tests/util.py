@@ -13,7 +13,7 @@ def model_cfg(spec: PolicySpec, precision="fp32") -> Cfg:
               patch_size=spec.patch_size, automodel_name="synthetic", dim=spec.dim, emb_dropout=0.0, lora=spec.lora,
               r=spec.r, lora_alpha=spec.lora_alpha, lora_dropout=spec.lora_dropout, target_modules=["q_proj", "v_proj"],
               threshold=0.5, text_encoder=None, pick_place_model="pick_place_convdecoder",
-              fusion_model="concat_transformer", depth=spec.depth, heads=spec.heads, mlp_ratio=spec.mlp_ratio, dropout=0.0,
+              fusion_model=getattr(spec, "fusion_model", "concat_transformer"), depth=spec.depth, heads=spec.heads, mlp_ratio=spec.mlp_ratio, dropout=0.0,
               precision=precision, pretrained=False,
               tower_config=dict(tower_layers=spec.tower_layers, tower_heads=spec.tower_heads, tower_mlp=spec.tower_mlp,
                                 vocab_size=spec.vocab_size, text_len=spec.text_len))
