@@ -152,6 +152,7 @@ _PROTOS = {
     "bfk_attention_bwd": (i32, [C.POINTER(AttentionArgs), vp]),
     "bfk_cross_attention_fwd": (i32, [C.POINTER(CrossAttentionArgs), vp]),
     "bfk_cross_attention_bwd": (i32, [C.POINTER(CrossAttentionArgs), vp]),
+    "bfk_cross_attention_weights": (i32, [C.POINTER(CrossAttentionArgs), vp, vp]),
     "bfk_im2col": (i32, [vp, i32, i32, i32, i32, i32, vp, i64, i32, vp]),
     "bfk_text_embed": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "bfk_lora_down": (i32, [vp, i64, i32, i32, i32, vp, f32, u64, vp]),

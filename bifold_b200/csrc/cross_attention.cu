@@ -184,6 +184,41 @@ __global__ void __launch_bounds__(XA_WARPS * 32) xattn_bwd_dkv_kernel(bfk_cross_
   }
 }
 
+// attention weights averaged over the heads (MultiheadAttention(need_weights=True, average_attn_weights=True), fusion.py:117-124):
+// block per (query row, sample); warp w recomputes the rows of heads w, w + 4, ... from the stored log-sum-exp and adds them into
+// its own shared-memory row; the four rows are combined in a fixed order.  smem: 4 * (hd + nk) floats.
+template <typename T>
+__global__ void __launch_bounds__(XA_WARPS * 32) xattn_weights_kernel(bfk_cross_attention_args a, float* __restrict__ weights) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int hd = a.hd, HD = a.H * a.hd, nk = a.nk;
+  float* q_s = smem + warp * (nk + hd);
+  float* w_s = q_s + hd;
+  for (int j = lane; j < nk; j += 32) w_s[j] = 0.f;
+  const T* base = reinterpret_cast<const T*>(a.qkv) + (long long)b * a.Nf * a.ld_qkv;
+  for (int h = warp; h < a.H; h += XA_WARPS) {
+    __syncwarp();
+    const T* q = base + (long long)(a.q0 + i) * a.ld_qkv + h * hd;
+    for (int d = lane; d < hd; d += 32) q_s[d] = to_f32<T>(q[d]);
+    __syncwarp();
+    const float* bias = xa_bias_row(a, b, h);
+    const float lse = a.lse[((long long)b * a.H + h) * a.nq + i];
+    for (int j = lane; j < nk; j += 32) {
+      const float s = a.scale * xa_dot<T>(q_s, base + (long long)(a.k0 + j) * a.ld_qkv + HD + h * hd, hd) + (bias ? bias[j] : 0.f);
+      w_s[j] += __expf(s - lse);
+    }
+  }
+  __syncthreads();
+  const float inv = 1.f / (float)a.H;
+  for (int j = threadIdx.x; j < nk; j += XA_WARPS * 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < XA_WARPS; ++w) t += smem[w * (nk + hd) + hd + j];
+    weights[((long long)b * a.nq + i) * nk + j] = t * inv;
+  }
+}
+
 template <typename K>
 static int xa_smem(K kernel, size_t bytes, const char* name) {
   if (bytes > 48 * 1024) {
@@ -223,7 +258,22 @@ static int xattn_bwd_launch(const bfk_cross_attention_args* a, cudaStream_t s) {
   return BFK_OK;
 }
 
+template <typename T>
+static int xattn_weights_launch(const bfk_cross_attention_args* a, float* weights, cudaStream_t s) {
+  const size_t smem = (size_t)XA_WARPS * (a->nk + a->hd) * sizeof(float);
+  if (int rc = xa_smem(xattn_weights_kernel<T>, smem, "bfk_cross_attention_weights")) return rc;
+  xattn_weights_kernel<T><<<dim3(a->nq, a->B), XA_WARPS * 32, smem, s>>>(*a, weights);
+  BFK_CHECK_LAUNCH("bfk_cross_attention_weights");
+  return BFK_OK;
+}
+
 }  // namespace bfk
+
+extern "C" int32_t bfk_cross_attention_weights(const bfk_cross_attention_args* a, float* weights, bfk_stream_t s_) {
+  using namespace bfk;
+  BFK_CHECK_ARG(xa_args_ok(a, false) && weights, "bfk_cross_attention_weights: bad arguments");
+  return a->dtype == BFK_BF16 ? xattn_weights_launch<__nv_bfloat16>(a, weights, to_stream(s_)) : xattn_weights_launch<float>(a, weights, to_stream(s_));
+}
 
 extern "C" int32_t bfk_cross_attention_fwd(const bfk_cross_attention_args* a, bfk_stream_t s_) {
   using namespace bfk;

@@ -131,9 +131,10 @@ class Kernels:
         self.launches += 3
         self.work["attn_flops"] += 8.0 * B * H * N * N * hd            # dP, dV, dK, dQ (recomputing S is not algorithmic work)
 
-    def cross_attention(self, qkv, out, lse, B, Nf, H, hd, q0, nq, k0, nk, scale, key_bias=None, dout=None, dqkv=None):
+    def cross_attention(self, qkv, out, lse, B, Nf, H, hd, q0, nq, k0, nk, scale, key_bias=None, dout=None, dqkv=None, weights=None):
         """Alternate fusion module (fusion.py:67-125): rows [q0, q0+nq) of every sample attend to rows [k0, k0+nk) of the packed
-        projection.  Forward when ``dout`` is None, else backward into ``dqkv``."""
+        projection.  Forward when ``dout`` is None (``weights``: optional fp32 [B, nq, nk] head-averaged attention weights), else
+        backward into ``dqkv``."""
         delta = torch.empty(B * H * nq, device=qkv.device, dtype=torch.float32) if dout is not None else None
         a = K.CrossAttentionArgs(B, Nf, H, hd, q0, nq, k0, nk, _dt(qkv), qkv.data_ptr(), 3 * H * hd, scale, K.ptr(key_bias),
                                  out.data_ptr(), H * hd, lse.data_ptr(), K.ptr(dout), H * hd, K.ptr(dqkv), 3 * H * hd, K.ptr(delta))
@@ -141,6 +142,9 @@ class Kernels:
             K.check(self.lib.bfk_cross_attention_fwd(C.byref(a), _stream()), "bfk_cross_attention_fwd")
             self.launches += 1
             self.work["attn_flops"] += 4.0 * B * H * nq * nk * hd
+            if weights is not None:
+                K.check(self.lib.bfk_cross_attention_weights(C.byref(a), weights.data_ptr(), _stream()), "bfk_cross_attention_weights")
+                self.launches += 1
         else:
             K.check(self.lib.bfk_cross_attention_bwd(C.byref(a), _stream()), "bfk_cross_attention_bwd")
             self.launches += 3
@@ -473,7 +477,9 @@ class Engine:
             bias = mask.view(B, Nf)[:, :nc].contiguous()
         att = torch.zeros(M, D, device=dev, dtype=T)          # condition rows stay zero: they meet zero gradients in the wgrad
         lse = torch.empty(B * H * nq, device=dev, dtype=torch.float32)
-        k.cross_attention(qkv, att, lse, B, Nf, H, hd, nc, nq, 0, nc, hd ** -0.5, key_bias=bias)
+        # the module's second return value (head-averaged weights, fusion.py:117-125) -> model output "attn_weights"
+        self.last_attn_weights = torch.empty(B, nq, nc, device=dev, dtype=torch.float32)
+        k.cross_attention(qkv, att, lse, B, Nf, H, hd, nc, nq, 0, nc, hd ** -0.5, key_bias=bias, weights=self.last_attn_weights)
         out = torch.empty(M, D, device=dev, dtype=torch.float32)
         k.gemm(att, self.xa_Wo, out, M, D, D, D, D, D, bias=self._p(xp + "out_proj.bias"))
         if save is not None:

@@ -440,7 +440,8 @@ class SigLip(BaseModel):
                                                    x.get("context_attention_mask") if cfg.sequential else None,
                                                    targets or [], self._param_list, self.training, need_grad, _want_argmax)
         self._last_key = key if _want_argmax else None
-        out = PolicyOutput(attn_weights=None)
+        # ConcatTransformer returns None here (fusion.py:64); CrossAttention the head-averaged weights (B, Nq, Nc), no autograd
+        out = PolicyOutput(attn_weights=getattr(self.engine, "last_attn_weights", None) if cfg.fusion_model == "crossattention" else None)
         if cfg.compute_mask:              # key order of the reference's return_dict (bifold/models/pickplace.py:64-69)
             out["mask_heatmap"] = heat[len(cfg.heads_out)]
         for i, h in enumerate(cfg.heads_out):

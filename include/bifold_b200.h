@@ -174,6 +174,9 @@ typedef struct {
 } bfk_cross_attention_args;
 BFK_API int32_t bfk_cross_attention_fwd(const bfk_cross_attention_args* a, bfk_stream_t s);
 BFK_API int32_t bfk_cross_attention_bwd(const bfk_cross_attention_args* a, bfk_stream_t s);
+/* weights[b, i, j] = mean over the heads of softmax(scores)[b, h, i, j] (fp32 [B, nq, nk]): the second return value of
+ * MultiheadAttention(need_weights=True, average_attn_weights=True), fusion.py:117-124; needs the forward's lse. */
+BFK_API int32_t bfk_cross_attention_weights(const bfk_cross_attention_args* a, float* weights, bfk_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------
  * Embeddings and token assembly.

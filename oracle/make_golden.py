@@ -81,6 +81,8 @@ def run_case(name: str, spec: PolicySpec, batch: int, full: bool):
         g[f"logits/{h}"] = probe(logits[h], full)
         g[f"heatmap/{h}"] = probe(out[f"{h}_heatmap"], full)
         g[f"logits_absmax/{h}"] = logits[h].abs().max().numpy()
+    if out.get("attn_weights") is not None:       # CrossAttention: head-averaged attention weights (bifold/models/fusion.py:117-125)
+        g["attn_weights"] = probe(out["attn_weights"], full)
     for k, p in model.named_parameters():
         if p.requires_grad:
             assert p.grad is not None, k

@@ -553,7 +553,8 @@ def test_cross_attention_fwd_bwd(kern, dtype, with_bias):
     out = torch.zeros(B * Nf, D, device="cuda", dtype=T)
     lse = torch.empty(B * H * nq, device="cuda")
     sc = hd ** -0.5
-    kern.cross_attention(qkv, out, lse, B, Nf, H, hd, q0, nq, k0, nk, sc, key_bias=bias)
+    wts = torch.empty(B, nq, nk, device="cuda")
+    kern.cross_attention(qkv, out, lse, B, Nf, H, hd, q0, nq, k0, nk, sc, key_bias=bias, weights=wts)
     dqkv = torch.zeros_like(qkv)
     kern.cross_attention(qkv, out, lse, B, Nf, H, hd, q0, nq, k0, nk, sc, key_bias=bias, dout=dout, dqkv=dqkv)
     torch.cuda.synchronize()
@@ -572,5 +573,6 @@ def test_cross_attention_fwd_bwd(kern, dtype, with_bias):
     got = out.float().view(B, Nf, D)
     assert (got[:, q0:q0 + nq] - ref).abs().max().item() <= tol * ref.abs().max().item()
     assert (got[:, :q0] == 0).all()                                        # rows outside the query range stay untouched
+    assert (wts - dots.softmax(-1).mean(1)).abs().max().item() <= (1e-5 if dtype == "fp32" else 2e-3)   # head-averaged weights
     gref = gx.reshape(B * Nf, 3 * D)
     assert (dqkv.float() - gref).abs().max().item() <= tol * gref.abs().max().item()

@@ -18,6 +18,24 @@ def _probe(t, full):
     return a if full else a.reshape(-1)[::PROBE][:4096]
 
 
+def _check_attn_weights(sd, sample, spec, g):
+    """CrossAttention's head-averaged attention weights (the module's second return value) against the reference's."""
+    b = sample["rgb"].shape[0]
+    img = torch.cat((sd["image_token"].expand(b, 1, -1), po.vision_tower(sd, sample["rgb"], spec, True)), dim=1)
+    txt = torch.cat((sd["text_token"].expand(b, 1, -1), po.text_tower(sd, sample["instruction"], spec, True)), dim=1)
+    if spec.name == "siglip_sequential":
+        c = sample["rgb_context"]
+        t, n = c.shape[1], img.shape[1]
+        ctx = po.vision_tower(sd, c.reshape(b * t, *c.shape[2:]), spec, True).view(b, t, n - 1, -1)
+        ctx = torch.cat((sd["image_token"][:, None].expand(b, t, 1, -1), ctx), dim=2).reshape(b, t * n, -1) + sd["context_pos_embedding"]
+        masks = torch.cat([torch.ones(b, txt.shape[1]), sample["context_attention_mask"].repeat_interleave(n, dim=1).float(),
+                           torch.ones(b, n)], dim=-1)
+        _, w = po.cross_attention(sd, (txt, ctx, img), [0, 1, 1], spec, masks, return_weights=True)
+    else:
+        _, w = po.cross_attention(sd, (txt, img), [0, 1], spec, None, return_weights=True)
+    np.testing.assert_allclose(w.detach().numpy(), g["attn_weights"], atol=1e-6, rtol=0)
+
+
 def _check_case(name):
     spec, batch, full = CASES[name]
     g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
@@ -28,6 +46,8 @@ def _check_case(name):
     work = dict(sd)
     work.update(leaves)
     logits = po.policy_logits(work, sample, spec, training=True)
+    if "attn_weights" in g.files:
+        _check_attn_weights(work, sample, spec, g)
     out = {f"{h}_heatmap": z.sigmoid() for h, z in logits.items()}
     loss, inter = po.bce_gaussmap(out, sample, spec)
     np.testing.assert_allclose(loss.item(), g["loss"], rtol=2e-5)
