@@ -157,6 +157,24 @@ class Kernels:
         self.launches += 1
 
 
+class _Nvtx:
+    """BFK_NVTX=1: NVTX ranges around the phases of a step (towers / fusion / tail, forward and backward) for nsys /
+    ncu --nvtx timelines.  Off by default: a range push / pop is a host call per phase."""
+    on = os.environ.get("BFK_NVTX") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Nvtx.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _Nvtx.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class LayerWeights:
     """Operand-dtype copies ("shadows") of one pre-LN transformer layer's weights."""
     __slots__ = ("ln1_w", "ln1_b", "Wqkv", "bqkv", "Acat", "Wo", "bo", "ln2_w", "ln2_b", "W1", "b1", "W2", "b2",
@@ -693,7 +711,8 @@ class Engine:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 txt = self._text_fwd(ids, tsave)                  # [B*L, D]
-            vis = self._vision_fwd(images.float(), vsave)         # [(B + B*T)*Np, D]
+            with _Nvtx("bfk.vision_tower_fwd"):
+                vis = self._vision_fwd(images.float(), vsave)     # [(B + B*T)*Np, D]
             main.wait_stream(self._side)
             txt.record_stream(main)
             ids.record_stream(self._side)
@@ -716,14 +735,16 @@ class Engine:
         del vis, txt
 
         x = X
-        if cfg.fusion_model == "crossattention":
-            x = self._xattn_fwd(X, B, Nf, mask, fsave)
-        for lw in self.fusion_layers:
-            x = self._layer_fwd(x, B, Nf, lw, cfg.heads, 1e-5, K.ACT_GELU_ERF, mask, fsave)
+        with _Nvtx("bfk.fusion_fwd"):
+            if cfg.fusion_model == "crossattention":
+                x = self._xattn_fwd(X, B, Nf, mask, fsave)
+            for lw in self.fusion_layers:
+                x = self._layer_fwd(x, B, Nf, lw, cfg.heads, 1e-5, K.ACT_GELU_ERF, mask, fsave)
 
         # ---- heatmap tail ----
         heads = len(cfg.heads_out)
-        tail = self._tail_fwd(x, B, Nf, targets, want_argmax, need_grad, pre=pre, X_in=X)
+        with _Nvtx("bfk.tail_fwd"):
+            tail = self._tail_fwd(x, B, Nf, targets, want_argmax, need_grad, pre=pre, X_in=X)
         if need_grad:
             ctx.update(vsave=vsave, tsave=tsave, fsave=fsave, mask=mask, xf=x, Nf=Nf, tail=tail, targets=targets,
                        heads=heads, X_in=X if cfg.compute_mask else None)
@@ -981,6 +1002,8 @@ class Engine:
         # ---- fusion transformer ----
         dx, dx_T = dX, (dX_T if dX_T is not None else dX)
         fsave = ctx["fsave"]
+        if _Nvtx.on:
+            torch.cuda.nvtx.range_push("bfk.fusion_bwd")
         if cfg.fusion_model == "crossattention":
             dx = self._xattn_bwd(dx, dx_T, fsave[0], B, Nf, ctx["mask"], grads)
             dx_T = None
@@ -991,6 +1014,8 @@ class Engine:
             if self.grad_ready_hook:
                 self._hook_after_off_chain(f"fusion.{l}")
         self._join_off_chain()
+        if _Nvtx.on:
+            torch.cuda.nvtx.range_pop()
         if dX_mask is not None:
             K.check(lib.bfk_add_inplace(dx.data_ptr(), dX_mask.data_ptr(), dx.numel(), st), "bfk_add_inplace")
             k.launches += 1
@@ -1026,7 +1051,8 @@ class Engine:
                     if self.grad_ready_hook:
                         self._hook_after_off_chain("text")
                     self._join_off_chain()
-                self._tower_bwd(dvis, ctx["vsave"], self.vis_layers, B + B * T_ctx, Np, vp + ".post_layernorm.weight", grads)
+                with _Nvtx("bfk.vision_tower_bwd"):
+                    self._tower_bwd(dvis, ctx["vsave"], self.vis_layers, B + B * T_ctx, Np, vp + ".post_layernorm.weight", grads)
                 main.wait_stream(self._side)
             else:
                 self._tower_bwd(dtxt, ctx["tsave"], self.text_layers, B, L, tp + ".final_layer_norm.weight", grads)
