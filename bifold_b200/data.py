@@ -84,8 +84,12 @@ class DevicePrefetcher:
 class ScalarReader:
     """Device scalars -> host through a small pinned ring, read one step late (no launch-queue stall)."""
 
+    _pinned = {}     # depth -> pinned ring, allocated once per process (cudaHostAlloc costs up to a millisecond and may synchronise)
+
     def __init__(self, device: torch.device, depth: int = 2):
-        self.buf = torch.empty(depth, dtype=torch.float32).pin_memory()
+        if depth not in ScalarReader._pinned:
+            ScalarReader._pinned[depth] = torch.empty(depth, dtype=torch.float32).pin_memory()
+        self.buf = ScalarReader._pinned[depth]
         self.events: List[Optional[torch.cuda.Event]] = [None] * depth
         self.depth, self.n = depth, 0
         self.values: List[float] = []
