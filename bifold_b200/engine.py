@@ -204,6 +204,7 @@ class Engine:
         self._side = None
         self.fuse_lora_down = os.environ.get("BFK_FUSE_LORA_DOWN", "1") != "0"
         self.overlap_wgrad = os.environ.get("BFK_OVERLAP_WGRAD", "1") != "0"
+        self.use_opt_shadow = os.environ.get("BFK_OPT_SHADOW", "1") != "0"     # fusion GEMM weights: bf16 copies written by the Adam kernel
         self._wgrad_streams, self._wgrad_busy = {}, False
 
     # ------------------------------------------------------------------------------------------------
@@ -279,12 +280,33 @@ class Engine:
             w = self._p(n[k])
             if self.T == torch.float32:
                 setattr(lw, k, w)
+                continue
+            sh = self._opt_shadow(self.params[n[k]]) if self.use_opt_shadow else None
+            if sh is not None:
+                # the optimizer's Adam kernel keeps this bf16 copy current (FusedAdam.ensure_shadow): a cast is only needed when
+                # the parameter changed some other way (load_state_dict, manual edits)
+                setattr(lw, k, sh)
+                par = self.params[n[k]]
+                if getattr(par, "_bfk_shadow_ver", None) != par._version:
+                    segs.append((w, sh.data_ptr(), w.shape[0], w.shape[1], w.shape[1], 1.0, self.T))
+                    par._bfk_shadow_ver = par._version
             else:
                 cur = getattr(lw, k, None) if hasattr(lw, k) else None
                 if cur is None or cur.shape != w.shape:
                     cur = torch.empty_like(w, dtype=self.T)
                     setattr(lw, k, cur)
                 segs.append((w, cur.data_ptr(), w.shape[0], w.shape[1], w.shape[1], 1.0, self.T))
+
+    def _opt_shadow(self, par):
+        """bf16 view of `par` inside its optimizer's flat shadow buffer, or None (no FusedAdam yet / parameter re-homed)."""
+        info = getattr(par, "_bfk_opt", None)
+        if info is None:
+            return None
+        opt, gi, off = info[0](), info[1], info[2]
+        st = opt._flat.get(gi) if opt is not None else None
+        if st is None or par.data_ptr() != st["p"].data_ptr() + 4 * off or par.dtype != torch.float32:
+            return None
+        return opt.ensure_shadow(gi)[off:off + par.numel()].view(par.shape)
 
     def _refresh_trainable(self):
         """ONE launch (bfk_multi_cast) re-derives every operand-dtype copy of the trainable weights."""

@@ -8,6 +8,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import weakref
+
 import torch
 
 from . import _cabi as K
@@ -58,13 +60,34 @@ class FusedAdam(torch.optim.Optimizer):
             s["step"] = torch.tensor(float(step))
             s["exp_avg"] = m[o:o + p.numel()].view(p.shape)
             s["exp_avg_sq"] = v[o:o + p.numel()].view(p.shape)
-        st = dict(ps=ps, offs=offs, tot=tot, p=flat, m=m, v=v, step=step)
+        st = dict(ps=ps, offs=offs, tot=tot, p=flat, m=m, v=v, step=step, shadow=None)
         self._flat[gi] = st
+        for p, o in zip(ps, offs):          # lets bifold_b200.engine find the group's bf16 shadow (ensure_shadow)
+            p._bfk_opt = (weakref.ref(self), gi, o)
+            p._bfk_shadow_ver = None
         return st
 
-    def _launch(self, n, p, g, m, v, group, step, dyn=None):
+    def ensure_shadow(self, gi):
+        """bf16 copy of the flat parameter buffer of group ``gi``, same element offsets, kept current by the Adam kernel itself
+        (2 extra bytes written per parameter instead of a separate cast pass over every trainable GEMM weight).  Created on the
+        first request (the engine asks for it in bf16 mode); ``p._bfk_shadow_ver == p._version`` marks a parameter's slice as
+        current."""
+        st = self._flat[gi]
+        if st["shadow"] is None:
+            st["shadow"] = torch.empty(st["tot"], device=st["p"].device, dtype=torch.bfloat16)
+            st["shadow"].copy_(st["p"])
+            for p in st["ps"]:
+                p._bfk_shadow_ver = p._version
+        return st["shadow"]
+
+    def _mark_shadow(self, st):
+        if st.get("shadow") is not None:
+            for p in st["ps"]:
+                p._bfk_shadow_ver = p._version
+
+    def _launch(self, n, p, g, m, v, group, step, dyn=None, shadow=None):
         b1, b2 = group["betas"]
-        a = K.AdamWArgs(n, p, g, m, v, None, group["lr"], b1, b2, group["eps"], group["weight_decay"],
+        a = K.AdamWArgs(n, p, g, m, v, shadow, group["lr"], b1, b2, group["eps"], group["weight_decay"],
                         int(group["decoupled"]), step, float(self.grad_scale), K.ptr(dyn))
         K.check(K.load().bfk_adamw(C.byref(a), torch.cuda.current_stream().cuda_stream), "bfk_adamw")
         self.launches += 1
@@ -104,6 +127,7 @@ class FusedAdam(torch.optim.Optimizer):
             # the replayed kernels wrote the parameters through raw pointers: an eager forward after a replay must
             # re-derive its operand copies (Engine.prepare compares version counters)
             torch._C._increment_version(st["ps"])
+            self._mark_shadow(st)           # the replayed Adam kernel wrote the bf16 shadow too
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -134,10 +158,12 @@ class FusedAdam(torch.optim.Optimizer):
                                                    torch.cuda.current_stream().cuda_stream), "bfk_adamw_advance")
                 self.launches += 1
                 self._launch(st["tot"], st["p"].data_ptr(), g0.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(), group, st["step"],
-                             dyn=st["dyn"])
+                             dyn=st["dyn"], shadow=K.ptr(st["shadow"]))
             elif flat_ok:
-                self._launch(st["tot"], st["p"].data_ptr(), g0.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(), group, st["step"])
+                self._launch(st["tot"], st["p"].data_ptr(), g0.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(), group, st["step"],
+                             shadow=K.ptr(st["shadow"]))
             else:
+                st["shadow"] = None         # per-tensor launches (foreign gradients): the engine goes back to its own cast pass
                 for p, o in zip(ps, offs):
                     if p.grad is None:
                         continue
@@ -148,6 +174,7 @@ class FusedAdam(torch.optim.Optimizer):
                                  st["v"].data_ptr() + 4 * o, group, st["step"])
             # the kernels wrote through raw pointers: tell torch (and the engine's operand-copy cache) the values changed
             torch._C._increment_version(ps)
+            self._mark_shadow(st)
         return loss
 
 
