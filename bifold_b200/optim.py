@@ -163,7 +163,7 @@ class FusedAdam(torch.optim.Optimizer):
                 self._launch(st["tot"], st["p"].data_ptr(), g0.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(), group, st["step"],
                              shadow=K.ptr(st["shadow"]))
             else:
-                st["shadow"] = None         # per-tensor launches (foreign gradients): the engine goes back to its own cast pass
+                sh = st["shadow"].data_ptr() if st["shadow"] is not None else None
                 for p, o in zip(ps, offs):
                     if p.grad is None:
                         continue
@@ -171,7 +171,7 @@ class FusedAdam(torch.optim.Optimizer):
                     if g.data_ptr() % 16:
                         g = g.clone()
                     self._launch(p.numel(), st["p"].data_ptr() + 4 * o, g.data_ptr(), st["m"].data_ptr() + 4 * o,
-                                 st["v"].data_ptr() + 4 * o, group, st["step"])
+                                 st["v"].data_ptr() + 4 * o, group, st["step"], shadow=(sh + 2 * o) if sh is not None else None)
             # the kernels wrote through raw pointers: tell torch (and the engine's operand-copy cache) the values changed
             torch._C._increment_version(ps)
             self._mark_shadow(st)
